@@ -1,0 +1,285 @@
+"""Autograd-facing wrappers over the C ABI (one kernel launch per forward, lazy rescale on backward).
+
+Design notes
+  * Forward launches compute the loss AND the gradient for an upstream gradient of 1.0 in the same
+    pass over the head maps.  ``backward`` only launches ``cnh_scale_inplace``, which reads the real
+    upstream gradient from device memory and returns immediately when it is exactly 1.0 (the
+    ``loss.backward()`` case) -- no host synchronisation anywhere.
+  * The gradients handed to autograd are the tensors written by the forward launch (no copy), so a
+    graph may be backpropagated once; a second backward raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+_ACCURATE = os.environ.get("CNH_ACCURATE_MATH", "0") == "1"
+_NO_STASH = os.environ.get("CNH_NO_STASH", "0") == "1"
+
+
+def default_flags() -> int:
+    return (L.FLAG_ACCURATE_MATH if _ACCURATE else 0) | (L.FLAG_NO_STASH if _NO_STASH else 0)
+
+
+class HeadSpec:
+    """One masked gather-L1 head: prediction map, target rows, mask and weights."""
+
+    def __init__(self, fmap, target, mask, weight, angle_weight=1.0, angle_mode=L.ANGLE_NONE,
+                 elementwise_mask=False):
+        self.fmap, self.target, self.mask = fmap, target, mask
+        self.weight, self.angle_weight = float(weight), float(angle_weight)
+        self.angle_mode, self.elementwise_mask = int(angle_mode), bool(elementwise_mask)
+
+
+def _as_mask(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.uint8:
+        t = t.to(torch.uint8)
+    return L.require(t, "mask", torch.uint8)
+
+
+def fill_detloss_args(hm, gt, ind, heads: Sequence[HeadSpec], hm_weight, prob, grads, scalars, partials,
+                      norm=None, norm_out=None, flags=None, b_global=None) -> L.DetLossArgs:
+    B, Cc, H, W = hm.shape
+    a = L.DetLossArgs()
+    a.B, a.C, a.H, a.W = B, Cc, H, W
+    a.M = ind.shape[1] if ind is not None else 0
+    a.n_heads = len(heads)
+    a.flags = default_flags() if flags is None else flags
+    a.B_global = B if b_global is None else b_global
+    a.hm_logits, a.hm_gt, a.prob = hm.data_ptr(), gt.data_ptr(), prob.data_ptr()
+    a.grad_hm = L.ptr(grads[0]) if grads is not None else None
+    a.ind = L.ptr(ind)
+    a.hm_weight = float(hm_weight)
+    for i, h in enumerate(heads):
+        hd = a.heads[i]
+        hd.map, hd.target, hd.mask = h.fmap.data_ptr(), h.target.data_ptr(), h.mask.data_ptr()
+        hd.grad = L.ptr(grads[1 + i]) if grads is not None else None
+        hd.D = h.fmap.shape[1]
+        hd.angle_mode = h.angle_mode
+        hd.elementwise_mask = 1 if h.elementwise_mask else 0
+        hd.weight, hd.angle_weight = h.weight, h.angle_weight
+    a.scalars, a.partials = L.ptr(scalars), L.ptr(partials)
+    a.norm, a.norm_out = L.ptr(norm), L.ptr(norm_out)
+    return a
+
+
+def _check_heads(hm, gt, ind, heads):
+    B, Cc, H, W = hm.shape
+    if gt.shape != hm.shape:
+        raise RuntimeError(f"cnhead: batch['hm'] {tuple(gt.shape)} does not match output['hm'] {tuple(hm.shape)}")
+    if len(heads) > L.MAX_HEADS:
+        raise RuntimeError("cnhead: at most 3 regression heads")
+    M = ind.shape[1]
+    if ind.shape[0] != B:
+        raise RuntimeError("cnhead: batch['ind'] batch dimension mismatch")
+    for h in heads:
+        D = h.fmap.shape[1]
+        if h.fmap.shape[0] != B or tuple(h.fmap.shape[2:]) != (H, W):
+            raise RuntimeError(f"cnhead: head map {tuple(h.fmap.shape)} does not match heat map {tuple(hm.shape)}")
+        if tuple(h.target.shape) != (B, M, D):
+            raise RuntimeError(f"cnhead: head target {tuple(h.target.shape)} != {(B, M, D)}")
+        want = (B, M, D) if h.elementwise_mask else (B, M)
+        if tuple(h.mask.shape) != want:
+            raise RuntimeError(f"cnhead: head mask {tuple(h.mask.shape)} != {want}")
+
+
+class _DetectionLossFn(torch.autograd.Function):
+    """inputs: hm logits, then one map per head.  Outputs: scalars[8], clamped prob, partials."""
+
+    @staticmethod
+    def forward(ctx, meta, hm, *maps):
+        gt, ind, specs, hm_weight = meta
+        heads = [HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode, s.elementwise_mask)
+                 for m, s in zip(maps, specs)]
+        need_grad = any(ctx.needs_input_grad[1:])
+        prob = torch.empty_like(hm)
+        grads = [torch.empty_like(hm)] + [torch.empty_like(m) for m in maps] if need_grad else None
+        scalars = torch.empty(L.SCALARS, dtype=torch.float32, device=hm.device)
+        partials = torch.empty(hm.shape[0], L.PARTIALS, dtype=torch.float64, device=hm.device)
+        a = fill_detloss_args(hm, gt, ind, heads, hm_weight, prob, grads, scalars, partials)
+        nbytes = L.lib().cnh_detloss_workspace_bytes(C.byref(a))
+        ws = L.workspace("detloss", nbytes, hm.device)
+        L.check(L.lib().cnh_detloss_fused(C.byref(a), ws.data_ptr(), ws.numel(), L.stream_ptr()), "detloss_fused")
+        ctx.grads = grads
+        ctx.used = False
+        ctx.mark_non_differentiable(prob, partials)
+        return scalars, prob, partials
+
+    @staticmethod
+    def backward(ctx, g_scalars, _g_prob, _g_partials):
+        if ctx.grads is None:
+            raise RuntimeError("cnhead: DetectionLoss was run without gradients")
+        if ctx.used:
+            raise RuntimeError("cnhead: the fused DetectionLoss graph can be backpropagated only once "
+                               "(its gradients were produced by the forward launch); run forward again")
+        ctx.used = True
+        grads = ctx.grads
+        g = L.require(g_scalars, "grad_output")
+        s = L.ScaleArgs()
+        s.n_tensors = len(grads)
+        base = g.data_ptr()
+        for i, t in enumerate(grads):
+            s.data[i] = t.data_ptr()
+            s.count[i] = t.numel()
+            s.fa[i] = base                      # d/d(total loss)
+            s.fb[i] = base + 4 * (1 + i)        # d/d(hm_loss | head-i loss) if a stat is differentiated
+        L.check(L.lib().cnh_scale_inplace(C.byref(s), L.stream_ptr()), "scale_inplace")
+        out = [None] + [gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[1:])]
+        return tuple(out)
+
+
+class _Spec:
+    __slots__ = ("target", "mask", "weight", "angle_weight", "angle_mode", "elementwise_mask")
+
+
+def detection_loss(hm: torch.Tensor, gt: torch.Tensor, ind: torch.Tensor, heads: Sequence[HeadSpec],
+                   hm_weight: float = 1.0):
+    """Fused DetectionLoss core.  Returns (scalars[8], prob, partials[B,12]); see include/cnhead.h."""
+    hm = L.require(hm, "output['hm']")
+    gt = L.require(gt, "batch['hm']")
+    ind = L.require(ind, "batch['ind']", torch.int64)
+    specs, maps = [], []
+    for h in heads:
+        sp = _Spec()
+        sp.target = L.require(h.target, "head target")
+        sp.mask = _as_mask(h.mask)
+        sp.weight, sp.angle_weight = h.weight, h.angle_weight
+        sp.angle_mode, sp.elementwise_mask = h.angle_mode, h.elementwise_mask
+        specs.append(sp)
+        maps.append(L.require(h.fmap, "head map"))
+    _check_heads(hm, gt, ind, [HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode,
+                                        s.elementwise_mask) for m, s in zip(maps, specs)])
+    return _DetectionLossFn.apply((gt, ind, specs, float(hm_weight)), hm, *maps)
+
+
+# ----------------------------------------------------------------------------------------------
+# channel-softmax losses
+# ----------------------------------------------------------------------------------------------
+class _SoftmaxLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mode, eta, n_total):
+        N, Cc, H, W = x.shape
+        need_grad = ctx.needs_input_grad[0]
+        grad = torch.empty_like(x) if need_grad else None
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        nbytes = L.lib().cnh_softmax_workspace_bytes(N, Cc, H, W)
+        ws = L.workspace("softmax", nbytes, x.device)
+        L.check(L.lib().cnh_softmax_loss(x.data_ptr(), L.ptr(grad), out.data_ptr(), N, Cc, H, W,
+                                         n_total if n_total else N, mode, float(eta if eta is not None else 0.0),
+                                         ws.data_ptr(), ws.numel(), L.stream_ptr()), "softmax_loss")
+        ctx.grad = grad
+        ctx.used = False
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        if ctx.used:
+            raise RuntimeError("cnhead: this fused loss can be backpropagated only once; run forward again")
+        ctx.used = True
+        g = L.require(g_out, "grad_output")
+        s = L.ScaleArgs()
+        s.n_tensors = 1
+        s.data[0], s.count[0], s.fa[0], s.fb[0] = ctx.grad.data_ptr(), ctx.grad.numel(), g.data_ptr(), None
+        L.check(L.lib().cnh_scale_inplace(C.byref(s), L.stream_ptr()), "scale_inplace")
+        return ctx.grad, None, None, None
+
+
+def softmax_loss(x: torch.Tensor, mode: int, eta: Optional[float] = None, n_total: int = 0) -> torch.Tensor:
+    x = L.require(x, "outputs['hm']")
+    if x.dim() != 4:
+        raise RuntimeError(f"cnhead: expected [N,C,H,W] logits, got {tuple(x.shape)}")
+    return _SoftmaxLossFn.apply(x, mode, eta, n_total)
+
+
+class _EntropyMapFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        N, Cc, H, W = x.shape
+        out = torch.empty_like(x)
+        L.check(L.lib().cnh_entropy_map_fwd(x.data_ptr(), out.data_ptr(), N, Cc, H, W, L.stream_ptr()),
+                "entropy_map_fwd")
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = L.require(g, "grad_output")
+        N, Cc, H, W = x.shape
+        gin = torch.empty_like(x)
+        L.check(L.lib().cnh_entropy_map_bwd(x.data_ptr(), g.data_ptr(), gin.data_ptr(), N, Cc, H, W,
+                                            L.stream_ptr()), "entropy_map_bwd")
+        return gin
+
+
+def entropy_map(x: torch.Tensor) -> torch.Tensor:
+    x = L.require(x, "hm")
+    if x.dim() != 4:
+        raise RuntimeError(f"cnhead: expected [N,C,H,W] logits, got {tuple(x.shape)}")
+    return _EntropyMapFn.apply(x)
+
+
+class _BceConstFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, label):
+        need_grad = ctx.needs_input_grad[0]
+        grad = torch.empty_like(y) if need_grad else None
+        out = torch.empty((), dtype=torch.float32, device=y.device)
+        L.check(L.lib().cnh_bce_const(y.data_ptr(), L.ptr(grad), out.data_ptr(), y.numel(), float(label),
+                                      L.stream_ptr()), "bce_const")
+        ctx.grad = grad
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        return ctx.grad * g_out, None          # a [N,1,h/32,w/32] discriminator map: tiny
+
+
+def bce_const(y: torch.Tensor, label: float) -> torch.Tensor:
+    return _BceConstFn.apply(L.require(y, "y_pred"), float(label))
+
+
+# ----------------------------------------------------------------------------------------------
+# decode
+# ----------------------------------------------------------------------------------------------
+def decode(heat, wh, reg=None, kps=None, K=100, rotated=False, apply_sigmoid=False, box_scale=1.0,
+           return_inds=False):
+    heat = L.require(heat.detach(), "heat")
+    wh = L.require(wh.detach(), "wh")
+    reg = L.require(reg.detach(), "reg") if reg is not None else None
+    kps = L.require(kps.detach(), "kps") if kps is not None else None
+    if heat.dim() != 4 or wh.dim() != 4:
+        raise RuntimeError("cnhead: decode expects [B,C,H,W] heat and [B,D,H,W] wh")
+    B, Cc, H, W = heat.shape
+    if wh.shape[0] != B or tuple(wh.shape[2:]) != (H, W):
+        raise RuntimeError(f"cnhead: wh {tuple(wh.shape)} does not match heat {tuple(heat.shape)}")
+    if reg is not None and tuple(reg.shape) != (B, 2, H, W):
+        raise RuntimeError(f"cnhead: reg {tuple(reg.shape)} != {(B, 2, H, W)}")
+    K = int(K)
+    a = L.DecodeArgs()
+    a.B, a.C, a.H, a.W, a.K, a.D = B, Cc, H, W, K, wh.shape[1]
+    a.rotated = 1 if rotated else 0
+    a.nk = kps.shape[1] // 2 if kps is not None else 0
+    dets = torch.empty(B, K, 7 if rotated else 6, dtype=torch.float32, device=heat.device)
+    inds = torch.empty(B, K, dtype=torch.int64, device=heat.device) if return_inds else None
+    kout = torch.empty(B, K, a.nk, 2, dtype=torch.float32, device=heat.device) if kps is not None else None
+    a.heat, a.wh, a.reg, a.kps = heat.data_ptr(), wh.data_ptr(), L.ptr(reg), L.ptr(kps)
+    a.dets, a.inds_out, a.kps_out = dets.data_ptr(), L.ptr(inds), L.ptr(kout)
+    a.apply_sigmoid = 1 if apply_sigmoid else 0
+    a.box_scale = float(box_scale)
+    nbytes = L.lib().cnh_decode_workspace_bytes(C.byref(a))
+    if nbytes == 0:
+        L.check(-2, "decode")
+    ws = L.workspace("decode", nbytes, heat.device)
+    L.check(L.lib().cnh_decode(C.byref(a), ws.data_ptr(), ws.numel(), L.stream_ptr()), "decode")
+    res = (dets,)
+    if kps is not None:
+        res += (kout,)
+    if return_inds:
+        res += (inds,)
+    return res[0] if len(res) == 1 else res

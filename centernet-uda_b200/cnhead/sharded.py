@@ -1,0 +1,155 @@
+"""Batch-sharded DetectionLoss / UDA losses: one process per GPU, each rank owns B/G samples.
+
+The reference runs the loss on one GPU over the whole batch (nn.DataParallel gathers the head maps to
+cuda:0, utils/helper.py:75-80, uda/base.py:64-68).  Here every rank runs the fused kernels on its own
+samples; the only coupling between samples is through the batch-wide normalisers (num_pos,
+losses/centernet.py:87-94; mask.sum(), :120,130,213), so the exchange is:
+
+    cnh_detloss_count   -> this shard's [num_pos, mask counts]            (reads targets only)
+    all_reduce(SUM)        4 doubles over NCCL / NVLink                   <- the one collective the
+    cnh_detloss_main    -> probabilities, FINAL gradients, per-sample partials    gradients wait for
+    all_gather             per-sample partial rows [B/G, 12] doubles      (loss VALUE only, off the
+    cnh_detloss_finalize-> loss scalars, summed in global sample order     critical path of backward)
+
+Integer-valued counts are exact in float64 and the per-sample partial rows do not depend on how the
+batch is sharded, so every rank obtains scalars bit-identical to the single-device launch, and
+gradients bit-identical on the heat map.  Decode needs no exchange at all.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import functional as F
+
+
+# ---- collective plumbing (device-agnostic: exercised with gloo on CPU in tests) ------------------
+def exchange_normalisers(norm_local: torch.Tensor, group=None, async_op: bool = False):
+    """[num_pos, cnt_head0, cnt_head1, cnt_head2] of this shard (float64) -> batch-wide sums, in place."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(norm_local, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def gather_partials(partials: torch.Tensor, group=None) -> torch.Tensor:
+    """per-sample rows of this shard [b, 12] -> rows of the whole batch in rank order [G*b, 12]."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return partials
+    world = dist.get_world_size(group)
+    out = partials.new_empty((world * partials.shape[0], partials.shape[1]))
+    dist.all_gather_into_tensor(out, partials.contiguous(), group=group)
+    return out
+
+
+def shard_slice(batch: int, rank: int, world: int) -> slice:
+    """samples [rank*B/G, (rank+1)*B/G) -- the batch must divide evenly (as DataParallel's scatter
+    would require for equal shards)."""
+    if batch % world != 0:
+        raise ValueError(f"global batch {batch} is not divisible by world size {world}")
+    per = batch // world
+    return slice(rank * per, (rank + 1) * per)
+
+
+# ---- CUDA path --------------------------------------------------------------------------------------
+class _ShardedDetectionLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, meta, hm, *maps):
+        gt, ind, specs, hm_weight, group = meta
+        heads = [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode, s.elementwise_mask)
+                 for m, s in zip(maps, specs)]
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        dev = hm.device
+        prob = torch.empty_like(hm)
+        grads = [torch.empty_like(hm)] + [torch.empty_like(m) for m in maps]
+        scalars = torch.empty(L.SCALARS, dtype=torch.float32, device=dev)
+        partials = torch.empty(hm.shape[0], L.PARTIALS, dtype=torch.float64, device=dev)
+        norm = torch.empty(4, dtype=torch.float64, device=dev)
+        a = F.fill_detloss_args(hm, gt, ind, heads, hm_weight, prob, grads, None, partials,
+                                norm=norm, norm_out=norm, b_global=hm.shape[0] * world)
+        ws = L.workspace("detloss", L.lib().cnh_detloss_workspace_bytes(C.byref(a)), dev)
+        st = L.stream_ptr()
+        L.check(L.lib().cnh_detloss_count(C.byref(a), ws.data_ptr(), ws.numel(), st), "detloss_count")
+        exchange_normalisers(norm, group)
+        L.check(L.lib().cnh_detloss_main(C.byref(a), ws.data_ptr(), ws.numel(), st), "detloss_main")
+        all_rows = gather_partials(partials, group)
+        a.scalars = scalars.data_ptr()
+        L.check(L.lib().cnh_detloss_finalize(C.byref(a), all_rows.data_ptr(), all_rows.shape[0], st),
+                "detloss_finalize")
+        ctx.grads = grads
+        ctx.used = False
+        ctx.mark_non_differentiable(prob, all_rows)
+        return scalars, prob, all_rows
+
+    backward = staticmethod(F._DetectionLossFn.backward)
+
+
+def detection_loss_sharded(hm, gt, ind, heads: Sequence[F.HeadSpec], hm_weight=1.0, group=None):
+    hm = L.require(hm, "output['hm']")
+    gt = L.require(gt, "batch['hm']")
+    ind = L.require(ind, "batch['ind']", torch.int64)
+    specs, maps = [], []
+    for h in heads:
+        sp = F._Spec()
+        sp.target = L.require(h.target, "head target")
+        sp.mask = F._as_mask(h.mask)
+        sp.weight, sp.angle_weight = h.weight, h.angle_weight
+        sp.angle_mode, sp.elementwise_mask = h.angle_mode, h.elementwise_mask
+        specs.append(sp)
+        maps.append(L.require(h.fmap, "head map"))
+    F._check_heads(hm, gt, ind, [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode,
+                                            s.elementwise_mask) for m, s in zip(maps, specs)])
+    if not any(t.requires_grad for t in [hm] + maps) or not torch.is_grad_enabled():
+        # validation: no gradients -> no normaliser exchange; only the loss value is reduced
+        scalars, prob, partials = F.detection_loss(hm, gt, ind, heads, hm_weight)
+        rows = gather_partials(partials, group)
+        if rows is not partials:
+            a = F.fill_detloss_args(hm, gt, ind, [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight,
+                                                             s.angle_mode, s.elementwise_mask)
+                                                  for m, s in zip(maps, specs)],
+                                    hm_weight, prob, None, scalars, partials)
+            L.check(L.lib().cnh_detloss_finalize(C.byref(a), rows.data_ptr(), rows.shape[0], L.stream_ptr()),
+                    "detloss_finalize")
+        return scalars, prob, rows
+    return _ShardedDetectionLossFn.apply((gt, ind, specs, float(hm_weight), group), hm, *maps)
+
+
+def make_sharded_loss(base_cls):
+    """DetectionLoss whose forward takes THIS RANK's slice of the batch and returns the loss of the
+    whole (global) batch; gradients are those of the global loss w.r.t. the local head maps."""
+
+    class ShardedDetectionLoss(base_cls):
+        def __init__(self, *args, group=None, **kwargs):
+            super().__init__(*args, **kwargs)
+            self.group = group
+
+        def forward(self, output, batch):
+            if self.with_keypoints and self.kp_indices is not None:
+                raise NotImplementedError("limb-length keypoint term is not sharded")
+            heads = self._heads(output, batch)
+            scalars, prob, rows = detection_loss_sharded(output['hm'], batch['hm'], batch['ind'], heads,
+                                                         self.hm_weight, self.group)
+            output['hm'] = prob
+            stats = {'centernet_loss': scalars[0], 'hm_loss': scalars[1], 'wh_loss': scalars[2],
+                     'off_loss': scalars[3]}
+            if self.with_keypoints:
+                stats['kp_loss'] = scalars[4]
+            self.last_partials = rows
+            return scalars[0], stats
+
+    return ShardedDetectionLoss
+
+
+def softmax_loss_sharded(x: torch.Tensor, mode: int, eta: Optional[float] = None, group=None) -> torch.Tensor:
+    """Entropy / max-squares over a sharded target-domain batch: the normaliser is static (global N), so
+    gradients need no exchange; the reported scalar is all-reduced (detached from the graph)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    loss = F.softmax_loss(x, mode, eta, n_total=x.shape[0] * world)
+    if world > 1:
+        total = loss.detach().clone()
+        dist.all_reduce(total, group=group)
+        loss = loss + (total - loss.detach())       # value = global loss, gradient = local contribution
+    return loss

@@ -1,0 +1,87 @@
+// Shared helpers for libcnhead_sm100 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "cnhead.h"
+
+namespace cnh {
+
+constexpr int kThreads = 256;            // every streaming kernel uses 8 warps per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr float kLo = 1e-4f;             // utils/tensor.py:6 clamp bounds
+constexpr float kHi = 1.0f - 1e-4f;
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int sm_count();                          // SMs of the current device (cached)
+
+#define CNH_REQUIRE(cond, code, ...)      \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::cnh::set_error(__VA_ARGS__);      \
+      return (code);                      \
+    }                                     \
+  } while (0)
+
+#define CNH_CUDA(expr)                                        \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return ::cnh::cuda_fail(_e, #expr); \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum with a fixed reduction tree (lane tree, then warps in order): the result
+// depends only on the per-thread inputs, never on scheduling.  `red` holds kWarps values.
+// Every thread returns the total.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();                       // protect `red` from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  T t = red[0];
+#pragma unroll
+  for (int w = 1; w < kWarps; ++w) t += red[w];
+  return t;
+}
+
+// sigmoid pieces.  FAST: ex2.approx / rcp.approx / lg2.approx (3 MUFU ops per element);
+// accurate: libdevice expf/logf and an IEEE divide.
+template <bool FAST>
+__device__ __forceinline__ float sigmoidf_(float x) {
+  if (FAST) return __fdividef(1.0f, 1.0f + __expf(-x));
+  return 1.0f / (1.0f + expf(-x));
+}
+template <bool FAST>
+__device__ __forceinline__ float logf_(float x) {
+  return FAST ? __logf(x) : logf(x);
+}
+__device__ __forceinline__ float clamp_prob(float s) { return fminf(fmaxf(s, kLo), kHi); }
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void stg_stream(float4* p, float4 v) { __stcs(p, v); }
+
+}  // namespace cnh

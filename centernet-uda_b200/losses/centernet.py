@@ -1,0 +1,83 @@
+"""``losses.centernet.DetectionLoss`` -- drop-in for the reference module of the same dotted name
+(losses/centernet.py:7-56), backed by ONE fused sm_100a launch (csrc/detloss.cu) instead of ~100
+eager kernels.  Same constructor kwargs (configs/defaults.yaml:21-26), same call
+``crit(output_dict, batch_dict) -> (loss, stats)``, same stat keys, same post-condition
+``output['hm'] = clamp(sigmoid(output['hm']), 1e-4, 1-1e-4)`` that decode relies on
+(uda/base.py:76-77).
+
+Deliberate differences (no caller depends on them):
+  * the head tensors and ``batch['wh'|'reg'|'kps']`` are NOT modified in place (the reference
+    sigmoid-s ``output['hm']`` storage and masks the targets in place);
+  * the returned probability map carries no autograd history;
+  * a graph can be backpropagated once (gradients are produced by the forward launch).
+CUDA fp32 tensors only: CPU tensors raise ``RuntimeError`` (there is no fallback path).
+"""
+import torch
+
+from cnhead import _lib as _L
+from cnhead import functional as _F
+from cnhead._dropin import reexport as _reexport
+
+
+class DetectionLoss(torch.nn.Module):
+    def __init__(self, hm_weight, wh_weight, off_weight, kp_weight=None, angle_weight=1.0, periodic=False,
+                 kp_indices=None, kp_distance_weight=0.1, kp_distance_weight_l1=False):
+        super().__init__()
+        self.hm_weight, self.wh_weight, self.off_weight = hm_weight, wh_weight, off_weight
+        self.angle_weight, self.periodic = angle_weight, periodic
+        self.with_keypoints = kp_weight is not None or kp_indices is not None
+        self.kp_weight = kp_weight
+        self.kp_indices = torch.tensor(kp_indices) if kp_indices else None
+        self.kp_distance_weight, self.kp_distance_weight_l1 = kp_distance_weight, kp_distance_weight_l1
+
+    def _heads(self, output, batch):
+        wh = output['wh']
+        mode = _L.ANGLE_NONE
+        if wh.shape[1] == 3:                      # losses/centernet.py:112 / :15-19
+            mode = _L.ANGLE_PERIODIC if self.periodic else _L.ANGLE_SIGMOID
+        elif self.periodic:
+            raise RuntimeError("DetectionLoss(periodic=True) needs a 3-channel 'wh' head")
+        heads = [_F.HeadSpec(wh, batch['wh'], batch['reg_mask'], self.wh_weight, self.angle_weight, mode),
+                 _F.HeadSpec(output['reg'], batch['reg'], batch['reg_mask'], self.off_weight)]
+        if self.with_keypoints:                   # losses/centernet.py:143-151
+            heads.append(_F.HeadSpec(output['kps'], batch['kps'], batch['kp_reg_mask'],
+                                     1.0 if self.kp_weight is None else self.kp_weight,
+                                     elementwise_mask=True))
+        return heads
+
+    def forward(self, output, batch):
+        heads = self._heads(output, batch)
+        scalars, prob, partials = _F.detection_loss(output['hm'], batch['hm'], batch['ind'], heads,
+                                                    self.hm_weight)
+        output['hm'] = prob                        # losses/centernet.py:34
+        loss, hm_loss, wh_loss, off_loss = scalars[0], scalars[1], scalars[2], scalars[3]
+        stats = {'centernet_loss': loss, 'hm_loss': hm_loss, 'wh_loss': wh_loss, 'off_loss': off_loss}
+        if self.with_keypoints:
+            kp_loss = scalars[4]
+            if self.kp_indices is not None:        # limb-length term, O(B*M*pairs): losses/centernet.py:153-187
+                dist = self._limb_term(output['kps'], batch)
+                kp_loss = kp_loss + dist
+                loss = loss + dist
+                stats['centernet_loss'] = loss
+            stats['kp_loss'] = kp_loss
+        self.last_partials = partials
+        return loss, stats
+
+    def _limb_term(self, kps_map, batch):
+        ind, mask = batch['ind'], batch['kp_reg_mask'].float()
+        b, d = kps_map.shape[:2]
+        pred = kps_map.reshape(b, d, -1).gather(2, ind.unsqueeze(1).expand(-1, d, -1)).transpose(1, 2) * mask
+        tgt = batch['kps'] * mask
+        n, c, k2 = tgt.shape
+        pairs = self.kp_indices.to(ind.device)
+        p, t = pred.reshape(n, c, k2 // 2, 2), tgt.reshape(n, c, k2 // 2, 2)
+        pa, pb, ta, tb = p[:, :, pairs[:, 0]], p[:, :, pairs[:, 1]], t[:, :, pairs[:, 0]], t[:, :, pairs[:, 1]]
+        if self.kp_distance_weight_l1:
+            dp, dt = (pa - pb).abs().sum(-1), (ta - tb).abs().sum(-1)
+        else:
+            dp = (((pa - pb) ** 2).sum(-1) + 1e4) ** 0.5
+            dt = (((ta - tb) ** 2).sum(-1) + 1e4) ** 0.5
+        return (dp - dt).abs().sum() / (mask.sum() + 1e-4) * self.kp_distance_weight
+
+
+_reexport(__name__, __file__, globals())

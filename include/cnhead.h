@@ -1,0 +1,182 @@
+/*
+ * cnhead.h -- C ABI of libcnhead_sm100.so: hand-written sm_100a CUDA kernels for the
+ * CenterNet-UDA per-pixel head path (detection loss fwd+bwd, UDA target-domain losses,
+ * detection decode).  This is the drop-in boundary: the Python plugin modules
+ * (losses.centernet.DetectionLoss, losses.entropy.EntropyLoss, losses.max_square.
+ * MaxSquareLoss, losses.advent.AdventLoss, utils.image.entropy_map,
+ * backends.decode.decode_detection) bind exactly these entry points through ctypes.
+ * Reference interface each one replaces is cited as file:line relative to the
+ * scheckmedia/centernet-uda checkout.
+ *
+ * Conventions (all entry points)
+ *   - plain C: raw DEVICE pointers, int sizes, float parameters; no torch types.
+ *   - the caller owns every buffer including the workspace; the library never
+ *     allocates, frees or synchronises.  All work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), so calls compose with CUDA graphs.
+ *   - tensors are fp32, contiguous, NCHW; indices are int64; masks are uint8.
+ *   - return value: 0 = success, < 0 = argument error (CNH_E_*), > 0 = cudaError_t.
+ *     cnh_last_error() returns a thread-local message for the last non-zero return.
+ *   - workspaces must be zero-filled ONCE by the caller (cudaMemset) and may then be
+ *     reused by later calls on the same stream: kernels leave their counters zeroed.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef CNHEAD_H_
+#define CNHEAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNH_VERSION 100 /* major*100 + minor */
+
+typedef void* cnh_stream_t; /* cudaStream_t */
+
+enum {
+  CNH_OK = 0,
+  CNH_E_NULL = -1,       /* required pointer is NULL                      */
+  CNH_E_SHAPE = -2,      /* unsupported / inconsistent dimensions         */
+  CNH_E_ALIGN = -3,      /* pointer not aligned as required               */
+  CNH_E_WORKSPACE = -4,  /* workspace too small                           */
+  CNH_E_UNSUPPORTED = -5 /* parameter combination not implemented         */
+};
+
+/* angle handling of channel 2 of a 3-channel size head */
+enum {
+  CNH_ANGLE_NONE = 0,    /* plain L1 on every channel (losses/centernet.py:128-131)          */
+  CNH_ANGLE_SIGMOID = 1, /* |sc(pred) - sc(target)|   (losses/centernet.py:112-126)           */
+  CNH_ANGLE_PERIODIC = 2 /* RAPiD periodic L1         (losses/centernet.py:192-223)           */
+};
+
+/* flags */
+enum {
+  CNH_FLAG_ACCURATE_MATH = 1, /* expf/logf/IEEE divide instead of ex2/lg2/rcp.approx */
+  CNH_FLAG_NO_STASH = 2       /* force the two-pass (pre-count) schedule             */
+};
+
+/* One masked gather-L1 regression head (replaces RegL1Loss / PeriodicRegL1Loss /
+ * KPSL1Loss main term, losses/centernet.py:98-133, 192-223, 136-151). */
+typedef struct cnh_head {
+  const float* map;      /* [B,D,H,W] predictions                                    */
+  const float* target;   /* [B,M,D]                                                  */
+  const uint8_t* mask;   /* [B,M] or, if elementwise_mask, [B,M,D]                   */
+  float* grad;           /* [B,D,H,W] out: dLoss/dmap (dense, zero-filled) or NULL   */
+  int32_t D;
+  int32_t angle_mode;    /* CNH_ANGLE_*; only used when D == 3                       */
+  int32_t elementwise_mask;
+  float weight;          /* wh_weight / off_weight / kp_weight                       */
+  float angle_weight;
+  int32_t _pad;
+} cnh_head;
+
+#define CNH_MAX_HEADS 3
+#define CNH_PARTIALS 12 /* doubles per sample, see below */
+#define CNH_SCALARS 8   /* floats, see below             */
+
+/* per-sample partials row (double[CNH_PARTIALS]):
+ *   [0] sum(pos_loss + neg_loss)   [1] num_pos
+ *   [2+3h] sum|l1| of head h       [3+3h] angle sum of head h   [4+3h] sum(mask_expanded)
+ * scalar block (float[CNH_SCALARS]):
+ *   [0] total loss  [1] hm_loss  [2..4] head losses  [5] num_pos  [6] reserved [7] reserved */
+typedef struct cnh_detloss_args {
+  int32_t B, C, H, W, M;
+  int32_t n_heads;
+  int32_t flags;
+  int32_t B_global;        /* sharded runs: global batch (only documents intent) */
+  const float* hm_logits;  /* [B,C,H,W] raw logits (NOT modified)                                */
+  const float* hm_gt;      /* [B,C,H,W] gaussian-splat target                                    */
+  float* prob;             /* [B,C,H,W] out: clamp(sigmoid(x),1e-4,1-1e-4) (utils/tensor.py:5-7) */
+  float* grad_hm;          /* [B,C,H,W] out: dLoss/dlogits, or NULL for forward only             */
+  const int64_t* ind;      /* [B,M] flat y*W+x                                                   */
+  float hm_weight;
+  int32_t _pad;
+  cnh_head heads[CNH_MAX_HEADS];
+  float* scalars;          /* [CNH_SCALARS] out (fused / finalize)                               */
+  double* partials;        /* [B,CNH_PARTIALS] out                                               */
+  const double* norm;      /* [4] in (cnh_detloss_main): global num_pos, mask counts per head    */
+  double* norm_out;        /* [4] out (cnh_detloss_count): this shard's num_pos, mask counts     */
+} cnh_detloss_args;
+
+int cnh_version(void);
+const char* cnh_last_error(void);
+
+/* ---- DetectionLoss (losses/centernet.py:7-95,98-133,192-223) ---------------------------
+ * cnh_detloss_fused: ONE cooperative launch = sigmoid+clamp, penalty-reduced focal loss,
+ * masked gather-L1 heads, all gradients (upstream gradient 1.0), scalars and partials.
+ * Small problems keep the raw heat-map gradient in registers across the grid barrier
+ * (16 B per heat-map element of HBM traffic); large ones pre-count num_pos (20 B). */
+size_t cnh_detloss_workspace_bytes(const cnh_detloss_args* a);
+int cnh_detloss_fused(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
+                      cnh_stream_t stream);
+/* Sharded (one process per GPU) schedule: count -> all-reduce(norm_out) -> main ->
+ * all-gather(partials) -> finalize.  Gradients are final after cnh_detloss_main. */
+int cnh_detloss_count(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
+                      cnh_stream_t stream);
+int cnh_detloss_main(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
+                     cnh_stream_t stream);
+/* partials: [B_total,CNH_PARTIALS] (device) summed in row order -> a->scalars.
+ * Only weights / D / angle_mode / n_heads of `a` are read. */
+int cnh_detloss_finalize(const cnh_detloss_args* a, const double* partials, int32_t B_total,
+                         cnh_stream_t stream);
+
+/* In-place gradient rescale by an upstream gradient that lives on the device:
+ * g[i] *= (fa ? *fa : 0) + (fb ? *fb : 0); exits immediately when the factor is 1.0
+ * (autograd's grad_output for `loss.backward()`).  Up to 4 tensors per launch. */
+typedef struct cnh_scale_args {
+  int32_t n_tensors;
+  int32_t _pad;
+  float* data[4];
+  int64_t count[4];
+  const float* fa[4];
+  const float* fb[4];
+} cnh_scale_args;
+int cnh_scale_inplace(const cnh_scale_args* a, cnh_stream_t stream);
+
+/* ---- UDA target-domain losses over a channel softmax ---------------------------------
+ * mode: 0 entropy (losses/entropy.py:24-25), 1 entropy with eta (losses/entropy.py:18-22),
+ *       2 max-squares (losses/max_square.py:6-14).
+ * logits [N,C,H,W]; grad (nullable) receives dLoss/dlogits for upstream gradient 1.0;
+ * n_total = N of the GLOBAL batch (normaliser); loss_out[0] = this shard's contribution
+ * (sum over shards == reference loss on the concatenated batch). */
+enum { CNH_SOFTMAX_ENTROPY = 0, CNH_SOFTMAX_ENTROPY_ETA = 1, CNH_SOFTMAX_MAX_SQUARE = 2 };
+size_t cnh_softmax_workspace_bytes(int32_t N, int32_t C, int32_t H, int32_t W);
+int cnh_softmax_loss(const float* logits, float* grad, float* loss_out, int32_t N, int32_t C,
+                     int32_t H, int32_t W, int32_t n_total, int32_t mode, float eta,
+                     void* workspace, size_t workspace_bytes, cnh_stream_t stream);
+/* utils/image.py:121-124 entropy_map: out = -p*log2(p+1e-30)/log2(C) */
+int cnh_entropy_map_fwd(const float* logits, float* out, int32_t N, int32_t C, int32_t H,
+                        int32_t W, cnh_stream_t stream);
+int cnh_entropy_map_bwd(const float* logits, const float* grad_out, float* grad_in, int32_t N,
+                        int32_t C, int32_t H, int32_t W, cnh_stream_t stream);
+/* losses/advent.py:10-18: mean BCE-with-logits against a constant label; grad nullable. */
+int cnh_bce_const(const float* y, float* grad, float* loss_out, int64_t n, float label,
+                  cnh_stream_t stream);
+
+/* ---- decode (backends/decode.py:6-76) ---------------------------------------------------
+ * heat [B,C,H,W] probabilities in [0,1]; wh [B,D,H,W] (D = 2, or 3 when rotated);
+ * reg [B,2,H,W] or NULL (+0.5); kps [B,2*nk,H,W] or NULL.
+ * dets [B,K,6] = (x1,y1,x2,y2,score,class) or, rotated, [B,K,7] = (x,y,w,h,angle,score,class),
+ * sorted by score descending, ties broken by LOWER flat index c*H*W + y*W + x.
+ * inds_out (nullable) [B,K] int64 receives that flat index; kps_out (nullable) [B,K,nk,2]. */
+typedef struct cnh_decode_args {
+  int32_t B, C, H, W, K, D, nk, rotated;
+  const float* heat;
+  const float* wh;
+  const float* reg;
+  const float* kps;
+  float* dets;
+  int64_t* inds_out;
+  float* kps_out;
+  int32_t apply_sigmoid;   /* 1: heat holds raw logits; clamp(sigmoid) fused in (export.py:31-33) */
+  float box_scale;         /* multiply the 4 box columns (uda/base.py:90 down_ratio); 1.0 = off   */
+} cnh_decode_args;
+size_t cnh_decode_workspace_bytes(const cnh_decode_args* a);
+int cnh_decode(const cnh_decode_args* a, void* workspace, size_t workspace_bytes,
+               cnh_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNHEAD_H_ */

@@ -1,0 +1,394 @@
+"""GPU parity: the CUDA path (through the reference-facing plugin modules -> C ABI) against the
+committed reference fixtures and against the CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north star): decode scores / classes / indices bit-exact (ties -> lower flat
+index); losses 1e-5 relative; gradients and boxes 1e-5 normwise relative (max|a-b| / max|b|);
+clamped probabilities within 4 fp32 ulp of 1.0 (2.4e-7 absolute: ex2/rcp.approx vs ATen's sigmoid).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import golden_head_case, golden_names, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+PROB_ATOL = 2.4e-7
+
+
+def dev(d):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items()}
+
+
+def run_plugin_loss(out, bt, kw, grad_scale=1.0, need_grad=True):
+    from losses.centernet import DetectionLoss
+    crit = DetectionLoss(**kw)
+    leaves = {k: v.cuda().requires_grad_(need_grad) for k, v in out.items()}
+    work = dict(leaves)
+    tgt = dev(bt)
+    keep = {k: v.clone() for k, v in tgt.items()}
+    if need_grad:
+        loss, stats = crit(work, tgt)
+        (loss * grad_scale).backward()
+    else:
+        with torch.no_grad():
+            loss, stats = crit(work, tgt)
+    for k in tgt:                                   # targets are never modified
+        assert torch.equal(tgt[k], keep[k]), k
+    grads = {k: (v.grad.cpu() if v.grad is not None else None) for k, v in leaves.items()}
+    return loss.detach().cpu(), {k: v.detach().cpu() for k, v in stats.items()}, work["hm"].detach().cpu(), grads
+
+
+def assert_loss_close(stats, ref_stats, grads, ref_grads, prob, ref_prob):
+    for k, v in ref_stats.items():
+        assert rel_err(stats[k], v) <= TOL, (k, float(stats[k]), float(v))
+    assert (prob.double() - torch.as_tensor(ref_prob).double()).abs().max().item() <= PROB_ATOL
+    for k, v in ref_grads.items():
+        assert grads[k] is not None, k
+        assert rel_err(grads[k], v) <= TOL, (k, rel_err(grads[k], v))
+
+
+@pytest.mark.parametrize("name", golden_names("detloss_"))
+def test_detection_loss_vs_reference_fixture(name):
+    g = load_golden(name)
+    out, bt, kw, gs = golden_head_case(g)
+    loss, stats, prob, grads = run_plugin_loss(out, bt, kw, gs)
+    ref_stats = {k[5:]: g[k] for k in g if k.startswith("stat_")}
+    ref_grads = {k[5:]: g[k] for k in g if k.startswith("grad_")}
+    assert_loss_close(stats, ref_stats, grads, ref_grads, prob, g["prob"])
+    assert rel_err(loss, g["stat_centernet_loss"]) <= TOL
+
+
+@pytest.mark.parametrize("name", ["detloss_plain", "detloss_angle_periodic", "detloss_no_positive"])
+def test_detection_loss_forward_only(name):
+    g = load_golden(name)
+    out, bt, kw, _ = golden_head_case(g)
+    loss, stats, prob, grads = run_plugin_loss(out, bt, kw, need_grad=False)
+    assert rel_err(loss, g["stat_centernet_loss"]) <= TOL
+    assert all(v is None for v in grads.values())
+    assert (prob.double() - torch.from_numpy(g["prob"]).double()).abs().max().item() <= PROB_ATOL
+
+
+@pytest.mark.parametrize("cfg_name,batch", [("cfg1", None), ("cfg2", None), ("cfg3", None), ("cfg5", 2)])
+def test_detection_loss_vs_oracle_synthetic(cfg_name, batch):
+    from cnhead import synthetic
+    cfg = synthetic.CONFIGS[cfg_name]
+    data = synthetic.make_inputs(cfg, batch=batch)
+    kw = synthetic.loss_kwargs(cfg)
+    rl, rs, rp, rg = oracle.detection_loss_with_grads(data["output"], data["batch"], **kw)
+    loss, stats, prob, grads = run_plugin_loss(data["output"], data["batch"], kw)
+    assert_loss_close(stats, rs, grads, rg, prob, rp)
+
+
+def test_second_backward_raises():
+    g = load_golden("detloss_plain")
+    out, bt, kw, _ = golden_head_case(g)
+    from losses.centernet import DetectionLoss
+    leaves = {k: v.cuda().requires_grad_(True) for k, v in out.items()}
+    loss, _ = DetectionLoss(**kw)(dict(leaves), dev(bt))
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError):
+        loss.backward()
+
+
+def test_cpu_tensor_raises():
+    g = load_golden("detloss_plain")
+    out, bt, kw, _ = golden_head_case(g)
+    from losses.centernet import DetectionLoss
+    with pytest.raises(RuntimeError):
+        DetectionLoss(**kw)(dict(out), bt)
+
+
+def _capi_schedules(out, bt, kw, flags):
+    """Run the fused launch with `flags`, and the count -> main -> finalize schedule; return both."""
+    import ctypes as C
+    from cnhead import _lib as L, functional as F
+    hm, wh, reg = (out[k].cuda().contiguous() for k in ("hm", "wh", "reg"))
+    gt, ind = bt["hm"].cuda(), bt["ind"].cuda()
+    mask = bt["reg_mask"].cuda()
+    mode = L.ANGLE_NONE if wh.shape[1] != 3 else (L.ANGLE_PERIODIC if kw.get("periodic") else L.ANGLE_SIGMOID)
+    heads = [F.HeadSpec(wh, bt["wh"].cuda(), mask, kw["wh_weight"], kw.get("angle_weight", 1.0), mode),
+             F.HeadSpec(reg, bt["reg"].cuda(), mask, kw["off_weight"])]
+    res = {}
+    for tag in ("fused", "split"):
+        prob = torch.empty_like(hm)
+        grads = [torch.full_like(hm, 7.0), torch.full_like(wh, 7.0), torch.full_like(reg, 7.0)]
+        scal = torch.zeros(L.SCALARS, device="cuda")
+        part = torch.zeros(hm.shape[0], L.PARTIALS, dtype=torch.float64, device="cuda")
+        norm = torch.zeros(4, dtype=torch.float64, device="cuda")
+        a = F.fill_detloss_args(hm, gt, ind, heads, kw["hm_weight"], prob, grads, scal, part,
+                                norm=norm, norm_out=norm, flags=flags)
+        ws = torch.zeros(L.lib().cnh_detloss_workspace_bytes(C.byref(a)), dtype=torch.uint8, device="cuda")
+        st = L.stream_ptr()
+        if tag == "fused":
+            L.check(L.lib().cnh_detloss_fused(C.byref(a), ws.data_ptr(), ws.numel(), st), "fused")
+        else:
+            L.check(L.lib().cnh_detloss_count(C.byref(a), ws.data_ptr(), ws.numel(), st), "count")
+            a.scalars = None
+            L.check(L.lib().cnh_detloss_main(C.byref(a), ws.data_ptr(), ws.numel(), st), "main")
+            a.scalars = scal.data_ptr()
+            L.check(L.lib().cnh_detloss_finalize(C.byref(a), part.data_ptr(), hm.shape[0], st), "finalize")
+        torch.cuda.synchronize()
+        assert int(ws[:64].sum()) == 0, "workspace counters must be left zeroed"
+        res[tag] = (scal.cpu(), prob.cpu(), [x.cpu() for x in grads], part.cpu())
+    return res
+
+
+@pytest.mark.parametrize("name", ["detloss_plain", "detloss_angle_periodic", "detloss_no_positive",
+                                  "detloss_weights_gradscale"])
+@pytest.mark.parametrize("flags", [0, 2, 1, 3])
+def test_schedules_agree_bitwise(name, flags):
+    """STASH vs PRECOUNT vs COUNT+MAIN+FINALIZE: identical scalars, partials and heat-map gradients
+    (the sharded schedule reproduces the single-launch result bit for bit)."""
+    g = load_golden(name)
+    out, bt, kw, _ = golden_head_case(g)
+    res = _capi_schedules(out, bt, kw, flags)
+    ref = _capi_schedules(out, bt, kw, flags & 1)["fused"]      # stash schedule, same math mode
+    for tag in ("fused", "split"):
+        scal, prob, grads, part = res[tag]
+        assert torch.equal(scal[:6], ref[0][:6]), tag
+        assert torch.equal(prob, ref[1]), tag
+        assert torch.equal(grads[0], ref[2][0]), tag
+        assert torch.equal(part, ref[3]), tag
+        for a_, b_ in zip(grads[1:], ref[2][1:]):               # atomics on duplicate centres
+            assert rel_err(a_, b_) <= 1e-6
+    assert rel_err(res["fused"][0][0], g["stat_centernet_loss"]) <= TOL
+
+
+def test_large_problem_precount_schedule():
+    """enough chunks that the register stash cannot hold them -> PRECOUNT (reverse second pass)."""
+    from cnhead import synthetic
+    cfg = synthetic.CONFIGS["cfg5"]
+    data = synthetic.make_inputs(cfg, batch=6)                   # 6*320 = 1920 chunks > 2*444
+    kw = synthetic.loss_kwargs(cfg)
+    rl, rs, rp, rg = oracle.detection_loss_with_grads(data["output"], data["batch"], **kw)
+    loss, stats, prob, grads = run_plugin_loss(data["output"], data["batch"], kw)
+    assert_loss_close(stats, rs, grads, rg, prob, rp)
+
+
+# ---------------------------------------------------------------------------------------------
+# decode
+# ---------------------------------------------------------------------------------------------
+def run_decode(heat, wh, reg, kps, K, rotated):
+    from backends.decode import decode_detection
+    res = decode_detection(heat.cuda(), wh.cuda(), None if reg is None else reg.cuda(),
+                           kps=None if kps is None else kps.cuda(), K=K, rotated=rotated)
+    if kps is not None:
+        return res[0].cpu(), res[1].cpu()
+    return res.cpu(), None
+
+
+def assert_decode_exact(heat, wh, reg, kps, K, rotated):
+    ref = oracle.decode_stable(heat, wh, reg, kps, K=K, rotated=rotated)
+    dets, kout = run_decode(heat, wh, reg, kps, K, rotated)
+    sc = 5 if rotated else 4
+    assert torch.equal(dets[..., sc], ref[0][..., sc]), "scores must be bit-exact"
+    assert torch.equal(dets[..., sc + 1], ref[0][..., sc + 1]), "classes must be bit-exact"
+    from cnhead import functional as F
+    inds = F.decode(heat.cuda(), wh.cuda(), None if reg is None else reg.cuda(), K=K, rotated=rotated,
+                    return_inds=True)[-1].cpu()
+    assert torch.equal(inds, ref[1]), "flat indices must be bit-exact"
+    assert rel_err(dets, ref[0]) <= TOL
+    if not rotated:
+        assert torch.equal(dets, ref[0]), "axis-aligned boxes are single fp32 adds: bit-exact"
+    if kps is not None:
+        assert torch.equal(kout, ref[2])
+
+
+@pytest.mark.parametrize("name", golden_names("decode_"))
+def test_decode_vs_reference_fixture(name):
+    g = load_golden(name)
+    heat, wh = torch.from_numpy(g["heat"]), torch.from_numpy(g["wh"])
+    reg = torch.from_numpy(g["reg"]) if "reg" in g else None
+    kps = torch.from_numpy(g["kps"]) if "kps" in g else None
+    K, rotated = int(g["K"]), bool(g["rotated"])
+    assert_decode_exact(heat, wh, reg, kps, K, rotated)
+    dets, _ = run_decode(heat, wh, reg, kps, K, rotated)
+    sc = 5 if rotated else 4
+    assert np.array_equal(dets[..., sc].numpy(), g["dets"][..., sc])     # score multiset == reference
+    s = g["dets"][..., sc]
+    if all(len(np.unique(s[b])) == len(s[b]) for b in range(s.shape[0])) and "fewer" not in name:
+        assert rel_err(dets, g["dets"]) <= TOL                             # no ties: equals torch.topk too
+
+
+@pytest.mark.parametrize("B,C,H,W,K,rotated,use_reg,nk,sigma", [
+    (16, 6, 128, 128, 150, False, True, 0, 2.0),      # cfg2
+    (1, 6, 128, 128, 100, False, True, 0, 2.0),       # cfg1
+    (16, 6, 128, 128, 150, True, True, 0, 2.0),       # cfg3 rotated
+    (2, 80, 128, 128, 150, False, True, 0, 1.0),      # cfg5 classes
+    (2, 3, 200, 200, 150, False, True, 0, 2.0),       # 800x800 validation maps, two x tiles
+    (2, 3, 40, 300, 50, False, False, 0, 2.0),        # three x tiles, reg=None
+    (3, 2, 33, 30, 20, False, True, 2, 2.0),          # W % 4 != 0 -> non-TMA loader, keypoints
+    (2, 2, 17, 23, 11, True, True, 0, 2.0),           # odd everything
+    (2, 1, 64, 64, 1024, False, True, 0, 2.0),        # K at the supported maximum, > #peaks
+    (2, 4, 128, 128, 150, False, True, 0, 8.0),       # saturated logits: thousands of ties at 1-1e-4
+])
+def test_decode_vs_oracle(B, C, H, W, K, rotated, use_reg, nk, sigma):
+    g = torch.Generator().manual_seed(B * 1000 + C * 100 + H + W + K)
+    heat = oracle.sigmoid_clamp(torch.randn(B, C, H, W, generator=g) * sigma - 2.19)
+    wh = torch.rand(B, 3 if rotated else 2, H, W, generator=g) * 40
+    if rotated:
+        wh[:, 2] = torch.randn(B, H, W, generator=g)
+    reg = torch.rand(B, 2, H, W, generator=g) if use_reg else None
+    kps = torch.randn(B, 2 * nk, H, W, generator=g) * 4 if nk else None
+    assert_decode_exact(heat, wh, reg, kps, K, rotated)
+
+
+def test_decode_after_loss_uses_rebound_probabilities():
+    """uda/base.py:43,76-82: decode reads output['hm'] as rebound by DetectionLoss."""
+    from cnhead import synthetic
+    from losses.centernet import DetectionLoss
+    from backends.decode import decode_detection
+    cfg = synthetic.CONFIGS["cfg2"]
+    data = synthetic.make_inputs(cfg, batch=4, hm_sigma=2.0)
+    out = dev(data["output"])
+    with torch.no_grad():
+        DetectionLoss(**synthetic.loss_kwargs(cfg))(out, dev(data["batch"]))
+        dets = decode_detection(out["hm"], out["wh"], out["reg"], K=cfg.K).cpu()
+    ref = oracle.decode_stable(out["hm"].cpu(), data["output"]["wh"], data["output"]["reg"], K=cfg.K)[0]
+    assert torch.equal(dets, ref)
+
+
+def test_decode_fused_sigmoid_and_scale():
+    """export.py:31-56: clamp(sigmoid) fused into decode, boxes scaled by down_ratio."""
+    from cnhead import functional as F
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn(2, 3, 64, 64, generator=g) * 2 - 2.19
+    wh, reg = torch.rand(2, 2, 64, 64, generator=g) * 30, torch.rand(2, 2, 64, 64, generator=g)
+    dets, inds = F.decode(logits.cuda(), wh.cuda(), reg.cuda(), K=50, apply_sigmoid=True, box_scale=4.0,
+                          return_inds=True)
+    heat_gpu = torch.sigmoid(logits.cuda()).clamp(1e-4, 1 - 1e-4).cpu()
+    ref, rinds = oracle.decode_stable(heat_gpu, wh, reg, K=50)
+    ref = ref.clone()
+    ref[..., :4] *= 4.0
+    assert rel_err(dets.cpu()[..., 4], ref[..., 4]) <= TOL
+    same = (inds.cpu() == rinds)
+    assert same.float().mean() > 0.98            # in-kernel sigmoid may differ from ATen by an ulp
+    assert rel_err(dets.cpu()[same], ref[same]) <= TOL
+
+
+def test_decode_K_larger_than_plane_raises():
+    from backends.decode import decode_detection
+    with pytest.raises(RuntimeError):
+        decode_detection(torch.rand(1, 2, 4, 4).cuda(), torch.rand(1, 2, 4, 4).cuda(), K=17)
+
+
+# ---------------------------------------------------------------------------------------------
+# UDA losses
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("uda_"))
+def test_uda_losses_vs_reference_fixture(name):
+    from losses.entropy import EntropyLoss
+    from losses.max_square import MaxSquareLoss
+    from utils.image import entropy_map
+    g = load_golden(name)
+    eta = None if np.isnan(g["eta"]) else float(g["eta"])
+    w = float(g["w"])
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    le, st = EntropyLoss(eta=eta)({"hm": x}, None)
+    unweighted = le.detach().clone()
+    le *= w                                          # uda/entropy_minimization.py:28 (in place)
+    le.backward()
+    assert rel_err(unweighted.cpu(), g["entropy"]) <= TOL
+    assert rel_err(x.grad.cpu(), g["entropy_grad"]) <= TOL
+    x2 = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    lm, _ = MaxSquareLoss()({"hm": x2}, None)
+    unweighted = lm.detach().clone()
+    lm *= w
+    lm.backward()
+    assert rel_err(unweighted.cpu(), g["max_square"]) <= TOL
+    assert rel_err(x2.grad.cpu(), g["max_square_grad"]) <= TOL
+    x3 = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    im = entropy_map(x3)
+    im.backward(torch.from_numpy(g["info_up"]).cuda())
+    assert rel_err(im.detach().cpu(), g["info_map"]) <= TOL
+    assert rel_err(x3.grad.cpu(), g["info_grad"]) <= TOL
+
+
+@pytest.mark.parametrize("N,C,H,W", [(16, 6, 128, 128), (2, 80, 64, 64), (3, 5, 7, 9), (1, 1, 8, 8)])
+def test_uda_losses_vs_oracle(N, C, H, W):
+    from cnhead import _lib as L, functional as F
+    g = torch.Generator().manual_seed(N + C + H)
+    x = torch.randn(N, C, H, W, generator=g) * 1.5
+    for kind, mode in (("entropy", L.SOFTMAX_ENTROPY), ("max_square", L.SOFTMAX_MAX_SQUARE)):
+        rl, rg = oracle.softmax_loss_with_grad(x, kind)
+        xc = x.cuda().requires_grad_(True)
+        l = F.softmax_loss(xc, mode)
+        l.backward()
+        if C == 1 and kind == "entropy":             # log2(1) = 0 in the normaliser: reference gives nan
+            assert not torch.isfinite(rl) and not torch.isfinite(l.cpu())
+            continue
+        assert rel_err(l.detach().cpu(), rl) <= TOL, kind
+        assert rel_err(xc.grad.cpu(), rg) <= TOL, kind
+    if C > 1:
+        up = torch.randn(N, C, H, W, generator=g)
+        rm, rgi = oracle.self_information_backward(x, up)
+        xc = x.cuda().requires_grad_(True)
+        m = F.entropy_map(xc)
+        m.backward(up.cuda())
+        assert rel_err(m.detach().cpu(), rm) <= TOL
+        assert rel_err(xc.grad.cpu(), rgi) <= TOL
+
+
+@pytest.mark.parametrize("name", golden_names("advent_"))
+def test_advent_vs_reference_fixture(name):
+    from losses.advent import AdventLoss
+    g = load_golden(name)
+    y = torch.from_numpy(g["y"]).cuda().requires_grad_(True)
+    l, st = AdventLoss()(y, int(g["label"]))
+    l2 = l * 1.0
+    l2 /= 2.0                                        # adversarial_entropy_minimization.py:122
+    l2.backward()
+    assert rel_err(l.detach().cpu(), g["loss"]) <= TOL
+    assert rel_err(y.grad.cpu() * 2.0, g["grad"]) <= TOL
+    assert "advent_loss" in st
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full sizes
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties_cfg5_shard():
+    """cfg5 per-GPU shard (16 x 80 x 128 x 128): properties that need no CPU reference."""
+    from cnhead import synthetic
+    from losses.centernet import DetectionLoss
+    from backends.decode import decode_detection
+    cfg = synthetic.CONFIGS["cfg5"]
+    data = synthetic.make_inputs(cfg, batch=16, hm_sigma=2.0)
+    out = {k: v.cuda().requires_grad_(True) for k, v in data["output"].items()}
+    work = dict(out)
+    bt = dev(data["batch"])
+    loss, stats = DetectionLoss(**synthetic.loss_kwargs(cfg))(work, bt)
+    loss.backward()
+    p = work["hm"]
+    # (1) probabilities are clamp(sigmoid): bounds, monotone in the logit
+    assert float(p.min()) >= 1e-4 and float(p.max()) <= 1 - 1e-4
+    assert (p - torch.sigmoid(out["hm"].detach()).clamp(1e-4, 1 - 1e-4)).abs().max().item() <= PROB_ATOL
+    # (2) loss decomposition and num_pos
+    assert rel_err(loss.detach().cpu(), (stats["hm_loss"] + stats["wh_loss"] + stats["off_loss"]).cpu()) <= 1e-6
+    # (3) regression gradients live exactly on the object centres
+    nz = (out["wh"].grad != 0).flatten(2).any(1)
+    centres = torch.zeros_like(nz)
+    centres.scatter_(1, bt["ind"], bt["reg_mask"].bool())
+    assert not (nz & ~centres).any()
+    # (4) heat-map gradient sign: positive targets pull the logit up (negative gradient)
+    gpos = out["hm"].grad[bt["hm"] == 1]
+    assert (gpos <= 0).all()
+    assert (out["hm"].grad[bt["hm"] < 1] >= 0).all()
+    # (5) decode: sorted, scores are values of the map at the returned peaks, peaks are 3x3 maxima
+    from cnhead import functional as F
+    dets, inds = F.decode(p, out["wh"].detach(), out["reg"].detach(), K=cfg.K, return_inds=True)
+    s = dets[..., 4]
+    assert (s[:, :-1] >= s[:, 1:]).all()
+    flat = p.flatten(1)
+    assert torch.equal(flat.gather(1, inds), s)
+    hmax = torch.nn.functional.max_pool2d(p, 3, 1, 1).flatten(1)
+    assert torch.equal(hmax.gather(1, inds), s)
+    # (6) decode is deterministic and idempotent w.r.t. its own output ordering
+    dets2 = decode_detection(p, out["wh"].detach(), out["reg"].detach(), K=cfg.K)
+    assert torch.equal(dets, dets2)
+    # (7) the K-th score bounds every unreturned peak
+    nms = flat * (hmax == flat)
+    nms.scatter_(1, inds, 0.0)
+    assert (nms.max(1).values <= s[:, -1]).all()
