@@ -1,0 +1,474 @@
+#!/usr/bin/env python
+"""bench.py -- heatmaps/s of the CenterNet head hot path (DetectionLoss fwd+bwd + decode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+One step = one pass of the hot path over one synthetic batch of the workload (default cfg2: batch 16,
+6 classes, 128x128 heat maps, max_detections 150, per GPU -- weak scaling): DetectionLoss forward,
+its backward, and decode_detection of the same head tensors.
+  value  : device-resident inputs, the three launches of a step replayed from CUDA graphs over
+           rotating buffer sets that together exceed the L2 (HBM-cold), timed with CUDA events.
+  e2e    : the same step through the reference-facing plugin API (losses.centernet.DetectionLoss,
+           loss.backward(), backends.decode.decode_detection) with PINNED HOST inputs: H2D copy of the
+           head maps and targets, D2H read of the loss and the detections inside the timed region.
+  roofline: the dominant kernel (fused detection-loss launch) timed alone with CUDA events.
+  cpu_baseline / --impl reference: the oracle port of the reference's PyTorch path on the host cores.
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "centernet-uda_b200")
+for _p in (PKG, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "heatmaps/s (DetectionLoss fwd+bwd + decode)"
+UNIT = "heatmaps/s"
+L2_BYTES = 126 * 2 ** 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=40)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(cfg, batch):
+    extra = " + rotated/periodic angle head" if cfg.angle else ""
+    return (f"{cfg.name}: batch {batch} per GPU, {cfg.classes} classes, {cfg.height}x{cfg.width} heat maps, "
+            f"DetectionLoss fwd+bwd + decode K={cfg.K}{extra}")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step(oracle, data, kw, cfg):
+    loss, stats, prob, grads = oracle.detection_loss_with_grads(data["output"], data["batch"], **kw)
+    with torch.no_grad():
+        dets = oracle.decode_two_stage(prob, data["output"]["wh"], data["output"]["reg"], K=cfg.K, rotated=cfg.rotated)
+    return loss, dets
+
+
+def time_cpu(cfg, batch, steps, warmup, budget_s=None):
+    import oracle
+    from cnhead import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    data = synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0)
+    kw = synthetic.loss_kwargs(cfg)
+    for _ in range(warmup):
+        cpu_step(oracle, data, kw, cfg)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        cpu_step(oracle, data, kw, cfg)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return batch * done / dt, dt / done * 1e3, done, torch.get_num_threads()
+
+
+def run_reference(args, cfg, batch, rank):
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    value, ms, done, cores = time_cpu(cfg, batch, steps, max(1, min(args.warmup, 3)), budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cfg, batch), "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{done} steps of one {cfg.name} batch ({batch} samples) on the host: oracle port of "
+                                   f"the reference's PyTorch-CPU DetectionLoss fwd+bwd + decode (the Python reference "
+                                   f"cannot travel to the GPU box)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class BufferSet:
+    """device-resident head maps, targets and outputs of one step."""
+
+    def __init__(self, data, cfg, dev):
+        from cnhead import _lib as L, functional as F
+        o, b = data["output"], data["batch"]
+        self.hm, self.wh, self.reg = (o[k].to(dev) for k in ("hm", "wh", "reg"))
+        self.gt, self.ind, self.mask = b["hm"].to(dev), b["ind"].to(dev), b["reg_mask"].to(dev)
+        self.wh_t, self.reg_t = b["wh"].to(dev), b["reg"].to(dev)
+        self.prob = torch.empty_like(self.hm)
+        self.grads = [torch.empty_like(self.hm), torch.empty_like(self.wh), torch.empty_like(self.reg)]
+        self.scalars = torch.zeros(L.SCALARS, device=dev)
+        self.partials = torch.zeros(self.hm.shape[0], L.PARTIALS, dtype=torch.float64, device=dev)
+        self.norm = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.ones = torch.ones(L.SCALARS, device=dev)          # upstream gradient of loss.backward()
+        self.dets = torch.empty(self.hm.shape[0], cfg.K, 7 if cfg.rotated else 6, device=dev)
+        mode = L.ANGLE_NONE if not cfg.angle else (L.ANGLE_PERIODIC if cfg.periodic else L.ANGLE_SIGMOID)
+        self.heads = [F.HeadSpec(self.wh, self.wh_t, self.mask, 0.1, 1.0, mode),
+                      F.HeadSpec(self.reg, self.reg_t, self.mask, 1.0)]
+
+    def nbytes(self):
+        ts = [self.hm, self.wh, self.reg, self.gt, self.prob] + self.grads
+        return sum(t.numel() * t.element_size() for t in ts)
+
+
+class DeviceStep:
+    """the launches of one step through the C ABI on device-resident buffers."""
+
+    def __init__(self, sets, cfg, world, group):
+        import ctypes as C
+        from cnhead import _lib as L, functional as F, sharded
+        self.C, self.L, self.sharded, self.world, self.group, self.cfg = C, L, sharded, world, group, cfg
+        self.sets = sets
+        self.lib = L.lib()
+        dev = sets[0].hm.device
+        self.loss_args, self.scale_args, self.dec_args = [], [], []
+        for s in sets:
+            a = F.fill_detloss_args(s.hm, s.gt, s.ind, s.heads, 1.0, s.prob, s.grads, s.scalars, s.partials,
+                                    norm=s.norm, norm_out=s.norm, b_global=s.hm.shape[0] * world)
+            sc = L.ScaleArgs()
+            sc.n_tensors = 3
+            for i, t in enumerate(s.grads):
+                sc.data[i], sc.count[i] = t.data_ptr(), t.numel()
+                sc.fa[i], sc.fb[i] = s.ones.data_ptr(), None
+            d = L.DecodeArgs()
+            B, Cc, H, W = s.hm.shape
+            d.B, d.C, d.H, d.W, d.K, d.D = B, Cc, H, W, cfg.K, s.wh.shape[1]
+            d.rotated, d.nk = (1 if cfg.rotated else 0), 0
+            d.heat, d.wh, d.reg, d.kps = s.prob.data_ptr(), s.wh.data_ptr(), s.reg.data_ptr(), None
+            d.dets, d.inds_out, d.kps_out = s.dets.data_ptr(), None, None
+            d.apply_sigmoid, d.box_scale = 0, 1.0
+            self.loss_args.append(a)
+            self.scale_args.append(sc)
+            self.dec_args.append(d)
+        self.ws_loss = torch.zeros(self.lib.cnh_detloss_workspace_bytes(C.byref(self.loss_args[0])) + 256,
+                                   dtype=torch.uint8, device=dev)
+        self.ws_dec = torch.zeros(self.lib.cnh_decode_workspace_bytes(C.byref(self.dec_args[0])) + 256,
+                                  dtype=torch.uint8, device=dev)
+        self.launches_per_step = 3 if world == 1 else 5
+
+    def loss_only(self, i):
+        C, L = self.C, self.L
+        a = self.loss_args[i]
+        L.check(self.lib.cnh_detloss_fused(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), L.stream_ptr()),
+                "detloss_fused")
+
+    def step(self, i):
+        C, L = self.C, self.L
+        st = L.stream_ptr()
+        a, s = self.loss_args[i], self.sets[i]
+        if self.world == 1:
+            L.check(self.lib.cnh_detloss_fused(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), st), "fused")
+        else:
+            a.scalars = None
+            L.check(self.lib.cnh_detloss_count(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), st), "count")
+            self.sharded.exchange_normalisers(s.norm, self.group)
+            L.check(self.lib.cnh_detloss_main(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), st), "main")
+            rows = self.sharded.gather_partials(s.partials, self.group)
+            a.scalars = s.scalars.data_ptr()
+            L.check(self.lib.cnh_detloss_finalize(C.byref(a), rows.data_ptr(), rows.shape[0], st), "finalize")
+        L.check(self.lib.cnh_scale_inplace(C.byref(self.scale_args[i]), st), "scale")            # backward
+        L.check(self.lib.cnh_decode(C.byref(self.dec_args[i]), self.ws_dec.data_ptr(), self.ws_dec.numel(), st),
+                "decode")
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world, dev):
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_loop(fn, steps, warmup, world, dev):
+    """W untimed + exactly K timed calls of fn(i), bracketed by barrier + synchronize; device time, max over ranks."""
+    for i in range(warmup):
+        fn(i)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+
+class GraphRunner:
+    """fn(i) for buffer set i, captured once per set plus one graph holding a whole round of all sets
+    (so that replay cost on the host is amortised); falls back to eager launches if capture fails."""
+
+    def __init__(self, fn, n_sets, stream, use_graph, rank):
+        self.fn, self.n, self.graphs, self.round = fn, n_sets, None, None
+        if not use_graph:
+            return
+        try:
+            self.graphs = []
+            for i in range(n_sets):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    fn(i)
+                self.graphs.append(g)
+            self.round = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.round, stream=stream):
+                for i in range(n_sets):
+                    fn(i)
+        except Exception as e:                       # e.g. a collective that cannot be captured
+            if rank == 0:
+                print(f"[bench] graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            self.graphs, self.round = None, None
+            torch.cuda.synchronize()
+
+    def run(self, count):
+        """exactly `count` steps, continuing the rotation over buffer sets"""
+        if self.graphs is None:
+            for i in range(count):
+                self.fn(i % self.n)
+            return
+        for _ in range(count // self.n):
+            self.round.replay()
+        for i in range(count % self.n):
+            self.graphs[i].replay()
+
+    def timed(self, steps, warmup, world, dev):
+        self.run(warmup)
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.run(steps)
+        e1.record()
+        barrier(world)
+        return max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+
+def run_ours(args, cfg, batch, rank, local_rank, world):
+    from cnhead import synthetic
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device for --impl ours"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    group = None
+    steps, warmup = args.steps, max(3, args.warmup)
+
+    # rotating buffer sets: together > 2x L2 so every step reads its inputs from HBM
+    probe = BufferSet(synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, sample_offset=rank * batch), cfg, dev)
+    n_sets = max(2, min(16, -(-2 * L2_BYTES // probe.nbytes())))
+    if probe.nbytes() > L2_BYTES:
+        n_sets = 2
+    sets = [probe] + [BufferSet(synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, seed_offset=1 + i,
+                                                      sample_offset=rank * batch), cfg, dev)
+                      for i in range(n_sets - 1)]
+    dstep = DeviceStep(sets, cfg, world, group)
+    side = torch.cuda.Stream(device=dev)
+
+    # ---- value: device-resident, graph-replayed ------------------------------------------------------
+    use_graph = not args.no_graph
+    with torch.cuda.stream(side):
+        for i in range(n_sets):                      # warm every kernel / tensor map before capture
+            dstep.step(i)
+            dstep.loss_only(i)
+        torch.cuda.synchronize()
+        run_step = GraphRunner(dstep.step, n_sets, side, use_graph, rank)
+        run_loss = GraphRunner(dstep.loss_only, n_sets, side, use_graph and world == 1, rank)
+        clocks = Clocks(local_rank)
+        clocks.start()
+        ms_total = run_step.timed(steps, warmup, world, dev)
+        # ---- roofline: the dominant kernel alone, same buffers, CUDA events on its stream -------------------
+        ms_kernel = run_loss.timed(steps, warmup, 1, dev) / steps if world == 1 else None
+        clk = clocks.stop()
+    graphs = run_step.graphs
+    ms_step = ms_total / steps
+    value = batch * world * steps / (ms_total * 1e-3)
+
+    # ---- e2e: plugin API, pinned host inputs, H2D + D2H inside the timed region ------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(cfg, batch, rank, world, dev, steps, warmup)
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy), of measured" if "hbm_gbs" in peaks else "6650 GB/s fallback"
+    hw = cfg.height * cfg.width
+    loss_bytes = batch * (16 * cfg.classes * hw + 4 * (cfg.wh_channels + 2) * hw)
+    roof = None
+    if ms_kernel:
+        achieved = loss_bytes / (ms_kernel * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg.name)
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": "detloss_kernel (fused sigmoid-clamp-focal fwd+bwd + gather-L1 heads)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "bytes_per_launch": loss_bytes, "us_per_launch": ms_kernel * 1e3, "peak_source": peak_src}
+    step_bytes = batch * cfg.bytes_per_sample()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(cfg, batch), "global_batch": batch * world,
+                   "l2": f"rotating {n_sets} buffer sets of {probe.nbytes() / 2**20:.1f} MiB "
+                         f"({n_sets * probe.nbytes() / 2**20:.0f} MiB > 126 MiB L2): HBM-cold every step",
+                   "launch": "CUDA graph replay" if graphs else "eager stream launches",
+                   "parallelism": "single GPU" if world == 1 else f"batch-sharded dp{world}, NCCL all-reduce of normalisers"},
+        "step_algorithmic_bytes": step_bytes,
+        "step_hbm_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+        "roofline": roof,
+        "e2e": e2e,
+        "gpu_launches": dstep.launches_per_step * steps,
+        "clocks": clk,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        v, ms, done, cores = time_cpu(cfg, batch, 60, 2, budget_s=12.0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{done} steps of one {cfg.name} batch ({batch} samples): oracle port of the "
+                                          f"reference's PyTorch-CPU path, {ms:.1f} ms/step"}
+    print(json.dumps(line), flush=True)
+
+
+def run_e2e(cfg, batch, rank, world, dev, steps, warmup):
+    from cnhead import synthetic, sharded
+    from losses.centernet import DetectionLoss
+    from backends.decode import decode_detection
+    kw = synthetic.loss_kwargs(cfg)
+    crit = DetectionLoss(**kw) if world == 1 else sharded.make_sharded_loss(DetectionLoss)(**kw)
+    n_host = 4
+    host = []
+    for i in range(n_host):
+        d = synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, seed_offset=20 + i, sample_offset=rank * batch)
+        host.append(({k: v.pin_memory() for k, v in d["output"].items()},
+                     {k: v.pin_memory() for k, v in d["batch"].items()}))
+    h2d = sum(v.numel() * v.element_size() for grp in host[0] for v in grp.values())
+    dets_host = torch.empty(batch, cfg.K, 7 if cfg.rotated else 6).pin_memory()
+    loss_host = torch.empty(1).pin_memory()
+    d2h = dets_host.numel() * 4 + 4
+
+    def step(i):
+        o, b = host[i % n_host]
+        out = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in o.items()}
+        bt = {k: v.to(dev, non_blocking=True) for k, v in b.items()}
+        work = dict(out)
+        loss, stats = crit(work, bt)
+        loss.backward()
+        dets = decode_detection(work["hm"], work["wh"].detach(), work["reg"].detach(), K=cfg.K, rotated=cfg.rotated)
+        dets_host.copy_(dets, non_blocking=True)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller reads the results every step
+
+    e2e_steps = min(steps, 200)
+    ms = timed_loop(step, e2e_steps, min(warmup, 10), world, dev)
+    return {"value": batch * world * e2e_steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": ms / e2e_steps, "steps": e2e_steps,
+            "api": "losses.centernet.DetectionLoss + loss.backward() + backends.decode.decode_detection"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from cnhead import synthetic
+    cfg = synthetic.CONFIGS[args.config]
+    batch = args.batch or (cfg.batch if cfg.name != "cfg5" else 16)
+    if args.impl == "reference":
+        run_reference(args, cfg, batch, rank)
+        return
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, cfg, batch, rank, local_rank, world)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -275,7 +275,7 @@ def decode(heat, wh, reg=None, kps=None, K=100, rotated=False, apply_sigmoid=Fal
     nbytes = L.lib().cnh_decode_workspace_bytes(C.byref(a))
     if nbytes == 0:
         L.check(-2, "decode")
-    ws = L.workspace("decode", nbytes, heat.device)
+    ws = L.workspace(f"decode:{B}x{Cc}x{H}x{W}:{K}", nbytes, heat.device)   # layout depends on the dims
     L.check(L.lib().cnh_decode(C.byref(a), ws.data_ptr(), ws.numel(), L.stream_ptr()), "decode")
     res = (dets,)
     if kps is not None:

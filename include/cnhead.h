@@ -18,6 +18,8 @@
  *     cnh_last_error() returns a thread-local message for the last non-zero return.
  *   - workspaces must be zero-filled ONCE by the caller (cudaMemset) and may then be
  *     reused by later calls on the same stream: kernels leave their counters zeroed.
+ *     cnh_decode's workspace layout depends on (B,C,H,W,K): reuse it only for calls with
+ *     the same dimensions, or zero it again.
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef CNHEAD_H_

@@ -215,6 +215,33 @@ def decode_stable(heat, wh, reg=None, kps=None, K=100, rotated=False, nms_size=3
     return dets, order
 
 
+def decode_two_stage(heat, wh, reg=None, K=100, rotated=False):
+    """backends/decode.py:16-76 with the reference's own selection structure: top-K per class over
+    H*W, then top-K over the C*K survivors (torch.topk: tie order unspecified).  Used as the timed
+    CPU baseline (bench.py); parity is judged against ``decode_stable``."""
+    b, c, h, w = heat.shape
+    nms = peak_scores(heat)
+    s1, i1 = torch.topk(nms.reshape(b, c, -1), K)                       # :19
+    s2, i2 = torch.topk(s1.reshape(b, -1), K)                            # :25
+    cls = (i2 // K).to(heat.dtype)                                      # :26
+    pix = torch.gather(i1.reshape(b, -1), 1, i2)                        # :27-28
+    ys = (pix // w).to(heat.dtype).unsqueeze(-1)
+    xs = (pix % w).to(heat.dtype).unsqueeze(-1)
+    if reg is not None:
+        off = gather_rows(reg, pix)
+        xs, ys = xs + off[..., 0:1], ys + off[..., 1:2]
+    else:
+        xs, ys = xs + 0.5, ys + 0.5
+    size = gather_rows(wh, pix)
+    if not rotated:
+        box = torch.cat([xs - size[..., 0:1] / 2, ys - size[..., 1:2] / 2,
+                         xs + size[..., 0:1] / 2, ys + size[..., 1:2] / 2], dim=2)
+    else:
+        box = torch.cat([xs, ys, size[..., 0:1], size[..., 1:2],
+                         sigmoid_clamp(size[..., 2:3]) * 360.0 - 180.0], dim=2)
+    return torch.cat([box, s2.unsqueeze(-1), cls.unsqueeze(-1)], dim=2)
+
+
 # --------------------------------------------------------------------------- #
 # losses/entropy.py, losses/max_square.py, losses/advent.py, utils/image.py
 # --------------------------------------------------------------------------- #

@@ -65,6 +65,14 @@ def test_decode_matches_reference(name):
             assert rel_err(res[2][b], g["kps_out"][b]) <= TOL
 
 
+@pytest.mark.parametrize("name", ["decode_plain", "decode_rotated", "decode_K150"])
+def test_two_stage_baseline_decode_matches_reference(name):
+    g = load_golden(name)
+    heat, wh, reg = (torch.from_numpy(g[k]) for k in ("heat", "wh", "reg"))
+    dets = oracle.decode_two_stage(heat, wh, reg, K=int(g["K"]), rotated=bool(g["rotated"]))
+    assert np.array_equal(dets.numpy(), g["dets"])
+
+
 def test_decode_tie_rule_is_lower_flat_index():
     g = load_golden("decode_plateau")
     heat, wh, reg = (torch.from_numpy(g[k]) for k in ("heat", "wh", "reg"))
