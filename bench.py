@@ -175,7 +175,7 @@ class BufferSet:
         self.prob = torch.empty_like(self.hm)
         self.grads = [torch.empty_like(self.hm), torch.empty_like(self.wh), torch.empty_like(self.reg)]
         self.scalars = torch.zeros(L.SCALARS, device=dev)
-        self.partials = torch.zeros(self.hm.shape[0], L.PARTIALS, dtype=torch.float64, device=dev)
+        self.totals = torch.zeros(L.TOTALS, dtype=torch.int64, device=dev)
         self.norm = torch.zeros(4, dtype=torch.float64, device=dev)
         self.ones = torch.ones(L.SCALARS, device=dev)          # upstream gradient of loss.backward()
         self.dets = torch.empty(self.hm.shape[0], cfg.K, 7 if cfg.rotated else 6, device=dev)
@@ -200,7 +200,7 @@ class DeviceStep:
         dev = sets[0].hm.device
         self.loss_args, self.scale_args, self.dec_args = [], [], []
         for s in sets:
-            a = F.fill_detloss_args(s.hm, s.gt, s.ind, s.heads, 1.0, s.prob, s.grads, s.scalars, s.partials,
+            a = F.fill_detloss_args(s.hm, s.gt, s.ind, s.heads, 1.0, s.prob, s.grads, s.scalars, s.totals,
                                     norm=s.norm, norm_out=s.norm, b_global=s.hm.shape[0] * world)
             sc = L.ScaleArgs()
             sc.n_tensors = 3
@@ -240,9 +240,9 @@ class DeviceStep:
             L.check(self.lib.cnh_detloss_count(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), st), "count")
             self.sharded.exchange_normalisers(s.norm, self.group)
             L.check(self.lib.cnh_detloss_main(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), st), "main")
-            rows = self.sharded.gather_partials(s.partials, self.group)
+            self.sharded.reduce_totals(s.totals, self.group)
             a.scalars = s.scalars.data_ptr()
-            L.check(self.lib.cnh_detloss_finalize(C.byref(a), rows.data_ptr(), rows.shape[0], st), "finalize")
+            L.check(self.lib.cnh_detloss_finalize(C.byref(a), s.totals.data_ptr(), st), "finalize")
         L.check(self.lib.cnh_scale_inplace(C.byref(self.scale_args[i]), st), "scale")            # backward
         L.check(self.lib.cnh_decode(C.byref(self.dec_args[i]), self.ws_dec.data_ptr(), self.ws_dec.numel(), st),
                 "decode")

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libcnhead_sm100.so")
 
 MAX_HEADS = 3
-PARTIALS = 12
+TOTALS = 24
 SCALARS = 8
 ANGLE_NONE, ANGLE_SIGMOID, ANGLE_PERIODIC = 0, 1, 2
 FLAG_ACCURATE_MATH, FLAG_NO_STASH = 1, 2
@@ -36,7 +36,7 @@ class DetLossArgs(C.Structure):
                 ("hm_logits", C.c_void_p), ("hm_gt", C.c_void_p), ("prob", C.c_void_p), ("grad_hm", C.c_void_p),
                 ("ind", C.c_void_p), ("hm_weight", C.c_float), ("_pad", C.c_int32),
                 ("heads", Head * MAX_HEADS),
-                ("scalars", C.c_void_p), ("partials", C.c_void_p), ("norm", C.c_void_p), ("norm_out", C.c_void_p)]
+                ("scalars", C.c_void_p), ("totals", C.c_void_p), ("norm", C.c_void_p), ("norm_out", C.c_void_p)]
 
 
 class ScaleArgs(C.Structure):
@@ -80,7 +80,7 @@ def lib() -> C.CDLL:
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(DetLossArgs), vp, sz, st]
         L.cnh_detloss_finalize.restype = C.c_int
-        L.cnh_detloss_finalize.argtypes = [C.POINTER(DetLossArgs), vp, i32, st]
+        L.cnh_detloss_finalize.argtypes = [C.POINTER(DetLossArgs), vp, st]
         L.cnh_scale_inplace.restype = C.c_int
         L.cnh_scale_inplace.argtypes = [C.POINTER(ScaleArgs), st]
         L.cnh_softmax_workspace_bytes.restype = sz

@@ -42,7 +42,7 @@ def _as_mask(t: torch.Tensor) -> torch.Tensor:
     return L.require(t, "mask", torch.uint8)
 
 
-def fill_detloss_args(hm, gt, ind, heads: Sequence[HeadSpec], hm_weight, prob, grads, scalars, partials,
+def fill_detloss_args(hm, gt, ind, heads: Sequence[HeadSpec], hm_weight, prob, grads, scalars, totals,
                       norm=None, norm_out=None, flags=None, b_global=None) -> L.DetLossArgs:
     B, Cc, H, W = hm.shape
     a = L.DetLossArgs()
@@ -63,7 +63,7 @@ def fill_detloss_args(hm, gt, ind, heads: Sequence[HeadSpec], hm_weight, prob, g
         hd.angle_mode = h.angle_mode
         hd.elementwise_mask = 1 if h.elementwise_mask else 0
         hd.weight, hd.angle_weight = h.weight, h.angle_weight
-    a.scalars, a.partials = L.ptr(scalars), L.ptr(partials)
+    a.scalars, a.totals = L.ptr(scalars), L.ptr(totals)
     a.norm, a.norm_out = L.ptr(norm), L.ptr(norm_out)
     return a
 
@@ -89,7 +89,7 @@ def _check_heads(hm, gt, ind, heads):
 
 
 class _DetectionLossFn(torch.autograd.Function):
-    """inputs: hm logits, then one map per head.  Outputs: scalars[8], clamped prob, partials."""
+    """inputs: hm logits, then one map per head.  Outputs: scalars[8], clamped prob, totals[24]."""
 
     @staticmethod
     def forward(ctx, meta, hm, *maps):
@@ -100,18 +100,18 @@ class _DetectionLossFn(torch.autograd.Function):
         prob = torch.empty_like(hm)
         grads = [torch.empty_like(hm)] + [torch.empty_like(m) for m in maps] if need_grad else None
         scalars = torch.empty(L.SCALARS, dtype=torch.float32, device=hm.device)
-        partials = torch.empty(hm.shape[0], L.PARTIALS, dtype=torch.float64, device=hm.device)
-        a = fill_detloss_args(hm, gt, ind, heads, hm_weight, prob, grads, scalars, partials)
+        totals = torch.empty(L.TOTALS, dtype=torch.int64, device=hm.device)
+        a = fill_detloss_args(hm, gt, ind, heads, hm_weight, prob, grads, scalars, totals)
         nbytes = L.lib().cnh_detloss_workspace_bytes(C.byref(a))
         ws = L.workspace("detloss", nbytes, hm.device)
         L.check(L.lib().cnh_detloss_fused(C.byref(a), ws.data_ptr(), ws.numel(), L.stream_ptr()), "detloss_fused")
         ctx.grads = grads
         ctx.used = False
-        ctx.mark_non_differentiable(prob, partials)
-        return scalars, prob, partials
+        ctx.mark_non_differentiable(prob, totals)
+        return scalars, prob, totals
 
     @staticmethod
-    def backward(ctx, g_scalars, _g_prob, _g_partials):
+    def backward(ctx, g_scalars, _g_prob, _g_totals):
         if ctx.grads is None:
             raise RuntimeError("cnhead: DetectionLoss was run without gradients")
         if ctx.used:
@@ -139,7 +139,7 @@ class _Spec:
 
 def detection_loss(hm: torch.Tensor, gt: torch.Tensor, ind: torch.Tensor, heads: Sequence[HeadSpec],
                    hm_weight: float = 1.0):
-    """Fused DetectionLoss core.  Returns (scalars[8], prob, partials[B,12]); see include/cnhead.h."""
+    """Fused DetectionLoss core.  Returns (scalars[8], prob, totals[24] int64); see include/cnhead.h."""
     hm = L.require(hm, "output['hm']")
     gt = L.require(gt, "batch['hm']")
     ind = L.require(ind, "batch['ind']", torch.int64)

@@ -7,13 +7,13 @@ losses/centernet.py:87-94; mask.sum(), :120,130,213), so the exchange is:
 
     cnh_detloss_count   -> this shard's [num_pos, mask counts]            (reads targets only)
     all_reduce(SUM)        4 doubles over NCCL / NVLink                   <- the one collective the
-    cnh_detloss_main    -> probabilities, FINAL gradients, per-sample partials    gradients wait for
-    all_gather             per-sample partial rows [B/G, 12] doubles      (loss VALUE only, off the
-    cnh_detloss_finalize-> loss scalars, summed in global sample order     critical path of backward)
+    cnh_detloss_main    -> probabilities, FINAL gradients, exact totals   gradients wait for
+    all_reduce(SUM)        24 int64 words (fixed-point sums, counts)      (loss VALUE only, off the
+    cnh_detloss_finalize-> loss scalars                                    critical path of backward)
 
-Integer-valued counts are exact in float64 and the per-sample partial rows do not depend on how the
-batch is sharded, so every rank obtains scalars bit-identical to the single-device launch, and
-gradients bit-identical on the heat map.  Decode needs no exchange at all.
+The totals are exact integers (2^-40 fixed point as hi/lo words), so their sum does not depend on
+how the batch is sharded or on the reduction order: every rank obtains scalars bit-identical to the
+single-device launch, and gradients bit-identical on the heat map.  Decode needs no exchange.
 """
 from __future__ import annotations
 
@@ -35,14 +35,11 @@ def exchange_normalisers(norm_local: torch.Tensor, group=None, async_op: bool = 
     return dist.all_reduce(norm_local, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
-def gather_partials(partials: torch.Tensor, group=None) -> torch.Tensor:
-    """per-sample rows of this shard [b, 12] -> rows of the whole batch in rank order [G*b, 12]."""
+def reduce_totals(totals: torch.Tensor, group=None, async_op: bool = False):
+    """exact per-shard totals (int64[24]) -> totals of the whole batch, in place (integer SUM)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return partials
-    world = dist.get_world_size(group)
-    out = partials.new_empty((world * partials.shape[0], partials.shape[1]))
-    dist.all_gather_into_tensor(out, partials.contiguous(), group=group)
-    return out
+        return None
+    return dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
 def shard_slice(batch: int, rank: int, world: int) -> slice:
@@ -66,23 +63,22 @@ class _ShardedDetectionLossFn(torch.autograd.Function):
         prob = torch.empty_like(hm)
         grads = [torch.empty_like(hm)] + [torch.empty_like(m) for m in maps]
         scalars = torch.empty(L.SCALARS, dtype=torch.float32, device=dev)
-        partials = torch.empty(hm.shape[0], L.PARTIALS, dtype=torch.float64, device=dev)
+        totals = torch.empty(L.TOTALS, dtype=torch.int64, device=dev)
         norm = torch.empty(4, dtype=torch.float64, device=dev)
-        a = F.fill_detloss_args(hm, gt, ind, heads, hm_weight, prob, grads, None, partials,
+        a = F.fill_detloss_args(hm, gt, ind, heads, hm_weight, prob, grads, None, totals,
                                 norm=norm, norm_out=norm, b_global=hm.shape[0] * world)
         ws = L.workspace("detloss", L.lib().cnh_detloss_workspace_bytes(C.byref(a)), dev)
         st = L.stream_ptr()
         L.check(L.lib().cnh_detloss_count(C.byref(a), ws.data_ptr(), ws.numel(), st), "detloss_count")
         exchange_normalisers(norm, group)
         L.check(L.lib().cnh_detloss_main(C.byref(a), ws.data_ptr(), ws.numel(), st), "detloss_main")
-        all_rows = gather_partials(partials, group)
+        reduce_totals(totals, group)
         a.scalars = scalars.data_ptr()
-        L.check(L.lib().cnh_detloss_finalize(C.byref(a), all_rows.data_ptr(), all_rows.shape[0], st),
-                "detloss_finalize")
+        L.check(L.lib().cnh_detloss_finalize(C.byref(a), totals.data_ptr(), st), "detloss_finalize")
         ctx.grads = grads
         ctx.used = False
-        ctx.mark_non_differentiable(prob, all_rows)
-        return scalars, prob, all_rows
+        ctx.mark_non_differentiable(prob, totals)
+        return scalars, prob, totals
 
     backward = staticmethod(F._DetectionLossFn.backward)
 
@@ -104,16 +100,15 @@ def detection_loss_sharded(hm, gt, ind, heads: Sequence[F.HeadSpec], hm_weight=1
                                             s.elementwise_mask) for m, s in zip(maps, specs)])
     if not any(t.requires_grad for t in [hm] + maps) or not torch.is_grad_enabled():
         # validation: no gradients -> no normaliser exchange; only the loss value is reduced
-        scalars, prob, partials = F.detection_loss(hm, gt, ind, heads, hm_weight)
-        rows = gather_partials(partials, group)
-        if rows is not partials:
+        scalars, prob, totals = F.detection_loss(hm, gt, ind, heads, hm_weight)
+        if reduce_totals(totals, group) is not None or (dist.is_initialized() and dist.get_world_size(group) > 1):
             a = F.fill_detloss_args(hm, gt, ind, [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight,
                                                              s.angle_mode, s.elementwise_mask)
                                                   for m, s in zip(maps, specs)],
-                                    hm_weight, prob, None, scalars, partials)
-            L.check(L.lib().cnh_detloss_finalize(C.byref(a), rows.data_ptr(), rows.shape[0], L.stream_ptr()),
+                                    hm_weight, prob, None, scalars, totals)
+            L.check(L.lib().cnh_detloss_finalize(C.byref(a), totals.data_ptr(), L.stream_ptr()),
                     "detloss_finalize")
-        return scalars, prob, rows
+        return scalars, prob, totals
     return _ShardedDetectionLossFn.apply((gt, ind, specs, float(hm_weight), group), hm, *maps)
 
 
@@ -130,14 +125,14 @@ def make_sharded_loss(base_cls):
             if self.with_keypoints and self.kp_indices is not None:
                 raise NotImplementedError("limb-length keypoint term is not sharded")
             heads = self._heads(output, batch)
-            scalars, prob, rows = detection_loss_sharded(output['hm'], batch['hm'], batch['ind'], heads,
+            scalars, prob, totals = detection_loss_sharded(output['hm'], batch['hm'], batch['ind'], heads,
                                                          self.hm_weight, self.group)
             output['hm'] = prob
             stats = {'centernet_loss': scalars[0], 'hm_loss': scalars[1], 'wh_loss': scalars[2],
                      'off_loss': scalars[3]}
             if self.with_keypoints:
                 stats['kp_loss'] = scalars[4]
-            self.last_partials = rows
+            self.last_totals = totals
             return scalars[0], stats
 
     return ShardedDetectionLoss

@@ -33,7 +33,13 @@ int sm_count() {
   return cached;
 }
 
+static long long* g_debug = nullptr;
+long long* debug_buffer() { return g_debug; }
+
 }  // namespace cnh
+
+// not part of the public ABI: tools/ install a device buffer [grid][16] of int64 for stage timestamps
+extern "C" void cnh_debug_set_buffer(void* p) { cnh::g_debug = static_cast<long long*>(p); }
 
 extern "C" int cnh_version(void) { return CNH_VERSION; }
 extern "C" const char* cnh_last_error(void) { return cnh::g_err; }

@@ -18,6 +18,7 @@ constexpr float kHi = 1.0f - 1e-4f;
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int sm_count();                          // SMs of the current device (cached)
+long long* debug_buffer();               // device buffer for in-kernel stage timestamps, or nullptr
 
 #define CNH_REQUIRE(cond, code, ...)      \
   do {                                    \
@@ -68,18 +69,53 @@ __device__ __forceinline__ T block_sum(T v, T* red) {
   return t;
 }
 
-// sigmoid pieces.  FAST: ex2.approx / rcp.approx / lg2.approx (3 MUFU ops per element);
+// MUFU approximations with flush-to-zero: one instruction each (the non-ftz intrinsics expand to
+// 4-6 instructions of denormal handling that this path never needs: probabilities are clamped
+// to [1e-4, 1-1e-4] and exp(-x) underflowing to 0 still yields sigmoid = 1).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2eF = 1.4426950408889634f;
+constexpr float kLn2F = 0.6931471805599453f;
+
+// sigmoid pieces.  FAST: ex2/rcp/lg2.approx.ftz (3 MUFU ops per heat-map element);
 // accurate: libdevice expf/logf and an IEEE divide.
 template <bool FAST>
 __device__ __forceinline__ float sigmoidf_(float x) {
-  if (FAST) return __fdividef(1.0f, 1.0f + __expf(-x));
+  if (FAST) return rcp_ftz(1.0f + ex2_ftz(x * -kLog2eF));
   return 1.0f / (1.0f + expf(-x));
 }
 template <bool FAST>
 __device__ __forceinline__ float logf_(float x) {
-  return FAST ? __logf(x) : logf(x);
+  return FAST ? lg2_ftz(x) * kLn2F : logf(x);
+}
+// log in the unit the fast path accumulates in: log2 (FAST; scaled by ln2 once per thread) or ln.
+template <bool FAST>
+__device__ __forceinline__ float log_unit(float x) {
+  return FAST ? lg2_ftz(x) : logf(x);
 }
 __device__ __forceinline__ float clamp_prob(float s) { return fminf(fmaxf(s, kLo), kHi); }
+
+// stage timestamps for tools/ (enabled only when cnh_debug_set_buffer() installed a buffer)
+__device__ __forceinline__ void dbg_stamp(long long* dbg, int slot) {
+  if (dbg != nullptr && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[(long long)blockIdx.x * 16 + slot] = t;
+  }
+}
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ void stg_stream(float4* p, float4 v) { __stcs(p, v); }

@@ -7,8 +7,9 @@
 // ld.global.cs) and written once (clamped probability + gradient).  The gradient needs
 // the batch-wide num_pos, which is only known after everything has been read:
 //   * STASH    (small problems): the raw gradient of <= kStash chunks per CTA stays in
-//               registers across a cooperative grid barrier, then is scaled and stored:
-//               16 B/element, the algorithmic floor.
+//               registers across a grid barrier, then is scaled and stored: 16 B/element,
+//               the algorithmic floor.  The barrier's arrival atomic carries the CTA's
+//               num_pos, a dedicated CTA computes the scalars while the others store.
 //   * PRECOUNT (large problems): phase 0 counts num_pos over the target only (forward
 //               order), grid barrier, phase 1 does the full pass in REVERSE order so the
 //               tail of the target is still in the 126 MB L2: <= 20 B/element.
@@ -16,10 +17,15 @@
 //               normalisers supplied by the caller (the all-reduce of a sharded run sits
 //               between them).
 //   * FWD: no gradients (validation under no_grad): 12 B/element.
-// Reductions are deterministic: fixed-shape block trees -> per-chunk partials -> per-sample
-// double sums in chunk order -> batch sum in sample order.  The per-sample partials are
-// independent of grid size and of how samples are sharded over GPUs, so a sharded run
-// reproduces the single-device loss bit for bit.
+// Regression heads are warp-granular work items (zero-fill of a 16 KB piece of a dense
+// gradient plane + the object slots whose centre falls into it), dealt to the CTAs that
+// hold the fewest heat-map chunks.
+//
+// Reductions are EXACT and order-independent: every chunk / item partial (a float produced
+// by a fixed-shape tree) is converted to 2^-40 fixed point and added with integer atomics
+// into a (hi, lo) pair of 64-bit accumulators.  Integer addition is associative, so the
+// totals -- and the loss -- are bit-identical for any grid size, any schedule and any
+// sharding of the batch over GPUs (a sharded run all-reduces the 24 integers).
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -31,16 +37,22 @@ namespace cnh {
 constexpr int kVec = 4;                       // float4 per thread per chunk
 constexpr int kElemsPerThread = kVec * 4;
 constexpr int kChunk = kThreads * kElemsPerThread;   // 4096 heat-map elements
-constexpr int kStash = 2;                     // chunks a CTA may keep in registers
-constexpr int kPiece = kThreads * 16;         // 4096 floats of one regression plane
+constexpr int kStash = 1;                     // chunks a CTA may keep in registers (probability + raw gradient)
+constexpr int kPiece = 4096;                  // floats of one regression plane per work item
+constexpr int kSlotsPerLane = 8;              // STASH keeps <= 8 object slots per lane (M <= 256)
+constexpr int kQ = CNH_TOTALS / 2;            // quantities: focal, num_pos, 3 x (l1, angle, count), spare
 
 enum Mode { M_STASH = 0, M_PRECOUNT = 1, M_MAIN = 2, M_COUNT = 3, M_FWD = 4 };
 
-struct WsHeader {                             // 64 bytes, zero between launches
-  int npos_total;
-  int cnt_total[CNH_MAX_HEADS];
+// Workspace header.  `parity` selects the live accumulator / barrier set.  Ticket modes leave their
+// set zeroed (the last CTA cleans up); STASH leaves it dirty, flips parity and cleans the OTHER set,
+// which the launch before it used -- so nothing has to be reset on the critical path.
+struct WsHeader {
+  unsigned parity;
   unsigned done;
-  int pad[11];
+  unsigned pad[2];
+  unsigned long long bar[2][2];               // STASH barriers [parity][0 = chunk CTAs: arrivals << 32 | num_pos, 1 = item CTAs]
+  long long acc[2][CNH_TOTALS];               // [q] = hi word, [kQ + q] = lo word
 };
 
 struct Geo {
@@ -53,12 +65,24 @@ struct Geo {
   int n_items;
   int n_count;             // B * n_heads
   int vec_planes;          // regression planes can be zero-filled with float4 stores
-  float* chunk_sum;        // [n_chunks]
-  int* chunk_npos;         // [n_chunks]
-  float* item_l1;          // [n_items]
-  float* item_ang;         // [n_items]
+  int stash_slots;         // STASH may keep the slots of an item in registers (M <= 256)
+  int chunk_ctas, item_ctas;   // STASH roles
   WsHeader* hdr;
+  long long* dbg;
 };
+
+// ---- exact accumulation ---------------------------------------------------------------------
+__device__ __forceinline__ void acc_add_fixed(long long* acc, int q, float v) {
+  const long long f = __double2ll_rn((double)v * 1099511627776.0);        // 2^40
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc + q), (unsigned long long)(f >> 32));
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc + kQ + q), (unsigned long long)(f & 0xffffffffll));
+}
+__device__ __forceinline__ void acc_add_int(long long* acc, int q, long long n) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc + kQ + q), (unsigned long long)n);
+}
+__device__ __host__ __forceinline__ double fixed_to_double(long long hi, long long lo) {
+  return ((double)hi * 4294967296.0 + (double)lo) * (1.0 / 1099511627776.0);
+}
 
 // ---- focal element ----------------------------------------------------------------------
 // term = log(p)(1-p)^2 [gt==1]  or  log(1-p) p^2 (1-gt)^4 [gt<1]   (losses/centernet.py:82-84)
@@ -66,6 +90,7 @@ struct Geo {
 //        +((1-s)^3 - 2 s (1-s)^2 log s)            for gt == 1
 //        -(1-gt)^4 (s^3 - 2 s^2 (1-s) log(1-s))    for gt <  1
 // so one log and no second reciprocal per element.
+// FAST accumulates `term` in log2 units (the caller multiplies the per-thread sum by ln2 once).
 template <bool FAST>
 __device__ __forceinline__ void focal_elem(float x, float gt, float& p, float& term, float& graw,
                                            int& npos) {
@@ -78,15 +103,17 @@ __device__ __forceinline__ void focal_elem(float x, float gt, float& p, float& t
   const float q = __fsub_rn(1.0f, p);
   const float arg = pos ? p : q;              // argument of the log
   const float a = pos ? q : p;                // the squared factor
-  const float L = logf_<FAST>(arg);
+  const float L = log_unit<FAST>(arg);
   const float omg = __fsub_rn(1.0f, gt);
   float w4 = __fmul_rn(omg, omg);
   w4 = __fmul_rn(w4, w4);
   const float wgt = pos ? 1.0f : (neg ? w4 : 0.0f);
   const float a2 = __fmul_rn(a, a);
   term = __fmul_rn(__fmul_rn(L, a2), wgt);
-  const float inner = __fmaf_rn(-__fmul_rn(__fmul_rn(2.0f, a2), arg), L, __fmul_rn(a2, a));
-  graw = (p == s) ? (pos ? inner : -__fmul_rn(wgt, inner)) : 0.0f;   // clamp passes gradient inclusively
+  constexpr float k2 = FAST ? 2.0f * kLn2F : 2.0f;       // d/dp of a^2 log(arg), log in its unit
+  const float inner = __fmaf_rn(-__fmul_rn(__fmul_rn(k2, a2), arg), L, __fmul_rn(a2, a));
+  const float sw = pos ? 1.0f : -wgt;
+  graw = (p == s) ? __fmul_rn(sw, inner) : 0.0f;         // clamp passes gradient inclusively
   npos += pos ? 1 : 0;
 }
 
@@ -111,12 +138,12 @@ __device__ __forceinline__ void block_reduce2(float& s, int& n, float* red_f, in
   n = tn;
 }
 
-// One chunk of the heat map.  WRITE_GRAD: scale known, store the gradient now.
-// Otherwise (STASH) the raw gradient is returned in `graw`.
-template <bool NEED_GRAD, bool WRITE_GRAD, bool FAST, bool VEC>
-__device__ __forceinline__ void focal_chunk(const cnh_detloss_args& a, const Geo& g, int chunk,
-                                            float scale, float (&graw)[kElemsPerThread],
-                                            float* red_f, int* red_i) {
+// One chunk of the heat map.  WRITE_GRAD: scale known, store the gradient now; otherwise (STASH)
+// the raw gradient is returned in `graw` and (KEEP_P) the probabilities in `pkeep`, unstored.  Adds the chunk's loss sum to acc; returns its num_pos.
+template <bool NEED_GRAD, bool WRITE_GRAD, bool KEEP_P, bool FAST, bool VEC>
+__device__ __forceinline__ int focal_chunk(const cnh_detloss_args& a, const Geo& g, long long* acc, int chunk,
+                                           float scale, float (&graw)[kElemsPerThread],
+                                           float (&pkeep)[kElemsPerThread], float* red_f, int* red_i) {
   const int b = chunk / g.cps, j = chunk - b * g.cps;
   const long long in_sample = (long long)j * kChunk;
   const long long base = (long long)b * g.CHW + in_sample;
@@ -159,7 +186,9 @@ __device__ __forceinline__ void focal_chunk(const cnh_detloss_args& a, const Geo
       focal_elem<FAST>(xs[4 * v + e], gs[4 * v + e], ps[e], term, gr[e], npos);
       sum = __fadd_rn(sum, term);
       if (NEED_GRAD) graw[4 * v + e] = WRITE_GRAD ? __fmul_rn(gr[e], scale) : gr[e];
+      if (KEEP_P) pkeep[4 * v + e] = ps[e];
     }
+    if (KEEP_P) continue;                     // STASH: nothing is stored before the grid barrier
     if (VEC) {
       if (off < n) {
         *reinterpret_cast<float4*>(pp + off) = make_float4(ps[0], ps[1], ps[2], ps[3]);
@@ -176,16 +205,16 @@ __device__ __forceinline__ void focal_chunk(const cnh_detloss_args& a, const Geo
         }
     }
   }
+  if (FAST) sum = __fmul_rn(sum, kLn2F);      // log2 -> natural log, once per thread
   block_reduce2(sum, npos, red_f, red_i);
-  if (threadIdx.x == 0) {
-    g.chunk_sum[chunk] = sum;
-    g.chunk_npos[chunk] = npos;
-  }
+  if (threadIdx.x == 0) acc_add_fixed(acc, 0, sum);
+  return npos;
 }
 
 template <bool VEC>
 __device__ __forceinline__ void focal_store_stash(const cnh_detloss_args& a, const Geo& g, int chunk,
-                                                  float scale, const float (&graw)[kElemsPerThread]) {
+                                                  float scale, const float (&graw)[kElemsPerThread],
+                                                  const float (&pkeep)[kElemsPerThread]) {
   const int b = chunk / g.cps, j = chunk - b * g.cps;
   const long long in_sample = (long long)j * kChunk;
   const long long base = (long long)b * g.CHW + in_sample;
@@ -195,19 +224,25 @@ __device__ __forceinline__ void focal_store_stash(const cnh_detloss_args& a, con
   for (int v = 0; v < kVec; ++v) {
     const int off = v * kThreads * 4 + threadIdx.x * 4;
     if (VEC) {
-      if (off < n)
+      if (off < n) {
+        *reinterpret_cast<float4*>(a.prob + base + off) =
+            make_float4(pkeep[4 * v], pkeep[4 * v + 1], pkeep[4 * v + 2], pkeep[4 * v + 3]);
         stg_stream(reinterpret_cast<float4*>(a.grad_hm + base + off),
                    make_float4(__fmul_rn(graw[4 * v], scale), __fmul_rn(graw[4 * v + 1], scale),
                                __fmul_rn(graw[4 * v + 2], scale), __fmul_rn(graw[4 * v + 3], scale)));
+      }
     } else {
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (off + e < n) a.grad_hm[base + off + e] = __fmul_rn(graw[4 * v + e], scale);
+        if (off + e < n) {
+          a.prob[base + off + e] = pkeep[4 * v + e];
+          a.grad_hm[base + off + e] = __fmul_rn(graw[4 * v + e], scale);
+        }
     }
   }
 }
 
-// num_pos of one chunk from the target only (phase 0 of PRECOUNT / COUNT).
+// num_pos of one chunk from the target only (phase 0 of PRECOUNT / COUNT), per thread.
 template <bool VEC>
 __device__ __forceinline__ int count_chunk(const cnh_detloss_args& a, const Geo& g, int chunk) {
   const int b = chunk / g.cps, j = chunk - b * g.cps;
@@ -233,7 +268,11 @@ __device__ __forceinline__ int count_chunk(const cnh_detloss_args& a, const Geo&
   return npos;
 }
 
-// ---- masked gather-L1 heads -----------------------------------------------------------------
+// ---- masked gather-L1 heads: warp-granular work items -----------------------------------------
+__device__ __forceinline__ const cnh_head& head_of(const cnh_detloss_args& a, int h) {
+  return h == 0 ? a.heads[0] : (h == 1 ? a.heads[1] : a.heads[2]);   // no local copy of the params
+}
+
 struct ItemRef {
   int h, b, d, p0, p1;
 };
@@ -246,7 +285,7 @@ __device__ __forceinline__ ItemRef decode_item(const cnh_detloss_args& a, const 
   const int local = item - g.item0[r.h];
   const int piece = local % g.ppp;
   const int plane = local / g.ppp;
-  const int D = a.heads[r.h].D;
+  const int D = head_of(a, r.h).D;
   r.d = plane % D;
   r.b = plane / D;
   r.p0 = piece * kPiece;
@@ -254,174 +293,201 @@ __device__ __forceinline__ ItemRef decode_item(const cnh_detloss_args& a, const 
   return r;
 }
 
-__device__ __forceinline__ void l1_zero_fill(const cnh_detloss_args& a, const Geo& g, const ItemRef& r) {
-  const cnh_head& hd = a.heads[r.h];
+__device__ __forceinline__ void l1_zero_fill_warp(const cnh_detloss_args& a, const Geo& g, const ItemRef& r) {
+  const cnh_head& hd = head_of(a, r.h);
+  const int lane = threadIdx.x & 31;
   float* __restrict__ dst = hd.grad + ((long long)r.b * hd.D + r.d) * g.HW;
   if (g.vec_planes) {
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int off = r.p0 + v * kThreads * 4 + threadIdx.x * 4;
-      if (off < r.p1) *reinterpret_cast<float4*>(dst + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int off = r.p0 + lane * 4; off < r.p1; off += 128)
+      *reinterpret_cast<float4*>(dst + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int off = r.p0 + lane; off < r.p1; off += 32) dst[off] = 0.f;
+  }
+}
+
+__device__ __forceinline__ void l1_zero_fill_block(const cnh_detloss_args& a, const Geo& g, const ItemRef& r) {
+  const cnh_head& hd = head_of(a, r.h);
+  float* __restrict__ dst = hd.grad + ((long long)r.b * hd.D + r.d) * g.HW;
+  if (g.vec_planes) {
+    for (int off = r.p0 + threadIdx.x * 4; off < r.p1; off += kThreads * 4)
+      *reinterpret_cast<float4*>(dst + off) = make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
     for (int off = r.p0 + threadIdx.x; off < r.p1; off += kThreads) dst[off] = 0.f;
   }
 }
 
-// Forward terms (and, when SCATTER, the gradient scatter) of the object slots whose centre
-// falls inside this item's piece of the plane.  inv_denom = 1 / (sum(mask_expanded) + 1e-4).
-template <bool FORWARD, bool SCATTER, bool FAST>
-__device__ __forceinline__ void l1_slots(const cnh_detloss_args& a, const Geo& g, const ItemRef& r,
-                                         float inv_denom, float& l1_acc, float& ang_acc) {
-  const cnh_head& hd = a.heads[r.h];
-  const int D = hd.D;
-  const bool is_angle = (D == 3 && r.d == 2 && hd.angle_mode != CNH_ANGLE_NONE);
-  const float* __restrict__ plane = hd.map + ((long long)r.b * D + r.d) * g.HW;
-  float* __restrict__ gplane = SCATTER ? hd.grad + ((long long)r.b * D + r.d) * g.HW : nullptr;
+// |.| term and d(term)/d(pred*m) (times m*w) of one object slot of one channel.
+template <bool FAST>
+__device__ __forceinline__ void l1_slot_math(const cnh_head& hd, bool is_angle, float pred, float tgt, float m,
+                                             float& val, float& gv) {
   constexpr float kPi = 3.14159265358979323846f;          // float(np.pi)
   constexpr float kHalfPi = 1.57079632679489661923f;      // float(np.pi / 2)
   constexpr float kDeg = 0.017453292519943295f;           // torch.deg2rad constant
-  for (int k = threadIdx.x; k < a.M; k += kThreads) {
-    const long long slot = (long long)r.b * a.M + k;
-    const long long i = a.ind[slot];
-    if (i < r.p0 || i >= r.p1) continue;
-    const float m = (float)(hd.elementwise_mask ? hd.mask[slot * D + r.d] : hd.mask[slot]);
-    const float pv = plane[i] * m;                          // pred *= mask   (centernet.py:108)
-    const float tv = hd.target[slot * D + r.d] * m;         // target *= mask (centernet.py:109)
-    float val, gcoef;                                       // |.| term and d(term)/d(pred*m)
-    if (!is_angle) {
-      const float diff = pv - tv;
+  const float pv = pred * m;                              // pred *= mask   (centernet.py:108)
+  const float tv = tgt * m;                               // target *= mask (centernet.py:109)
+  float gcoef;
+  if (!is_angle) {
+    const float diff = pv - tv;
+    val = fabsf(diff);
+    gcoef = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
+  } else {
+    const float s = sigmoidf_<FAST>(pv);
+    const float sc = clamp_prob(s);
+    const float ds = (sc == s) ? s * (1.f - s) : 0.f;
+    if (hd.angle_mode == CNH_ANGLE_SIGMOID) {             // centernet.py:112-126
+      const float diff = sc - clamp_prob(sigmoidf_<FAST>(tv));
       val = fabsf(diff);
-      gcoef = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
-    } else {
-      const float s = sigmoidf_<FAST>(pv);
-      const float sc = clamp_prob(s);
-      const float ds = (sc == s) ? s * (1.f - s) : 0.f;
-      if (hd.angle_mode == CNH_ANGLE_SIGMOID) {             // centernet.py:112-126
-        const float diff = sc - clamp_prob(sigmoidf_<FAST>(tv));
-        val = fabsf(diff);
-        gcoef = ((diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f)) * ds;
-      } else {                                              // centernet.py:203-220
-        const float pa = sc * 2.f * kPi - kPi;
-        const float ta = tv * kDeg;
-        float rem = fmodf((pa - ta) - kHalfPi, kPi);
-        if (rem != 0.f && rem < 0.f) rem += kPi;
-        const float diff = rem - kHalfPi;
-        val = fabsf(diff);
-        gcoef = ((diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f)) * 2.f * kPi * ds;
+      gcoef = ((diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f)) * ds;
+    } else {                                              // centernet.py:203-220
+      const float pa = sc * 2.f * kPi - kPi;
+      const float ta = tv * kDeg;
+      float rem = fmodf((pa - ta) - kHalfPi, kPi);
+      if (rem != 0.f && rem < 0.f) rem += kPi;
+      const float diff = rem - kHalfPi;
+      val = fabsf(diff);
+      gcoef = ((diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f)) * 2.f * kPi * ds;
+    }
+  }
+  gv = gcoef * m * (is_angle ? hd.angle_weight : hd.weight);
+}
+
+// One warp, one item: zero-fill of the piece (ZERO), forward terms of the slots inside it (added to
+// acc), and either the scatter itself (SCATTER, inv_denom known) or the slots' (index, coefficient)
+// kept in registers for a scatter after the grid barrier (KEEP).  Every lane owns slots lane,
+// lane+32, ...  Two dependent memory round trips: {index, mask, target} then {prediction}; the
+// zero-fill stores are issued between them so that they never delay a load.
+template <bool ZERO, bool FORWARD, bool SCATTER, bool KEEP, bool FAST>
+__device__ __forceinline__ void l1_item_warp(const cnh_detloss_args& a, const Geo& g, long long* acc,
+                                             const ItemRef& r, float inv_denom, int (&keep_i)[kSlotsPerLane],
+                                             float (&keep_g)[kSlotsPerLane]) {
+  const cnh_head& hd = head_of(a, r.h);
+  const int lane = threadIdx.x & 31;
+  const int D = hd.D;
+  const bool is_angle = (D == 3 && r.d == 2 && hd.angle_mode != CNH_ANGLE_NONE);
+  const float* __restrict__ plane = hd.map + ((long long)r.b * D + r.d) * g.HW;
+  float* __restrict__ gplane = hd.grad ? hd.grad + ((long long)r.b * D + r.d) * g.HW : nullptr;
+  float l1 = 0.f, ang = 0.f;
+  for (int k0 = 0; k0 < a.M || (ZERO && k0 == 0); k0 += 32 * kSlotsPerLane) {
+    long long idx[kSlotsPerLane];
+    float mk[kSlotsPerLane], tg[kSlotsPerLane];
+    // round trip 1: centre index, mask and target of up to 8 slots per lane, all in flight together
+#pragma unroll
+    for (int u = 0; u < kSlotsPerLane; ++u) {
+      const int k = k0 + u * 32 + lane;
+      idx[u] = -1;
+      mk[u] = 0.f;
+      tg[u] = 0.f;
+      if (k < a.M) {
+        const long long slot = (long long)r.b * a.M + k;
+        idx[u] = __ldg(a.ind + slot);
+        mk[u] = (float)(hd.elementwise_mask ? __ldg(hd.mask + slot * D + r.d) : __ldg(hd.mask + slot));
+        tg[u] = __ldg(hd.target + slot * D + r.d);
       }
     }
-    if (FORWARD) {
-      if (is_angle) ang_acc += val; else l1_acc += val;
+    if (ZERO && k0 == 0) {
+      l1_zero_fill_warp(a, g, r);
+      if (SCATTER) __syncwarp();
     }
-    if (SCATTER) {
-      const float w = is_angle ? hd.angle_weight : hd.weight;
-      const float gv = gcoef * m * w * inv_denom;
-      if (gv != 0.f) atomicAdd(gplane + i, gv);             // duplicates of `ind` accumulate
+    // round trip 2: prediction at the centre
+    float pr[kSlotsPerLane];
+#pragma unroll
+    for (int u = 0; u < kSlotsPerLane; ++u) {
+      const bool in = (idx[u] >= r.p0 && idx[u] < r.p1);
+      pr[u] = 0.f;
+      if (in) pr[u] = __ldg(plane + idx[u]); else idx[u] = -1;
+    }
+#pragma unroll
+    for (int u = 0; u < kSlotsPerLane; ++u) {
+      float val = 0.f, gv = 0.f;
+      if (idx[u] >= 0) {
+        l1_slot_math<FAST>(hd, is_angle, pr[u], tg[u], mk[u], val, gv);
+        if (FORWARD) { if (is_angle) ang += val; else l1 += val; }
+        if (SCATTER && gv != 0.f) atomicAdd(gplane + idx[u], gv * inv_denom);   // duplicate centres accumulate
+      }
+      if (KEEP && k0 == 0) {
+        keep_i[u] = (idx[u] >= 0 && gv != 0.f) ? (int)idx[u] : -1;
+        keep_g[u] = gv;
+      }
+    }
+  }
+  if (FORWARD) {
+    l1 = warp_sum(l1);
+    ang = warp_sum(ang);
+    if (lane == 0) {
+      if (l1 != 0.f) acc_add_fixed(acc, 2 + 3 * r.h, l1);
+      if (ang != 0.f) acc_add_fixed(acc, 3 + 3 * r.h, ang);
     }
   }
 }
 
-__device__ __forceinline__ void l1_store_partials(const Geo& g, int item, float l1, float ang,
-                                                  float* red_f) {
-  l1 = block_sum(l1, red_f);
-  ang = block_sum(ang, red_f);
-  if (threadIdx.x == 0) {
-    g.item_l1[item] = l1;
-    g.item_ang[item] = ang;
-  }
-}
-
-// sum(mask_expanded) of one (head, sample): D * sum(mask[b,:]) or sum(mask[b,:,:]).
-__device__ __forceinline__ void count_unit(const cnh_detloss_args& a, const Geo& g, int unit, int* red_i,
-                                           bool add_total) {
+// sum(mask_expanded) of one (head, sample): D * sum(mask[b,:]) or sum(mask[b,:,:]); one warp.
+__device__ __forceinline__ void count_unit_warp(const cnh_detloss_args& a, long long* acc, int unit) {
   const int h = unit / a.B, b = unit - h * a.B;
-  const cnh_head& hd = a.heads[h];
+  const cnh_head& hd = head_of(a, h);
+  const int lane = threadIdx.x & 31;
   const int n = hd.elementwise_mask ? a.M * hd.D : a.M;
   const uint8_t* __restrict__ mp = hd.mask + (long long)b * n;
   int c = 0;
-  for (int k = threadIdx.x; k < n; k += kThreads) c += mp[k];
-  c = block_sum(c, red_i);
+  for (int k = lane; k < n; k += 32) c += __ldg(mp + k);
+  c = warp_sum(c);
   if (!hd.elementwise_mask) c *= hd.D;
-  if (threadIdx.x == 0) {
-    a.partials[(long long)b * CNH_PARTIALS + 4 + 3 * h] = (double)c;
-    if (add_total) atomicAdd(&g.hdr->cnt_total[h], c);
-  }
+  if (lane == 0 && c) acc_add_int(acc, 4 + 3 * h, c);
 }
 
 // ---- finalisation -------------------------------------------------------------------------
-// partials rows -> scalars, mirroring the reference's fp32 arithmetic
-// (centernet.py:91-95,119-131,213-222,42).  Run by one CTA; columns are summed in row order.
-__device__ void combine_partials(const cnh_detloss_args& a, const double* part, int Btot, float* out,
-                                 double* sh /* [CNH_PARTIALS] */) {
-  if (threadIdx.x < CNH_PARTIALS) {
-    double s = 0.0;   // rows may have been written by this very launch: read through L2
-    for (int b = 0; b < Btot; ++b) s += __ldcg(part + (long long)b * CNH_PARTIALS + threadIdx.x);
-    sh[threadIdx.x] = s;
+// 24 accumulator words -> scalars, mirroring the reference's fp32 arithmetic
+// (centernet.py:91-95,119-131,213-222,42).  One thread.
+__device__ void scalars_from_totals(const cnh_detloss_args& a, const long long* tot, float* out) {
+  double q[kQ];
+#pragma unroll
+  for (int i = 0; i < kQ; ++i) q[i] = 0.0;
+  q[0] = fixed_to_double(tot[0], tot[kQ + 0]);
+  q[1] = (double)tot[kQ + 1];
+#pragma unroll
+  for (int h = 0; h < CNH_MAX_HEADS; ++h) {
+    q[2 + 3 * h] = fixed_to_double(tot[2 + 3 * h], tot[kQ + 2 + 3 * h]);
+    q[3 + 3 * h] = fixed_to_double(tot[3 + 3 * h], tot[kQ + 3 + 3 * h]);
+    q[4 + 3 * h] = (double)tot[kQ + 4 + 3 * h];
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const float fsum = (float)sh[0], npos = (float)sh[1];
-    float hm = (npos == 0.f) ? (0.f - fsum) : (0.f - fsum / npos);
-    hm *= a.hm_weight;
-    float total = hm;
-    out[1] = hm;
-    for (int h = 0; h < CNH_MAX_HEADS; ++h) {
-      float l = 0.f;
-      if (h < a.n_heads) {
-        const cnh_head& hd = a.heads[h];
-        const float denom = (float)sh[4 + 3 * h] + 1e-4f;
-        l = (float)sh[2 + 3 * h] / denom * hd.weight;
-        if (hd.D == 3 && hd.angle_mode != CNH_ANGLE_NONE)
-          l += (float)sh[3 + 3 * h] / denom * hd.angle_weight;
-        total += l;
-      }
-      out[2 + h] = l;
+  const float fsum = (float)q[0], npos = (float)q[1];
+  float hm = (npos == 0.f) ? (0.f - fsum) : (0.f - fsum / npos);
+  hm *= a.hm_weight;
+  float total = hm;
+  out[1] = hm;
+#pragma unroll
+  for (int h = 0; h < CNH_MAX_HEADS; ++h) {
+    float l = 0.f;
+    if (h < a.n_heads) {
+      const cnh_head& hd = a.heads[h];
+      const float denom = (float)q[4 + 3 * h] + 1e-4f;
+      l = (float)q[2 + 3 * h] / denom * hd.weight;
+      if (hd.D == 3 && hd.angle_mode != CNH_ANGLE_NONE) l += (float)q[3 + 3 * h] / denom * hd.angle_weight;
+      total += l;
     }
-    out[0] = total;
-    out[5] = npos;
-    out[6] = 0.f;
-    out[7] = 0.f;
+    out[2 + h] = l;
   }
+  out[0] = total;
+  out[5] = npos;
+  out[6] = 0.f;
+  out[7] = 0.f;
 }
 
-// chunk / item partials -> per-sample rows (double), one warp per sample.
-__device__ void build_partials(const cnh_detloss_args& a, const Geo& g, bool with_items) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int b = warp; b < a.B; b += kWarps) {
-    double s = 0.0;
-    int n = 0;
-    for (int j = lane; j < g.cps; j += 32) {
-      s += (double)__ldcg(g.chunk_sum + (long long)b * g.cps + j);
-      n += __ldcg(g.chunk_npos + (long long)b * g.cps + j);
-    }
-    s = warp_sum(s);
-    n = warp_sum(n);
-    double* row = a.partials + (long long)b * CNH_PARTIALS;
-    if (lane == 0) {
-      row[0] = s;
-      row[1] = (double)n;
-      row[11] = 0.0;
-    }
-    for (int h = 0; h < CNH_MAX_HEADS; ++h) {
-      double l1 = 0.0, ang = 0.0;
-      if (with_items && h < a.n_heads) {
-        const int per = a.heads[h].D * g.ppp;
-        const int first = g.item0[h] + b * per;
-        for (int t = lane; t < per; t += 32) {
-          l1 += (double)__ldcg(g.item_l1 + first + t);
-          ang += (double)__ldcg(g.item_ang + first + t);
-        }
-        l1 = warp_sum(l1);
-        ang = warp_sum(ang);
-      }
-      if (lane == 0) {
-        row[2 + 3 * h] = l1;
-        row[3 + 3 * h] = ang;
-        if (h >= a.n_heads) row[4 + 3 * h] = 0.0;
-      }
-    }
+// Read the live accumulator set (written by other CTAs: through L2), publish it to a.totals,
+// compute the scalars.  Threads 0..23 load one word each; thread 0 finishes.
+__device__ void finalize_from_acc(const cnh_detloss_args& a, const long long* acc, long long* sh_tot) {
+  if (threadIdx.x < CNH_TOTALS) {
+    const long long v = __ldcg(acc + threadIdx.x);
+    sh_tot[threadIdx.x] = v;
+    if (a.totals != nullptr) a.totals[threadIdx.x] = v;
   }
+  __syncthreads();
+  if (threadIdx.x == 0 && a.scalars != nullptr) scalars_from_totals(a, sh_tot, a.scalars);
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
 template <int MODE, bool FAST, bool VEC>
@@ -429,145 +495,207 @@ __global__ void __launch_bounds__(kThreads, 3)
 detloss_kernel(const cnh_detloss_args a, const Geo g) {
   __shared__ float red_f[kWarps];
   __shared__ int red_i[kWarps];
-  __shared__ double sh_cols[CNH_PARTIALS];
+  __shared__ long long sh_tot[CNH_TOTALS];
   __shared__ unsigned sh_ticket;
+  __shared__ unsigned sh_parity;
+  __shared__ int sh_norm[1 + CNH_MAX_HEADS];
   const int bid = blockIdx.x, grid = gridDim.x;
+  const int warp = threadIdx.x >> 5;
   constexpr bool kGrad = (MODE == M_STASH || MODE == M_PRECOUNT || MODE == M_MAIN);
 
+  dbg_stamp(g.dbg, 0);
+  if (threadIdx.x == 0) sh_parity = __ldcg(&g.hdr->parity) & 1u;
+  __syncthreads();
+  const unsigned par = sh_parity;
+  long long* acc = g.hdr->acc[par];
+  int keep_i[kSlotsPerLane];
+  float keep_g[kSlotsPerLane];
+
   if (MODE == M_STASH) {
-    // ---- phase 1: everything that does not need the normalisers -----------------------
-    float stash[kStash][kElemsPerThread];
-#pragma unroll
-    for (int r = 0; r < kStash; ++r) {
-      const int chunk = bid + r * grid;
-      if (chunk < g.n_chunks) {
-        focal_chunk<true, false, FAST, VEC>(a, g, chunk, 0.f, stash[r], red_f, red_i);
-        if (threadIdx.x == 0) atomicAdd(&g.hdr->npos_total, g.chunk_npos[chunk]);
-      }
-    }
-    const int n_other = g.n_items + g.n_count;
-    // regression work is dealt from the LAST CTA backwards: those hold the fewest chunks
-    for (int o = grid - 1 - bid; o < n_other; o += grid) {
-      if (o < g.n_items) {
-        const ItemRef r = decode_item(a, g, o);
-        l1_zero_fill(a, g, r);
-        float l1 = 0.f, ang = 0.f;
-        l1_slots<true, false, FAST>(a, g, r, 0.f, l1, ang);
-        l1_store_partials(g, o, l1, ang, red_f);
-      } else {
-        count_unit(a, g, o - g.n_items, red_i, true);
-      }
-    }
-    __threadfence();
-    cg::this_grid().sync();
-    // ---- phase 2: normalisers are final ------------------------------------------------
-    const int npos = __ldcg(&g.hdr->npos_total);
-    const float scale = (npos == 0) ? -a.hm_weight : -a.hm_weight / (float)npos;
-#pragma unroll
-    for (int r = 0; r < kStash; ++r) {
-      const int chunk = bid + r * grid;
-      if (chunk < g.n_chunks) focal_store_stash<VEC>(a, g, chunk, scale, stash[r]);
-    }
-    for (int o = grid - 1 - bid; o < g.n_items; o += grid) {
-      const ItemRef r = decode_item(a, g, o);
-      const float inv = 1.f / ((float)__ldcg(&g.hdr->cnt_total[r.h]) + 1e-4f);
-      float l1 = 0.f, ang = 0.f;
-      l1_slots<false, true, FAST>(a, g, r, inv, l1, ang);
-    }
-  } else {
-    float scale = 0.f;
-    float inv_denom[CNH_MAX_HEADS] = {0.f, 0.f, 0.f};
-    if (MODE == M_PRECOUNT || MODE == M_COUNT) {
-      // ---- phase 0: normalisers from the targets only ----------------------------------
-      int cta_npos = 0;
-      for (int chunk = bid; chunk < g.n_chunks; chunk += grid) {
-        int c = count_chunk<VEC>(a, g, chunk);
-        c = block_sum(c, red_i);
-        if (MODE == M_COUNT && threadIdx.x == 0) g.chunk_npos[chunk] = c;
-        cta_npos += c;
-      }
-      if (threadIdx.x == 0 && cta_npos) atomicAdd(&g.hdr->npos_total, cta_npos);
-      for (int u = grid - 1 - bid; u < g.n_count; u += grid) count_unit(a, g, u, red_i, true);
-    }
-    if (MODE == M_PRECOUNT) {
-      __threadfence();
-      cg::this_grid().sync();
-      const int npos = __ldcg(&g.hdr->npos_total);
-      scale = (npos == 0) ? -a.hm_weight : -a.hm_weight / (float)npos;
-      for (int h = 0; h < a.n_heads; ++h)
-        inv_denom[h] = 1.f / ((float)__ldcg(&g.hdr->cnt_total[h]) + 1e-4f);
-    }
-    if (MODE == M_MAIN) {
-      const float npos = (float)a.norm[0];
-      scale = (npos == 0.f) ? -a.hm_weight : -a.hm_weight / npos;
-      for (int h = 0; h < a.n_heads; ++h) inv_denom[h] = 1.f / ((float)a.norm[1 + h] + 1e-4f);
-    }
-    if (MODE != M_COUNT) {
-      // ---- the streaming pass (reverse chunk order after a pre-count: L2 reuse) ---------
-      float unused[kElemsPerThread];
-      for (int u = bid; u < g.n_chunks; u += grid) {
-        const int chunk = (MODE == M_PRECOUNT) ? g.n_chunks - 1 - u : u;
-        focal_chunk<kGrad, kGrad, FAST, VEC>(a, g, chunk, scale, unused, red_f, red_i);
-      }
-      const int n_other = g.n_items + (MODE == M_FWD ? g.n_count : 0);
-      for (int o = grid - 1 - bid; o < n_other; o += grid) {
+    // Three roles, so that no CTA carries both the gradient stash and the slot registers:
+    //   [0, item_ctas)                      regression items, one per warp and round (launched first:
+    //                                       their two dependent round trips are the longest chain)
+    //   [item_ctas, item_ctas+chunk_ctas)   heat-map chunks (raw gradient kept in registers)
+    //   grid-1                              the scalars, while the others store
+    // Two barrier words: chunk CTAs only wait for each other (the arrival atomic carries num_pos),
+    // item CTAs only for each other (mask counts); the finaliser waits for both.
+    unsigned long long* bar_chunk = &g.hdr->bar[par][0];
+    unsigned long long* bar_item = &g.hdr->bar[par][1];
+    auto arrive = [&](unsigned long long* bar, int payload) {      // call from thread 0 after __syncthreads
+      __threadfence();                                             // cumulative: orders the CTA's adds
+      atomicAdd(bar, (1ull << 32) | (unsigned long long)(unsigned)payload);
+    };
+    auto wait_for = [&](unsigned long long* bar, int count) -> unsigned {
+      unsigned long long v;
+      do { v = ld_acquire_u64(bar); } while ((unsigned)(v >> 32) < (unsigned)count);
+      return (unsigned)(v & 0xffffffffull);
+    };
+    if (bid < g.item_ctas) {
+      const int n_other = g.n_items + g.n_count;
+      const int first = bid * kWarps + warp;
+      const int step = g.item_ctas * kWarps;
+      int my_item = -1;
+      for (int o = first; o < n_other; o += step) {
         if (o < g.n_items) {
           const ItemRef r = decode_item(a, g, o);
-          float l1 = 0.f, ang = 0.f;
-          if (kGrad) {
-            l1_zero_fill(a, g, r);
-            __syncthreads();
-            l1_slots<true, true, FAST>(a, g, r, inv_denom[r.h], l1, ang);
+          if (g.stash_slots && o == first) {
+            l1_item_warp<false, true, false, true, FAST>(a, g, acc, r, 0.f, keep_i, keep_g);
+            my_item = o;
           } else {
-            l1_slots<true, false, FAST>(a, g, r, 0.f, l1, ang);
+            l1_item_warp<false, true, false, false, FAST>(a, g, acc, r, 0.f, keep_i, keep_g);
           }
-          l1_store_partials(g, o, l1, ang, red_f);
         } else {
-          count_unit(a, g, o - g.n_items, red_i, false);
+          count_unit_warp(a, acc, o - g.n_items);
         }
+      }
+      dbg_stamp(g.dbg, 2);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        arrive(bar_item, 0);
+        wait_for(bar_item, g.item_ctas);                   // mask counts are complete
+        wait_for(bar_chunk, g.chunk_ctas);                 // the gradient planes are zero-filled
+#pragma unroll
+        for (int h = 0; h < CNH_MAX_HEADS; ++h) sh_norm[1 + h] = (int)__ldcg(acc + kQ + 4 + 3 * h);
+      }
+      __syncthreads();
+      dbg_stamp(g.dbg, 3);
+      for (int o = first; o < g.n_items; o += step) {
+        const ItemRef r = decode_item(a, g, o);
+        const float inv = 1.f / ((float)sh_norm[1 + r.h] + 1e-4f);
+        if (o == my_item) {                                // slots kept in registers: no reload
+          const cnh_head& hd = head_of(a, r.h);
+          float* __restrict__ gplane = hd.grad + ((long long)r.b * hd.D + r.d) * g.HW;
+#pragma unroll
+          for (int u = 0; u < kSlotsPerLane; ++u)
+            if (keep_i[u] >= 0) atomicAdd(gplane + keep_i[u], keep_g[u] * inv);
+        } else {
+          l1_item_warp<false, false, true, false, FAST>(a, g, acc, r, inv, keep_i, keep_g);
+        }
+      }
+      dbg_stamp(g.dbg, 6);
+    } else if (bid < grid - 1) {
+      const int cb = bid - g.item_ctas;
+      float stash[kStash][kElemsPerThread], pstash[kStash][kElemsPerThread];
+      int cta_npos = 0;
+      // the dense regression-gradient planes are zero-filled here, spread over every SM; the item
+      // CTAs scatter into them only after this barrier
+      for (int o = cb; o < g.n_items; o += g.chunk_ctas) l1_zero_fill_block(a, g, decode_item(a, g, o));
+#pragma unroll
+      for (int r = 0; r < kStash; ++r) {
+        const int chunk = cb + r * g.chunk_ctas;
+        if (chunk < g.n_chunks)
+          cta_npos += focal_chunk<true, false, true, FAST, VEC>(a, g, acc, chunk, 0.f, stash[r], pstash[r], red_f, red_i);
+      }
+      dbg_stamp(g.dbg, 1);
+      if (threadIdx.x == 0) {                              // focal_chunk ends with a block barrier
+        arrive(bar_chunk, cta_npos);
+        sh_norm[0] = (int)wait_for(bar_chunk, g.chunk_ctas);
+      }
+      __syncthreads();
+      dbg_stamp(g.dbg, 3);
+      const int npos = sh_norm[0];
+      const float scale = (npos == 0) ? -a.hm_weight : -a.hm_weight / (float)npos;
+#pragma unroll
+      for (int r = 0; r < kStash; ++r) {
+        const int chunk = cb + r * g.chunk_ctas;
+        if (chunk < g.n_chunks) focal_store_stash<VEC>(a, g, chunk, scale, stash[r], pstash[r]);
+      }
+      dbg_stamp(g.dbg, 5);
+    } else {
+      // the scalars, while the workers store their gradients; then retire the OTHER accumulator set
+      if (threadIdx.x == 0) {
+        const unsigned npos = wait_for(bar_chunk, g.chunk_ctas);
+        wait_for(bar_item, g.item_ctas);
+        acc_add_int(acc, 1, (long long)npos);              // num_pos joins the totals
+        __threadfence();
+      }
+      __syncthreads();
+      dbg_stamp(g.dbg, 3);
+      finalize_from_acc(a, acc, sh_tot);
+      if (threadIdx.x < CNH_TOTALS) g.hdr->acc[par ^ 1u][threadIdx.x] = 0ll;
+      if (threadIdx.x == 0) {
+        g.hdr->bar[par ^ 1u][0] = 0ull;
+        g.hdr->bar[par ^ 1u][1] = 0ull;
+        g.hdr->parity = par ^ 1u;
+      }
+    }
+    dbg_stamp(g.dbg, 7);
+    return;
+  }
+
+  float scale = 0.f;
+  float inv_denom[CNH_MAX_HEADS] = {0.f, 0.f, 0.f};
+  if (MODE == M_PRECOUNT || MODE == M_COUNT) {
+    // ---- phase 0: normalisers from the targets only ----------------------------------
+    int npos = 0;
+    for (int chunk = bid; chunk < g.n_chunks; chunk += grid) npos += count_chunk<VEC>(a, g, chunk);
+    npos = block_sum(npos, red_i);
+    if (threadIdx.x == 0 && npos) acc_add_int(acc, 1, npos);
+    for (int u = (grid - 1 - bid) * kWarps + warp; u < g.n_count; u += grid * kWarps) count_unit_warp(a, acc, u);
+  }
+  if (MODE == M_PRECOUNT) {
+    cg::this_grid().sync();
+    const long long npos = __ldcg(acc + kQ + 1);
+    scale = (npos == 0) ? -a.hm_weight : -a.hm_weight / (float)npos;
+#pragma unroll
+    for (int h = 0; h < CNH_MAX_HEADS; ++h) inv_denom[h] = 1.f / ((float)__ldcg(acc + kQ + 4 + 3 * h) + 1e-4f);
+  }
+  if (MODE == M_MAIN) {
+    const float npos = (float)a.norm[0];
+    scale = (npos == 0.f) ? -a.hm_weight : -a.hm_weight / npos;
+#pragma unroll
+    for (int h = 0; h < CNH_MAX_HEADS; ++h) inv_denom[h] = 1.f / ((float)a.norm[1 + h] + 1e-4f);
+  }
+  if (MODE != M_COUNT) {
+    // ---- the streaming pass (reverse chunk order after a pre-count: L2 reuse) ---------
+    float unused[kElemsPerThread];
+    int npos = 0;
+    for (int u = bid; u < g.n_chunks; u += grid) {
+      const int chunk = (MODE == M_PRECOUNT) ? g.n_chunks - 1 - u : u;
+      npos += focal_chunk<kGrad, kGrad, false, FAST, VEC>(a, g, acc, chunk, scale, unused, unused, red_f, red_i);
+    }
+    if (MODE != M_PRECOUNT && threadIdx.x == 0 && npos) acc_add_int(acc, 1, npos);   // PRECOUNT counted in phase 0
+    const int n_other = g.n_items + (MODE == M_PRECOUNT ? 0 : g.n_count);
+    for (int o = (grid - 1 - bid) * kWarps + warp; o < n_other; o += grid * kWarps) {
+      if (o < g.n_items) {
+        const ItemRef r = decode_item(a, g, o);
+        if (kGrad) {
+          const float inv = r.h == 0 ? inv_denom[0] : (r.h == 1 ? inv_denom[1] : inv_denom[2]);
+          l1_item_warp<true, true, true, false, FAST>(a, g, acc, r, inv, keep_i, keep_g);
+        } else {
+          l1_item_warp<false, true, false, false, FAST>(a, g, acc, r, 0.f, keep_i, keep_g);
+        }
+      } else {
+        count_unit_warp(a, acc, o - g.n_items);
       }
     }
   }
 
-  // ---- last CTA: per-sample partials, scalars, reset the workspace counters -------------
-  __threadfence();
+  // ---- last CTA: totals, scalars, leave the accumulator set zeroed -------------------------
   __syncthreads();
-  if (threadIdx.x == 0) sh_ticket = atomicAdd(&g.hdr->done, 1u);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    sh_ticket = atomicAdd(&g.hdr->done, 1u);
+  }
   __syncthreads();
   if (sh_ticket != (unsigned)(grid - 1)) return;
   __threadfence();
   if (MODE == M_COUNT) {
-    // per-sample num_pos rows + this shard's totals
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int b = warp; b < a.B; b += kWarps) {
-      int n = 0;
-      for (int j = lane; j < g.cps; j += 32) n += __ldcg(g.chunk_npos + (long long)b * g.cps + j);
-      n = warp_sum(n);
-      if (lane == 0) a.partials[(long long)b * CNH_PARTIALS + 1] = (double)n;
-    }
     if (threadIdx.x == 0) {
-      a.norm_out[0] = (double)__ldcg(&g.hdr->npos_total);
-      for (int h = 0; h < CNH_MAX_HEADS; ++h)
-        a.norm_out[1 + h] = (h < a.n_heads) ? (double)__ldcg(&g.hdr->cnt_total[h]) : 0.0;
+      a.norm_out[0] = (double)__ldcg(acc + kQ + 1);
+      for (int h = 0; h < CNH_MAX_HEADS; ++h) a.norm_out[1 + h] = (double)__ldcg(acc + kQ + 4 + 3 * h);
     }
   } else {
-    build_partials(a, g, true);
-    __threadfence();
-    __syncthreads();
-    if (a.scalars != nullptr) combine_partials(a, a.partials, a.B, a.scalars, sh_cols);
+    finalize_from_acc(a, acc, sh_tot);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    g.hdr->npos_total = 0;
-    for (int h = 0; h < CNH_MAX_HEADS; ++h) g.hdr->cnt_total[h] = 0;
-    g.hdr->done = 0;
-  }
+  if (threadIdx.x < CNH_TOTALS) acc[threadIdx.x] = 0ll;
+  if (threadIdx.x == 0) g.hdr->done = 0;
 }
 
-__global__ void __launch_bounds__(kThreads)
-detloss_finalize_kernel(const cnh_detloss_args a, const double* __restrict__ partials, int Btot) {
-  __shared__ double sh_cols[CNH_PARTIALS];
-  combine_partials(a, partials, Btot, a.scalars, sh_cols);
+__global__ void __launch_bounds__(32)
+detloss_finalize_kernel(const cnh_detloss_args a, const long long* __restrict__ totals) {
+  if (threadIdx.x == 0) scalars_from_totals(a, totals, a.scalars);
 }
 
 // g *= factor (factor read from device scalars); nothing to do when factor == 1.
@@ -606,7 +734,6 @@ static int validate(const cnh_detloss_args* a, bool need_grad_ptrs) {
   CNH_REQUIRE(a->n_heads >= 0 && a->n_heads <= CNH_MAX_HEADS, CNH_E_SHAPE, "detloss: n_heads=%d",
               a->n_heads);
   CNH_REQUIRE(a->hm_logits && a->hm_gt && a->prob, CNH_E_NULL, "detloss: hm_logits/hm_gt/prob is NULL");
-  CNH_REQUIRE(a->partials != nullptr, CNH_E_NULL, "detloss: partials is NULL");
   CNH_REQUIRE(a->n_heads == 0 || a->M == 0 || a->ind != nullptr, CNH_E_NULL, "detloss: ind is NULL");
   for (int h = 0; h < a->n_heads; ++h) {
     const cnh_head& hd = a->heads[h];
@@ -625,8 +752,6 @@ static int validate(const cnh_detloss_args* a, bool need_grad_ptrs) {
   }
   return CNH_OK;
 }
-
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static Geo make_geo(const cnh_detloss_args* a, void* ws) {
   Geo g;
@@ -647,24 +772,15 @@ static Geo make_geo(const cnh_detloss_args* a, void* ws) {
   g.n_items = it;
   g.n_count = a->B * a->n_heads;
   g.vec_planes = vec_planes ? 1 : 0;
-  char* p = static_cast<char*>(ws);
-  g.hdr = reinterpret_cast<WsHeader*>(p);
-  p += sizeof(WsHeader);
-  g.chunk_sum = reinterpret_cast<float*>(p);
-  p += align_up((size_t)g.n_chunks * 4, 16);
-  g.chunk_npos = reinterpret_cast<int*>(p);
-  p += align_up((size_t)g.n_chunks * 4, 16);
-  g.item_l1 = reinterpret_cast<float*>(p);
-  p += align_up((size_t)it * 4, 16);
-  g.item_ang = reinterpret_cast<float*>(p);
+  g.stash_slots = (a->M <= 32 * kSlotsPerLane) ? 1 : 0;
+  g.chunk_ctas = 0;
+  g.item_ctas = 0;
+  g.hdr = static_cast<WsHeader*>(ws);
+  g.dbg = debug_buffer();
   return g;
 }
 
-static size_t ws_bytes(const cnh_detloss_args* a) {
-  Geo g = make_geo(a, nullptr);
-  int items = g.item0[CNH_MAX_HEADS];
-  return sizeof(WsHeader) + 2 * align_up((size_t)g.n_chunks * 4, 16) + 2 * align_up((size_t)items * 4, 16);
-}
+static size_t ws_bytes(const cnh_detloss_args*) { return (sizeof(WsHeader) + 255) / 256 * 256; }
 
 static bool use_vec(const cnh_detloss_args* a, const Geo& g) {
   return (g.CHW % 4 == 0) && aligned16(a->hm_logits) && aligned16(a->hm_gt) && aligned16(a->prob) &&
@@ -696,6 +812,12 @@ static int launch(const void* kernel, bool cooperative, int grid, const cnh_detl
   return CNH_OK;
 }
 
+static int units_to_grid(long long chunks, long long warp_units, int cap) {
+  long long want = chunks + (warp_units + kWarps - 1) / kWarps;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
 }  // namespace cnh
 
 using namespace cnh;
@@ -711,25 +833,32 @@ extern "C" int cnh_detloss_fused(const cnh_detloss_args* a, void* workspace, siz
   CNH_REQUIRE(a->scalars != nullptr, CNH_E_NULL, "detloss_fused: scalars is NULL");
   CNH_REQUIRE(workspace != nullptr && workspace_bytes >= ws_bytes(a), CNH_E_WORKSPACE,
               "detloss_fused: workspace %zu < %zu bytes", workspace_bytes, ws_bytes(a));
-  const Geo g = make_geo(a, workspace);
+  Geo g = make_geo(a, workspace);
   const bool fast = !(a->flags & CNH_FLAG_ACCURATE_MATH), vec = use_vec(a, g);
-  const int units = g.n_chunks + g.n_items + g.n_count;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->grad_hm == nullptr) {
     const void* k = pick_kernel<M_FWD>(fast, vec);
-    return launch(k, false, units < max_resident_ctas(k) ? units : max_resident_ctas(k), a, g, st);
+    return launch(k, false, units_to_grid(g.n_chunks, g.n_items + g.n_count, max_resident_ctas(k)), a, g, st);
   }
   const void* ks = pick_kernel<M_STASH>(fast, vec);
   const int cap = max_resident_ctas(ks);
-  if (!(a->flags & CNH_FLAG_NO_STASH) && g.n_chunks <= (long long)cap * kStash) {
-    int grid = units < cap ? units : cap;
-    const int need = (g.n_chunks + kStash - 1) / kStash;
-    if (grid < need) grid = need;
-    return launch(ks, true, grid, a, g, st);
+  {
+    // roles: item CTAs (one warp per item and round; at most a quarter of the machine), chunk CTAs
+    // (<= kStash chunks each), one finaliser
+    const long long warp_units = (long long)g.n_items + g.n_count;
+    long long item_ctas = (warp_units + kWarps - 1) / kWarps;
+    if (item_ctas > cap / 4) item_ctas = cap / 4;
+    if (item_ctas < 1) item_ctas = 1;
+    long long chunk_ctas = cap - 1 - item_ctas;
+    if (chunk_ctas > g.n_chunks) chunk_ctas = g.n_chunks;
+    if (!(a->flags & CNH_FLAG_NO_STASH) && chunk_ctas >= 1 && g.n_chunks <= chunk_ctas * kStash) {
+      g.chunk_ctas = (int)chunk_ctas;
+      g.item_ctas = (int)item_ctas;
+      return launch(ks, true, (int)(chunk_ctas + item_ctas + 1), a, g, st);
+    }
   }
   const void* kp = pick_kernel<M_PRECOUNT>(fast, vec);
-  const int capp = max_resident_ctas(kp);
-  return launch(kp, true, units < capp ? units : capp, a, g, st);
+  return launch(kp, true, units_to_grid(g.n_chunks, g.n_items + g.n_count, max_resident_ctas(kp)), a, g, st);
 }
 
 extern "C" int cnh_detloss_count(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
@@ -740,8 +869,8 @@ extern "C" int cnh_detloss_count(const cnh_detloss_args* a, void* workspace, siz
               "detloss_count: workspace %zu < %zu bytes", workspace_bytes, ws_bytes(a));
   const Geo g = make_geo(a, workspace);
   const void* k = pick_kernel<M_COUNT>(true, use_vec(a, g));
-  const int units = g.n_chunks + g.n_count, cap = max_resident_ctas(k);
-  return launch(k, false, units < cap ? units : cap, a, g, static_cast<cudaStream_t>(stream));
+  return launch(k, false, units_to_grid(g.n_chunks, g.n_count, max_resident_ctas(k)), a, g,
+                static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cnh_detloss_main(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
@@ -749,21 +878,21 @@ extern "C" int cnh_detloss_main(const cnh_detloss_args* a, void* workspace, size
   if (int rc = validate(a, true)) return rc;
   CNH_REQUIRE(a->grad_hm != nullptr, CNH_E_NULL, "detloss_main: grad_hm is NULL (use cnh_detloss_fused for forward only)");
   CNH_REQUIRE(a->norm != nullptr, CNH_E_NULL, "detloss_main: norm is NULL");
+  CNH_REQUIRE(a->totals != nullptr, CNH_E_NULL, "detloss_main: totals is NULL");
   CNH_REQUIRE(workspace != nullptr && workspace_bytes >= ws_bytes(a), CNH_E_WORKSPACE,
               "detloss_main: workspace %zu < %zu bytes", workspace_bytes, ws_bytes(a));
   const Geo g = make_geo(a, workspace);
   const void* k = pick_kernel<M_MAIN>(!(a->flags & CNH_FLAG_ACCURATE_MATH), use_vec(a, g));
-  const int units = g.n_chunks + g.n_items, cap = max_resident_ctas(k);
-  return launch(k, false, units < cap ? units : cap, a, g, static_cast<cudaStream_t>(stream));
+  return launch(k, false, units_to_grid(g.n_chunks, g.n_items + g.n_count, max_resident_ctas(k)), a, g,
+                static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int cnh_detloss_finalize(const cnh_detloss_args* a, const double* partials, int32_t B_total,
-                                    cnh_stream_t stream) {
-  CNH_REQUIRE(a != nullptr && partials != nullptr && a->scalars != nullptr, CNH_E_NULL,
-              "detloss_finalize: args/partials/scalars is NULL");
-  CNH_REQUIRE(B_total > 0 && a->n_heads >= 0 && a->n_heads <= CNH_MAX_HEADS, CNH_E_SHAPE,
-              "detloss_finalize: B_total=%d n_heads=%d", B_total, a->n_heads);
-  detloss_finalize_kernel<<<1, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(*a, partials, B_total);
+extern "C" int cnh_detloss_finalize(const cnh_detloss_args* a, const int64_t* totals, cnh_stream_t stream) {
+  CNH_REQUIRE(a != nullptr && totals != nullptr && a->scalars != nullptr, CNH_E_NULL,
+              "detloss_finalize: args/totals/scalars is NULL");
+  CNH_REQUIRE(a->n_heads >= 0 && a->n_heads <= CNH_MAX_HEADS, CNH_E_SHAPE, "detloss_finalize: n_heads=%d", a->n_heads);
+  detloss_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      *a, reinterpret_cast<const long long*>(totals));
   CNH_CUDA(cudaGetLastError());
   return CNH_OK;
 }

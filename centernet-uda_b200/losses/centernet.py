@@ -47,7 +47,7 @@ class DetectionLoss(torch.nn.Module):
 
     def forward(self, output, batch):
         heads = self._heads(output, batch)
-        scalars, prob, partials = _F.detection_loss(output['hm'], batch['hm'], batch['ind'], heads,
+        scalars, prob, totals = _F.detection_loss(output['hm'], batch['hm'], batch['ind'], heads,
                                                     self.hm_weight)
         output['hm'] = prob                        # losses/centernet.py:34
         loss, hm_loss, wh_loss, off_loss = scalars[0], scalars[1], scalars[2], scalars[3]
@@ -60,7 +60,7 @@ class DetectionLoss(torch.nn.Module):
                 loss = loss + dist
                 stats['centernet_loss'] = loss
             stats['kp_loss'] = kp_loss
-        self.last_partials = partials
+        self.last_totals = totals
         return loss, stats
 
     def _limb_term(self, kps_map, batch):

@@ -74,12 +74,15 @@ typedef struct cnh_head {
 } cnh_head;
 
 #define CNH_MAX_HEADS 3
-#define CNH_PARTIALS 12 /* doubles per sample, see below */
-#define CNH_SCALARS 8   /* floats, see below             */
+#define CNH_TOTALS 24  /* int64 words, see below */
+#define CNH_SCALARS 8  /* floats, see below      */
 
-/* per-sample partials row (double[CNH_PARTIALS]):
- *   [0] sum(pos_loss + neg_loss)   [1] num_pos
- *   [2+3h] sum|l1| of head h       [3+3h] angle sum of head h   [4+3h] sum(mask_expanded)
+/* totals (int64[CNH_TOTALS]): exact batch sums as (hi, lo) pairs, word q = hi, word 12+q = lo;
+ * value = (hi * 2^32 + lo) * 2^-40 for the fixed-point sums, lo alone for the integer counts.
+ *   q = 0 sum(pos_loss + neg_loss)   q = 1 num_pos (count)
+ *   q = 2+3h sum|l1| of head h       q = 3+3h angle sum of head h    q = 4+3h sum(mask_expanded) (count)
+ * Integer addition is associative: totals of batch shards may simply be added (all-reduce SUM)
+ * and give bit-identical scalars to a single launch over the whole batch.
  * scalar block (float[CNH_SCALARS]):
  *   [0] total loss  [1] hm_loss  [2..4] head losses  [5] num_pos  [6] reserved [7] reserved */
 typedef struct cnh_detloss_args {
@@ -96,7 +99,7 @@ typedef struct cnh_detloss_args {
   int32_t _pad;
   cnh_head heads[CNH_MAX_HEADS];
   float* scalars;          /* [CNH_SCALARS] out (fused / finalize)                               */
-  double* partials;        /* [B,CNH_PARTIALS] out                                               */
+  int64_t* totals;         /* [CNH_TOTALS] out: this launch's exact sums (nullable for fused)    */
   const double* norm;      /* [4] in (cnh_detloss_main): global num_pos, mask counts per head    */
   double* norm_out;        /* [4] out (cnh_detloss_count): this shard's num_pos, mask counts     */
 } cnh_detloss_args;
@@ -106,22 +109,21 @@ const char* cnh_last_error(void);
 
 /* ---- DetectionLoss (losses/centernet.py:7-95,98-133,192-223) ---------------------------
  * cnh_detloss_fused: ONE cooperative launch = sigmoid+clamp, penalty-reduced focal loss,
- * masked gather-L1 heads, all gradients (upstream gradient 1.0), scalars and partials.
+ * masked gather-L1 heads, all gradients (upstream gradient 1.0), scalars and totals.
  * Small problems keep the raw heat-map gradient in registers across the grid barrier
  * (16 B per heat-map element of HBM traffic); large ones pre-count num_pos (20 B). */
 size_t cnh_detloss_workspace_bytes(const cnh_detloss_args* a);
 int cnh_detloss_fused(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
                       cnh_stream_t stream);
 /* Sharded (one process per GPU) schedule: count -> all-reduce(norm_out) -> main ->
- * all-gather(partials) -> finalize.  Gradients are final after cnh_detloss_main. */
+ * all-reduce(totals) -> finalize.  Gradients are final after cnh_detloss_main. */
 int cnh_detloss_count(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
                       cnh_stream_t stream);
 int cnh_detloss_main(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
                      cnh_stream_t stream);
-/* partials: [B_total,CNH_PARTIALS] (device) summed in row order -> a->scalars.
+/* totals: int64[CNH_TOTALS] on the device (e.g. the all-reduced sum over shards) -> a->scalars.
  * Only weights / D / angle_mode / n_heads of `a` are read. */
-int cnh_detloss_finalize(const cnh_detloss_args* a, const double* partials, int32_t B_total,
-                         cnh_stream_t stream);
+int cnh_detloss_finalize(const cnh_detloss_args* a, const int64_t* totals, cnh_stream_t stream);
 
 /* In-place gradient rescale by an upstream gradient that lives on the device:
  * g[i] *= (fa ? *fa : 0) + (fb ? *fb : 0); exits immediately when the factor is 1.0

@@ -101,7 +101,7 @@ def test_cpu_tensor_raises():
         DetectionLoss(**kw)(dict(out), bt)
 
 
-def _capi_schedules(out, bt, kw, flags):
+def _capi_schedules(out, bt, kw, flags, repeats=1):
     """Run the fused launch with `flags`, and the count -> main -> finalize schedule; return both."""
     import ctypes as C
     from cnhead import _lib as L, functional as F
@@ -112,27 +112,32 @@ def _capi_schedules(out, bt, kw, flags):
     heads = [F.HeadSpec(wh, bt["wh"].cuda(), mask, kw["wh_weight"], kw.get("angle_weight", 1.0), mode),
              F.HeadSpec(reg, bt["reg"].cuda(), mask, kw["off_weight"])]
     res = {}
+    ws = None
     for tag in ("fused", "split"):
-        prob = torch.empty_like(hm)
-        grads = [torch.full_like(hm, 7.0), torch.full_like(wh, 7.0), torch.full_like(reg, 7.0)]
-        scal = torch.zeros(L.SCALARS, device="cuda")
-        part = torch.zeros(hm.shape[0], L.PARTIALS, dtype=torch.float64, device="cuda")
-        norm = torch.zeros(4, dtype=torch.float64, device="cuda")
-        a = F.fill_detloss_args(hm, gt, ind, heads, kw["hm_weight"], prob, grads, scal, part,
-                                norm=norm, norm_out=norm, flags=flags)
-        ws = torch.zeros(L.lib().cnh_detloss_workspace_bytes(C.byref(a)), dtype=torch.uint8, device="cuda")
-        st = L.stream_ptr()
-        if tag == "fused":
-            L.check(L.lib().cnh_detloss_fused(C.byref(a), ws.data_ptr(), ws.numel(), st), "fused")
-        else:
-            L.check(L.lib().cnh_detloss_count(C.byref(a), ws.data_ptr(), ws.numel(), st), "count")
-            a.scalars = None
-            L.check(L.lib().cnh_detloss_main(C.byref(a), ws.data_ptr(), ws.numel(), st), "main")
-            a.scalars = scal.data_ptr()
-            L.check(L.lib().cnh_detloss_finalize(C.byref(a), part.data_ptr(), hm.shape[0], st), "finalize")
-        torch.cuda.synchronize()
-        assert int(ws[:64].sum()) == 0, "workspace counters must be left zeroed"
-        res[tag] = (scal.cpu(), prob.cpu(), [x.cpu() for x in grads], part.cpu())
+        for rep in range(repeats):
+            prob = torch.empty_like(hm)
+            grads = [torch.full_like(hm, 7.0), torch.full_like(wh, 7.0), torch.full_like(reg, 7.0)]
+            scal = torch.zeros(L.SCALARS, device="cuda")
+            tot = torch.zeros(L.TOTALS, dtype=torch.int64, device="cuda")
+            norm = torch.zeros(4, dtype=torch.float64, device="cuda")
+            a = F.fill_detloss_args(hm, gt, ind, heads, kw["hm_weight"], prob, grads, scal, tot,
+                                    norm=norm, norm_out=norm, flags=flags)
+            if ws is None:       # ONE workspace, zeroed once, shared by every schedule and repeat
+                ws = torch.zeros(L.lib().cnh_detloss_workspace_bytes(C.byref(a)), dtype=torch.uint8, device="cuda")
+            st = L.stream_ptr()
+            if tag == "fused":
+                L.check(L.lib().cnh_detloss_fused(C.byref(a), ws.data_ptr(), ws.numel(), st), "fused")
+            else:
+                L.check(L.lib().cnh_detloss_count(C.byref(a), ws.data_ptr(), ws.numel(), st), "count")
+                a.scalars = None
+                L.check(L.lib().cnh_detloss_main(C.byref(a), ws.data_ptr(), ws.numel(), st), "main")
+                a.scalars = scal.data_ptr()
+                L.check(L.lib().cnh_detloss_finalize(C.byref(a), tot.data_ptr(), st), "finalize")
+            torch.cuda.synchronize()
+            cur = (scal.cpu(), prob.cpu(), [x.cpu() for x in grads], tot.cpu())
+            if rep:              # the workspace is reusable without re-zeroing
+                assert torch.equal(cur[0], res[tag][0]) and torch.equal(cur[3], res[tag][3])
+            res[tag] = cur
     return res
 
 
@@ -140,21 +145,42 @@ def _capi_schedules(out, bt, kw, flags):
                                   "detloss_weights_gradscale"])
 @pytest.mark.parametrize("flags", [0, 2, 1, 3])
 def test_schedules_agree_bitwise(name, flags):
-    """STASH vs PRECOUNT vs COUNT+MAIN+FINALIZE: identical scalars, partials and heat-map gradients
-    (the sharded schedule reproduces the single-launch result bit for bit)."""
+    """STASH vs PRECOUNT vs COUNT+MAIN+FINALIZE: identical scalars, exact totals and heat-map
+    gradients (the sharded schedule reproduces the single-launch result bit for bit), and the
+    workspace can be reused across launches and schedules without being zeroed again."""
     g = load_golden(name)
     out, bt, kw, _ = golden_head_case(g)
-    res = _capi_schedules(out, bt, kw, flags)
+    res = _capi_schedules(out, bt, kw, flags, repeats=3)
     ref = _capi_schedules(out, bt, kw, flags & 1)["fused"]      # stash schedule, same math mode
     for tag in ("fused", "split"):
-        scal, prob, grads, part = res[tag]
+        scal, prob, grads, tot = res[tag]
         assert torch.equal(scal[:6], ref[0][:6]), tag
         assert torch.equal(prob, ref[1]), tag
         assert torch.equal(grads[0], ref[2][0]), tag
-        assert torch.equal(part, ref[3]), tag
+        assert torch.equal(tot, ref[3]), tag
         for a_, b_ in zip(grads[1:], ref[2][1:]):               # atomics on duplicate centres
             assert rel_err(a_, b_) <= 1e-6
     assert rel_err(res["fused"][0][0], g["stat_centernet_loss"]) <= TOL
+
+
+def test_totals_of_shards_add_up_exactly():
+    """exact integer totals: sum over batch shards == totals of the whole batch, bit for bit."""
+    import ctypes as C
+    from cnhead import _lib as L, functional as F, synthetic
+    cfg = synthetic.CONFIGS["cfg2"]
+    data = synthetic.make_inputs(cfg, batch=8)
+
+    def totals_of(sl):
+        o = {k: v[sl].cuda().contiguous() for k, v in data["output"].items()}
+        b = {k: v[sl].cuda().contiguous() for k, v in data["batch"].items()}
+        heads = [F.HeadSpec(o["wh"], b["wh"], b["reg_mask"], 0.1), F.HeadSpec(o["reg"], b["reg"], b["reg_mask"], 1.0)]
+        with torch.no_grad():
+            _, _, tot = F.detection_loss(o["hm"], b["hm"], b["ind"], heads, 1.0)
+        return tot.cpu()
+
+    whole = totals_of(slice(0, 8))
+    parts = totals_of(slice(0, 2)) + totals_of(slice(2, 4)) + totals_of(slice(4, 8))
+    assert torch.equal(whole, parts)
 
 
 def test_large_problem_precount_schedule():

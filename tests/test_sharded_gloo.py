@@ -1,6 +1,6 @@
 """world_size-2 test of the sharded schedule's host logic on CPU (gloo): shard slicing, the
-normaliser all-reduce, the rank-ordered all-gather of per-sample partial rows, and that combining
-them reproduces the single-process loss.  The per-sample rows are produced here by the oracle (the
+normaliser all-reduce, the integer all-reduce of the exact per-shard totals, and that combining
+them reproduces the single-process loss.  The per-shard totals are produced here by the oracle (the
 CUDA kernels that produce them on a GPU are covered by tests/test_gpu_parity.py and, across real
 GPUs, by tests/test_gpu_multi.py)."""
 import os
@@ -21,44 +21,51 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def oracle_rows(output, batch, periodic):
-    """per-sample partial rows with the layout of include/cnhead.h (float64)."""
+def oracle_totals(output, batch, periodic):
+    """this shard's exact totals in the layout of include/cnhead.h: int64[24], word q = hi and
+    word 12+q = lo of the 2^-40 fixed-point sum (lo alone for the integer counts)."""
+    import math
     import oracle
-    B = output["hm"].shape[0]
-    rows = torch.zeros(B, 12, dtype=torch.float64)
-    for b in range(B):
-        prob = oracle.sigmoid_clamp(output["hm"][b:b + 1].double())
-        pos, neg, npos = oracle.focal_terms(prob, batch["hm"][b:b + 1].double())
-        rows[b, 0], rows[b, 1] = pos + neg, npos
-        for h, (key, tkey) in enumerate((("wh", "wh"), ("reg", "reg"))):
-            fmap = output[key][b:b + 1].double()
-            D = fmap.shape[1]
-            pred = oracle.gather_rows(fmap, batch["ind"][b:b + 1])
-            m = batch["reg_mask"][b:b + 1].unsqueeze(2).expand_as(pred).double()
-            pred, tgt = pred * m, batch[tkey][b:b + 1].double() * m
-            rows[b, 4 + 3 * h] = m.sum()
-            if D == 3:
-                rows[b, 2 + 3 * h] = (pred[..., :2] - tgt[..., :2]).abs().sum()
-                if periodic:
-                    import math
-                    pa = oracle.sigmoid_clamp(pred[..., 2:3]) * 2 * math.pi - math.pi
-                    ta = torch.deg2rad(tgt[..., 2:3])
-                    rows[b, 3 + 3 * h] = (torch.remainder(pa - ta - math.pi / 2, math.pi) - math.pi / 2).abs().sum()
-                else:
-                    rows[b, 3 + 3 * h] = (oracle.sigmoid_clamp(pred[..., 2:3]) - oracle.sigmoid_clamp(tgt[..., 2:3])).abs().sum()
+    q = [0.0] * 12
+    ints = {}
+    prob = oracle.sigmoid_clamp(output["hm"].double())
+    pos, neg, npos = oracle.focal_terms(prob, batch["hm"].double())
+    q[0], ints[1] = float(pos + neg), int(npos)
+    for h, key in enumerate(("wh", "reg")):
+        fmap = output[key].double()
+        D = fmap.shape[1]
+        pred = oracle.gather_rows(fmap, batch["ind"])
+        m = batch["reg_mask"].unsqueeze(2).expand_as(pred).double()
+        pred, tgt = pred * m, batch[key].double() * m
+        ints[4 + 3 * h] = int(m.sum())
+        if D == 3:
+            q[2 + 3 * h] = float((pred[..., :2] - tgt[..., :2]).abs().sum())
+            if periodic:
+                pa = oracle.sigmoid_clamp(pred[..., 2:3]) * 2 * math.pi - math.pi
+                ta = torch.deg2rad(tgt[..., 2:3])
+                q[3 + 3 * h] = float((torch.remainder(pa - ta - math.pi / 2, math.pi) - math.pi / 2).abs().sum())
             else:
-                rows[b, 2 + 3 * h] = (pred - tgt).abs().sum()
-    return rows
+                q[3 + 3 * h] = float((oracle.sigmoid_clamp(pred[..., 2:3]) - oracle.sigmoid_clamp(tgt[..., 2:3])).abs().sum())
+        else:
+            q[2 + 3 * h] = float((pred - tgt).abs().sum())
+    tot = torch.zeros(24, dtype=torch.int64)
+    for i, v in enumerate(q):
+        f = int(round(v * 2.0 ** 40))
+        tot[i], tot[12 + i] = f >> 32, f & 0xffffffff
+    for i, v in ints.items():
+        tot[12 + i] = v
+    return tot
 
 
-def combine_rows(rows, kw, D_wh):
-    """what cnh_detloss_finalize computes (csrc/detloss.cu combine_partials), in float64."""
-    s = rows.sum(0)
-    hm = (-s[0] if s[1] == 0 else -s[0] / s[1]) * kw["hm_weight"]
-    wh = s[2] / (s[4] + 1e-4) * kw["wh_weight"]
+def scalars_from_totals(tot, kw, D_wh):
+    """what cnh_detloss_finalize computes (csrc/detloss.cu scalars_from_totals), in float64."""
+    val = lambda i: (int(tot[i]) * 2 ** 32 + int(tot[12 + i])) / 2.0 ** 40
+    cnt = lambda i: int(tot[12 + i])
+    hm = (-val(0) if cnt(1) == 0 else -val(0) / cnt(1)) * kw["hm_weight"]
+    wh = val(2) / (cnt(4) + 1e-4) * kw["wh_weight"]
     if D_wh == 3:
-        wh = wh + s[3] / (s[4] + 1e-4) * kw.get("angle_weight", 1.0)
-    off = s[5] / (s[7] + 1e-4) * kw["off_weight"]
+        wh = wh + val(3) / (cnt(4) + 1e-4) * kw.get("angle_weight", 1.0)
+    off = val(5) / (cnt(7) + 1e-4) * kw["off_weight"]
     return hm + wh + off, hm, wh, off
 
 
@@ -76,23 +83,20 @@ def _worker(rank, world, port, cfg_name, results):
         per = B // world
         mine = synthetic.make_inputs(cfg, batch=per, sample_offset=sl.start)      # only this rank's samples
         kw = synthetic.loss_kwargs(cfg)
-        rows = oracle_rows(mine["output"], mine["batch"], cfg.periodic)
-        norm = torch.stack([rows[:, 1].sum(), rows[:, 4].sum(), rows[:, 7].sum(), torch.tensor(0.0, dtype=torch.float64)])
+        tot = oracle_totals(mine["output"], mine["batch"], cfg.periodic)
+        norm = torch.tensor([float(tot[13]), float(tot[16]), float(tot[19]), 0.0], dtype=torch.float64)
         sharded.exchange_normalisers(norm)
-        all_rows = sharded.gather_partials(rows)
-        assert all_rows.shape == (B, 12)
-        assert torch.equal(all_rows[sl], rows)                                     # rank order == sample order
-        total = combine_rows(all_rows, kw, cfg.wh_channels)
+        sharded.reduce_totals(tot)
+        total = scalars_from_totals(tot, kw, cfg.wh_channels)
         whole = synthetic.make_inputs(cfg, batch=B)
         ref_loss, ref_stats, _ = oracle.detection_loss({k: v.double() for k, v in whole["output"].items()},
                                                        whole["batch"], **kw)
         assert abs(float(total[0]) - float(ref_loss)) <= 1e-9 * abs(float(ref_loss))
-        assert float(norm[0]) == float((whole["batch"]["hm"] == 1).sum())
+        assert float(norm[0]) == float((whole["batch"]["hm"] == 1).sum()) == float(tot[13])
         assert float(norm[1]) == float(whole["batch"]["reg_mask"].sum()) * cfg.wh_channels
-        # every rank holds the same scalars
-        mine_t = torch.tensor([float(t) for t in total], dtype=torch.float64)
-        both = [torch.zeros_like(mine_t) for _ in range(world)]
-        dist.all_gather(both, mine_t)
+        # every rank holds the same exact totals, hence the same scalars
+        both = [torch.zeros_like(tot) for _ in range(world)]
+        dist.all_gather(both, tot)
         assert all(torch.equal(both[0], b) for b in both)
         results[rank] = float(total[0])
     finally:
@@ -118,6 +122,5 @@ def test_shard_slice():
 
 def test_single_process_is_a_no_op():
     from cnhead import sharded
-    rows = torch.arange(24, dtype=torch.float64).reshape(2, 12)
-    assert sharded.gather_partials(rows) is rows
+    assert sharded.reduce_totals(torch.arange(24, dtype=torch.int64)) is None
     assert sharded.exchange_normalisers(torch.ones(4, dtype=torch.float64)) is None

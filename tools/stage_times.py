@@ -1,0 +1,44 @@
+"""In-kernel stage timestamps (globaltimer, ns) for the fused loss and the decode launch on cfg2/cfg5."""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "centernet-uda_b200"), ROOT]
+import torch, bench
+from cnhead import _lib as L, synthetic
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+cfg = synthetic.CONFIGS[name]
+batch = cfg.batch if name != "cfg5" else 16
+dev = torch.device("cuda", 0)
+sets = [bench.BufferSet(synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, seed_offset=i), cfg, dev) for i in range(4)]
+d = bench.DeviceStep(sets, cfg, 1, None)
+lib = d.lib
+lib.cnh_debug_set_buffer.argtypes = [C.c_void_p]
+dbg = torch.zeros(65536, 16, dtype=torch.int64, device=dev)
+def show(tag, nslots, extra=()):
+    torch.cuda.synchronize()
+    t = dbg.cpu()
+    used = (t[:, 0] != 0).nonzero().flatten()
+    t = t[used]
+    t0 = t[:, 0].min()
+    print(f"--- {tag}: {len(used)} CTAs; kernel span {(t[:, :nslots].max() - t0).item() / 1e3:.2f} us")
+    for sl in range(nslots):
+        col = t[:, sl]
+        ok = col != 0
+        if ok.any():
+            rel = (col[ok] - t0).float() / 1e3
+            print(f"  stamp {sl:2d}: n={int(ok.sum()):4d}  min {rel.min():7.2f}  median {rel.median():7.2f}  max {rel.max():7.2f} us")
+    for e in extra:
+        col = t[:, e]; ok = t[:, 9] != 0
+        if ok.any(): print(f"  value {e}: {col[ok].tolist()[:16]}")
+for it in range(3):
+    for i in range(4):
+        d.step(i)
+torch.cuda.synchronize()
+lib.cnh_debug_set_buffer(dbg.data_ptr())
+for rep in range(2):
+    dbg.zero_(); torch.cuda.synchronize()
+    d.loss_only(rep)
+    show(f"detloss {name} rep{rep}", 8)
+    dbg.zero_(); torch.cuda.synchronize()
+    L.check(lib.cnh_decode(C.byref(d.dec_args[rep]), d.ws_dec.data_ptr(), d.ws_dec.numel(), L.stream_ptr()), "d")
+    show(f"decode {name} rep{rep}", 11, extra=(12, 13))
+lib.cnh_debug_set_buffer(None)
