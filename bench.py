@@ -41,8 +41,8 @@ L2_BYTES = 126 * 2 ** 20
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=8000)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
@@ -442,7 +442,7 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup):
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the caller reads the results every step
 
-    e2e_steps = min(steps, 200)
+    e2e_steps = min(steps, 1000)
     ms = timed_loop(step, e2e_steps, min(warmup, 10), world, dev)
     return {"value": batch * world * e2e_steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "ms_per_step": ms / e2e_steps, "steps": e2e_steps,

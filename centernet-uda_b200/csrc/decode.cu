@@ -509,6 +509,7 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_args a,
   __syncthreads();
   dbg_stamp(g.dbg, 7);
   const int m = (int)s.cnt;                  // survivors (may exceed kKeyCap: then s.keys is partial)
+  dbg_stamp(g.dbg, 11);
   int got = 0;                               // keys to sort; the first min(got, K) ranks are real detections
   const u64* sort_src = sel;
   if (m <= kMaxK) {
@@ -567,6 +568,7 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_args a,
       if (active && part == 0 && rank < kMaxK) sorted[rank] = k;
     }
   }
+  dbg_stamp(g.dbg, 14);
   __syncthreads();
   if (got > K) got = K;
   // fewer than K peaks: zero-score filler at the lowest flat indices that are not candidates
