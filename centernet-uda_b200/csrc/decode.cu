@@ -1,29 +1,32 @@
-// Detection decode for sm_100a in ONE launch (replaces backends/decode.py:6-76: max_pool2d
-// + 4 element-wise passes + two torch.topk sorts + 3 full-map transpose copies).
+// Detection decode for sm_100a in ONE persistent launch (replaces backends/decode.py:6-76:
+// max_pool2d + 4 element-wise passes + two torch.topk sorts + 3 full-map transpose copies).
 //
-// Stage 1 (every CTA = one tile of 32 rows x <=128 columns of one class plane):
-//   * the tile plus a 1-pixel halo is staged in shared memory by ONE TMA bulk-tensor copy
-//     (cp.async.bulk.tensor.3d, SASS UTMALDG) from a [B*C, H, W] tensor map; out-of-range
-//     rows/columns are zero-filled by the TMA unit, which equals max-pool's -inf padding
-//     because heat >= 0.  (W % 4 != 0 or a misaligned base falls back to guarded loads.)
-//   * while the copy is in flight the CTA reads the sample's GLOBAL score histogram (1024
-//     linear bins over [0,1], filled by the tiles that already finished) and derives a
-//     threshold below which no peak can reach the sample's top K any more.
-//   * 3x3 peak test with a rolling 3-row window in registers: one LDS.128 per row per
-//     lane, left/right neighbours by warp shuffle.
-//   * peaks >= threshold are compacted to 64-bit keys (score_bits << 32) | ~flat_index --
-//     descending key order == score descending, ties to the LOWER flat index c*HW+y*W+x --
-//     and counted in a LOCAL 4096-bin histogram.  If the tile holds more than K of them, a
-//     block suffix scan over the histogram finds the bin of its K-th score and only keys
-//     in bins >= it are forwarded (a few more than K; exact radix select only if a bin is
-//     overfull, i.e. massive ties).  The tile adds its counts to the global histogram.
-// Stage 2 (the last tile CTA of each sample, elected by an atomic ticket): final threshold
-//   from the complete global histogram, survivors of all tiles into shared memory, the same
-//   histogram selection, rank sort of the <= K+few keys, zero-score filler when the sample
-//   has fewer than K peaks (ascending flat index, as a stable sort would), gather of
-//   reg / wh / angle / keypoints straight from NCHW, box assembly.
+// Work unit = one tile of 16 rows x <=128 columns of one class plane.  Every CTA owns a contiguous
+// range of tiles (sample-major) and walks it with a 2-stage TMA ring: while tile t is processed,
+// tile t+1 (+ halo) is already being staged in shared memory by cp.async.bulk.tensor.3d (SASS
+// UTMALDG) from a [B*C, H, W] tensor map; out-of-range rows/columns are zero-filled by the TMA
+// unit, which equals max-pool's -inf padding because heat >= 0.  (W % 4 != 0 or a misaligned base
+// falls back to guarded loads.)
+//
+// Per tile:
+//   * threshold-first scan: a row of the tile is only examined further if some pixel reaches the
+//     sample's current pruning threshold (one LDS.128 + 4 compares + a ballot per warp-row), so
+//     once the threshold has tightened a tile costs little more than its TMA transfer;
+//   * surviving pixels get the 3x3 peak test from shared memory; peaks become 64-bit keys
+//     (score_bits << 32) | ~flat_index -- descending key order == score descending, ties to the
+//     LOWER flat index c*HW + y*W + x -- and are counted in a LOCAL 4096-bin histogram;
+//   * a tile with more than K peaks keeps only the bins >= that of its K-th score (block suffix
+//     scan; exact MSB radix select only when a bin is overfull, i.e. massive ties), adds its
+//     counts to the sample's GLOBAL 1024-bin histogram and republishes the sample's threshold;
+//   * kept keys are staged in shared memory and flushed once per (CTA, sample): one reservation
+//     atomic for a dense slice of the sample's candidate list, one ticket atomic.
+// The CTA whose ticket completes a sample merges it: final threshold from the global histogram,
+// survivors into shared memory, histogram selection, rank sort of the <= K+few keys, zero-score
+// filler when the sample has fewer than K peaks (ascending flat index, as a stable sort would),
+// gather of reg / wh / angle / keypoints straight from NCHW, box assembly.
 // No full sort, no transposes: heat is read from HBM exactly once (4*C*H*W bytes/sample).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -32,31 +35,41 @@ namespace cnh {
 
 typedef unsigned long long u64;
 
-constexpr int kRows = 32;                 // tile rows
 constexpr int kCols = 128;                // max tile columns
 constexpr int kPadL = 4;                  // left halo padded to 4 floats: interior is 16B aligned
 constexpr int kBoxWMax = kCols + 2 * kPadL;
-constexpr int kTileFloats = (kRows + 2) * kBoxWMax;
-constexpr int kKeyCap = kRows * kCols;    // worst case: every pixel of the tile is a peak
+// tile height: 16 rows (deep TMA ring, many tiles per CTA) or 32 rows (one tile per CTA, small problems)
+__host__ __device__ constexpr int tile_floats(int rows) { return ((rows + 2) * kBoxWMax + 31) / 32 * 32; }   // 128-byte multiples
+constexpr int kMergeKeyCap = 4096;        // survivors the merge kernel can hold in shared memory
 constexpr int kMaxK = 1024;
 constexpr int kFineBins = 4096;           // local histogram: bin = min(4095, int(score * 4096))
 constexpr int kCoarseBins = 1024;         // per-sample global histogram: fine bin >> 2
 constexpr int kSlack = 64;                // a tile forwards at most K + kSlack keys
+constexpr int kStageCap = kMaxK + kSlack; // staging buffer (keys) per CTA
+
+struct SampleState {                      // zero between launches
+  unsigned cand_cnt;
+  unsigned thr_bits;
+  unsigned pad[2];
+};
 
 struct DecGeo {
-  int HW, tiles_x, tiles_y, tiles_per_plane, tiles_per_sample, box_w, use_tma, slot;
-  unsigned* tiles_done;                   // [B]                        zero between launches
+  int HW, rows, tiles_x, tiles_y, tiles_per_plane, tiles_per_sample, box_w, use_tma, slot, n_stages;
+  long long n_tiles;
+  SampleState* state;                     // [B]                        zero between launches
   unsigned* ghist;                        // [B][kCoarseBins]           zero between launches
-  unsigned* tile_cnt;                     // [B][tiles_per_sample]      rewritten by every launch
-  u64* cand;                              // [B][tiles_per_sample][slot]
+  u64* cand;                              // [B][tiles_per_sample * slot]  dense per-sample lists
   long long* dbg;
 };
 
-struct __align__(128) DecSmem {
-  float tile[kTileFloats];                // stage 2 reuses it: sel = [0,kMaxK), sorted = [kMaxK,2*kMaxK)
-  u64 keys[kKeyCap];
-  unsigned hist[kFineBins / 2];           // 16-bit counters packed in pairs; radix select uses [0,256)
-  u64 mbar;
+constexpr int kMaxStages = 8;
+template <int KEYS>
+struct __align__(128) DecSmemT {            // followed in dynamic shared memory by the TMA ring: n_stages tiles
+  static constexpr int kKeyCap = KEYS;    // worst case: every pixel of the tile is a peak
+  u64 keys[KEYS];
+  u64 stage[kStageCap];                   // merge: `sorted`
+  unsigned hist[kFineBins / 2];           // 16-bit counters packed in pairs; radix select uses [0,256); merge: `sel`
+  u64 mbar[kMaxStages];
   u64 sh_prefix;
   unsigned cnt;
   unsigned cnt2;
@@ -66,8 +79,10 @@ struct __align__(128) DecSmem {
   unsigned sh_bin;
   unsigned sh_above;
   unsigned sh_inbin;
+  unsigned sh_base;
   unsigned warp_tot[kWarps];
 };
+static_assert(sizeof(unsigned) * (kFineBins / 2) >= sizeof(u64) * kMaxK, "merge `sel` aliases the histogram");
 
 // ---- TMA / mbarrier PTX ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,7 +144,8 @@ __device__ __forceinline__ void hist_add(unsigned* hist, int bin) {
 // Highest fine bin t with count(bins >= t) >= need, from the packed 16-bit histogram
 // (thread i owns bins [16i, 16i+16)).  Results in s.sh_bin / s.sh_above / s.sh_inbin;
 // needs total >= need.  Ends with a barrier.
-__device__ void find_kth_bin(DecSmem& s, unsigned need) {
+template <class SM>
+__device__ __noinline__ void find_kth_bin(SM& s, unsigned need) {
   const int tid = threadIdx.x;
   unsigned c[16], v = 0;
 #pragma unroll
@@ -160,7 +176,8 @@ __device__ void find_kth_bin(DecSmem& s, unsigned need) {
 // Threshold from the sample's global coarse histogram: score bits of the lower edge of the highest
 // coarse bin t with count(bins >= t) >= K, or 0 if fewer than K peaks are known.  Thread i owns
 // coarse bins [4i, 4i+4).  Result in s.sh_thr (also returned); ends with a barrier.
-__device__ unsigned global_threshold(const unsigned* ghist, unsigned K, DecSmem& s) {
+template <class SM>
+__device__ __noinline__ unsigned global_threshold(const unsigned* ghist, unsigned K, SM& s) {
   const int tid = threadIdx.x;
   const uint4 g4 = __ldcg(reinterpret_cast<const uint4*>(ghist) + tid);
   const unsigned c[4] = {g4.x, g4.y, g4.z, g4.w};
@@ -187,8 +204,8 @@ __device__ unsigned global_threshold(const unsigned* ghist, unsigned K, DecSmem&
 // for_each(f) must call f(key) for every key, each thread visiting a disjoint subset.
 // Returns T such that exactly `need` keys are >= T (keys are unique; #keys > need >= 1).
 // MSB-first, 8-bit digits, early exit as soon as the remaining bin is taken whole.
-template <class ForEach>
-__device__ u64 radix_select_kth(ForEach for_each, int need, DecSmem& s) {
+template <class ForEach, class SM>
+__device__ u64 radix_select_kth(ForEach for_each, int need, SM& s) {
   u64 prefix = 0, mask = 0;
   unsigned remaining = (unsigned)need;
   for (int shift = 56; shift >= 0; shift -= 8) {
@@ -248,7 +265,7 @@ __device__ __forceinline__ void append_if(bool keep, u64 key, u64* dst, unsigned
 }
 
 // is flat position a positive-score peak?  (global-memory version for the filler path)
-__device__ bool is_candidate_global(const cnh_decode_args& a, int b, long long flat, int HW) {
+__device__ __noinline__ bool is_candidate_global(const cnh_decode_args& a, int b, long long flat, int HW) {
   const int c = (int)(flat / HW), pix = (int)(flat - (long long)c * HW);
   const int y = pix / a.W, x = pix - y * a.W;
   const float* plane = a.heat + ((long long)b * a.C + c) * HW;
@@ -266,240 +283,39 @@ __device__ bool is_candidate_global(const cnh_decode_args& a, int b, long long f
   return m == v;
 }
 
-__global__ void __launch_bounds__(kThreads)
-decode_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_args a, const DecGeo g) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  DecSmem& s = *reinterpret_cast<DecSmem*>(smem_raw);
+// ---- stage 2: merge one sample (run by the CTA whose ticket completed it) ---------------------
+typedef DecSmemT<kMergeKeyCap> MergeSmem;
+__device__ void merge_sample(const cnh_decode_args& a, const DecGeo& g, MergeSmem& s, int b) {
+  constexpr int kKeyCap = MergeSmem::kKeyCap;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K;
-
-  // ---- which tile ------------------------------------------------------------------------
-  const int t = blockIdx.x;
-  const int b = t / g.tiles_per_sample;
-  const int ts = t - b * g.tiles_per_sample;
-  const int c = ts / g.tiles_per_plane;
-  const int tp = ts - c * g.tiles_per_plane;
-  const int ty = tp / g.tiles_x, tx = tp - ty * g.tiles_x;
-  const int y0 = ty * kRows, x0 = tx * kCols;
-  const int rows = min(kRows, a.H - y0), cols = min(kCols, a.W - x0);
-  const int plane = b * a.C + c;
-  const int BW = g.box_w;
   unsigned* ghist = g.ghist + (long long)b * kCoarseBins;
-
-  dbg_stamp(g.dbg, 0);
-  if (tid == 0) {
-    s.cnt = 0;
-    s.cnt2 = 0;
-    if (g.use_tma) {
-      mbar_init(&s.mbar, 1);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&s.mbar, (unsigned)(BW * (kRows + 2) * sizeof(float)));
-      tma_load_3d(s.tile, &tmap, &s.mbar, x0 - kPadL, y0 - 1, plane);
-    }
-  }
-  // while the tile is in flight: clear the local histogram, derive the pruning threshold from what
-  // the finished tiles of this sample have published
-#pragma unroll
-  for (int j = 0; j < kFineBins / 2 / kThreads; ++j) s.hist[tid + j * kThreads] = 0u;
-  const unsigned thr = global_threshold(ghist, (unsigned)K, s);     // contains barriers
-  dbg_stamp(g.dbg, 1);
-  if (g.use_tma) {
-    mbar_wait(&s.mbar, 0);
-  } else {
-    const float* src = a.heat + (long long)plane * g.HW;
-    for (int i = tid; i < (kRows + 2) * BW; i += kThreads) {
-      const int r = i / BW, cc = i - r * BW;
-      const int gy = y0 - 1 + r, gx = x0 - kPadL + cc;
-      s.tile[i] = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) ? __ldcs(src + (long long)gy * a.W + gx) : 0.f;
-    }
-    __syncthreads();
-  }
-  if (a.apply_sigmoid) {                  // export.py:31-33: logits in, clamp(sigmoid) fused
-    for (int i = tid; i < (kRows + 2) * BW; i += kThreads) {
-      const int r = i / BW, cc = i - r * BW;
-      const int gy = y0 - 1 + r, gx = x0 - kPadL + cc;
-      const bool in = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W);
-      s.tile[i] = in ? clamp_prob(1.0f / (1.0f + expf(-s.tile[i]))) : 0.f;
-    }
-    __syncthreads();
-  }
-
-  dbg_stamp(g.dbg, 2);
-  // ---- 3x3 peaks: warp w owns rows [4w, 4w+4), lane owns columns [4*lane, 4*lane+4) -------
-  constexpr int kRowsPerWarp = kRows / kWarps;
-  {
-    const int r_begin = warp * kRowsPerWarp;
-    float hm[3][4];                        // horizontal 3-max of rows r-1, r, r+1
-    float cv[kRowsPerWarp][4];             // centre values of the warp's rows
-    float4 ctr = make_float4(0.f, 0.f, 0.f, 0.f), nxt = ctr;
-    auto load_row = [&](int tr, float (&h)[4], float4& centre) {   // tr: tile row incl. halo
-      const float* row = s.tile + tr * BW + kPadL;
-      const float4 v = *reinterpret_cast<const float4*>(row + 4 * lane);
-      float left = __shfl_up_sync(0xffffffffu, v.w, 1);
-      float right = __shfl_down_sync(0xffffffffu, v.x, 1);
-      if (lane == 0) left = row[-1];
-      if (lane == 31) right = row[4 * 32];
-      h[0] = fmaxf(fmaxf(left, v.x), v.y);
-      h[1] = fmaxf(fmaxf(v.x, v.y), v.z);
-      h[2] = fmaxf(fmaxf(v.y, v.z), v.w);
-      h[3] = fmaxf(fmaxf(v.z, v.w), right);
-      centre = v;
-    };
-    float4 dummy;
-    load_row(r_begin + 0, hm[0], dummy);       // halo row above
-    load_row(r_begin + 1, hm[1], ctr);
-    unsigned flags = 0;                        // bit 4*rr + e
-#pragma unroll
-    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-      const int r = r_begin + rr;
-      load_row(r + 2, hm[2], nxt);
-      cv[rr][0] = ctr.x; cv[rr][1] = ctr.y; cv[rr][2] = ctr.z; cv[rr][3] = ctr.w;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float m = fmaxf(fmaxf(hm[0][e], hm[1][e]), hm[2][e]);
-        const bool ok = (r < rows) && (4 * lane + e < cols) && (cv[rr][e] == m) && (cv[rr][e] > 0.f) &&
-                        (__float_as_uint(cv[rr][e]) >= thr);
-        flags |= ok ? (1u << (4 * rr + e)) : 0u;
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { hm[0][e] = hm[1][e]; hm[1][e] = hm[2][e]; }
-      ctr = nxt;
-    }
-    // one warp-aggregated append for the warp's 4 x 128 pixels
-    const int mine = __popc(flags);
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total) {
-      unsigned base = 0;
-      if (lane == 31) base = atomicAdd(&s.cnt, (unsigned)total);
-      base = __shfl_sync(0xffffffffu, base, 31);
-      unsigned pos = base + (unsigned)(incl - mine);
-#pragma unroll
-      for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-        const unsigned flat0 = (unsigned)c * (unsigned)g.HW + (unsigned)(y0 + r_begin + rr) * (unsigned)a.W +
-                               (unsigned)(x0 + 4 * lane);
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (flags & (1u << (4 * rr + e))) {
-            const unsigned bits = __float_as_uint(cv[rr][e]);
-            s.keys[pos++] = ((u64)bits << 32) | (u64)(0xffffffffu - (flat0 + e));
-            hist_add(s.hist, fine_bin(bits));
-          }
-      }
-    }
-  }
-  __syncthreads();
-  const int n = (int)s.cnt;
-  dbg_stamp(g.dbg, 3);
-
-  // ---- publish this tile's counts to the sample's global histogram (fire-and-forget REDs) -------
-  if (n > 0) {
-    unsigned cc[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const unsigned w = s.hist[8 * tid + j];
-      cc[j >> 1] += (w & 0xffffu) + (w >> 16);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (cc[j]) atomicAdd(&ghist[4 * tid + j], cc[j]);
-  }
-
-  // ---- forward the tile's best keys into its slot of the sample's candidate list ------------------
-  u64* slot = g.cand + ((long long)b * g.tiles_per_sample + ts) * g.slot;
-  unsigned forwarded = (unsigned)n;
-  if (n > K) {
-    find_kth_bin(s, (unsigned)K);
-    const unsigned keep_n = s.sh_above + s.sh_inbin;
-    if (keep_n <= (unsigned)g.slot) {
-      const int tbin = (int)s.sh_bin;
-      for (int i0 = 0; i0 < n; i0 += kThreads) {
-        const int i = i0 + tid;
-        const u64 k = (i < n) ? s.keys[i] : 0ull;
-        append_if((i < n) && fine_bin((unsigned)(k >> 32)) >= tbin, k, slot, &s.cnt2, (unsigned)g.slot);
-      }
-      forwarded = keep_n;
-    } else {                               // massive ties inside one bin: exact selection
-      const u64* keys = s.keys;
-      const u64 T = radix_select_kth([&](auto f) { for (int i = tid; i < n; i += kThreads) f(keys[i]); }, K, s);
-      for (int i0 = 0; i0 < n; i0 += kThreads) {
-        const int i = i0 + tid;
-        const u64 k = (i < n) ? s.keys[i] : 0ull;
-        append_if((i < n) && k >= T, k, slot, &s.cnt2, (unsigned)g.slot);
-      }
-      forwarded = (unsigned)K;
-    }
-  } else {
-    for (int i = tid; i < n; i += kThreads) slot[i] = s.keys[i];
-  }
-
-  dbg_stamp(g.dbg, 4);
-  // ---- elect the last tile of this sample ---------------------------------------------------
-  __syncthreads();                         // the CTA's slot writes and histogram REDs are issued ...
-  if (tid == 0) {
-    g.tile_cnt[(long long)b * g.tiles_per_sample + ts] = forwarded;
-    __threadfence();                       // ... and ordered before the ticket (cumulative fence)
-    s.sh_flag = (atomicAdd(&g.tiles_done[b], 1u) == (unsigned)(g.tiles_per_sample - 1)) ? 1u : 0u;
-  }
-  __syncthreads();
-  dbg_stamp(g.dbg, 5);
-  if (!s.sh_flag) return;
-  __threadfence();
-
-  // ---- stage 2: merge ------------------------------------------------------------------------
-  static_assert(sizeof(float) * kTileFloats >= 2 * kMaxK * sizeof(u64), "stage-2 buffers alias the tile");
-  u64* const sel = reinterpret_cast<u64*>(s.tile);
-  u64* const sorted = sel + kMaxK;
-  unsigned* const sh_cnt = reinterpret_cast<unsigned*>(sorted + kMaxK);      // per-tile counts, if they fit
-  constexpr int kCntCap = (int)((sizeof(float) * kTileFloats - 2 * kMaxK * sizeof(u64)) / sizeof(unsigned));
-  const unsigned* tcnt = g.tile_cnt + (long long)b * g.tiles_per_sample;
   const u64* cand = g.cand + (long long)b * g.tiles_per_sample * g.slot;
-  const bool cnt_in_smem = g.tiles_per_sample <= kCntCap;
-#pragma unroll
+  u64* const sel = reinterpret_cast<u64*>(s.hist);
+  u64* const sorted = s.stage;
+  dbg_stamp(g.dbg, 5);
   for (int j = 0; j < kFineBins / 2 / kThreads; ++j) s.hist[tid + j * kThreads] = 0u;
   if (tid == 0) { s.cnt = 0; s.cnt2 = 0; }
-  if (cnt_in_smem)                                  // same round trip as the histogram read below
-    for (int i = tid; i < g.tiles_per_sample; i += kThreads) sh_cnt[i] = __ldcg(tcnt + i);
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // PDL: the tile kernel's writes are visible from here
+  const unsigned nc = __ldcg(&g.state[b].cand_cnt);                         // same round trip as the histogram
   const unsigned thr_final = global_threshold(ghist, (unsigned)K, s);        // barriers inside
   dbg_stamp(g.dbg, 6);
-  // survivors (score >= final threshold) of every tile -> shared memory keys + fine histogram.
-  // One warp per tile, 8 keys per lane per batch, the next batch in flight while this one is used.
+  // survivors (score >= final threshold) -> shared memory keys + fine histogram; dense list, 8
+  // independent loads in flight per thread
   auto for_each_survivor = [&](auto f) {
     constexpr int kB = 8;
-    const int batches_per_tile = (g.slot + 32 * kB - 1) / (32 * kB);
-    const int n_batches = ((g.tiles_per_sample - warp + kWarps - 1) / kWarps) * batches_per_tile;   // this warp's
-    u64 cur[kB], nxt[kB];
-    unsigned cur_n = 0, nxt_n = 0;
-    auto issue = [&](int q, u64 (&k)[kB], unsigned& valid) {
-      const int tile = warp + kWarps * (q / batches_per_tile);
-      const unsigned i0 = (unsigned)(q % batches_per_tile) * 32u * kB;
-      const unsigned nt = cnt_in_smem ? sh_cnt[tile] : __ldcg(tcnt + tile);
-      valid = nt > i0 ? nt - i0 : 0u;
-      const u64* src = cand + (long long)tile * g.slot + i0;
+    for (unsigned e0 = 0; e0 < nc; e0 += kB * kThreads) {
+      u64 k[kB];
 #pragma unroll
       for (int j = 0; j < kB; ++j) {
-        const unsigned i = (unsigned)lane + 32u * j;
-        k[j] = (i < valid) ? __ldcg(src + i) : 0ull;
+        const unsigned e = e0 + j * kThreads + tid;
+        k[j] = (e < nc) ? __ldcg(cand + e) : 0ull;
       }
-    };
-    if (n_batches > 0) issue(0, cur, cur_n);
-    for (int q = 0; q < n_batches; ++q) {
-      if (q + 1 < n_batches) issue(q + 1, nxt, nxt_n);
-      if (cur_n)
 #pragma unroll
-        for (int j = 0; j < kB; ++j) {
-          if (32u * j >= cur_n) break;                         // warp-uniform
-          const unsigned i = (unsigned)lane + 32u * j;
-          f(i < cur_n && (unsigned)(cur[j] >> 32) >= thr_final, cur[j]);
-        }
-#pragma unroll
-      for (int j = 0; j < kB; ++j) cur[j] = nxt[j];
-      cur_n = nxt_n;
+      for (int j = 0; j < kB; ++j) {
+        if (e0 + j * kThreads >= nc) break;                                 // block-uniform
+        f(e0 + j * kThreads + tid < nc && (unsigned)(k[j] >> 32) >= thr_final, k[j]);
+      }
     }
   };
   for_each_survivor([&](bool ok, u64 k) {
@@ -509,7 +325,6 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_args a,
   __syncthreads();
   dbg_stamp(g.dbg, 7);
   const int m = (int)s.cnt;                  // survivors (may exceed kKeyCap: then s.keys is partial)
-  dbg_stamp(g.dbg, 11);
   int got = 0;                               // keys to sort; the first min(got, K) ranks are real detections
   const u64* sort_src = sel;
   if (m <= kMaxK) {
@@ -517,7 +332,7 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_args a,
     got = m;
   } else if (m <= kKeyCap) {
     const u64* keys = s.keys;
-    find_kth_bin(s, (unsigned)K);
+    find_kth_bin(s, (unsigned)K);            // ends with a barrier: the histogram is dead afterwards
     const unsigned keep_n = s.sh_above + s.sh_inbin;
     if (keep_n <= (unsigned)kMaxK) {
       const int tbin = (int)s.sh_bin;
@@ -538,13 +353,38 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_args a,
     }
   } else {
     // more survivors than shared memory holds (heavy ties): exact radix select straight from the
-    // candidate slots in global memory
+    // sample's candidate list in global memory
     const u64 T = radix_select_kth([&](auto f) { for_each_survivor([&](bool ok, u64 k) { if (ok) f(k); }); }, K, s);
     for_each_survivor([&](bool ok, u64 k) { append_if(ok && k >= T, k, sel, &s.cnt2, (unsigned)kMaxK); });
     got = K;
   }
   __syncthreads();
   dbg_stamp(g.dbg, 8);
+  if (got <= kThreads) {
+    // <= 256 keys: one key per thread, bitonic sort (descending; padding 0 sorts last).  Exchange
+    // distances below 32 are warp shuffles, the rest go through shared memory.
+    u64 k = (tid < got) ? sort_src[tid] : 0ull;
+    __syncthreads();                                       // sort_src may alias `sorted`'s neighbours: settle reads
+    for (int size = 2; size <= kThreads; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        u64 other;
+        if (stride >= 32) {
+          sorted[tid] = k;
+          __syncthreads();
+          other = sorted[tid ^ stride];
+          __syncthreads();
+        } else {
+          other = __shfl_xor_sync(0xffffffffu, k, stride);
+        }
+        const bool up = ((tid & size) == 0);               // this block sorts descending
+        const bool lower = ((tid & stride) == 0);
+        const bool take_max = (up == lower);
+        const u64 mx = k > other ? k : other, mn = k > other ? other : k;
+        k = take_max ? mx : mn;
+      }
+    }
+    sorted[tid] = k;
+  } else {
   // rank sort (keys are unique): position = number of larger keys.  T lanes share a key when there
   // are fewer keys than threads (T = 8, 4, 2 or 1), each scanning every T-th key.
   {
@@ -568,7 +408,9 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_args a,
       if (active && part == 0 && rank < kMaxK) sorted[rank] = k;
     }
   }
-  dbg_stamp(g.dbg, 14);
+  }
+  dbg_stamp(g.dbg, 11);
+  if (g.dbg && tid == 0) { g.dbg[(long long)blockIdx.x * 16 + 12] = m; g.dbg[(long long)blockIdx.x * 16 + 13] = got; }
   __syncthreads();
   if (got > K) got = K;
   // fewer than K peaks: zero-score filler at the lowest flat indices that are not candidates
@@ -591,7 +433,6 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_args a,
   }
   __syncthreads();
   dbg_stamp(g.dbg, 9);
-  if (g.dbg && tid == 0) { g.dbg[(long long)blockIdx.x * 16 + 12] = m; g.dbg[(long long)blockIdx.x * 16 + 13] = got; }
   // ---- gather + box assembly (backends/decode.py:44-74) -----------------------------------------
   const int ncol = a.rotated ? 7 : 6;
   for (int r = tid; r < K; r += kThreads) {
@@ -638,9 +479,303 @@ decode_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_args a,
   }
   dbg_stamp(g.dbg, 10);
   // ---- leave the per-sample state zeroed for the next launch ---------------------------------
-#pragma unroll
+  __syncthreads();
   for (int j = 0; j < kCoarseBins / kThreads; ++j) ghist[tid + j * kThreads] = 0u;
-  if (tid == 0) g.tiles_done[b] = 0u;
+  if (tid == 0) {
+    g.state[b].cand_cnt = 0u;
+    g.state[b].thr_bits = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+decode_merge_kernel(const cnh_decode_args a, const DecGeo g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  merge_sample(a, g, *reinterpret_cast<MergeSmem*>(smem_raw), (int)blockIdx.x);
+}
+
+template <int kRows>
+__global__ void __launch_bounds__(kThreads)
+decode_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_args a, const DecGeo g) {
+  typedef DecSmemT<kRows * kCols> DecSmem;
+  constexpr int kTileFloats = tile_floats(kRows);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  DecSmem& s = *reinterpret_cast<DecSmem*>(smem_raw);
+  float* const ring = reinterpret_cast<float*>(smem_raw + sizeof(DecSmem));
+  const int S = g.n_stages;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = a.K;
+  const int BW = g.box_w;
+  // this CTA's contiguous tile range
+  const long long lo = g.n_tiles * blockIdx.x / gridDim.x, hi = g.n_tiles * (blockIdx.x + 1) / gridDim.x;
+  dbg_stamp(g.dbg, 0);
+  if (lo >= hi) return;
+
+  // tile cursor: (sample, class, tile row, tile column), advanced without divisions
+  struct Cursor { int b, c, ty, tx; };
+  auto cursor_at = [&](long long t) {
+    Cursor q;
+    q.b = (int)(t / g.tiles_per_sample);
+    const int ts = (int)(t - (long long)q.b * g.tiles_per_sample);
+    q.c = ts / g.tiles_per_plane;
+    const int tp = ts - q.c * g.tiles_per_plane;
+    q.ty = tp / g.tiles_x;
+    q.tx = tp - q.ty * g.tiles_x;
+    return q;
+  };
+  auto advance = [&](Cursor& q) {
+    if (++q.tx == g.tiles_x) {
+      q.tx = 0;
+      if (++q.ty == g.tiles_y) {
+        q.ty = 0;
+        if (++q.c == a.C) { q.c = 0; ++q.b; }
+      }
+    }
+  };
+  auto issue_tile = [&](const Cursor& q, int buf) {       // thread 0 only
+    mbar_expect_tx(&s.mbar[buf], (unsigned)(BW * (kRows + 2) * sizeof(float)));
+    tma_load_3d(ring + (size_t)buf * kTileFloats, &tmap, &s.mbar[buf], q.tx * kCols - kPadL, q.ty * kRows - 1,
+                q.b * a.C + q.c);
+  };
+  Cursor cur = cursor_at(lo), pre = cur;                  // tile being processed / next tile to prefetch
+  long long pre_t = lo;
+
+  if (tid == 0) {
+    s.cnt = 0;
+    s.cnt2 = 0;
+    if (g.use_tma) {
+      for (int i = 0; i < S; ++i) mbar_init(&s.mbar[i], 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      for (int i = 0; i < S && pre_t < hi; ++i, ++pre_t, advance(pre)) issue_tile(pre, i);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kFineBins / 2 / kThreads; ++j) s.hist[tid + j * kThreads] = 0u;
+
+  int cur_b = cur.b;
+  long long dbg_heavy = 0, dbg_cands = 0;
+  unsigned stage_n = 0;                     // keys staged for cur_b (uniform)
+  unsigned tiles_staged = 0;                // tiles of cur_b processed since the last flush (uniform)
+  unsigned thr = 0;                         // pruning threshold (score bits) for cur_b
+  if (tid == 0) s.sh_thr = __ldcg(&g.state[cur_b].thr_bits);
+  __syncthreads();
+  thr = s.sh_thr;
+
+  // flush the staged keys of sample b into a dense slice of its candidate list
+  auto flush = [&](int b) {
+    if (stage_n == 0) return;
+    if (tid == 0) s.sh_base = atomicAdd(&g.state[b].cand_cnt, stage_n);
+    __syncthreads();
+    u64* dst = g.cand + (long long)b * g.tiles_per_sample * g.slot + s.sh_base;
+    for (unsigned i = tid; i < stage_n; i += kThreads) dst[i] = s.stage[i];
+    __syncthreads();
+    stage_n = 0;
+  };
+
+  for (long long t = lo; t < hi; ++t) {
+    const bool dbg_it = (t == lo + 2) && ((int)blockIdx.x >= a.B);
+    if (dbg_it) dbg_stamp(g.dbg, 6);
+    const int buf = (int)((t - lo) % S), phase = (int)(((t - lo) / S) & 1);
+    const int b = cur.b, c = cur.c, y0 = cur.ty * kRows, x0 = cur.tx * kCols;
+    if (b != cur_b) {
+      flush(cur_b);
+      cur_b = b;
+      tiles_staged = 0;
+      if (tid == 0) s.sh_thr = __ldcg(&g.state[b].thr_bits);
+      __syncthreads();
+      thr = s.sh_thr;
+    }
+    const int rows = min(kRows, a.H - y0), cols = min(kCols, a.W - x0);
+    float* tile = ring + (size_t)buf * kTileFloats;
+    if (g.use_tma) {
+      mbar_wait(&s.mbar[buf], (unsigned)phase);
+    } else {
+      const float* src = a.heat + ((long long)b * a.C + c) * g.HW;
+      for (int i = tid; i < (kRows + 2) * BW; i += kThreads) {
+        const int r = i / BW, cc = i - r * BW;
+        const int gy = y0 - 1 + r, gx = x0 - kPadL + cc;
+        tile[i] = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) ? __ldcs(src + (long long)gy * a.W + gx) : 0.f;
+      }
+      __syncthreads();
+    }
+    if (a.apply_sigmoid) {                  // export.py:31-33: logits in, clamp(sigmoid) fused
+      for (int i = tid; i < (kRows + 2) * BW; i += kThreads) {
+        const int r = i / BW, cc = i - r * BW;
+        const int gy = y0 - 1 + r, gx = x0 - kPadL + cc;
+        const bool in = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W);
+        tile[i] = in ? clamp_prob(1.0f / (1.0f + expf(-tile[i]))) : 0.f;
+      }
+      __syncthreads();
+    }
+    if (t == lo) dbg_stamp(g.dbg, 1);
+    if (dbg_it) dbg_stamp(g.dbg, 7);
+
+    // ---- threshold-first scan: warp w owns rows {2w, 2w+1}, lane owns columns [4*lane, 4*lane+4) ----
+    {
+      const float thr_f = __uint_as_float(thr);
+      constexpr int kRowsPerWarp = kRows / kWarps;
+      float cv[kRowsPerWarp][4];
+      unsigned flags = 0;                     // bit 4*rr + e
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int r = warp * kRowsPerWarp + rr;
+        const float* row = tile + (r + 1) * BW + kPadL;
+        const float4 v = *reinterpret_cast<const float4*>(row + 4 * lane);
+        cv[rr][0] = v.x; cv[rr][1] = v.y; cv[rr][2] = v.z; cv[rr][3] = v.w;
+        const bool row_ok = r < rows;
+        unsigned pass = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          pass |= (row_ok && (4 * lane + e < cols) && cv[rr][e] > 0.f && cv[rr][e] >= thr_f) ? (1u << e) : 0u;
+        const unsigned hit = __ballot_sync(0xffffffffu, pass != 0u);
+        if (hit == 0u) continue;                                       // nothing in this row can matter
+        if (__popc(hit) <= 6) {
+          // sparse row (the steady state once the threshold has tightened): each lane tests its own
+          // few pixels against their 8 neighbours straight from shared memory
+          if (pass) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (pass & (1u << e)) {
+                const float* p = row + 4 * lane + e;
+                const float m = fmaxf(fmaxf(fmaxf(p[-BW - 1], p[-BW]), fmaxf(p[-BW + 1], p[-1])),
+                                      fmaxf(fmaxf(p[1], p[BW - 1]), fmaxf(p[BW], p[BW + 1])));
+                if (cv[rr][e] >= m) flags |= 1u << (4 * rr + e);
+              }
+          }
+          continue;
+        }
+        // dense row: 3x3 maximum for the whole row, rows r-1, r, r+1 (tile rows r, r+1, r+2),
+        // neighbours by shuffle
+        float m[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int dr = 0; dr < 3; ++dr) {
+          const float* rw = tile + (r + dr) * BW + kPadL;
+          const float4 u = (dr == 1) ? v : *reinterpret_cast<const float4*>(rw + 4 * lane);
+          float left = __shfl_up_sync(0xffffffffu, u.w, 1);
+          float right = __shfl_down_sync(0xffffffffu, u.x, 1);
+          if (lane == 0) left = rw[-1];
+          if (lane == 31) right = rw[4 * 32];
+          m[0] = fmaxf(m[0], fmaxf(fmaxf(left, u.x), u.y));
+          m[1] = fmaxf(m[1], fmaxf(fmaxf(u.x, u.y), u.z));
+          m[2] = fmaxf(m[2], fmaxf(fmaxf(u.y, u.z), u.w));
+          m[3] = fmaxf(m[3], fmaxf(fmaxf(u.z, u.w), right));
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if ((pass & (1u << e)) && cv[rr][e] == m[e]) flags |= 1u << (4 * rr + e);
+      }
+      // one warp-aggregated append for the warp's rows
+      const int mine = __popc(flags);
+      if (__ballot_sync(0xffffffffu, mine != 0) != 0u) {
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned base = 0;
+        if (lane == 31) base = atomicAdd(&s.cnt, (unsigned)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        unsigned pos = base + (unsigned)(incl - mine);
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+          const unsigned flat0 = (unsigned)c * (unsigned)g.HW +
+                                 (unsigned)(y0 + warp * kRowsPerWarp + rr) * (unsigned)a.W + (unsigned)(x0 + 4 * lane);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (flags & (1u << (4 * rr + e))) {
+              const unsigned bits = __float_as_uint(cv[rr][e]);
+              s.keys[pos++] = ((u64)bits << 32) | (u64)(0xffffffffu - (flat0 + e));
+              hist_add(s.hist, fine_bin(bits));
+            }
+        }
+      }
+    }
+    if (dbg_it) dbg_stamp(g.dbg, 8);
+    __syncthreads();                          // tile[buf] is free; keys / histogram complete
+    const int n = (int)s.cnt;
+    if (tid == 0 && g.use_tma && pre_t < hi) { issue_tile(pre, buf); ++pre_t; advance(pre); }   // refill the ring
+    dbg_heavy += (n > K); dbg_cands += n;
+    if (t == lo) dbg_stamp(g.dbg, 3);
+    if (dbg_it) dbg_stamp(g.dbg, 9);
+
+    if (n > 0) {
+      // publish this tile's counts to the sample's global histogram (fire-and-forget REDs)
+      unsigned cc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const unsigned w = s.hist[8 * tid + j];
+        cc[j >> 1] += (w & 0xffffu) + (w >> 16);
+      }
+      unsigned* ghist = g.ghist + (long long)b * kCoarseBins;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (cc[j]) atomicAdd(&ghist[4 * tid + j], cc[j]);
+      // make room in the staging buffer
+      const unsigned incoming = (unsigned)min(n, g.slot);
+      if (stage_n + incoming > (unsigned)kStageCap) flush(b);
+      if (n > K) {
+        find_kth_bin(s, (unsigned)K);
+        const unsigned keep_n = s.sh_above + s.sh_inbin;
+        if (tid == 0) s.cnt2 = 0;
+        __syncthreads();
+        if (keep_n <= (unsigned)g.slot) {
+          const int tbin = (int)s.sh_bin;
+          for (int i0 = 0; i0 < n; i0 += kThreads) {
+            const int i = i0 + tid;
+            const u64 k = (i < n) ? s.keys[i] : 0ull;
+            append_if((i < n) && fine_bin((unsigned)(k >> 32)) >= tbin, k, s.stage + stage_n, &s.cnt2,
+                      (unsigned)g.slot);
+          }
+          stage_n += keep_n;
+        } else {                               // massive ties inside one bin: exact selection
+          const u64* keys = s.keys;
+          const u64 T = radix_select_kth([&](auto f) { for (int i = tid; i < n; i += kThreads) f(keys[i]); }, K, s);
+          for (int i0 = 0; i0 < n; i0 += kThreads) {
+            const int i = i0 + tid;
+            const u64 k = (i < n) ? s.keys[i] : 0ull;
+            append_if((i < n) && k >= T, k, s.stage + stage_n, &s.cnt2, (unsigned)g.slot);
+          }
+          stage_n += (unsigned)K;
+        }
+        // a heavy tile republishes the sample's threshold from everything known so far
+        __syncthreads();
+        if (t + 1 < hi) {                      // (pointless if this CTA has no further tile to prune)
+          const unsigned t_new = global_threshold(ghist, (unsigned)K, s);
+          if (tid == 0 && t_new > thr) atomicMax(&g.state[b].thr_bits, t_new);
+          if (t_new > thr) thr = t_new;
+        }
+      } else {
+        for (int i = tid; i < n; i += kThreads) s.stage[stage_n + i] = s.keys[i];
+        stage_n += (unsigned)n;
+      }
+      __syncthreads();
+      // clean the local histogram and counters for the next tile
+#pragma unroll
+      for (int j = 0; j < kFineBins / 2 / kThreads; ++j) s.hist[tid + j * kThreads] = 0u;
+      if (tid == 0) { s.cnt = 0; s.cnt2 = 0; }
+    }
+    if (dbg_it) dbg_stamp(g.dbg, 10);
+    ++tiles_staged;
+    advance(cur);
+    // keep the pruning threshold current: for the first tiles of a sample just read the published
+    // word; every 8th tile recompute it from the sample's global histogram and republish
+    if (((t - lo) & 7) == 7) {
+      const unsigned t_new = global_threshold(g.ghist + (long long)b * kCoarseBins, (unsigned)K, s);
+      if (t_new > thr) {
+        thr = t_new;
+        if (tid == 0) atomicMax(&g.state[b].thr_bits, t_new);
+      }
+    } else if (tiles_staged <= 2) {
+      if (tid == 0) s.sh_thr = __ldcg(&g.state[b].thr_bits);
+      __syncthreads();
+      if (s.sh_thr > thr) thr = s.sh_thr;
+    }
+  }
+  dbg_stamp(g.dbg, 4);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (g.dbg && tid == 0) { long long* d = g.dbg + (long long)blockIdx.x * 16; d[12] = dbg_heavy; d[13] = dbg_cands; d[14] = thr; d[15] = hi - lo; }
+  flush(cur_b);
 }
 
 // ---- host ---------------------------------------------------------------------------------------
@@ -684,33 +819,32 @@ static int validate(const cnh_decode_args* a) {
 
 static size_t up128(size_t v) { return (v + 127) / 128 * 128; }
 
-static DecGeo make_geo(const cnh_decode_args* a, void* ws) {
+static DecGeo make_geo(const cnh_decode_args* a, void* ws, int rows) {
   DecGeo g;
+  g.rows = rows;
   g.HW = a->H * a->W;
   g.tiles_x = (a->W + kCols - 1) / kCols;
-  g.tiles_y = (a->H + kRows - 1) / kRows;
+  g.tiles_y = (a->H + g.rows - 1) / g.rows;
   g.tiles_per_plane = g.tiles_x * g.tiles_y;
   g.tiles_per_sample = g.tiles_per_plane * a->C;
+  g.n_tiles = (long long)a->B * g.tiles_per_sample;
   const int tw = a->W < kCols ? a->W : kCols;
   g.box_w = ((tw + 3) / 4) * 4 + 2 * kPadL;
   g.use_tma = 0;
   g.dbg = debug_buffer();
   g.slot = a->K + kSlack;
   char* p = static_cast<char*>(ws);
-  g.tiles_done = reinterpret_cast<unsigned*>(p);
-  p += up128((size_t)a->B * sizeof(unsigned));
+  g.state = reinterpret_cast<SampleState*>(p);
+  p += up128((size_t)a->B * sizeof(SampleState));
   g.ghist = reinterpret_cast<unsigned*>(p);
   p += up128((size_t)a->B * kCoarseBins * sizeof(unsigned));
-  g.tile_cnt = reinterpret_cast<unsigned*>(p);
-  p += up128((size_t)a->B * g.tiles_per_sample * sizeof(unsigned));
   g.cand = reinterpret_cast<u64*>(p);
   return g;
 }
 
 static size_t decode_ws_bytes(const cnh_decode_args* a) {
-  DecGeo g = make_geo(a, nullptr);
-  return up128((size_t)a->B * sizeof(unsigned)) + up128((size_t)a->B * kCoarseBins * sizeof(unsigned)) +
-         up128((size_t)a->B * g.tiles_per_sample * sizeof(unsigned)) +
+  DecGeo g = make_geo(a, nullptr, 16);     // 16-row tiling has the most tiles: sizes the candidate lists
+  return up128((size_t)a->B * sizeof(SampleState)) + up128((size_t)a->B * kCoarseBins * sizeof(unsigned)) +
          (size_t)a->B * g.tiles_per_sample * g.slot * sizeof(u64);
 }
 
@@ -727,30 +861,69 @@ extern "C" int cnh_decode(const cnh_decode_args* a, void* workspace, size_t work
   if (int rc = validate(a)) return rc;
   CNH_REQUIRE(workspace != nullptr && workspace_bytes >= cnh_decode_workspace_bytes(a), CNH_E_WORKSPACE,
               "decode: workspace %zu < %zu bytes", workspace_bytes, cnh_decode_workspace_bytes(a));
-  DecGeo g = make_geo(a, workspace);
+  // ---- configuration: 32-row tiles + single buffer when every CTA gets at most one tile (small
+  // problems: latency matters), else 16-row tiles walked by persistent CTAs with a 4-deep TMA ring.
+  struct Cfg { int rows, stages; const void* kernel; size_t smem; int ctas_per_sm; };
+  static Cfg cfgs[2] = {
+      {32, 1, (const void*)decode_tiles_kernel<32>, sizeof(DecSmemT<32 * kCols>) + 1 * sizeof(float) * tile_floats(32), 0},
+      {16, 4, (const void*)decode_tiles_kernel<16>, sizeof(DecSmemT<16 * kCols>) + 4 * sizeof(float) * tile_floats(16), 0}};
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CNH_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    for (Cfg& c : cfgs) CNH_CUDA(cudaFuncSetAttribute(c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    CNH_CUDA(cudaFuncSetAttribute(decode_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  for (Cfg& c : cfgs)
+    if (c.ctas_per_sm == 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, c.kernel, kThreads, c.smem) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = 1;
+      }
+      c.ctas_per_sm = n;
+    }
+  const int sms = sm_count();
+  const long long tiles32 = (long long)a->B * a->C * ((a->H + 31) / 32) * ((a->W + kCols - 1) / kCols);
+  const Cfg& cfg = (tiles32 <= (long long)cfgs[0].ctas_per_sm * sms) ? cfgs[0] : cfgs[1];
+  DecGeo g = make_geo(a, workspace, cfg.rows);
+  g.n_stages = cfg.stages;
+  CNH_REQUIRE(g.n_tiles < (1ll << 31), CNH_E_SHAPE, "decode: too many tiles");
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   EncodeTiledFn enc = encode_fn();
   if (enc != nullptr && a->W % 4 == 0 && aligned16(a->heat)) {
     const cuuint64_t dims[3] = {(cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B * (cuuint64_t)a->C};
     const cuuint64_t strides[2] = {(cuuint64_t)a->W * 4, (cuuint64_t)a->W * (cuuint64_t)a->H * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)g.box_w, (cuuint32_t)(kRows + 2), 1};
+    const cuuint32_t box[3] = {(cuuint32_t)g.box_w, (cuuint32_t)(cfg.rows + 2), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a->heat), dims, strides,
                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     g.use_tma = (r == CUDA_SUCCESS) ? 1 : 0;
   }
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  CNH_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    CNH_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem)));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  long long grid = (long long)cfg.ctas_per_sm * sms;          // persistent: every CTA walks a tile range
+  if (grid > g.n_tiles) grid = g.n_tiles;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    void* params[3] = {&tmap, const_cast<cnh_decode_args*>(a), &g};
+    CNH_CUDA(cudaLaunchKernel(cfg.kernel, dim3((unsigned)grid), dim3(kThreads), params, cfg.smem, st));
   }
-  const long long tiles = (long long)a->B * g.tiles_per_sample;
-  CNH_REQUIRE(tiles < (1ll << 31), CNH_E_SHAPE, "decode: too many tiles");
-  decode_kernel<<<(unsigned)tiles, kThreads, sizeof(DecSmem), static_cast<cudaStream_t>(stream)>>>(tmap, *a, g);
+  // merge: one CTA per sample; programmatic dependent launch lets its prologue overlap the tile kernel's tail
+  static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3((unsigned)a->B);
+  lc.blockDim = dim3(kThreads);
+  lc.dynamicSmemBytes = sizeof(MergeSmem);
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = use_pdl ? 1 : 0;
+  CNH_CUDA(cudaLaunchKernelEx(&lc, decode_merge_kernel, *a, g));
   CNH_CUDA(cudaGetLastError());
   return CNH_OK;
 }

@@ -16,9 +16,9 @@ dbg = torch.zeros(65536, 16, dtype=torch.int64, device=dev)
 def show(tag, nslots, extra=()):
     torch.cuda.synchronize()
     t = dbg.cpu()
-    used = (t[:, 0] != 0).nonzero().flatten()
+    used = ((t[:, 0] != 0) | (t[:, 5] != 0)).nonzero().flatten()
     t = t[used]
-    t0 = t[:, 0].min()
+    t0 = t[:, 0][t[:, 0] != 0].min() if (t[:, 0] != 0).any() else t[:, 5][t[:, 5] != 0].min()
     print(f"--- {tag}: {len(used)} CTAs; kernel span {(t[:, :nslots].max() - t0).item() / 1e3:.2f} us")
     for sl in range(nslots):
         col = t[:, sl]
@@ -40,5 +40,12 @@ for rep in range(2):
     show(f"detloss {name} rep{rep}", 8)
     dbg.zero_(); torch.cuda.synchronize()
     L.check(lib.cnh_decode(C.byref(d.dec_args[rep]), d.ws_dec.data_ptr(), d.ws_dec.numel(), L.stream_ptr()), "d")
-    show(f"decode {name} rep{rep}", 11, extra=(12, 13))
+    show(f"decode {name} rep{rep}", 12)
+    t = dbg.cpu(); used = t[:, 0] != 0
+    mg = t[:batch]; print("  merge m/got:", mg[:, 12].tolist()[:8], mg[:, 13].tolist()[:8])
+    used = used & (torch.arange(t.shape[0]) >= batch)
+    print("  per-CTA: tiles", t[used, 15].float().mean().item(), "heavy tiles", t[used, 12].float().mean().item(), "max", t[used, 12].max().item(),
+          "| candidates/tile", (t[used, 13].float() / t[used, 15].float().clamp(min=1)).mean().item(),
+          "| final thr (as prob) min/median", torch.tensor(t[used, 14].int().tolist(), dtype=torch.int32).view(torch.float32).min().item(),
+          torch.tensor(t[used, 14].int().tolist(), dtype=torch.int32).view(torch.float32).median().item())
 lib.cnh_debug_set_buffer(None)
