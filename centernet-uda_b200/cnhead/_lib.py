@@ -14,7 +14,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libcnhead_sm100.so")
+LIB_PATH = os.environ.get("CNH_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libcnhead_sm100.so")
 
 MAX_HEADS = 3
 TOTALS = 24
@@ -37,6 +37,14 @@ class DetLossArgs(C.Structure):
                 ("ind", C.c_void_p), ("hm_weight", C.c_float), ("_pad", C.c_int32),
                 ("heads", Head * MAX_HEADS),
                 ("scalars", C.c_void_p), ("totals", C.c_void_p), ("norm", C.c_void_p), ("norm_out", C.c_void_p)]
+
+
+MAX_PEERS = 8
+MAILBOX_BYTES = 4096
+
+
+class Peers(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("mailbox", C.c_void_p * MAX_PEERS)]
 
 
 class ScaleArgs(C.Structure):
@@ -79,6 +87,8 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(DetLossArgs), vp, sz, st]
+        L.cnh_detloss_fused_peers.restype = C.c_int
+        L.cnh_detloss_fused_peers.argtypes = [C.POINTER(DetLossArgs), C.POINTER(Peers), vp, sz, st]
         L.cnh_detloss_finalize.restype = C.c_int
         L.cnh_detloss_finalize.argtypes = [C.POINTER(DetLossArgs), vp, st]
         L.cnh_scale_inplace.restype = C.c_int

@@ -51,6 +51,98 @@ def shard_slice(batch: int, rank: int, world: int) -> slice:
     return slice(rank * per, (rank + 1) * per)
 
 
+# ---- peer mailboxes: the exchange folded into the fused kernel -------------------------------------
+class PeerMailbox:
+    """One zeroed 4 KiB mailbox per rank, mapped into every peer's address space (NVLink / NVSwitch).
+    `cnh_detloss_fused_peers` stores this rank's normalisers and exact totals into every peer's mailbox
+    and waits for theirs inside the kernel -- no collective call on the step path.
+
+    Mapping: torch symmetric memory when available, CUDA IPC handles otherwise."""
+
+    _cache = {}
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > L.MAX_PEERS:
+            raise RuntimeError(f"cnhead: peer exchange supports at most {L.MAX_PEERS} ranks per group")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.how, self._keep = None, []
+        try:
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty(L.MAILBOX_BYTES // 8, dtype=torch.int64, device=dev)
+            buf.zero_()
+            g = group if group is not None else dist.group.WORLD
+            hdl = symm.rendezvous(buf, g.group_name if hasattr(g, "group_name") else g)
+            self.ptrs = [int(p) for p in hdl.buffer_ptrs]
+            self._keep = [buf, hdl]
+            self.how = "symmetric_memory"
+        except Exception as exc:                       # noqa: BLE001 -- any failure: use CUDA IPC
+            self._symm_error = repr(exc)
+            buf = torch.zeros(L.MAILBOX_BYTES // 8, dtype=torch.int64, device=dev)
+            handle = buf.untyped_storage()._share_cuda_()
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle, group=group)
+            self.ptrs = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.ptrs.append(buf.data_ptr())
+                    continue
+                st = torch.UntypedStorage._new_shared_cuda(*h)
+                t = torch.empty(0, dtype=torch.int64, device=st.device).set_(st)
+                self._keep.append(t)
+                self.ptrs.append(t.data_ptr())
+            self._keep.append(buf)
+            self.how = "cuda_ipc"
+        torch.cuda.synchronize()
+        dist.barrier(group=group)                       # every mailbox is zeroed and mapped
+        self.c = L.Peers()
+        self.c.world, self.c.rank = self.world, self.rank
+        for r, p in enumerate(self.ptrs):
+            self.c.mailbox[r] = p
+
+    @classmethod
+    def get(cls, group=None):
+        key = (id(group), torch.cuda.current_device())
+        if key not in cls._cache:
+            cls._cache[key] = cls(group)
+        return cls._cache[key]
+
+
+class _PeersDetectionLossFn(torch.autograd.Function):
+    """single launch per rank: loss of the GLOBAL batch + gradients of the local head maps."""
+
+    @staticmethod
+    def forward(ctx, meta, hm, *maps):
+        gt, ind, specs, hm_weight, group = meta
+        heads = [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode, s.elementwise_mask)
+                 for m, s in zip(maps, specs)]
+        box = PeerMailbox.get(group)
+        dev = hm.device
+        prob = torch.empty_like(hm)
+        grads = [torch.empty_like(hm)] + [torch.empty_like(m) for m in maps]
+        scalars = torch.empty(L.SCALARS, dtype=torch.float32, device=dev)
+        totals = torch.empty(L.TOTALS, dtype=torch.int64, device=dev)
+        a = F.fill_detloss_args(hm, gt, ind, heads, hm_weight, prob, grads, scalars, totals,
+                                b_global=hm.shape[0] * box.world)
+        ws = L.workspace("detloss_peers", L.lib().cnh_detloss_workspace_bytes(C.byref(a)), dev)
+        L.check(L.lib().cnh_detloss_fused_peers(C.byref(a), C.byref(box.c), ws.data_ptr(), ws.numel(),
+                                                L.stream_ptr()), "detloss_fused_peers")
+        ctx.grads = grads
+        ctx.used = False
+        ctx.mark_non_differentiable(prob, totals)
+        return scalars, prob, totals
+
+    backward = staticmethod(F._DetectionLossFn.backward)
+
+
+def peers_schedule_fits(hm: torch.Tensor) -> bool:
+    """the in-kernel exchange needs the register-stash schedule: <= ~400 chunks of 4096 heat-map elements"""
+    b, c, h, w = hm.shape
+    return b * ((c * h * w + 4095) // 4096) <= 400
+
+
 # ---- CUDA path --------------------------------------------------------------------------------------
 class _ShardedDetectionLossFn(torch.autograd.Function):
     @staticmethod
@@ -83,7 +175,10 @@ class _ShardedDetectionLossFn(torch.autograd.Function):
     backward = staticmethod(F._DetectionLossFn.backward)
 
 
-def detection_loss_sharded(hm, gt, ind, heads: Sequence[F.HeadSpec], hm_weight=1.0, group=None):
+def detection_loss_sharded(hm, gt, ind, heads: Sequence[F.HeadSpec], hm_weight=1.0, group=None,
+                           exchange: str = "auto"):
+    """exchange: 'peers' (in-kernel NVLink mailboxes), 'nccl' (count -> all-reduce -> main), or 'auto'
+    (peers when the per-rank problem fits the register-stash schedule)."""
     hm = L.require(hm, "output['hm']")
     gt = L.require(gt, "batch['hm']")
     ind = L.require(ind, "batch['ind']", torch.int64)
@@ -109,7 +204,10 @@ def detection_loss_sharded(hm, gt, ind, heads: Sequence[F.HeadSpec], hm_weight=1
             L.check(L.lib().cnh_detloss_finalize(C.byref(a), totals.data_ptr(), L.stream_ptr()),
                     "detloss_finalize")
         return scalars, prob, totals
-    return _ShardedDetectionLossFn.apply((gt, ind, specs, float(hm_weight), group), hm, *maps)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    use_peers = world > 1 and (exchange == "peers" or (exchange == "auto" and peers_schedule_fits(hm)))
+    fn = _PeersDetectionLossFn if use_peers else _ShardedDetectionLossFn
+    return fn.apply((gt, ind, specs, float(hm_weight), group), hm, *maps)
 
 
 def make_sharded_loss(base_cls):
@@ -117,16 +215,17 @@ def make_sharded_loss(base_cls):
     whole (global) batch; gradients are those of the global loss w.r.t. the local head maps."""
 
     class ShardedDetectionLoss(base_cls):
-        def __init__(self, *args, group=None, **kwargs):
+        def __init__(self, *args, group=None, exchange="auto", **kwargs):
             super().__init__(*args, **kwargs)
             self.group = group
+            self.exchange = exchange
 
         def forward(self, output, batch):
             if self.with_keypoints and self.kp_indices is not None:
                 raise NotImplementedError("limb-length keypoint term is not sharded")
             heads = self._heads(output, batch)
             scalars, prob, totals = detection_loss_sharded(output['hm'], batch['hm'], batch['ind'], heads,
-                                                         self.hm_weight, self.group)
+                                                         self.hm_weight, self.group, self.exchange)
             output['hm'] = prob
             stats = {'centernet_loss': scalars[0], 'hm_loss': scalars[1], 'wh_loss': scalars[2],
                      'off_loss': scalars[3]}

@@ -120,4 +120,27 @@ __device__ __forceinline__ void dbg_stamp(long long* dbg, int slot) {
 __device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ void stg_stream(float4* p, float4 v) { __stcs(p, v); }
 
+// L2 residency control for the two-pass schedule: data read by phase 0 and re-read by phase 1 is
+// loaded with an evict_last policy; everything streamed once uses evict_first.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg_hint(const float4* ptr, unsigned long long policy) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ void stg_hint(float4* ptr, float4 v, unsigned long long policy) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+               :: "l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
+}
+
 }  // namespace cnh

@@ -32,6 +32,13 @@
 
 namespace cg = cooperative_groups;
 
+// L2 eviction-priority hints for the two-pass schedule (evict_last for the pre-counted target,
+// evict_first for everything streamed once) measured SLOWER on B200 (98 vs 88 us at the cfg5 shard):
+// off by default, kept for experiments.
+#ifndef CNH_L2_HINTS
+#define CNH_L2_HINTS 0
+#endif
+
 namespace cnh {
 
 constexpr int kVec = 4;                       // float4 per thread per chunk
@@ -50,10 +57,25 @@ enum Mode { M_STASH = 0, M_PRECOUNT = 1, M_MAIN = 2, M_COUNT = 3, M_FWD = 4 };
 struct WsHeader {
   unsigned parity;
   unsigned done;
-  unsigned pad[2];
+  unsigned epoch;                             // launches that used the peer exchange so far
+  unsigned pad;
   unsigned long long bar[2][2];               // STASH barriers [parity][0 = chunk CTAs: arrivals << 32 | num_pos, 1 = item CTAs]
   long long acc[2][CNH_TOTALS];               // [q] = hi word, [kQ + q] = lo word
 };
+
+// One mailbox slot per (parity, source rank), 32 words:
+//   [0]     (tag << 32) | num_pos of the source rank   -- sent first, all a chunk CTA needs
+//   [1..24] the source rank's exact totals (counts included)
+//   [31]    tag, stored (release.sys) after the totals
+constexpr int kSlotWords = 32;
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
 struct Geo {
   int HW;
@@ -67,6 +89,8 @@ struct Geo {
   int vec_planes;          // regression planes can be zero-filled with float4 stores
   int stash_slots;         // STASH may keep the slots of an item in registers (M <= 256)
   int chunk_ctas, item_ctas;   // STASH roles
+  int world, rank;             // peer exchange (world == 1: none)
+  unsigned long long* mailbox[CNH_MAX_PEERS];
   WsHeader* hdr;
   long long* dbg;
 };
@@ -117,6 +141,23 @@ __device__ __forceinline__ void focal_elem(float x, float gt, float& p, float& t
   npos += pos ? 1 : 0;
 }
 
+// Same arithmetic for an element known to have gt < 1 (no selects): bit-identical to focal_elem.
+template <bool FAST>
+__device__ __forceinline__ void focal_elem_neg(float x, float gt, float& p, float& term, float& graw) {
+  const float s = sigmoidf_<FAST>(x);
+  p = clamp_prob(s);
+  const float q = __fsub_rn(1.0f, p);
+  const float L = log_unit<FAST>(q);
+  const float omg = __fsub_rn(1.0f, gt);
+  float w4 = __fmul_rn(omg, omg);
+  w4 = __fmul_rn(w4, w4);
+  const float a2 = __fmul_rn(p, p);
+  term = __fmul_rn(__fmul_rn(L, a2), w4);
+  constexpr float k2 = FAST ? 2.0f * kLn2F : 2.0f;
+  const float inner = __fmaf_rn(-__fmul_rn(__fmul_rn(k2, a2), q), L, __fmul_rn(a2, p));
+  graw = (p == s) ? __fmul_rn(-w4, inner) : 0.0f;
+}
+
 __device__ __forceinline__ void block_reduce2(float& s, int& n, float* red_f, int* red_i) {
   s = warp_sum(s);
   n = warp_sum(n);
@@ -140,7 +181,7 @@ __device__ __forceinline__ void block_reduce2(float& s, int& n, float* red_f, in
 
 // One chunk of the heat map.  WRITE_GRAD: scale known, store the gradient now; otherwise (STASH)
 // the raw gradient is returned in `graw` and (KEEP_P) the probabilities in `pkeep`, unstored.  Adds the chunk's loss sum to acc; returns its num_pos.
-template <bool NEED_GRAD, bool WRITE_GRAD, bool KEEP_P, bool FAST, bool VEC>
+template <bool NEED_GRAD, bool WRITE_GRAD, bool KEEP_P, bool HINT, bool FAST, bool VEC>
 __device__ __forceinline__ int focal_chunk(const cnh_detloss_args& a, const Geo& g, long long* acc, int chunk,
                                            float scale, float (&graw)[kElemsPerThread],
                                            float (&pkeep)[kElemsPerThread], float* red_f, int* red_i) {
@@ -160,8 +201,13 @@ __device__ __forceinline__ int focal_chunk(const cnh_detloss_args& a, const Geo&
     if (VEC) {
       float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(2.f, 2.f, 2.f, 2.f);
       if (off < n) {
-        x4 = ldg_stream(reinterpret_cast<const float4*>(xp + off));
-        g4 = ldg_stream(reinterpret_cast<const float4*>(gp + off));
+        if (HINT) {                           // two-pass schedule: everything here is used for the last time
+          x4 = ldg_hint(reinterpret_cast<const float4*>(xp + off), l2_policy_evict_first());
+          g4 = ldg_hint(reinterpret_cast<const float4*>(gp + off), l2_policy_evict_first());
+        } else {
+          x4 = ldg_stream(reinterpret_cast<const float4*>(xp + off));
+          g4 = ldg_stream(reinterpret_cast<const float4*>(gp + off));
+        }
       }
       xs[4 * v + 0] = x4.x; xs[4 * v + 1] = x4.y; xs[4 * v + 2] = x4.z; xs[4 * v + 3] = x4.w;
       gs[4 * v + 0] = g4.x; gs[4 * v + 1] = g4.y; gs[4 * v + 2] = g4.z; gs[4 * v + 3] = g4.w;
@@ -176,6 +222,12 @@ __device__ __forceinline__ int focal_chunk(const cnh_detloss_args& a, const Geo&
   }
   float sum = 0.f;
   int npos = 0;
+  // positives are rare (one pixel per object): a warp whose 512 targets are all < 1 takes the
+  // select-free path (same bits, ~30 % fewer instructions)
+  bool special = false;
+#pragma unroll
+  for (int i = 0; i < kElemsPerThread; ++i) special |= !(gs[i] < 1.0f);
+  const bool generic = __any_sync(0xffffffffu, special);
 #pragma unroll
   for (int v = 0; v < kVec; ++v) {
     const int off = v * kThreads * 4 + threadIdx.x * 4;
@@ -183,7 +235,8 @@ __device__ __forceinline__ int focal_chunk(const cnh_detloss_args& a, const Geo&
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float term;
-      focal_elem<FAST>(xs[4 * v + e], gs[4 * v + e], ps[e], term, gr[e], npos);
+      if (generic) focal_elem<FAST>(xs[4 * v + e], gs[4 * v + e], ps[e], term, gr[e], npos);
+      else focal_elem_neg<FAST>(xs[4 * v + e], gs[4 * v + e], ps[e], term, gr[e]);
       sum = __fadd_rn(sum, term);
       if (NEED_GRAD) graw[4 * v + e] = WRITE_GRAD ? __fmul_rn(gr[e], scale) : gr[e];
       if (KEEP_P) pkeep[4 * v + e] = ps[e];
@@ -191,10 +244,17 @@ __device__ __forceinline__ int focal_chunk(const cnh_detloss_args& a, const Geo&
     if (KEEP_P) continue;                     // STASH: nothing is stored before the grid barrier
     if (VEC) {
       if (off < n) {
-        *reinterpret_cast<float4*>(pp + off) = make_float4(ps[0], ps[1], ps[2], ps[3]);
-        if (WRITE_GRAD)
-          stg_stream(reinterpret_cast<float4*>(a.grad_hm + base + off),
-                     make_float4(graw[4 * v], graw[4 * v + 1], graw[4 * v + 2], graw[4 * v + 3]));
+        if (HINT) {
+          stg_hint(reinterpret_cast<float4*>(pp + off), make_float4(ps[0], ps[1], ps[2], ps[3]), l2_policy_evict_first());
+          if (WRITE_GRAD)
+            stg_hint(reinterpret_cast<float4*>(a.grad_hm + base + off),
+                     make_float4(graw[4 * v], graw[4 * v + 1], graw[4 * v + 2], graw[4 * v + 3]), l2_policy_evict_first());
+        } else {
+          *reinterpret_cast<float4*>(pp + off) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+          if (WRITE_GRAD)
+            stg_stream(reinterpret_cast<float4*>(a.grad_hm + base + off),
+                       make_float4(graw[4 * v], graw[4 * v + 1], graw[4 * v + 2], graw[4 * v + 3]));
+        }
       }
     } else {
 #pragma unroll
@@ -243,7 +303,7 @@ __device__ __forceinline__ void focal_store_stash(const cnh_detloss_args& a, con
 }
 
 // num_pos of one chunk from the target only (phase 0 of PRECOUNT / COUNT), per thread.
-template <bool VEC>
+template <bool VEC, bool HINT>
 __device__ __forceinline__ int count_chunk(const cnh_detloss_args& a, const Geo& g, int chunk) {
   const int b = chunk / g.cps, j = chunk - b * g.cps;
   const long long in_sample = (long long)j * kChunk;
@@ -256,7 +316,8 @@ __device__ __forceinline__ int count_chunk(const cnh_detloss_args& a, const Geo&
     const int off = v * kThreads * 4 + threadIdx.x * 4;
     if (VEC) {
       if (off < n) {
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gp + off));   // keep in L2
+        const float4 g4 = HINT ? ldg_hint(reinterpret_cast<const float4*>(gp + off), l2_policy_evict_last())   // stay in L2 for phase 1
+                               : __ldg(reinterpret_cast<const float4*>(gp + off));
         npos += (g4.x == 1.f) + (g4.y == 1.f) + (g4.z == 1.f) + (g4.w == 1.f);
       }
     } else {
@@ -368,7 +429,7 @@ __device__ __forceinline__ void l1_item_warp(const cnh_detloss_args& a, const Ge
   float* __restrict__ gplane = hd.grad ? hd.grad + ((long long)r.b * D + r.d) * g.HW : nullptr;
   float l1 = 0.f, ang = 0.f;
   for (int k0 = 0; k0 < a.M || (ZERO && k0 == 0); k0 += 32 * kSlotsPerLane) {
-    long long idx[kSlotsPerLane];
+    int idx[kSlotsPerLane];                      // H*W < 2^30 (validated); out-of-range centres are ignored
     float mk[kSlotsPerLane], tg[kSlotsPerLane];
     // round trip 1: centre index, mask and target of up to 8 slots per lane, all in flight together
 #pragma unroll
@@ -379,7 +440,8 @@ __device__ __forceinline__ void l1_item_warp(const cnh_detloss_args& a, const Ge
       tg[u] = 0.f;
       if (k < a.M) {
         const long long slot = (long long)r.b * a.M + k;
-        idx[u] = __ldg(a.ind + slot);
+        const long long i64 = __ldg(a.ind + slot);
+        idx[u] = (i64 >= 0 && i64 < (long long)g.HW) ? (int)i64 : -1;
         mk[u] = (float)(hd.elementwise_mask ? __ldg(hd.mask + slot * D + r.d) : __ldg(hd.mask + slot));
         tg[u] = __ldg(hd.target + slot * D + r.d);
       }
@@ -405,7 +467,7 @@ __device__ __forceinline__ void l1_item_warp(const cnh_detloss_args& a, const Ge
         if (SCATTER && gv != 0.f) atomicAdd(gplane + idx[u], gv * inv_denom);   // duplicate centres accumulate
       }
       if (KEEP && k0 == 0) {
-        keep_i[u] = (idx[u] >= 0 && gv != 0.f) ? (int)idx[u] : -1;
+        keep_i[u] = (idx[u] >= 0 && gv != 0.f) ? idx[u] : -1;
         keep_g[u] = gv;
       }
     }
@@ -491,7 +553,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 }
 
 template <int MODE, bool FAST, bool VEC>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, (MODE == M_STASH || MODE == M_PRECOUNT) ? 3 : 4)
 detloss_kernel(const cnh_detloss_args a, const Geo g) {
   __shared__ float red_f[kWarps];
   __shared__ int red_i[kWarps];
@@ -504,9 +566,14 @@ detloss_kernel(const cnh_detloss_args a, const Geo g) {
   constexpr bool kGrad = (MODE == M_STASH || MODE == M_PRECOUNT || MODE == M_MAIN);
 
   dbg_stamp(g.dbg, 0);
-  if (threadIdx.x == 0) sh_parity = __ldcg(&g.hdr->parity) & 1u;
+  __shared__ unsigned sh_epoch;
+  if (threadIdx.x == 0) {
+    sh_parity = __ldcg(&g.hdr->parity) & 1u;
+    sh_epoch = __ldcg(&g.hdr->epoch);
+  }
   __syncthreads();
   const unsigned par = sh_parity;
+  const unsigned long long tag = (unsigned long long)sh_epoch + 1ull;   // peer exchange: this launch's tag
   long long* acc = g.hdr->acc[par];
   int keep_i[kSlotsPerLane];
   float keep_g[kSlotsPerLane];
@@ -554,8 +621,21 @@ detloss_kernel(const cnh_detloss_args a, const Geo g) {
         arrive(bar_item, 0);
         wait_for(bar_item, g.item_ctas);                   // mask counts are complete
         wait_for(bar_chunk, g.chunk_ctas);                 // the gradient planes are zero-filled
+        if (g.world > 1) {                                 // sharded: mask counts of every rank from the mailbox
+          const unsigned long long* box = g.mailbox[g.rank] + (size_t)(tag & 1ull) * CNH_MAX_PEERS * kSlotWords;
+          long long cnt[CNH_MAX_HEADS] = {0, 0, 0};
+          for (int r = 0; r < g.world; ++r) {
+            const unsigned long long* slot = box + (size_t)r * kSlotWords;
+            while (ld_acquire_sys(slot + 31) != tag) { }
 #pragma unroll
-        for (int h = 0; h < CNH_MAX_HEADS; ++h) sh_norm[1 + h] = (int)__ldcg(acc + kQ + 4 + 3 * h);
+            for (int h = 0; h < CNH_MAX_HEADS; ++h) cnt[h] += (long long)__ldcv(slot + 1 + kQ + 4 + 3 * h);
+          }
+#pragma unroll
+          for (int h = 0; h < CNH_MAX_HEADS; ++h) sh_norm[1 + h] = (int)cnt[h];
+        } else {
+#pragma unroll
+          for (int h = 0; h < CNH_MAX_HEADS; ++h) sh_norm[1 + h] = (int)__ldcg(acc + kQ + 4 + 3 * h);
+        }
       }
       __syncthreads();
       dbg_stamp(g.dbg, 3);
@@ -584,12 +664,23 @@ detloss_kernel(const cnh_detloss_args a, const Geo g) {
       for (int r = 0; r < kStash; ++r) {
         const int chunk = cb + r * g.chunk_ctas;
         if (chunk < g.n_chunks)
-          cta_npos += focal_chunk<true, false, true, FAST, VEC>(a, g, acc, chunk, 0.f, stash[r], pstash[r], red_f, red_i);
+          cta_npos += focal_chunk<true, false, true, false, FAST, VEC>(a, g, acc, chunk, 0.f, stash[r], pstash[r], red_f, red_i);
       }
       dbg_stamp(g.dbg, 1);
       if (threadIdx.x == 0) {                              // focal_chunk ends with a block barrier
         arrive(bar_chunk, cta_npos);
-        sh_norm[0] = (int)wait_for(bar_chunk, g.chunk_ctas);
+        if (g.world > 1) {                                 // sharded: num_pos of every rank, straight from the mailbox
+          const unsigned long long* box = g.mailbox[g.rank] + (size_t)(tag & 1ull) * CNH_MAX_PEERS * kSlotWords;
+          unsigned total = 0;
+          for (int r = 0; r < g.world; ++r) {
+            unsigned long long v;
+            do { v = ld_acquire_sys(box + (size_t)r * kSlotWords); } while ((v >> 32) != tag);
+            total += (unsigned)(v & 0xffffffffull);
+          }
+          sh_norm[0] = (int)total;
+        } else {
+          sh_norm[0] = (int)wait_for(bar_chunk, g.chunk_ctas);
+        }
       }
       __syncthreads();
       dbg_stamp(g.dbg, 3);
@@ -603,15 +694,53 @@ detloss_kernel(const cnh_detloss_args a, const Geo g) {
       dbg_stamp(g.dbg, 5);
     } else {
       // the scalars, while the workers store their gradients; then retire the OTHER accumulator set
-      if (threadIdx.x == 0) {
-        const unsigned npos = wait_for(bar_chunk, g.chunk_ctas);
+      const int t = threadIdx.x;
+      const unsigned mpar = (unsigned)(tag & 1ull);       // mailbox parity follows the exchange count, not `par`
+      if (t == 0) sh_norm[0] = (int)wait_for(bar_chunk, g.chunk_ctas);
+      __syncthreads();
+      // first, and alone on the critical path: this rank's num_pos inside the tag word of every peer's slot
+      if (g.world > 1 && t < g.world)
+        st_release_sys(g.mailbox[t] + ((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords,
+                       (tag << 32) | (unsigned long long)(unsigned)sh_norm[0]);
+      if (t == 0) {
         wait_for(bar_item, g.item_ctas);
-        acc_add_int(acc, 1, (long long)npos);              // num_pos joins the totals
+        acc_add_int(acc, 1, (long long)(unsigned)sh_norm[0]);   // num_pos joins the totals
         __threadfence();
       }
       __syncthreads();
       dbg_stamp(g.dbg, 3);
-      finalize_from_acc(a, acc, sh_tot);
+      if (g.world > 1) {
+        // ---- the rest of the exchange: exact totals (counts included), then the second tag --------
+        if (t < CNH_TOTALS) sh_tot[t] = __ldcg(acc + t);
+        __syncthreads();
+        if (t < g.world * CNH_TOTALS) {                    // thread = (destination rank, word)
+          const int dst = t / CNH_TOTALS, w = t % CNH_TOTALS;
+          g.mailbox[dst][((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords + 1 + w] = (unsigned long long)sh_tot[w];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (t < g.world) st_release_sys(g.mailbox[t] + ((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords + 31, tag);
+        // wait for every source rank's totals in the LOCAL mailbox, then sum (exact integers)
+        if (t < g.world) {
+          const unsigned long long* slot = g.mailbox[g.rank] + ((size_t)mpar * CNH_MAX_PEERS + t) * kSlotWords;
+          while (ld_acquire_sys(slot + 31) != tag) { }
+        }
+        __syncthreads();
+        if (t < CNH_TOTALS) {
+          long long sum = 0;
+          for (int r = 0; r < g.world; ++r)
+            sum += (long long)__ldcv(g.mailbox[g.rank] + ((size_t)mpar * CNH_MAX_PEERS + r) * kSlotWords + 1 + t);
+          sh_tot[t] = sum;
+          if (a.totals != nullptr) a.totals[t] = sum;
+        }
+        __syncthreads();
+        if (t == 0) {
+          if (a.scalars != nullptr) scalars_from_totals(a, sh_tot, a.scalars);
+          g.hdr->epoch = (unsigned)tag;
+        }
+      } else {
+        finalize_from_acc(a, acc, sh_tot);
+      }
       if (threadIdx.x < CNH_TOTALS) g.hdr->acc[par ^ 1u][threadIdx.x] = 0ll;
       if (threadIdx.x == 0) {
         g.hdr->bar[par ^ 1u][0] = 0ull;
@@ -628,7 +757,7 @@ detloss_kernel(const cnh_detloss_args a, const Geo g) {
   if (MODE == M_PRECOUNT || MODE == M_COUNT) {
     // ---- phase 0: normalisers from the targets only ----------------------------------
     int npos = 0;
-    for (int chunk = bid; chunk < g.n_chunks; chunk += grid) npos += count_chunk<VEC>(a, g, chunk);
+    for (int chunk = bid; chunk < g.n_chunks; chunk += grid) npos += count_chunk<VEC, (MODE == M_PRECOUNT) && CNH_L2_HINTS>(a, g, chunk);
     npos = block_sum(npos, red_i);
     if (threadIdx.x == 0 && npos) acc_add_int(acc, 1, npos);
     for (int u = (grid - 1 - bid) * kWarps + warp; u < g.n_count; u += grid * kWarps) count_unit_warp(a, acc, u);
@@ -652,7 +781,7 @@ detloss_kernel(const cnh_detloss_args a, const Geo g) {
     int npos = 0;
     for (int u = bid; u < g.n_chunks; u += grid) {
       const int chunk = (MODE == M_PRECOUNT) ? g.n_chunks - 1 - u : u;
-      npos += focal_chunk<kGrad, kGrad, false, FAST, VEC>(a, g, acc, chunk, scale, unused, unused, red_f, red_i);
+      npos += focal_chunk<kGrad, kGrad, false, (MODE == M_PRECOUNT) && CNH_L2_HINTS, FAST, VEC>(a, g, acc, chunk, scale, unused, unused, red_f, red_i);
     }
     if (MODE != M_PRECOUNT && threadIdx.x == 0 && npos) acc_add_int(acc, 1, npos);   // PRECOUNT counted in phase 0
     const int n_other = g.n_items + (MODE == M_PRECOUNT ? 0 : g.n_count);
@@ -775,6 +904,9 @@ static Geo make_geo(const cnh_detloss_args* a, void* ws) {
   g.stash_slots = (a->M <= 32 * kSlotsPerLane) ? 1 : 0;
   g.chunk_ctas = 0;
   g.item_ctas = 0;
+  g.world = 1;
+  g.rank = 0;
+  for (int i = 0; i < CNH_MAX_PEERS; ++i) g.mailbox[i] = nullptr;
   g.hdr = static_cast<WsHeader*>(ws);
   g.dbg = debug_buffer();
   return g;
@@ -827,13 +959,19 @@ extern "C" size_t cnh_detloss_workspace_bytes(const cnh_detloss_args* a) {
   return ws_bytes(a);
 }
 
-extern "C" int cnh_detloss_fused(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
-                                 cnh_stream_t stream) {
+static int detloss_fused_impl(const cnh_detloss_args* a, const cnh_peers* peers, void* workspace,
+                              size_t workspace_bytes, cnh_stream_t stream) {
   if (int rc = validate(a, true)) return rc;
   CNH_REQUIRE(a->scalars != nullptr, CNH_E_NULL, "detloss_fused: scalars is NULL");
   CNH_REQUIRE(workspace != nullptr && workspace_bytes >= ws_bytes(a), CNH_E_WORKSPACE,
               "detloss_fused: workspace %zu < %zu bytes", workspace_bytes, ws_bytes(a));
   Geo g = make_geo(a, workspace);
+  if (peers != nullptr && peers->world > 1) {
+    g.world = peers->world;
+    g.rank = peers->rank;
+    for (int i = 0; i < peers->world; ++i) g.mailbox[i] = static_cast<unsigned long long*>(peers->mailbox[i]);
+    CNH_REQUIRE(a->grad_hm != nullptr, CNH_E_UNSUPPORTED, "detloss_fused_peers: forward-only runs need no exchange before the loss value; use cnh_detloss_fused + an all-reduce of totals");
+  }
   const bool fast = !(a->flags & CNH_FLAG_ACCURATE_MATH), vec = use_vec(a, g);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->grad_hm == nullptr) {
@@ -857,8 +995,25 @@ extern "C" int cnh_detloss_fused(const cnh_detloss_args* a, void* workspace, siz
       return launch(ks, true, (int)(chunk_ctas + item_ctas + 1), a, g, st);
     }
   }
+  CNH_REQUIRE(g.world == 1, CNH_E_UNSUPPORTED,
+              "detloss_fused_peers: problem too large for the register-stash schedule (%d chunks); use count/main", g.n_chunks);
   const void* kp = pick_kernel<M_PRECOUNT>(fast, vec);
   return launch(kp, true, units_to_grid(g.n_chunks, g.n_items + g.n_count, max_resident_ctas(kp)), a, g, st);
+}
+
+extern "C" int cnh_detloss_fused(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
+                                 cnh_stream_t stream) {
+  return detloss_fused_impl(a, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cnh_detloss_fused_peers(const cnh_detloss_args* a, const cnh_peers* peers, void* workspace,
+                                       size_t workspace_bytes, cnh_stream_t stream) {
+  CNH_REQUIRE(peers != nullptr, CNH_E_NULL, "detloss_fused_peers: peers is NULL");
+  CNH_REQUIRE(peers->world >= 1 && peers->world <= CNH_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+              CNH_E_SHAPE, "detloss_fused_peers: world=%d rank=%d", peers->world, peers->rank);
+  for (int i = 0; i < peers->world; ++i)
+    CNH_REQUIRE(peers->mailbox[i] != nullptr, CNH_E_NULL, "detloss_fused_peers: mailbox[%d] is NULL", i);
+  return detloss_fused_impl(a, peers, workspace, workspace_bytes, stream);
 }
 
 extern "C" int cnh_detloss_count(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,

@@ -115,6 +115,22 @@ const char* cnh_last_error(void);
 size_t cnh_detloss_workspace_bytes(const cnh_detloss_args* a);
 int cnh_detloss_fused(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
                       cnh_stream_t stream);
+/* Sharded, fused exchange (one process per GPU, peer-mapped mailboxes over NVLink/NVSwitch): the same
+ * single launch as cnh_detloss_fused; the finaliser CTA stores this rank's normalisers and exact
+ * totals into every peer's mailbox (st.release.sys), waits for the peers' (ld.acquire.sys), and
+ * releases the local CTAs with the GLOBAL normalisers -- no collective library call on the step path.
+ * Every rank must issue the call (it spins until all peers have arrived).  Requires the STASH
+ * schedule (small per-rank problems); returns CNH_E_UNSUPPORTED otherwise (use count/main below).
+ * mailbox[r]: device pointer, valid on THIS device, to rank r's mailbox (CNH_MAILBOX_BYTES, zeroed
+ * once, symmetric allocation); mailbox[rank] is the local one. */
+#define CNH_MAX_PEERS 8
+#define CNH_MAILBOX_BYTES 4096
+typedef struct cnh_peers {
+  int32_t world, rank;
+  void* mailbox[CNH_MAX_PEERS];
+} cnh_peers;
+int cnh_detloss_fused_peers(const cnh_detloss_args* a, const cnh_peers* peers, void* workspace,
+                            size_t workspace_bytes, cnh_stream_t stream);
 /* Sharded (one process per GPU) schedule: count -> all-reduce(norm_out) -> main ->
  * all-reduce(totals) -> finalize.  Gradients are final after cnh_detloss_main. */
 int cnh_detloss_count(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
