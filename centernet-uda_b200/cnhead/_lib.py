@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(DetLossArgs), vp, sz, st]
+        L.cnh_detloss_single_wave.restype = C.c_int
+        L.cnh_detloss_single_wave.argtypes = [C.POINTER(DetLossArgs)]
         L.cnh_detloss_fused_peers.restype = C.c_int
         L.cnh_detloss_fused_peers.argtypes = [C.POINTER(DetLossArgs), C.POINTER(Peers), vp, sz, st]
         L.cnh_detloss_finalize.restype = C.c_int

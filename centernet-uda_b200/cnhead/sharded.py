@@ -138,9 +138,10 @@ class _PeersDetectionLossFn(torch.autograd.Function):
 
 
 def peers_schedule_fits(hm: torch.Tensor) -> bool:
-    """the in-kernel exchange needs the register-stash schedule: <= ~400 chunks of 4096 heat-map elements"""
+    """the in-kernel exchange needs the single-wave schedule (every 4096-element chunk of the heat map has
+    its own shared-memory stage): 2 stages x 3 CTAs x 148 SMs on a B200; cnh_detloss_single_wave() is exact"""
     b, c, h, w = hm.shape
-    return b * ((c * h * w + 4095) // 4096) <= 400
+    return b * ((c * h * w + 4095) // 4096) <= 880
 
 
 # ---- CUDA path --------------------------------------------------------------------------------------

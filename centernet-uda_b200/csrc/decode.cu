@@ -33,8 +33,6 @@
 
 namespace cnh {
 
-typedef unsigned long long u64;
-
 constexpr int kCols = 128;                // max tile columns
 constexpr int kPadL = 4;                  // left halo padded to 4 floats: interior is 16B aligned
 constexpr int kBoxWMax = kCols + 2 * kPadL;
@@ -83,32 +81,6 @@ struct __align__(128) DecSmemT {            // followed in dynamic shared memory
   unsigned warp_tot[kWarps];
 };
 static_assert(sizeof(unsigned) * (kFineBins / 2) >= sizeof(u64) * kMaxK, "merge `sel` aliases the histogram");
-
-// ---- TMA / mbarrier PTX ----------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u64* bar, int x, int y, int z) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
-}
 
 // ---- block-wide helpers ---------------------------------------------------------------------
 // Exclusive SUFFIX sum over threads (sum of v of all threads with a higher tid) and the total.

@@ -3,23 +3,32 @@
 // persistent launch.  Replaces losses/centernet.py:7-95,98-133,192-223 and
 // utils/tensor.py:5-25 of the reference (chains of ~100 eager ATen kernels).
 //
-// HBM-bound streaming work: every heat-map element is read once (logit + target, float4,
-// ld.global.cs) and written once (clamped probability + gradient).  The gradient needs
-// the batch-wide num_pos, which is only known after everything has been read:
-//   * STASH    (small problems): the raw gradient of <= kStash chunks per CTA stays in
-//               registers across a grid barrier, then is scaled and stored: 16 B/element,
-//               the algorithmic floor.  The barrier's arrival atomic carries the CTA's
-//               num_pos, a dedicated CTA computes the scalars while the others store.
-//   * PRECOUNT (large problems): phase 0 counts num_pos over the target only (forward
-//               order), grid barrier, phase 1 does the full pass in REVERSE order so the
-//               tail of the target is still in the 126 MB L2: <= 20 B/element.
-//   * COUNT + MAIN: the same two phases as separate launches with the batch-wide
-//               normalisers supplied by the caller (the all-reduce of a sharded run sits
-//               between them).
+// HBM-bound streaming work: every heat-map element is read once (logit + target) and written
+// once (clamped probability + gradient).  A heat-map CHUNK (4096 contiguous elements) is moved
+// into shared memory by the TMA unit -- 1-D bulk copies (cp.async.bulk, SASS UBLKCP), four 4 KB
+// sub-blocks per operand, each with its own mbarrier so that arithmetic starts as soon as the first
+// sub-block lands -- and consumed by a small ROLLED loop (one float4 of logits and targets per
+// thread and iteration).  The loop body is ~200 instructions: the previous fully unrolled
+// register-staged version spent more issue slots stalled on instruction fetch than on memory
+// (ncu: stall_no_instruction 7.2 vs long_scoreboard 5.6 per issue at the batch-16 shape).
+//
+// The gradient needs the batch-wide num_pos, which is only known after everything has been read:
+//   * STASH    (single wave: every chunk has its own shared-memory stage): the raw gradient
+//               overwrites the logits in the stage, the probabilities are stored at once; the
+//               grid barrier's arrival atomic carries the CTA's num_pos; afterwards the gradient
+//               is scaled and stored: 16 B/element, the algorithmic floor.  While the bulk loads
+//               are in flight the same CTAs do the regression-head work (one item per warp) and
+//               zero-fill the dense regression gradient planes.
+//   * PRECOUNT (large problems): phase 0 counts num_pos over the target only and records which
+//               4 KB sub-blocks of the target hold anything but zeros (gaussian-splat targets are
+//               sparse); grid barrier; phase 1 streams the chunks through a TMA ring in REVERSE
+//               order (the tail of the target is still in L2) and does not re-read all-zero
+//               sub-blocks of the target: ~16 B/element for sparse targets, <= 20 B/element always.
+//   * COUNT + MAIN: the same two phases as separate launches with the batch-wide normalisers
+//               supplied by the caller (the all-reduce of a sharded run sits between them).
 //   * FWD: no gradients (validation under no_grad): 12 B/element.
-// Regression heads are warp-granular work items (zero-fill of a 16 KB piece of a dense
-// gradient plane + the object slots whose centre falls into it), dealt to the CTAs that
-// hold the fewest heat-map chunks.
+// Regression heads are warp-granular work items (a 16 KB piece of a dense gradient plane + the
+// object slots whose centre falls into it).
 //
 // Reductions are EXACT and order-independent: every chunk / item partial (a float produced
 // by a fixed-shape tree) is converted to 2^-40 fixed point and added with integer atomics
@@ -27,44 +36,52 @@
 // totals -- and the loss -- are bit-identical for any grid size, any schedule and any
 // sharding of the batch over GPUs (a sharded run all-reduces the 24 integers).
 #include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
 
-// L2 eviction-priority hints for the two-pass schedule (evict_last for the pre-counted target,
-// evict_first for everything streamed once) measured SLOWER on B200 (98 vs 88 us at the cfg5 shard):
-// off by default, kept for experiments.
-#ifndef CNH_L2_HINTS
-#define CNH_L2_HINTS 0
-#endif
-
 namespace cnh {
 
-constexpr int kVec = 4;                       // float4 per thread per chunk
-constexpr int kElemsPerThread = kVec * 4;
-constexpr int kChunk = kThreads * kElemsPerThread;   // 4096 heat-map elements
-constexpr int kStash = 1;                     // chunks a CTA may keep in registers (probability + raw gradient)
+constexpr int kChunk = 4096;                  // heat-map elements per chunk (one shared-memory stage)
+constexpr int kSubs = 4;                      // sub-blocks per chunk, one mbarrier each
+constexpr int kSub = kChunk / kSubs;          // 1024 elements = one float4 per thread
+static_assert(kSub == kThreads * 4, "one float4 per thread and sub-block");
+constexpr int kMaxStages = 7;                 // 7 x 32 KB = 224 KB of the 227 KB a CTA may own
+constexpr int kStreamStages = 3;              // ring depth of the streaming schedule (2 CTAs per SM)
 constexpr int kPiece = 4096;                  // floats of one regression plane per work item
-constexpr int kSlotsPerLane = 8;              // STASH keeps <= 8 object slots per lane (M <= 256)
+constexpr int kSlotsPerLane = 8;              // object slots per lane and round of the synchronous item path
+constexpr int kKeep = 5;                      // STASH keeps <= 5 object slots per lane in registers (M <= 160)
 constexpr int kQ = CNH_TOTALS / 2;            // quantities: focal, num_pos, 3 x (l1, angle, count), spare
+constexpr int kCountUnroll = 3;               // chunks whose target loads are in flight together (phase 0)
 
-enum Mode { M_STASH = 0, M_PRECOUNT = 1, M_MAIN = 2, M_COUNT = 3, M_FWD = 4 };
+enum Mode { M_PRECOUNT = 1, M_MAIN = 2, M_COUNT = 3, M_FWD = 4 };
 
-// Workspace header.  `parity` selects the live accumulator / barrier set.  Ticket modes leave their
-// set zeroed (the last CTA cleans up); STASH leaves it dirty, flips parity and cleans the OTHER set,
-// which the launch before it used -- so nothing has to be reset on the critical path.
+struct __align__(128) Stage {
+  float x[kChunk];                            // logits; STASH: overwritten by the raw gradient
+  float g[kChunk];                            // target
+};
+
+// Workspace: header, then one sparsity word per chunk.  `parity` selects the live accumulator /
+// barrier set.  Ticket modes leave their set zeroed (the last CTA cleans up); STASH leaves it dirty,
+// flips parity and cleans the OTHER set, which the launch before it used -- so nothing has to be
+// reset on the critical path.
 struct WsHeader {
   unsigned parity;
   unsigned done;
   unsigned epoch;                             // launches that used the peer exchange so far
-  unsigned pad;
-  unsigned long long bar[2][2];               // STASH barriers [parity][0 = chunk CTAs: arrivals << 32 | num_pos, 1 = item CTAs]
+  unsigned flags_chunks;                      // COUNT left valid sparsity words for this many chunks ...
+  unsigned long long flags_gt;                // ... of this target tensor
+  unsigned long long bar[2][1 + CNH_MAX_HEADS];  // single wave [parity]: [0] chunk CTAs: arrivals << 32 | num_pos;
+                                              // [1 + h] mask-count units of head h: arrivals << 40 | sum(mask_expanded)
   long long acc[2][CNH_TOTALS];               // [q] = hi word, [kQ + q] = lo word
 };
+constexpr size_t kHeaderBytes = (sizeof(WsHeader) + 255) / 256 * 256;
 
 // One mailbox slot per (parity, source rank), 32 words:
-//   [0]     (tag << 32) | num_pos of the source rank   -- sent first, all a chunk CTA needs
+//   [0]     (tag << 32) | num_pos of the source rank   -- sent first, all the heat-map gradient needs
 //   [1..24] the source rank's exact totals (counts included)
 //   [31]    tag, stored (release.sys) after the totals
 constexpr int kSlotWords = 32;
@@ -76,6 +93,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
 struct Geo {
   int HW;
@@ -85,13 +107,18 @@ struct Geo {
   int ppp;                 // pieces per regression plane
   int item0[CNH_MAX_HEADS + 1];   // first item of each head; head h owns B*D_h*ppp items
   int n_items;
+  int small_items;         // n_items < 2^22: item indices are decomposed with float reciprocals
+  float inv_ppp, inv_D[CNH_MAX_HEADS];
   int n_count;             // B * n_heads
   int vec_planes;          // regression planes can be zero-filled with float4 stores
-  int stash_slots;         // STASH may keep the slots of an item in registers (M <= 256)
-  int chunk_ctas, item_ctas;   // STASH roles
-  int world, rank;             // peer exchange (world == 1: none)
+  int stash_slots;         // STASH may keep the slots of an item in registers (M <= 32 * kKeep)
+  int n_stages;            // shared-memory stages per CTA (STASH: chunks per CTA; streaming: ring depth)
+  int chunk_ctas;          // STASH: worker CTAs (the grid has one more: the finaliser)
+  int x_delay_ns;          // STASH: pause between issuing the target and the logit copies
+  int world, rank;         // peer exchange (world == 1: none)
   unsigned long long* mailbox[CNH_MAX_PEERS];
   WsHeader* hdr;
+  unsigned* sparse;        // [n_chunks] bit v: sub-block v of the chunk's target is not all zero
   long long* dbg;
 };
 
@@ -100,6 +127,16 @@ __device__ __forceinline__ void acc_add_fixed(long long* acc, int q, float v) {
   const long long f = __double2ll_rn((double)v * 1099511627776.0);        // 2^40
   atomicAdd(reinterpret_cast<unsigned long long*>(acc + q), (unsigned long long)(f >> 32));
   atomicAdd(reinterpret_cast<unsigned long long*>(acc + kQ + q), (unsigned long long)(f & 0xffffffffll));
+}
+// Single-wave schedule: every contribution also bumps a counter packed into the upper bits of BOTH words
+// (the sums stay far below: |hi| < 2^40, lo < 2^48 for <= 65535 contributions), so a reader that sees the
+// expected count in a word knows that word is complete -- no fence, no second signal.
+constexpr int kCntHi = 44, kCntLo = 48;
+constexpr int kMaxCounted = 60000;
+__device__ __forceinline__ void acc_add_counted(long long* acc, int q, float v) {
+  const long long f = __double2ll_rn((double)v * 1099511627776.0);        // 2^40
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc + q), (unsigned long long)((f >> 32) + (1ll << kCntHi)));
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc + kQ + q), (unsigned long long)((f & 0xffffffffll) + (1ll << kCntLo)));
 }
 __device__ __forceinline__ void acc_add_int(long long* acc, int q, long long n) {
   atomicAdd(reinterpret_cast<unsigned long long*>(acc + kQ + q), (unsigned long long)n);
@@ -158,16 +195,101 @@ __device__ __forceinline__ void focal_elem_neg(float x, float gt, float& p, floa
   graw = (p == s) ? __fmul_rn(-w4, inner) : 0.0f;
 }
 
+// ---- packed fp32 pairs (Blackwell FMUL2 / FADD2 / FFMA2): two IEEE round-to-nearest operations per
+// instruction and lane -- bit-identical to the scalar _rn intrinsics, half the issue slots on the fma pipe
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+__device__ __forceinline__ long long clock_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+// barrier of the 8 compute warps (threads 0..255); the single-wave kernel has a ninth warp that must not join
+__device__ __forceinline__ void sync_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Two elements known to have gt < 1, same operation sequence as focal_elem_neg on packed pairs:
+// bit-identical results.  `term` and `graw` come back as pairs.
+template <bool FAST>
+__device__ __forceinline__ void focal_pair_neg(float x0, float x1, float g0, float g1, float& p0, float& p1,
+                                               u64& term, u64& graw) {
+  float s0, s1, L0, L1;
+  if (FAST) {
+    float t0, t1;
+    upk(mul2(pk(x0, x1), pk(-kLog2eF, -kLog2eF)), t0, t1);
+    float u0, u1;
+    upk(add2(pk(1.0f, 1.0f), pk(ex2_ftz(t0), ex2_ftz(t1))), u0, u1);
+    s0 = rcp_ftz(u0);
+    s1 = rcp_ftz(u1);
+  } else {
+    s0 = sigmoidf_<false>(x0);
+    s1 = sigmoidf_<false>(x1);
+  }
+  p0 = clamp_prob(s0);
+  p1 = clamp_prob(s1);
+  const u64 p = pk(p0, p1);
+  const u64 q = add2(pk(1.0f, 1.0f), pk(-p0, -p1));          // 1 - p   (x + (-y) == x - y, exactly)
+  float q0, q1;
+  upk(q, q0, q1);
+  L0 = log_unit<FAST>(q0);
+  L1 = log_unit<FAST>(q1);
+  const u64 L = pk(L0, L1);
+  const u64 omg = add2(pk(1.0f, 1.0f), pk(-g0, -g1));
+  u64 w4 = mul2(omg, omg);
+  w4 = mul2(w4, w4);
+  const u64 a2 = mul2(p, p);
+  term = mul2(mul2(L, a2), w4);
+  constexpr float k2 = FAST ? 2.0f * kLn2F : 2.0f;
+  const u64 m = mul2(mul2(pk(k2, k2), a2), q);
+  float m0, m1;
+  upk(m, m0, m1);
+  const u64 inner = fma2(pk(-m0, -m1), L, mul2(a2, p));
+  float w0, w1;
+  upk(w4, w0, w1);
+  const u64 gr = mul2(pk(-w0, -w1), inner);
+  float r0, r1;
+  upk(gr, r0, r1);
+  graw = pk((p0 == s0) ? r0 : 0.0f, (p1 == s1) ? r1 : 0.0f);
+}
+
+__device__ __forceinline__ int block_sum_compute(int v, int* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  sync_compute();
+  if (lane == 0) red[warp] = v;
+  sync_compute();
+  int t = red[0];
+#pragma unroll
+  for (int w = 1; w < kWarps; ++w) t += red[w];
+  return t;
+}
+
 __device__ __forceinline__ void block_reduce2(float& s, int& n, float* red_f, int* red_i) {
   s = warp_sum(s);
   n = warp_sum(n);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
+  sync_compute();
   if (lane == 0) {
     red_f[warp] = s;
     red_i[warp] = n;
   }
-  __syncthreads();
+  sync_compute();
   float ts = red_f[0];
   int tn = red_i[0];
 #pragma unroll
@@ -179,151 +301,229 @@ __device__ __forceinline__ void block_reduce2(float& s, int& n, float* red_f, in
   n = tn;
 }
 
-// One chunk of the heat map.  WRITE_GRAD: scale known, store the gradient now; otherwise (STASH)
-// the raw gradient is returned in `graw` and (KEEP_P) the probabilities in `pkeep`, unstored.  Adds the chunk's loss sum to acc; returns its num_pos.
-template <bool NEED_GRAD, bool WRITE_GRAD, bool KEEP_P, bool HINT, bool FAST, bool VEC>
-__device__ __forceinline__ int focal_chunk(const cnh_detloss_args& a, const Geo& g, long long* acc, int chunk,
-                                           float scale, float (&graw)[kElemsPerThread],
-                                           float (&pkeep)[kElemsPerThread], float* red_f, int* red_i) {
+// ---- one chunk: shared-memory stage -> probability, loss terms, gradient ---------------------------
+struct ChunkRef {
+  long long base;          // element offset of the chunk in the heat-map tensors
+  int n;                   // valid elements (the last chunk of a sample may be short)
+};
+__device__ __forceinline__ ChunkRef chunk_ref(const Geo& g, int chunk) {
   const int b = chunk / g.cps, j = chunk - b * g.cps;
   const long long in_sample = (long long)j * kChunk;
-  const long long base = (long long)b * g.CHW + in_sample;
   const long long left = g.CHW - in_sample;
-  const int n = left < kChunk ? (int)left : kChunk;
-  const float* __restrict__ xp = a.hm_logits + base;
-  const float* __restrict__ gp = a.hm_gt + base;
-  float* __restrict__ pp = a.prob + base;
+  ChunkRef r;
+  r.base = (long long)b * g.CHW + in_sample;
+  r.n = left < kChunk ? (int)left : kChunk;
+  return r;
+}
 
-  float xs[kElemsPerThread], gs[kElemsPerThread];
+// thread 0: start the bulk copies of one chunk into `st`.  Sub-block v completes bar[v]; a sub-block of
+// the target whose bit in `gmask` is clear is known to be all zero and is not fetched.
+__device__ __forceinline__ void issue_chunk(const cnh_detloss_args& a, const ChunkRef& r, Stage& st, u64* bar,
+                                            unsigned gmask) {
 #pragma unroll
-  for (int v = 0; v < kVec; ++v) {
-    const int off = v * kThreads * 4 + threadIdx.x * 4;
-    if (VEC) {
-      float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(2.f, 2.f, 2.f, 2.f);
-      if (off < n) {
-        if (HINT) {                           // two-pass schedule: everything here is used for the last time
-          x4 = ldg_hint(reinterpret_cast<const float4*>(xp + off), l2_policy_evict_first());
-          g4 = ldg_hint(reinterpret_cast<const float4*>(gp + off), l2_policy_evict_first());
-        } else {
-          x4 = ldg_stream(reinterpret_cast<const float4*>(xp + off));
-          g4 = ldg_stream(reinterpret_cast<const float4*>(gp + off));
-        }
-      }
-      xs[4 * v + 0] = x4.x; xs[4 * v + 1] = x4.y; xs[4 * v + 2] = x4.z; xs[4 * v + 3] = x4.w;
-      gs[4 * v + 0] = g4.x; gs[4 * v + 1] = g4.y; gs[4 * v + 2] = g4.z; gs[4 * v + 3] = g4.w;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool ok = off + e < n;
-        xs[4 * v + e] = ok ? __ldcs(xp + off + e) : 0.f;
-        gs[4 * v + e] = ok ? __ldcs(gp + off + e) : 2.f;   // gt = 2: neither pos nor neg
-      }
-    }
+  for (int v = 0; v < kSubs; ++v) {
+    const int left = r.n - v * kSub;
+    if (left <= 0) break;
+    const unsigned bytes = (unsigned)(left < kSub ? left : kSub) * 4u;
+    const bool has_g = (gmask >> v) & 1u;
+    mbar_expect_tx(bar + v, has_g ? 2u * bytes : bytes);
+    bulk_load_1d(st.x + v * kSub, a.hm_logits + r.base + v * kSub, bytes, bar + v);
+    if (has_g) bulk_load_1d(st.g + v * kSub, a.hm_gt + r.base + v * kSub, bytes, bar + v);
   }
+}
+
+// Shapes the TMA unit cannot move (C*H*W % 4 != 0 or a misaligned base pointer): every thread copies,
+// guarded; elements past the end of the chunk become (x = 0, gt = 2), i.e. neither positive nor negative.
+__device__ __forceinline__ void fill_stage_sync(const cnh_detloss_args& a, const ChunkRef& r, Stage& st) {
+  sync_compute();
+  const float* __restrict__ xp = a.hm_logits + r.base;
+  const float* __restrict__ gp = a.hm_gt + r.base;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < kChunk; i += kThreads) {
+    const bool ok = i < r.n;
+    st.x[i] = ok ? __ldcs(xp + i) : 0.f;
+    st.g[i] = ok ? __ldcs(gp + i) : 2.f;
+  }
+  sync_compute();
+}
+
+// Consume one staged chunk: the probability goes straight to HBM; the gradient too when its scale is
+// known (NEED_GRAD && !KEEP), or (KEEP, single wave) it replaces the logits in the stage, unscaled.  Adds the chunk's loss sum to acc (COUNTED: self-validating words of the single-wave
+// schedule); returns its num_pos (every thread).  Ends with a barrier of the compute warps after the last
+// read of the stage.
+template <bool NEED_GRAD, bool COUNTED, bool FAST, bool VEC, bool KEEP = false>
+__device__ __forceinline__ int process_chunk(const cnh_detloss_args& a, long long* acc, const ChunkRef& r, Stage& st,
+                                             u64* bar, unsigned parity, unsigned gmask, float scale,
+                                             float* red_f, int* red_i) {
+  float* __restrict__ pp = a.prob + r.base;
+  float* __restrict__ gq = NEED_GRAD ? a.grad_hm + r.base : nullptr;
   float sum = 0.f;
   int npos = 0;
-  // positives are rare (one pixel per object): a warp whose 512 targets are all < 1 takes the
-  // select-free path (same bits, ~30 % fewer instructions)
-  bool special = false;
-#pragma unroll
-  for (int i = 0; i < kElemsPerThread; ++i) special |= !(gs[i] < 1.0f);
-  const bool generic = __any_sync(0xffffffffu, special);
-#pragma unroll
-  for (int v = 0; v < kVec; ++v) {
-    const int off = v * kThreads * 4 + threadIdx.x * 4;
-    float ps[4], gr[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float term;
-      if (generic) focal_elem<FAST>(xs[4 * v + e], gs[4 * v + e], ps[e], term, gr[e], npos);
-      else focal_elem_neg<FAST>(xs[4 * v + e], gs[4 * v + e], ps[e], term, gr[e]);
-      sum = __fadd_rn(sum, term);
-      if (NEED_GRAD) graw[4 * v + e] = WRITE_GRAD ? __fmul_rn(gr[e], scale) : gr[e];
-      if (KEEP_P) pkeep[4 * v + e] = ps[e];
+#pragma unroll 1
+  for (int v = 0; v < kSubs; ++v) {
+    if (v * kSub >= r.n) break;
+    const int off = v * kSub + threadIdx.x * 4;
+    if (VEC) mbar_wait(bar + v, parity);
+    float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool live = !VEC || off < r.n;      // VEC: n % 4 == 0, a float4 is all in or all out
+    if (live) {
+      x4 = *reinterpret_cast<const float4*>(st.x + off);
+      if ((gmask >> v) & 1u) g4 = *reinterpret_cast<const float4*>(st.g + off);
+    } else {
+      g4 = make_float4(2.f, 2.f, 2.f, 2.f);
     }
-    if (KEEP_P) continue;                     // STASH: nothing is stored before the grid barrier
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, gs[4] = {g4.x, g4.y, g4.z, g4.w};
+    // positives are rare (one pixel per object): a warp whose targets are all < 1 takes the
+    // select-free path (same bits, ~30 % fewer instructions)
+    const bool special = !(gs[0] < 1.0f) || !(gs[1] < 1.0f) || !(gs[2] < 1.0f) || !(gs[3] < 1.0f);
+    float ps[4], gr[4];
+    if (__any_sync(0xffffffffu, special)) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float term;
+        focal_elem<FAST>(xs[e], gs[e], ps[e], term, gr[e], npos);
+        sum = __fadd_rn(sum, term);
+      }
+    } else {
+      u64 t01, t23, g01, g23;
+      focal_pair_neg<FAST>(xs[0], xs[1], gs[0], gs[1], ps[0], ps[1], t01, g01);
+      focal_pair_neg<FAST>(xs[2], xs[3], gs[2], gs[3], ps[2], ps[3], t23, g23);
+      float t0, t1, t2, t3;
+      upk(t01, t0, t1);
+      upk(t23, t2, t3);
+      sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, t0), t1), t2), t3);   // same order as the scalar path
+      upk(g01, gr[0], gr[1]);
+      upk(g23, gr[2], gr[3]);
+    }
     if (VEC) {
-      if (off < n) {
-        if (HINT) {
-          stg_hint(reinterpret_cast<float4*>(pp + off), make_float4(ps[0], ps[1], ps[2], ps[3]), l2_policy_evict_first());
-          if (WRITE_GRAD)
-            stg_hint(reinterpret_cast<float4*>(a.grad_hm + base + off),
-                     make_float4(graw[4 * v], graw[4 * v + 1], graw[4 * v + 2], graw[4 * v + 3]), l2_policy_evict_first());
-        } else {
-          *reinterpret_cast<float4*>(pp + off) = make_float4(ps[0], ps[1], ps[2], ps[3]);
-          if (WRITE_GRAD)
-            stg_stream(reinterpret_cast<float4*>(a.grad_hm + base + off),
-                       make_float4(graw[4 * v], graw[4 * v + 1], graw[4 * v + 2], graw[4 * v + 3]));
+      if (live) {
+        *reinterpret_cast<float4*>(pp + off) = make_float4(ps[0], ps[1], ps[2], ps[3]);   // decode reads it next: default policy
+        if (NEED_GRAD && !KEEP) {
+          const u64 sc = pk(scale, scale);
+          float o0, o1, o2, o3;
+          upk(mul2(pk(gr[0], gr[1]), sc), o0, o1);
+          upk(mul2(pk(gr[2], gr[3]), sc), o2, o3);
+          stg_stream(reinterpret_cast<float4*>(gq + off), make_float4(o0, o1, o2, o3));
         }
       }
     } else {
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (off + e < n) {
+        if (off + e < r.n) {
           pp[off + e] = ps[e];
-          if (WRITE_GRAD) a.grad_hm[base + off + e] = graw[4 * v + e];
+          if (NEED_GRAD && !KEEP) gq[off + e] = __fmul_rn(gr[e], scale);
         }
     }
+    if (NEED_GRAD && KEEP) *reinterpret_cast<float4*>(st.x + off) = make_float4(gr[0], gr[1], gr[2], gr[3]);
   }
   if (FAST) sum = __fmul_rn(sum, kLn2F);      // log2 -> natural log, once per thread
   block_reduce2(sum, npos, red_f, red_i);
-  if (threadIdx.x == 0) acc_add_fixed(acc, 0, sum);
+  if (threadIdx.x == 0) {
+    if (COUNTED) acc_add_counted(acc, 0, sum); else acc_add_fixed(acc, 0, sum);
+  }
   return npos;
 }
 
+// Single wave, after the grid barrier: raw gradient (left in the stage by process_chunk<KEEP>) * scale -> HBM.
 template <bool VEC>
-__device__ __forceinline__ void focal_store_stash(const cnh_detloss_args& a, const Geo& g, int chunk,
-                                                  float scale, const float (&graw)[kElemsPerThread],
-                                                  const float (&pkeep)[kElemsPerThread]) {
-  const int b = chunk / g.cps, j = chunk - b * g.cps;
-  const long long in_sample = (long long)j * kChunk;
-  const long long base = (long long)b * g.CHW + in_sample;
-  const long long left = g.CHW - in_sample;
-  const int n = left < kChunk ? (int)left : kChunk;
-#pragma unroll
-  for (int v = 0; v < kVec; ++v) {
-    const int off = v * kThreads * 4 + threadIdx.x * 4;
+__device__ __forceinline__ void store_stash(const cnh_detloss_args& a, const ChunkRef& r, const Stage& st, float scale) {
+  float* __restrict__ gq = a.grad_hm + r.base;
+  const u64 sc = pk(scale, scale);
+#pragma unroll 1
+  for (int v = 0; v < kSubs; ++v) {
+    if (v * kSub >= r.n) break;
+    const int off = v * kSub + threadIdx.x * 4;
+    const float4 q = *reinterpret_cast<const float4*>(st.x + off);
     if (VEC) {
-      if (off < n) {
-        *reinterpret_cast<float4*>(a.prob + base + off) =
-            make_float4(pkeep[4 * v], pkeep[4 * v + 1], pkeep[4 * v + 2], pkeep[4 * v + 3]);
-        stg_stream(reinterpret_cast<float4*>(a.grad_hm + base + off),
-                   make_float4(__fmul_rn(graw[4 * v], scale), __fmul_rn(graw[4 * v + 1], scale),
-                               __fmul_rn(graw[4 * v + 2], scale), __fmul_rn(graw[4 * v + 3], scale)));
+      if (off < r.n) {
+        float o0, o1, o2, o3;
+        upk(mul2(pk(q.x, q.y), sc), o0, o1);
+        upk(mul2(pk(q.z, q.w), sc), o2, o3);
+        stg_stream(reinterpret_cast<float4*>(gq + off), make_float4(o0, o1, o2, o3));
       }
     } else {
+      const float qs[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (off + e < n) {
-          a.prob[base + off + e] = pkeep[4 * v + e];
-          a.grad_hm[base + off + e] = __fmul_rn(graw[4 * v + e], scale);
-        }
+        if (off + e < r.n) gq[off + e] = __fmul_rn(qs[e], scale);
     }
   }
 }
 
-// num_pos of one chunk from the target only (phase 0 of PRECOUNT / COUNT), per thread.
-template <bool VEC, bool HINT>
-__device__ __forceinline__ int count_chunk(const cnh_detloss_args& a, const Geo& g, int chunk) {
-  const int b = chunk / g.cps, j = chunk - b * g.cps;
-  const long long in_sample = (long long)j * kChunk;
-  const long long left = g.CHW - in_sample;
-  const int n = left < kChunk ? (int)left : kChunk;
-  const float* __restrict__ gp = a.hm_gt + (long long)b * g.CHW + in_sample;
+// Single-wave schedule, first pass: num_pos of a staged chunk from its target alone, sub-block by
+// sub-block as they land (the logits are still in flight).  Per thread.
+template <bool VEC>
+__device__ __forceinline__ int count_stage(const ChunkRef& r, const Stage& st, u64* gbar) {
   int npos = 0;
+#pragma unroll 1
+  for (int v = 0; v < kSubs; ++v) {
+    if (v * kSub >= r.n) break;
+    const int off = v * kSub + threadIdx.x * 4;
+    if (VEC) mbar_wait(gbar + v, 0u);
+    if (!VEC || off < r.n) {
+      const float4 t = *reinterpret_cast<const float4*>(st.g + off);
+      npos += (t.x == 1.f) + (t.y == 1.f) + (t.z == 1.f) + (t.w == 1.f);
+    }
+  }
+  return npos;
+}
+
+// thread 0: bulk copies of one operand of a chunk, sub-block v completes bar[v]
+__device__ __forceinline__ void issue_operand(const float* src, float* dst, int n, u64* bar) {
 #pragma unroll
-  for (int v = 0; v < kVec; ++v) {
-    const int off = v * kThreads * 4 + threadIdx.x * 4;
-    if (VEC) {
-      if (off < n) {
-        const float4 g4 = HINT ? ldg_hint(reinterpret_cast<const float4*>(gp + off), l2_policy_evict_last())   // stay in L2 for phase 1
-                               : __ldg(reinterpret_cast<const float4*>(gp + off));
-        npos += (g4.x == 1.f) + (g4.y == 1.f) + (g4.z == 1.f) + (g4.w == 1.f);
+  for (int v = 0; v < kSubs; ++v) {
+    const int left = n - v * kSub;
+    if (left <= 0) break;
+    const unsigned bytes = (unsigned)(left < kSub ? left : kSub) * 4u;
+    mbar_expect_tx(bar + v, bytes);
+    bulk_load_1d(dst + v * kSub, src + v * kSub, bytes, bar + v);
+  }
+}
+
+// Phase 0 of PRECOUNT / COUNT: num_pos of up to kCountUnroll chunks from the target only (their loads
+// are in flight together), and the chunks' sparsity words.  Per thread.
+template <bool VEC>
+__device__ __forceinline__ int count_chunks(const cnh_detloss_args& a, const Geo& g, int first, int stride) {
+  int npos = 0;
+  if (VEC) {
+    float4 q[kCountUnroll][kSubs];
+    int n[kCountUnroll];
+#pragma unroll
+    for (int u = 0; u < kCountUnroll; ++u) {
+      const int chunk = first + u * stride;
+      n[u] = 0;
+      if (chunk < g.n_chunks) {
+        const ChunkRef r = chunk_ref(g, chunk);
+        n[u] = r.n;
+        const float* __restrict__ gp = a.hm_gt + r.base;
+#pragma unroll
+        for (int v = 0; v < kSubs; ++v) {
+          const int off = v * kSub + threadIdx.x * 4;
+          q[u][v] = (off < r.n) ? __ldg(reinterpret_cast<const float4*>(gp + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
-    } else {
+    }
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (off + e < n) npos += (__ldg(gp + off + e) == 1.f);
+    for (int u = 0; u < kCountUnroll; ++u) {
+      if (n[u] == 0) continue;
+      unsigned nz = 0;
+#pragma unroll
+      for (int v = 0; v < kSubs; ++v) {
+        const float4 t = q[u][v];
+        npos += (t.x == 1.f) + (t.y == 1.f) + (t.z == 1.f) + (t.w == 1.f);
+        // (NaN != 0 is true: a NaN target marks its sub-block as occupied, as it must)
+        nz |= (t.x != 0.f || t.y != 0.f || t.z != 0.f || t.w != 0.f) ? (1u << v) : 0u;
+      }
+      nz = __reduce_or_sync(0xffffffffu, nz);
+      if (nz != 0u && (threadIdx.x & 31) == 0) atomicOr(g.sparse + first + u * stride, nz);
+    }
+  } else {
+    for (int u = 0; u < kCountUnroll; ++u) {
+      const int chunk = first + u * stride;
+      if (chunk >= g.n_chunks) break;
+      const ChunkRef r = chunk_ref(g, chunk);
+      const float* __restrict__ gp = a.hm_gt + r.base;
+      for (int i = threadIdx.x; i < r.n; i += kThreads) npos += (__ldg(gp + i) == 1.f);
     }
   }
   return npos;
@@ -337,6 +537,8 @@ __device__ __forceinline__ const cnh_head& head_of(const cnh_detloss_args& a, in
 struct ItemRef {
   int h, b, d, p0, p1;
 };
+// x / d for 0 <= x < 2^22 with inv = 1.0f / d (exact: the rounding error of the product stays below 0.5 / d)
+__device__ __forceinline__ int fast_div(int x, float inv) { return (int)(((float)x + 0.5f) * inv); }
 __device__ __forceinline__ ItemRef decode_item(const cnh_detloss_args& a, const Geo& g, int item) {
   ItemRef r;
   r.h = 0;
@@ -344,11 +546,19 @@ __device__ __forceinline__ ItemRef decode_item(const cnh_detloss_args& a, const 
   for (int h = 1; h < CNH_MAX_HEADS; ++h)
     if (h < a.n_heads && item >= g.item0[h]) r.h = h;
   const int local = item - g.item0[r.h];
-  const int piece = local % g.ppp;
-  const int plane = local / g.ppp;
   const int D = head_of(a, r.h).D;
-  r.d = plane % D;
-  r.b = plane / D;
+  int plane, piece;
+  if (g.small_items) {
+    plane = fast_div(local, g.inv_ppp);
+    piece = local - plane * g.ppp;
+    r.b = fast_div(plane, r.h == 0 ? g.inv_D[0] : (r.h == 1 ? g.inv_D[1] : g.inv_D[2]));
+    r.d = plane - r.b * D;
+  } else {
+    piece = local % g.ppp;
+    plane = local / g.ppp;
+    r.d = plane % D;
+    r.b = plane / D;
+  }
   r.p0 = piece * kPiece;
   r.p1 = min(g.HW, r.p0 + kPiece);
   return r;
@@ -417,10 +627,9 @@ __device__ __forceinline__ void l1_slot_math(const cnh_head& hd, bool is_angle, 
 // kept in registers for a scatter after the grid barrier (KEEP).  Every lane owns slots lane,
 // lane+32, ...  Two dependent memory round trips: {index, mask, target} then {prediction}; the
 // zero-fill stores are issued between them so that they never delay a load.
-template <bool ZERO, bool FORWARD, bool SCATTER, bool KEEP, bool FAST>
+template <bool ZERO, bool FORWARD, bool SCATTER, bool COUNTED, bool FAST>
 __device__ __forceinline__ void l1_item_warp(const cnh_detloss_args& a, const Geo& g, long long* acc,
-                                             const ItemRef& r, float inv_denom, int (&keep_i)[kSlotsPerLane],
-                                             float (&keep_g)[kSlotsPerLane]) {
+                                             const ItemRef& r, float inv_denom) {
   const cnh_head& hd = head_of(a, r.h);
   const int lane = threadIdx.x & 31;
   const int D = hd.D;
@@ -466,24 +675,83 @@ __device__ __forceinline__ void l1_item_warp(const cnh_detloss_args& a, const Ge
         if (FORWARD) { if (is_angle) ang += val; else l1 += val; }
         if (SCATTER && gv != 0.f) atomicAdd(gplane + idx[u], gv * inv_denom);   // duplicate centres accumulate
       }
-      if (KEEP && k0 == 0) {
-        keep_i[u] = (idx[u] >= 0 && gv != 0.f) ? idx[u] : -1;
-        keep_g[u] = gv;
-      }
     }
   }
   if (FORWARD) {
     l1 = warp_sum(l1);
     ang = warp_sum(ang);
     if (lane == 0) {
-      if (l1 != 0.f) acc_add_fixed(acc, 2 + 3 * r.h, l1);
-      if (ang != 0.f) acc_add_fixed(acc, 3 + 3 * r.h, ang);
+      if (COUNTED) {                                         // exactly one contribution per item, zero or not
+        acc_add_counted(acc, (is_angle ? 3 : 2) + 3 * r.h, is_angle ? ang : l1);
+      } else {
+        if (l1 != 0.f) acc_add_fixed(acc, 2 + 3 * r.h, l1);
+        if (ang != 0.f) acc_add_fixed(acc, 3 + 3 * r.h, ang);
+      }
     }
   }
 }
 
+
+// ---- the same item in three steps, for the single-wave schedule: the loads are issued before the
+// heat-map bulk copies (anything issued after them queues behind 12 MB of traffic), their results wait
+// in registers while the chunk is processed, and the arithmetic runs in the shadow of the grid barrier.
+// step 1: centre index, mask and target of the lane's slots
+// (nothing here may USE a loaded value: the warp must get past this point without waiting)
+__device__ __forceinline__ void item_load_slots(const cnh_detloss_args& a, const ItemRef& r, long long (&i64)[kKeep],
+                                                uint8_t (&mraw)[kKeep], float (&tg)[kKeep]) {
+  const cnh_head& hd = head_of(a, r.h);
+  const int lane = threadIdx.x & 31, D = hd.D;
+#pragma unroll
+  for (int u = 0; u < kKeep; ++u) {
+    const int k = u * 32 + lane;
+    i64[u] = -1;
+    mraw[u] = 0;
+    tg[u] = 0.f;
+    if (k < a.M) {
+      const long long slot = (long long)r.b * a.M + k;
+      i64[u] = __ldg(a.ind + slot);
+      mraw[u] = hd.elementwise_mask ? __ldg(hd.mask + slot * D + r.d) : __ldg(hd.mask + slot);
+      tg[u] = __ldg(hd.target + slot * D + r.d);
+    }
+  }
+}
+// step 2: prediction at the centres that fall into the item's piece (others are dropped)
+__device__ __forceinline__ void item_load_pred(const cnh_detloss_args& a, const ItemRef& r, const long long (&i64)[kKeep],
+                                               int (&idx)[kKeep], float (&pr)[kKeep], int HW) {
+  const cnh_head& hd = head_of(a, r.h);
+  const float* __restrict__ plane = hd.map + ((long long)r.b * hd.D + r.d) * HW;
+#pragma unroll
+  for (int u = 0; u < kKeep; ++u) {
+    const bool in = (i64[u] >= (long long)r.p0 && i64[u] < (long long)r.p1);     // p1 <= H*W: out-of-range centres are ignored
+    idx[u] = in ? (int)i64[u] : -1;
+    pr[u] = 0.f;
+    if (in) pr[u] = __ldg(plane + idx[u]);
+  }
+}
+// step 3: forward terms -> acc; afterwards idx[u] >= 0 marks a slot with a gradient, pr[u] = its coefficient
+template <bool FAST>
+__device__ __forceinline__ void item_math(const cnh_detloss_args& a, long long* acc, const ItemRef& r, int (&idx)[kKeep],
+                                          const float (&mk)[kKeep], const float (&tg)[kKeep], float (&pr)[kKeep]) {
+  const cnh_head& hd = head_of(a, r.h);
+  const bool is_angle = (hd.D == 3 && r.d == 2 && hd.angle_mode != CNH_ANGLE_NONE);
+  float l1 = 0.f, ang = 0.f;
+#pragma unroll
+  for (int u = 0; u < kKeep; ++u) {
+    float val = 0.f, gv = 0.f;
+    if (idx[u] >= 0) {
+      l1_slot_math<FAST>(hd, is_angle, pr[u], tg[u], mk[u], val, gv);
+      if (is_angle) ang += val; else l1 += val;
+    }
+    if (gv == 0.f) idx[u] = -1;
+    pr[u] = gv;
+  }
+  l1 = warp_sum(l1);
+  ang = warp_sum(ang);
+  if ((threadIdx.x & 31) == 0) acc_add_counted(acc, (is_angle ? 3 : 2) + 3 * r.h, is_angle ? ang : l1);
+}
+
 // sum(mask_expanded) of one (head, sample): D * sum(mask[b,:]) or sum(mask[b,:,:]); one warp.
-__device__ __forceinline__ void count_unit_warp(const cnh_detloss_args& a, long long* acc, int unit) {
+__device__ __forceinline__ int count_unit_value(const cnh_detloss_args& a, int unit) {
   const int h = unit / a.B, b = unit - h * a.B;
   const cnh_head& hd = head_of(a, h);
   const int lane = threadIdx.x & 31;
@@ -493,7 +761,11 @@ __device__ __forceinline__ void count_unit_warp(const cnh_detloss_args& a, long 
   for (int k = lane; k < n; k += 32) c += __ldg(mp + k);
   c = warp_sum(c);
   if (!hd.elementwise_mask) c *= hd.D;
-  if (lane == 0 && c) acc_add_int(acc, 4 + 3 * h, c);
+  return c;
+}
+__device__ __forceinline__ void count_unit_warp(const cnh_detloss_args& a, long long* acc, int unit) {
+  const int c = count_unit_value(a, unit);
+  if ((threadIdx.x & 31) == 0 && c) acc_add_int(acc, 4 + 3 * (unit / a.B), c);
 }
 
 // ---- finalisation -------------------------------------------------------------------------
@@ -546,82 +818,188 @@ __device__ void finalize_from_acc(const cnh_detloss_args& a, const long long* ac
   if (threadIdx.x == 0 && a.scalars != nullptr) scalars_from_totals(a, sh_tot, a.scalars);
 }
 
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 
-template <int MODE, bool FAST, bool VEC>
-__global__ void __launch_bounds__(kThreads, (MODE == M_STASH || MODE == M_PRECOUNT) ? 3 : 4)
-detloss_kernel(const cnh_detloss_args a, const Geo g) {
+// ================================================================================================
+// Single wave ("STASH" in the flags): every heat-map chunk has its own shared-memory stage in ONE wave
+// of CTAs, so each input byte is read exactly once and nothing intermediate is written: 16 B/element.
+// 9 warps per CTA.
+//   warps 0-7 of a worker: thread 0 issues the bulk copies of the CTA's chunks, TARGETS FIRST; the warps
+//             count num_pos from the target sub-blocks as they land, while the logits are still in
+//             flight, and arrive on the grid barrier (the arrival atomic carries the count: no fence);
+//             as the logits land: probabilities to HBM, loss sums, raw gradient into the stage; zero-fill
+//             of this CTA's pieces of the dense regression gradient planes; by then the barrier has
+//             resolved: scaled gradient from shared memory to HBM.
+//   warp 8 of a worker: regression units (items, mask counts), one per round.  Its two dependent round
+//             trips (centre index -> prediction) run beside the chunk pipeline; warp 0 prefetches the
+//             first one's lines into L2 before the bulk copies are issued (requests are served roughly
+//             in order: anything issued behind 12 MB of bulk traffic returns after it).
+//   finaliser (last CTA): the scalars.  The accumulator words carry contribution counters, the mask
+//             counts ride in the per-head barrier words: it polls until every word is complete.
+// ================================================================================================
+constexpr int kStashThreads = kThreads + 32;
+constexpr int kStashBars = 2 * kSubs;            // per stage: target sub-blocks, then logit sub-blocks
+
+template <bool FAST, bool VEC>
+__global__ void __launch_bounds__(kStashThreads, 3)
+detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Stage* const stages = reinterpret_cast<Stage*>(smem_raw);
+  __shared__ u64 mbar[kMaxStages * kStashBars];
   __shared__ float red_f[kWarps];
   __shared__ int red_i[kWarps];
   __shared__ long long sh_tot[CNH_TOTALS];
-  __shared__ unsigned sh_ticket;
-  __shared__ unsigned sh_parity;
   __shared__ int sh_norm[1 + CNH_MAX_HEADS];
+  __shared__ unsigned sh_hdr[2];
   const int bid = blockIdx.x, grid = gridDim.x;
-  const int warp = threadIdx.x >> 5;
-  constexpr bool kGrad = (MODE == M_STASH || MODE == M_PRECOUNT || MODE == M_MAIN);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool worker = bid < grid - 1;
+  const int S = g.n_stages, W = g.chunk_ctas;
+  // regression units (items, then mask-count units) are dealt round-robin over the worker CTAs: every SM
+  // gets some, and the CTA that zero-fills a piece of a gradient plane is the one that scatters into it
+  const int n_other = g.n_items + g.n_count;
+  constexpr unsigned long long kCountMask = (1ull << 40) - 1ull;
 
   dbg_stamp(g.dbg, 0);
-  __shared__ unsigned sh_epoch;
-  if (threadIdx.x == 0) {
-    sh_parity = __ldcg(&g.hdr->parity) & 1u;
-    sh_epoch = __ldcg(&g.hdr->epoch);
+  // every thread that touches the accumulators reads the header itself (all lanes of warps 0 and 8 load
+  // the same two words: one request, no shuffle that would make the warp wait before it has issued the rest)
+  unsigned par = 0, epoch = 0;
+  if (warp == 0 || warp == kWarps) {
+    par = __ldcg(&g.hdr->parity) & 1u;
+    epoch = __ldcg(&g.hdr->epoch);
   }
-  __syncthreads();
-  const unsigned par = sh_parity;
-  const unsigned long long tag = (unsigned long long)sh_epoch + 1ull;   // peer exchange: this launch's tag
-  long long* acc = g.hdr->acc[par];
-  int keep_i[kSlotsPerLane];
-  float keep_g[kSlotsPerLane];
+  auto wait_for = [&](const unsigned long long* bar, int count) -> unsigned {
+    unsigned long long v;
+    do { v = ld_acquire_u64(bar); } while ((unsigned)(v >> 32) < (unsigned)count);
+    return (unsigned)(v & 0xffffffffull);
+  };
 
-  if (MODE == M_STASH) {
-    // Three roles, so that no CTA carries both the gradient stash and the slot registers:
-    //   [0, item_ctas)                      regression items, one per warp and round (launched first:
-    //                                       their two dependent round trips are the longest chain)
-    //   [item_ctas, item_ctas+chunk_ctas)   heat-map chunks (raw gradient kept in registers)
-    //   grid-1                              the scalars, while the others store
-    // Two barrier words: chunk CTAs only wait for each other (the arrival atomic carries num_pos),
-    // item CTAs only for each other (mask counts); the finaliser waits for both.
-    unsigned long long* bar_chunk = &g.hdr->bar[par][0];
-    unsigned long long* bar_item = &g.hdr->bar[par][1];
-    auto arrive = [&](unsigned long long* bar, int payload) {      // call from thread 0 after __syncthreads
-      __threadfence();                                             // cumulative: orders the CTA's adds
-      atomicAdd(bar, (1ull << 32) | (unsigned long long)(unsigned)payload);
-    };
-    auto wait_for = [&](unsigned long long* bar, int count) -> unsigned {
-      unsigned long long v;
-      do { v = ld_acquire_u64(bar); } while ((unsigned)(v >> 32) < (unsigned)count);
-      return (unsigned)(v & 0xffffffffull);
-    };
-    if (bid < g.item_ctas) {
-      const int n_other = g.n_items + g.n_count;
-      const int first = bid * kWarps + warp;
-      const int step = g.item_ctas * kWarps;
-      int my_item = -1;
-      for (int o = first; o < n_other; o += step) {
-        if (o < g.n_items) {
-          const ItemRef r = decode_item(a, g, o);
-          if (g.stash_slots && o == first) {
-            l1_item_warp<false, true, false, true, FAST>(a, g, acc, r, 0.f, keep_i, keep_g);
-            my_item = o;
-          } else {
-            l1_item_warp<false, true, false, false, FAST>(a, g, acc, r, 0.f, keep_i, keep_g);
-          }
-        } else {
-          count_unit_warp(a, acc, o - g.n_items);
-        }
+  if (worker && warp < kWarps) {
+    // ================= compute warps =================
+    if (warp == 0 && bid < g.n_items && g.stash_slots) {
+      // L2 prefetch of the lines the regression warp's first round trip will touch
+      const ItemRef r = decode_item(a, g, bid);
+      const cnh_head& hd = head_of(a, r.h);
+      const int mask_row = a.M * (hd.elementwise_mask ? hd.D : 1);
+      const char* p0 = reinterpret_cast<const char*>(a.ind + (long long)r.b * a.M);
+      const char* p1 = reinterpret_cast<const char*>(hd.target + (long long)r.b * a.M * hd.D);
+      const char* p2 = reinterpret_cast<const char*>(hd.mask + (long long)r.b * mask_row);
+      for (int off = lane * 128; off < a.M * 8; off += 4096) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + off));
+      for (int off = lane * 128; off < a.M * hd.D * 4; off += 4096) asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + off));
+      for (int off = lane * 128; off < mask_row; off += 4096) asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + off));
+    }
+    if (tid == 0 && VEC) {
+      for (int i = 0; i < S * kStashBars; ++i) mbar_init(&mbar[i], 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      for (int r = 0; r < S; ++r) {                          // targets of every stage first ...
+        const int chunk = bid + r * W;
+        if (chunk >= g.n_chunks) break;
+        const ChunkRef cr = chunk_ref(g, chunk);
+        issue_operand(a.hm_gt + cr.base, stages[r].g, cr.n, &mbar[r * kStashBars]);
       }
-      dbg_stamp(g.dbg, 2);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        arrive(bar_item, 0);
-        wait_for(bar_item, g.item_ctas);                   // mask counts are complete
-        wait_for(bar_chunk, g.chunk_ctas);                 // the gradient planes are zero-filled
-        if (g.world > 1) {                                 // sharded: mask counts of every rank from the mailbox
+      if (g.x_delay_ns > 0) __nanosleep(g.x_delay_ns);
+      for (int r = 0; r < S; ++r) {                          // ... then the logits
+        const int chunk = bid + r * W;
+        if (chunk >= g.n_chunks) break;
+        const ChunkRef cr = chunk_ref(g, chunk);
+        issue_operand(a.hm_logits + cr.base, stages[r].x, cr.n, &mbar[r * kStashBars + kSubs]);
+      }
+    }
+    sync_compute();                                          // mbarriers initialised
+    // ---- pass 1: num_pos from the targets -----------------------------------------------------------
+    int npos = 0;
+#pragma unroll 1
+    for (int r = 0; r < S; ++r) {
+      const int chunk = bid + r * W;
+      if (chunk >= g.n_chunks) break;
+      const ChunkRef cr = chunk_ref(g, chunk);
+      if (!VEC) fill_stage_sync(a, cr, stages[r]);
+      npos += count_stage<VEC>(cr, stages[r], &mbar[r * kStashBars]);
+    }
+    npos = block_sum_compute(npos, red_i);
+    dbg_stamp(g.dbg, 1);
+    unsigned long long* bar_chunk = &g.hdr->bar[par][0];
+    // the arrival carries the count: nothing else has to be ordered before it (no fence)
+    if (tid == 0) atomicAdd(bar_chunk, (1ull << 32) | (unsigned long long)(unsigned)npos);
+    // ---- pass 2a, before the barrier resolves: probabilities to HBM, loss sums, raw gradient into the
+    // stage (the logits arrive while the other CTAs are still counting)
+    long long* acc = g.hdr->acc[par];                        // (thread 0 only: the others never touch it)
+#pragma unroll 1
+    for (int r = 0; r < S; ++r) {
+      const int chunk = bid + r * W;
+      if (chunk >= g.n_chunks) break;
+      process_chunk<true, true, FAST, VEC, true>(a, acc, chunk_ref(g, chunk), stages[r], &mbar[r * kStashBars + kSubs], 0u, 0xfu,
+                                                 0.f, red_f, red_i);
+    }
+    dbg_stamp(g.dbg, 4);
+    // zero-fill of this CTA's pieces of the regression gradient planes; warp 8 scatters after it
+    for (int o = bid; o < g.n_items; o += W) l1_zero_fill_block(a, g, decode_item(a, g, o));
+    asm volatile("bar.arrive 2, %0;" ::"n"(kStashThreads) : "memory");
+    if (tid == 0) {
+      if (g.world > 1) {                                     // sharded: num_pos of every rank, straight from the mailbox
+        const unsigned long long tag = (unsigned long long)epoch + 1ull;
+        const unsigned long long* box = g.mailbox[g.rank] + (size_t)(tag & 1ull) * CNH_MAX_PEERS * kSlotWords;
+        unsigned total = 0;
+        for (int r = 0; r < g.world; ++r) {
+          unsigned long long v;
+          do { v = ld_acquire_sys(box + (size_t)r * kSlotWords); } while ((v >> 32) != tag);
+          total += (unsigned)(v & 0xffffffffull);
+        }
+        sh_norm[0] = (int)total;
+      } else {
+        sh_norm[0] = (int)wait_for(bar_chunk, W);
+      }
+    }
+    sync_compute();
+    dbg_stamp(g.dbg, 3);
+    // ---- pass 2b: the gradient, scaled, from shared memory ------------------------------------------------
+    const int npos_all = sh_norm[0];
+    const float scale = (npos_all == 0) ? -a.hm_weight : -a.hm_weight / (float)npos_all;
+#pragma unroll 1
+    for (int r = 0; r < S; ++r) {
+      const int chunk = bid + r * W;
+      if (chunk >= g.n_chunks) break;
+      store_stash<VEC>(a, chunk_ref(g, chunk), stages[r], scale);
+    }
+    dbg_stamp(g.dbg, 5);
+  } else if (worker) {
+    // ================= regression warp =================
+    const bool dbg8 = g.dbg != nullptr && lane == 0;
+    const int first = bid, step = W;
+    const bool kept = g.stash_slots && first < g.n_items;    // the first item lives in registers
+    ItemRef kr;
+    int idx[kKeep];
+    long long i64[kKeep];
+    uint8_t mraw[kKeep];
+    float mk[kKeep], tg[kKeep], pr[kKeep];
+    if (kept) {
+      kr = decode_item(a, g, first);
+      item_load_slots(a, kr, i64, mraw, tg);
+    }
+    long long* acc = g.hdr->acc[par];
+    unsigned long long* bar_cnt = &g.hdr->bar[par][1];
+    if (kept) {
+      item_load_pred(a, kr, i64, idx, pr, g.HW);
+#pragma unroll
+      for (int u = 0; u < kKeep; ++u) mk[u] = (float)mraw[u];
+      if (dbg8) g.dbg[(long long)bid * 16 + 8] = clock_ns();
+      item_math<FAST>(a, acc, kr, idx, mk, tg, pr);
+    }
+    for (int o = kept ? first + step : first; o < n_other; o += step) {
+      if (o < g.n_items) {
+        l1_item_warp<false, true, false, true, FAST>(a, g, acc, decode_item(a, g, o), 0.f);
+      } else {                                               // mask count of one (head, sample): rides in the barrier word
+        const int unit = o - g.n_items, h = unit / a.B;
+        const int c = count_unit_value(a, unit);
+        if (lane == 0) atomicAdd(bar_cnt + h, (1ull << 40) | (unsigned long long)(unsigned)c);
+      }
+    }
+    if (dbg8) g.dbg[(long long)bid * 16 + 2] = clock_ns();
+    // ---- regression gradients: need the batch-wide mask counts and this CTA's zero-fill -----------------
+    asm volatile("bar.sync 2, %0;" ::"n"(kStashThreads) : "memory");
+    if (first < g.n_items) {
+      if (lane == 0) {
+        if (g.world > 1) {                                   // the mask counts of every rank arrive with the totals
+          const unsigned long long tag = (unsigned long long)epoch + 1ull;
           const unsigned long long* box = g.mailbox[g.rank] + (size_t)(tag & 1ull) * CNH_MAX_PEERS * kSlotWords;
           long long cnt[CNH_MAX_HEADS] = {0, 0, 0};
           for (int r = 0; r < g.world; ++r) {
@@ -633,134 +1011,158 @@ detloss_kernel(const cnh_detloss_args a, const Geo g) {
 #pragma unroll
           for (int h = 0; h < CNH_MAX_HEADS; ++h) sh_norm[1 + h] = (int)cnt[h];
         } else {
-#pragma unroll
-          for (int h = 0; h < CNH_MAX_HEADS; ++h) sh_norm[1 + h] = (int)__ldcg(acc + kQ + 4 + 3 * h);
-        }
-      }
-      __syncthreads();
-      dbg_stamp(g.dbg, 3);
-      for (int o = first; o < g.n_items; o += step) {
-        const ItemRef r = decode_item(a, g, o);
-        const float inv = 1.f / ((float)sh_norm[1 + r.h] + 1e-4f);
-        if (o == my_item) {                                // slots kept in registers: no reload
-          const cnh_head& hd = head_of(a, r.h);
-          float* __restrict__ gplane = hd.grad + ((long long)r.b * hd.D + r.d) * g.HW;
-#pragma unroll
-          for (int u = 0; u < kSlotsPerLane; ++u)
-            if (keep_i[u] >= 0) atomicAdd(gplane + keep_i[u], keep_g[u] * inv);
-        } else {
-          l1_item_warp<false, false, true, false, FAST>(a, g, acc, r, inv, keep_i, keep_g);
-        }
-      }
-      dbg_stamp(g.dbg, 6);
-    } else if (bid < grid - 1) {
-      const int cb = bid - g.item_ctas;
-      float stash[kStash][kElemsPerThread], pstash[kStash][kElemsPerThread];
-      int cta_npos = 0;
-      // the dense regression-gradient planes are zero-filled here, spread over every SM; the item
-      // CTAs scatter into them only after this barrier
-      for (int o = cb; o < g.n_items; o += g.chunk_ctas) l1_zero_fill_block(a, g, decode_item(a, g, o));
-#pragma unroll
-      for (int r = 0; r < kStash; ++r) {
-        const int chunk = cb + r * g.chunk_ctas;
-        if (chunk < g.n_chunks)
-          cta_npos += focal_chunk<true, false, true, false, FAST, VEC>(a, g, acc, chunk, 0.f, stash[r], pstash[r], red_f, red_i);
-      }
-      dbg_stamp(g.dbg, 1);
-      if (threadIdx.x == 0) {                              // focal_chunk ends with a block barrier
-        arrive(bar_chunk, cta_npos);
-        if (g.world > 1) {                                 // sharded: num_pos of every rank, straight from the mailbox
-          const unsigned long long* box = g.mailbox[g.rank] + (size_t)(tag & 1ull) * CNH_MAX_PEERS * kSlotWords;
-          unsigned total = 0;
-          for (int r = 0; r < g.world; ++r) {
+          const bool all_heads = first + step < g.n_items || !kept;
+          for (int h = 0; h < a.n_heads; ++h) {
+            if (!all_heads && h != kr.h) continue;
             unsigned long long v;
-            do { v = ld_acquire_sys(box + (size_t)r * kSlotWords); } while ((v >> 32) != tag);
-            total += (unsigned)(v & 0xffffffffull);
+            do { v = ld_acquire_u64(bar_cnt + h); } while ((int)(v >> 40) < a.B);
+            sh_norm[1 + h] = (int)(v & kCountMask);
           }
-          sh_norm[0] = (int)total;
-        } else {
-          sh_norm[0] = (int)wait_for(bar_chunk, g.chunk_ctas);
         }
       }
-      __syncthreads();
-      dbg_stamp(g.dbg, 3);
-      const int npos = sh_norm[0];
-      const float scale = (npos == 0) ? -a.hm_weight : -a.hm_weight / (float)npos;
+      __syncwarp();
+    }
+    if (dbg8) g.dbg[(long long)bid * 16 + 9] = clock_ns();
+    for (int o = first; o < g.n_items; o += step) {
+      const ItemRef r = (kept && o == first) ? kr : decode_item(a, g, o);
+      const float inv = 1.f / ((float)sh_norm[1 + r.h] + 1e-4f);
+      if (kept && o == first) {                              // slots kept in registers: no reload
+        const cnh_head& hd = head_of(a, r.h);
+        float* __restrict__ gplane = hd.grad + ((long long)r.b * hd.D + r.d) * g.HW;
 #pragma unroll
-      for (int r = 0; r < kStash; ++r) {
-        const int chunk = cb + r * g.chunk_ctas;
-        if (chunk < g.n_chunks) focal_store_stash<VEC>(a, g, chunk, scale, stash[r], pstash[r]);
-      }
-      dbg_stamp(g.dbg, 5);
-    } else {
-      // the scalars, while the workers store their gradients; then retire the OTHER accumulator set
-      const int t = threadIdx.x;
-      const unsigned mpar = (unsigned)(tag & 1ull);       // mailbox parity follows the exchange count, not `par`
-      if (t == 0) sh_norm[0] = (int)wait_for(bar_chunk, g.chunk_ctas);
-      __syncthreads();
-      // first, and alone on the critical path: this rank's num_pos inside the tag word of every peer's slot
-      if (g.world > 1 && t < g.world)
-        st_release_sys(g.mailbox[t] + ((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords,
-                       (tag << 32) | (unsigned long long)(unsigned)sh_norm[0]);
-      if (t == 0) {
-        wait_for(bar_item, g.item_ctas);
-        acc_add_int(acc, 1, (long long)(unsigned)sh_norm[0]);   // num_pos joins the totals
-        __threadfence();
-      }
-      __syncthreads();
-      dbg_stamp(g.dbg, 3);
-      if (g.world > 1) {
-        // ---- the rest of the exchange: exact totals (counts included), then the second tag --------
-        if (t < CNH_TOTALS) sh_tot[t] = __ldcg(acc + t);
-        __syncthreads();
-        if (t < g.world * CNH_TOTALS) {                    // thread = (destination rank, word)
-          const int dst = t / CNH_TOTALS, w = t % CNH_TOTALS;
-          g.mailbox[dst][((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords + 1 + w] = (unsigned long long)sh_tot[w];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (t < g.world) st_release_sys(g.mailbox[t] + ((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords + 31, tag);
-        // wait for every source rank's totals in the LOCAL mailbox, then sum (exact integers)
-        if (t < g.world) {
-          const unsigned long long* slot = g.mailbox[g.rank] + ((size_t)mpar * CNH_MAX_PEERS + t) * kSlotWords;
-          while (ld_acquire_sys(slot + 31) != tag) { }
-        }
-        __syncthreads();
-        if (t < CNH_TOTALS) {
-          long long sum = 0;
-          for (int r = 0; r < g.world; ++r)
-            sum += (long long)__ldcv(g.mailbox[g.rank] + ((size_t)mpar * CNH_MAX_PEERS + r) * kSlotWords + 1 + t);
-          sh_tot[t] = sum;
-          if (a.totals != nullptr) a.totals[t] = sum;
-        }
-        __syncthreads();
-        if (t == 0) {
-          if (a.scalars != nullptr) scalars_from_totals(a, sh_tot, a.scalars);
-          g.hdr->epoch = (unsigned)tag;
-        }
+        for (int u = 0; u < kKeep; ++u)
+          if (idx[u] >= 0) atomicAdd(gplane + idx[u], pr[u] * inv);
       } else {
-        finalize_from_acc(a, acc, sh_tot);
-      }
-      if (threadIdx.x < CNH_TOTALS) g.hdr->acc[par ^ 1u][threadIdx.x] = 0ll;
-      if (threadIdx.x == 0) {
-        g.hdr->bar[par ^ 1u][0] = 0ull;
-        g.hdr->bar[par ^ 1u][1] = 0ull;
-        g.hdr->parity = par ^ 1u;
+        l1_item_warp<false, false, true, false, FAST>(a, g, acc, r, inv);
       }
     }
-    dbg_stamp(g.dbg, 7);
-    return;
+    if (dbg8) g.dbg[(long long)bid * 16 + 6] = clock_ns();
+  } else {
+    // ================= finaliser: the scalars =================
+    if (tid == 0) { sh_hdr[0] = par; sh_hdr[1] = epoch; }
+    if (tid < CNH_TOTALS) sh_tot[tid] = 0ll;
+    __syncthreads();
+    par = sh_hdr[0];
+    epoch = sh_hdr[1];
+    const unsigned long long tag = (unsigned long long)epoch + 1ull;     // peer exchange: this launch's tag
+    const unsigned mpar = (unsigned)(tag & 1ull);                        // mailbox parity follows the exchange count
+    long long* acc = g.hdr->acc[par];
+    // retire the OTHER accumulator set (the launch before this one used it) while waiting
+    if (tid < CNH_TOTALS) g.hdr->acc[par ^ 1u][tid] = 0ll;
+    if (tid < 1 + CNH_MAX_HEADS) g.hdr->bar[par ^ 1u][tid] = 0ull;
+    if (tid == 0) sh_norm[0] = (int)wait_for(&g.hdr->bar[par][0], W);
+    __syncthreads();
+    // first, and alone on the critical path: this rank's num_pos inside the tag word of every peer's slot
+    if (g.world > 1 && tid < g.world)
+      st_release_sys(g.mailbox[tid] + ((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords,
+                     (tag << 32) | (unsigned long long)(unsigned)sh_norm[0]);
+    // every sum word validates itself: poll until it holds the expected number of contributions
+    if (tid < 14) {
+      const int qi = tid % 7, lo = tid / 7;                  // 7 sums (focal, then l1 / angle per head) x (hi, lo)
+      const int h = (qi - 1) >> 1, is_ang = (qi - 1) & 1;
+      const int q = qi == 0 ? 0 : 2 + 3 * h + is_ang;
+      long long expect = g.n_chunks;
+      if (qi > 0) {
+        expect = 0;
+        if (h < a.n_heads) {
+          const cnh_head& hd = head_of(a, h);
+          const int ang_ch = (hd.D == 3 && hd.angle_mode != CNH_ANGLE_NONE) ? 1 : 0;
+          expect = (long long)a.B * g.ppp * (is_ang ? ang_ch : hd.D - ang_ch);
+        }
+      }
+      long long clean = 0;
+      if (expect > 0) {
+        const unsigned long long* word = reinterpret_cast<const unsigned long long*>(acc + (lo ? kQ : 0) + q);
+        long long v;
+        if (lo) { do { v = (long long)ld_acquire_u64(word); } while ((v >> kCntLo) != expect); }
+        else { do { v = (long long)ld_acquire_u64(word); } while (((v + (1ll << (kCntHi - 1))) >> kCntHi) != expect); }
+        clean = v - (expect << (lo ? kCntLo : kCntHi));
+      }
+      sh_tot[(lo ? kQ : 0) + q] = clean;
+    } else if (tid < 14 + CNH_MAX_HEADS) {                   // mask counts: all B units of the head have arrived
+      const int h = tid - 14;
+      if (h < a.n_heads) {
+        unsigned long long v;
+        do { v = ld_acquire_u64(&g.hdr->bar[par][1 + h]); } while ((int)(v >> 40) < a.B);
+        sh_tot[kQ + 4 + 3 * h] = (long long)(v & kCountMask);
+      }
+    } else if (tid == 14 + CNH_MAX_HEADS) {
+      sh_tot[kQ + 1] = (long long)(unsigned)sh_norm[0];      // num_pos
+    }
+    __syncthreads();
+    dbg_stamp(g.dbg, 3);
+    if (g.world > 1) {
+      // ---- the rest of the exchange: exact totals (counts included), then the second tag --------
+      if (tid < g.world * CNH_TOTALS) {                      // thread = (destination rank, word)
+        const int dst = tid / CNH_TOTALS, w = tid % CNH_TOTALS;
+        g.mailbox[dst][((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords + 1 + w] = (unsigned long long)sh_tot[w];
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid < g.world) st_release_sys(g.mailbox[tid] + ((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords + 31, tag);
+      // wait for every source rank's totals in the LOCAL mailbox, then sum (exact integers)
+      if (tid < g.world) {
+        const unsigned long long* slot = g.mailbox[g.rank] + ((size_t)mpar * CNH_MAX_PEERS + tid) * kSlotWords;
+        while (ld_acquire_sys(slot + 31) != tag) { }
+      }
+      __syncthreads();
+      if (tid < CNH_TOTALS) {
+        long long sum = 0;
+        for (int r = 0; r < g.world; ++r)
+          sum += (long long)__ldcv(g.mailbox[g.rank] + ((size_t)mpar * CNH_MAX_PEERS + r) * kSlotWords + 1 + tid);
+        sh_tot[tid] = sum;
+      }
+      __syncthreads();
+      if (tid == 0) g.hdr->epoch = (unsigned)tag;
+    }
+    if (tid < CNH_TOTALS && a.totals != nullptr) a.totals[tid] = sh_tot[tid];
+    if (tid == 0 && a.scalars != nullptr) scalars_from_totals(a, sh_tot, a.scalars);
+    if (tid == 0) g.hdr->parity = par ^ 1u;                  // flip: the next launch uses the set cleaned above
   }
+  dbg_stamp(g.dbg, 7);
+}
+
+// ================================================================================================
+// Streaming schedules (PRECOUNT / MAIN / COUNT / FWD): persistent CTAs, chunks through a TMA ring.
+// ================================================================================================
+template <int MODE, bool FAST, bool VEC>
+__global__ void __launch_bounds__(kThreads, 2)
+detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Stage* const stages = reinterpret_cast<Stage*>(smem_raw);
+  __shared__ u64 mbar[kMaxStages * kSubs];
+  __shared__ float red_f[kWarps];
+  __shared__ int red_i[kWarps];
+  __shared__ long long sh_tot[CNH_TOTALS];
+  __shared__ unsigned sh_ticket;
+  __shared__ unsigned sh_mask[kMaxStages];
+  const int bid = blockIdx.x, grid = gridDim.x;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr bool kGrad = (MODE == M_PRECOUNT || MODE == M_MAIN);
+  const int S = g.n_stages;
+  long long* acc = g.hdr->acc[0];               // ticket modes leave the set zeroed: parity stays what it is
+
+  dbg_stamp(g.dbg, 0);
+  if (MODE != M_COUNT && VEC && tid == 0) {
+    for (int i = 0; i < S * kSubs; ++i) mbar_init(&mbar[i], 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  // accumulator set of the live parity
+  __shared__ unsigned sh_parity;
+  if (tid == 0) sh_parity = __ldcg(&g.hdr->parity) & 1u;
+  __syncthreads();
+  acc = g.hdr->acc[sh_parity];
 
   float scale = 0.f;
   float inv_denom[CNH_MAX_HEADS] = {0.f, 0.f, 0.f};
   if (MODE == M_PRECOUNT || MODE == M_COUNT) {
-    // ---- phase 0: normalisers from the targets only ----------------------------------
+    // ---- phase 0: normalisers and sparsity words from the targets only --------------------------
     int npos = 0;
-    for (int chunk = bid; chunk < g.n_chunks; chunk += grid) npos += count_chunk<VEC, (MODE == M_PRECOUNT) && CNH_L2_HINTS>(a, g, chunk);
+    for (int c = bid; c < g.n_chunks; c += kCountUnroll * grid) npos += count_chunks<VEC>(a, g, c, grid);
     npos = block_sum(npos, red_i);
-    if (threadIdx.x == 0 && npos) acc_add_int(acc, 1, npos);
+    if (tid == 0 && npos) acc_add_int(acc, 1, npos);
     for (int u = (grid - 1 - bid) * kWarps + warp; u < g.n_count; u += grid * kWarps) count_unit_warp(a, acc, u);
+    dbg_stamp(g.dbg, 1);
   }
   if (MODE == M_PRECOUNT) {
     cg::this_grid().sync();
@@ -768,6 +1170,7 @@ detloss_kernel(const cnh_detloss_args a, const Geo g) {
     scale = (npos == 0) ? -a.hm_weight : -a.hm_weight / (float)npos;
 #pragma unroll
     for (int h = 0; h < CNH_MAX_HEADS; ++h) inv_denom[h] = 1.f / ((float)__ldcg(acc + kQ + 4 + 3 * h) + 1e-4f);
+    dbg_stamp(g.dbg, 2);
   }
   if (MODE == M_MAIN) {
     const float npos = (float)a.norm[0];
@@ -776,23 +1179,54 @@ detloss_kernel(const cnh_detloss_args a, const Geo g) {
     for (int h = 0; h < CNH_MAX_HEADS; ++h) inv_denom[h] = 1.f / ((float)a.norm[1 + h] + 1e-4f);
   }
   if (MODE != M_COUNT) {
-    // ---- the streaming pass (reverse chunk order after a pre-count: L2 reuse) ---------
-    float unused[kElemsPerThread];
+    // ---- the streaming pass (reverse chunk order after a pre-count: L2 reuse) ---------------------
+    // sparsity words: PRECOUNT wrote them in phase 0; MAIN may use the ones a preceding COUNT left
+    // for this very target; FWD has none.  Whoever reads a word clears it (self-cleaning workspace).
+    bool sparse_ok = (MODE == M_PRECOUNT) && VEC;
+    if (MODE == M_MAIN && VEC)
+      sparse_ok = __ldcg(&g.hdr->flags_chunks) == (unsigned)g.n_chunks &&
+                  __ldcg(&g.hdr->flags_gt) == (unsigned long long)(uintptr_t)a.hm_gt;
+    const int my_n = bid < g.n_chunks ? (g.n_chunks - bid + grid - 1) / grid : 0;
+    auto chunk_at = [&](int i) { return (MODE == M_PRECOUNT) ? g.n_chunks - 1 - (bid + i * grid) : bid + i * grid; };
+    auto issue = [&](int i) {                                  // thread 0 only
+      const int chunk = chunk_at(i), s = i % S;
+      unsigned m = 0xfu;
+      if (sparse_ok) {
+        m = __ldcg(g.sparse + chunk);
+        g.sparse[chunk] = 0u;
+      }
+      sh_mask[s] = m;
+      issue_chunk(a, chunk_ref(g, chunk), stages[s], &mbar[s * kSubs], m);
+    };
+    if (VEC && tid == 0)
+      for (int i = 0; i < S && i < my_n; ++i) issue(i);
+    if (!VEC && tid < kMaxStages) sh_mask[tid] = 0xfu;
+    __syncthreads();
     int npos = 0;
-    for (int u = bid; u < g.n_chunks; u += grid) {
-      const int chunk = (MODE == M_PRECOUNT) ? g.n_chunks - 1 - u : u;
-      npos += focal_chunk<kGrad, kGrad, false, (MODE == M_PRECOUNT) && CNH_L2_HINTS, FAST, VEC>(a, g, acc, chunk, scale, unused, unused, red_f, red_i);
+#pragma unroll 1
+    for (int i = 0; i < my_n; ++i) {
+      const int s = i % S;
+      const ChunkRef cr = chunk_ref(g, chunk_at(i));
+      if (!VEC) fill_stage_sync(a, cr, stages[s]);
+      // (the mask word was written by thread 0 before its arrive on the stage's barriers; the wait
+      //  inside process_chunk acquires it -- read it after the first wait)
+      if (VEC) mbar_wait(&mbar[s * kSubs], (unsigned)((i / S) & 1));
+      const unsigned m = sh_mask[s];
+      npos += process_chunk<kGrad, false, FAST, VEC>(a, acc, cr, stages[s], &mbar[s * kSubs], (unsigned)((i / S) & 1), m,
+                                                     scale, red_f, red_i);
+      if (VEC && tid == 0 && i + S < my_n) issue(i + S);       // every thread is past its last read of stage s
     }
-    if (MODE != M_PRECOUNT && threadIdx.x == 0 && npos) acc_add_int(acc, 1, npos);   // PRECOUNT counted in phase 0
+    if (MODE != M_PRECOUNT && tid == 0 && npos) acc_add_int(acc, 1, npos);   // PRECOUNT counted in phase 0
+    dbg_stamp(g.dbg, 3);
     const int n_other = g.n_items + (MODE == M_PRECOUNT ? 0 : g.n_count);
     for (int o = (grid - 1 - bid) * kWarps + warp; o < n_other; o += grid * kWarps) {
       if (o < g.n_items) {
         const ItemRef r = decode_item(a, g, o);
         if (kGrad) {
           const float inv = r.h == 0 ? inv_denom[0] : (r.h == 1 ? inv_denom[1] : inv_denom[2]);
-          l1_item_warp<true, true, true, false, FAST>(a, g, acc, r, inv, keep_i, keep_g);
+          l1_item_warp<true, true, true, false, FAST>(a, g, acc, r, inv);
         } else {
-          l1_item_warp<false, true, false, false, FAST>(a, g, acc, r, 0.f, keep_i, keep_g);
+          l1_item_warp<false, true, false, false, FAST>(a, g, acc, r, 0.f);
         }
       } else {
         count_unit_warp(a, acc, o - g.n_items);
@@ -802,7 +1236,7 @@ detloss_kernel(const cnh_detloss_args a, const Geo g) {
 
   // ---- last CTA: totals, scalars, leave the accumulator set zeroed -------------------------
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     __threadfence();
     sh_ticket = atomicAdd(&g.hdr->done, 1u);
   }
@@ -810,16 +1244,20 @@ detloss_kernel(const cnh_detloss_args a, const Geo g) {
   if (sh_ticket != (unsigned)(grid - 1)) return;
   __threadfence();
   if (MODE == M_COUNT) {
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       a.norm_out[0] = (double)__ldcg(acc + kQ + 1);
       for (int h = 0; h < CNH_MAX_HEADS; ++h) a.norm_out[1 + h] = (double)__ldcg(acc + kQ + 4 + 3 * h);
+      g.hdr->flags_chunks = VEC ? (unsigned)g.n_chunks : 0u;
+      g.hdr->flags_gt = (unsigned long long)(uintptr_t)a.hm_gt;
     }
   } else {
     finalize_from_acc(a, acc, sh_tot);
+    if (tid == 0 && MODE == M_MAIN) g.hdr->flags_chunks = 0u;
   }
   __syncthreads();
-  if (threadIdx.x < CNH_TOTALS) acc[threadIdx.x] = 0ll;
-  if (threadIdx.x == 0) g.hdr->done = 0;
+  if (tid < CNH_TOTALS) acc[tid] = 0ll;
+  if (tid == 0) g.hdr->done = 0;
+  dbg_stamp(g.dbg, 4);
 }
 
 __global__ void __launch_bounds__(32)
@@ -828,8 +1266,10 @@ detloss_finalize_kernel(const cnh_detloss_args a, const long long* __restrict__ 
 }
 
 // g *= factor (factor read from device scalars); nothing to do when factor == 1.
+// Launched with programmatic stream serialisation: the launch overlaps the tail of the loss kernel.
 __global__ void __launch_bounds__(kThreads)
 scale_inplace_kernel(const cnh_scale_args s) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int t = 0; t < s.n_tensors; ++t) {
     const float f = (s.fa[t] ? __ldg(s.fa[t]) : 0.f) + (s.fb[t] ? __ldg(s.fb[t]) : 0.f);
     if (f == 1.0f) continue;
@@ -882,6 +1322,11 @@ static int validate(const cnh_detloss_args* a, bool need_grad_ptrs) {
   return CNH_OK;
 }
 
+static long long n_chunks_of(const cnh_detloss_args* a) {
+  const long long CHW = (long long)a->C * a->H * a->W;
+  return (long long)a->B * ((CHW + kChunk - 1) / kChunk);
+}
+
 static Geo make_geo(const cnh_detloss_args* a, void* ws) {
   Geo g;
   g.HW = a->H * a->W;
@@ -899,54 +1344,95 @@ static Geo make_geo(const cnh_detloss_args* a, void* ws) {
     }
   }
   g.n_items = it;
+  g.small_items = it < (1 << 22) ? 1 : 0;
+  g.inv_ppp = 1.0f / (float)g.ppp;
+  for (int h = 0; h < CNH_MAX_HEADS; ++h) g.inv_D[h] = h < a->n_heads ? 1.0f / (float)a->heads[h].D : 1.0f;
   g.n_count = a->B * a->n_heads;
   g.vec_planes = vec_planes ? 1 : 0;
-  g.stash_slots = (a->M <= 32 * kSlotsPerLane) ? 1 : 0;
+  g.stash_slots = (a->M <= 32 * kKeep) ? 1 : 0;
+  g.n_stages = kStreamStages;
   g.chunk_ctas = 0;
-  g.item_ctas = 0;
+  static const int x_delay = getenv("CNH_X_DELAY_NS") ? atoi(getenv("CNH_X_DELAY_NS")) : 0;
+  g.x_delay_ns = x_delay;
   g.world = 1;
   g.rank = 0;
   for (int i = 0; i < CNH_MAX_PEERS; ++i) g.mailbox[i] = nullptr;
   g.hdr = static_cast<WsHeader*>(ws);
+  g.sparse = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + kHeaderBytes);
   g.dbg = debug_buffer();
   return g;
 }
 
-static size_t ws_bytes(const cnh_detloss_args*) { return (sizeof(WsHeader) + 255) / 256 * 256; }
+static size_t ws_bytes(const cnh_detloss_args* a) {
+  return kHeaderBytes + ((size_t)n_chunks_of(a) * sizeof(unsigned) + 255) / 256 * 256;
+}
 
 static bool use_vec(const cnh_detloss_args* a, const Geo& g) {
   return (g.CHW % 4 == 0) && aligned16(a->hm_logits) && aligned16(a->hm_gt) && aligned16(a->prob) &&
          (a->grad_hm == nullptr || aligned16(a->grad_hm));
 }
 
+static const void* pick_stash(bool fast, bool vec) {
+  if (fast) return vec ? (const void*)detloss_stash_kernel<true, true> : (const void*)detloss_stash_kernel<true, false>;
+  return vec ? (const void*)detloss_stash_kernel<false, true> : (const void*)detloss_stash_kernel<false, false>;
+}
 template <int MODE>
-static const void* pick_kernel(bool fast, bool vec) {
-  if (fast) return vec ? (const void*)detloss_kernel<MODE, true, true> : (const void*)detloss_kernel<MODE, true, false>;
-  return vec ? (const void*)detloss_kernel<MODE, false, true> : (const void*)detloss_kernel<MODE, false, false>;
+static const void* pick_stream(bool fast, bool vec) {
+  if (fast) return vec ? (const void*)detloss_stream_kernel<MODE, true, true> : (const void*)detloss_stream_kernel<MODE, true, false>;
+  return vec ? (const void*)detloss_stream_kernel<MODE, false, true> : (const void*)detloss_stream_kernel<MODE, false, false>;
 }
 
-static int max_resident_ctas(const void* kernel) {
+// resident CTAs of `kernel` with `stages` shared-memory stages, on the current device (cached)
+static int resident_ctas(const void* kernel, int stages, int threads = kThreads) {
+  struct Entry { const void* k; int dev, stages, ctas; };
+  static thread_local Entry cache[64];
+  static thread_local int n_cache = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < n_cache; ++i)
+    if (cache[i].k == kernel && cache[i].dev == dev && cache[i].stages == stages) return cache[i].ctas;
+  const size_t smem = (size_t)stages * sizeof(Stage);
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) {
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxStages * sizeof(Stage))) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
-    per_sm = 1;
+    per_sm = 0;
   }
-  return per_sm * sm_count();
+  const int ctas = per_sm * sm_count();
+  if (n_cache < 64) cache[n_cache++] = Entry{kernel, dev, stages, ctas};
+  return ctas;
 }
 
-static int launch(const void* kernel, bool cooperative, int grid, const cnh_detloss_args* a, const Geo& g,
-                  cudaStream_t stream) {
+static int launch(const void* kernel, bool cooperative, int grid, int stages, const cnh_detloss_args* a, const Geo& g,
+                  cudaStream_t stream, int threads = kThreads) {
   void* params[2] = {const_cast<cnh_detloss_args*>(a), const_cast<Geo*>(&g)};
+  const size_t smem = (size_t)stages * sizeof(Stage);
   if (cooperative)
-    CNH_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kThreads), params, 0, stream));
+    CNH_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(threads), params, smem, stream));
   else
-    CNH_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(kThreads), params, 0, stream));
+    CNH_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), params, smem, stream));
   return CNH_OK;
 }
 
-static int units_to_grid(long long chunks, long long warp_units, int cap) {
-  long long want = chunks + (warp_units + kWarps - 1) / kWarps;
+// STASH plan: the smallest number of stages per CTA with which one wave holds every chunk
+static bool plan_stash(const void* kernel, Geo& g) {
+  if (g.n_chunks > kMaxCounted || g.n_items > kMaxCounted) return false;   // contribution counters are 16 bits
+  for (int S = 1; S <= kMaxStages; ++S) {
+    const long long cap = (long long)resident_ctas(kernel, S, kStashThreads) - 1;     // one CTA is the finaliser
+    if (cap >= 1 && cap * S >= g.n_chunks) {
+      g.n_stages = S;
+      g.chunk_ctas = (int)(cap < g.n_chunks ? cap : g.n_chunks);
+      return true;
+    }
+  }
+  return false;
+}
+
+static int stream_grid(const void* kernel, const Geo& g, long long warp_units, int stages = kStreamStages) {
+  long long want = g.n_chunks + (warp_units + kWarps - 1) / kWarps;
   if (want < 1) want = 1;
+  int cap = resident_ctas(kernel, stages);
+  if (cap < 1) cap = 1;
   return (int)(want < cap ? want : cap);
 }
 
@@ -957,6 +1443,12 @@ using namespace cnh;
 extern "C" size_t cnh_detloss_workspace_bytes(const cnh_detloss_args* a) {
   if (validate(a, false) != CNH_OK) return 0;
   return ws_bytes(a);
+}
+
+extern "C" int cnh_detloss_single_wave(const cnh_detloss_args* a) {
+  if (validate(a, false) != CNH_OK) return 0;
+  Geo g = make_geo(a, nullptr);
+  return plan_stash(pick_stash(!(a->flags & CNH_FLAG_ACCURATE_MATH), use_vec(a, g)), g) ? 1 : 0;
 }
 
 static int detloss_fused_impl(const cnh_detloss_args* a, const cnh_peers* peers, void* workspace,
@@ -975,30 +1467,19 @@ static int detloss_fused_impl(const cnh_detloss_args* a, const cnh_peers* peers,
   const bool fast = !(a->flags & CNH_FLAG_ACCURATE_MATH), vec = use_vec(a, g);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->grad_hm == nullptr) {
-    const void* k = pick_kernel<M_FWD>(fast, vec);
-    return launch(k, false, units_to_grid(g.n_chunks, g.n_items + g.n_count, max_resident_ctas(k)), a, g, st);
+    const void* k = pick_stream<M_FWD>(fast, vec);
+    return launch(k, false, stream_grid(k, g, g.n_items + g.n_count), kStreamStages, a, g, st);
   }
-  const void* ks = pick_kernel<M_STASH>(fast, vec);
-  const int cap = max_resident_ctas(ks);
-  {
-    // roles: item CTAs (one warp per item and round; at most a quarter of the machine), chunk CTAs
-    // (<= kStash chunks each), one finaliser
-    const long long warp_units = (long long)g.n_items + g.n_count;
-    long long item_ctas = (warp_units + kWarps - 1) / kWarps;
-    if (item_ctas > cap / 4) item_ctas = cap / 4;
-    if (item_ctas < 1) item_ctas = 1;
-    long long chunk_ctas = cap - 1 - item_ctas;
-    if (chunk_ctas > g.n_chunks) chunk_ctas = g.n_chunks;
-    if (!(a->flags & CNH_FLAG_NO_STASH) && chunk_ctas >= 1 && g.n_chunks <= chunk_ctas * kStash) {
-      g.chunk_ctas = (int)chunk_ctas;
-      g.item_ctas = (int)item_ctas;
-      return launch(ks, true, (int)(chunk_ctas + item_ctas + 1), a, g, st);
-    }
+  const void* ks = pick_stash(fast, vec);
+  if (!(a->flags & CNH_FLAG_NO_STASH) && plan_stash(ks, g)) {
+    static const bool no_coop = (getenv("CNH_NO_COOP") != nullptr);      // experiment: plain launch of the single wave
+    return launch(ks, !no_coop, g.chunk_ctas + 1, g.n_stages, a, g, st, kStashThreads);
   }
   CNH_REQUIRE(g.world == 1, CNH_E_UNSUPPORTED,
-              "detloss_fused_peers: problem too large for the register-stash schedule (%d chunks); use count/main", g.n_chunks);
-  const void* kp = pick_kernel<M_PRECOUNT>(fast, vec);
-  return launch(kp, true, units_to_grid(g.n_chunks, g.n_items + g.n_count, max_resident_ctas(kp)), a, g, st);
+              "detloss_fused_peers: problem too large for the single-wave schedule (%d chunks); use count/main", g.n_chunks);
+  g.n_stages = kStreamStages;
+  const void* kp = pick_stream<M_PRECOUNT>(fast, vec);
+  return launch(kp, true, stream_grid(kp, g, g.n_items + g.n_count), kStreamStages, a, g, st);
 }
 
 extern "C" int cnh_detloss_fused(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
@@ -1023,9 +1504,8 @@ extern "C" int cnh_detloss_count(const cnh_detloss_args* a, void* workspace, siz
   CNH_REQUIRE(workspace != nullptr && workspace_bytes >= ws_bytes(a), CNH_E_WORKSPACE,
               "detloss_count: workspace %zu < %zu bytes", workspace_bytes, ws_bytes(a));
   const Geo g = make_geo(a, workspace);
-  const void* k = pick_kernel<M_COUNT>(true, use_vec(a, g));
-  return launch(k, false, units_to_grid(g.n_chunks, g.n_count, max_resident_ctas(k)), a, g,
-                static_cast<cudaStream_t>(stream));
+  const void* k = pick_stream<M_COUNT>(true, use_vec(a, g));
+  return launch(k, false, stream_grid(k, g, g.n_count, 0), 0, a, g, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cnh_detloss_main(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
@@ -1037,8 +1517,8 @@ extern "C" int cnh_detloss_main(const cnh_detloss_args* a, void* workspace, size
   CNH_REQUIRE(workspace != nullptr && workspace_bytes >= ws_bytes(a), CNH_E_WORKSPACE,
               "detloss_main: workspace %zu < %zu bytes", workspace_bytes, ws_bytes(a));
   const Geo g = make_geo(a, workspace);
-  const void* k = pick_kernel<M_MAIN>(!(a->flags & CNH_FLAG_ACCURATE_MATH), use_vec(a, g));
-  return launch(k, false, units_to_grid(g.n_chunks, g.n_items + g.n_count, max_resident_ctas(k)), a, g,
+  const void* k = pick_stream<M_MAIN>(!(a->flags & CNH_FLAG_ACCURATE_MATH), use_vec(a, g));
+  return launch(k, false, stream_grid(k, g, g.n_items + g.n_count), kStreamStages, a, g,
                 static_cast<cudaStream_t>(stream));
 }
 
@@ -1065,7 +1545,18 @@ extern "C" int cnh_scale_inplace(const cnh_scale_args* s, cnh_stream_t stream) {
   long long want = (most / 4 + kThreads - 1) / kThreads;
   const int cap = sm_count() * 8;
   const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-  scale_inplace_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(*s);
+  static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3(kThreads);
+  lc.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = use_pdl ? 1 : 0;
+  CNH_CUDA(cudaLaunchKernelEx(&lc, scale_inplace_kernel, *s));
   CNH_CUDA(cudaGetLastError());
   return CNH_OK;
 }

@@ -110,17 +110,22 @@ const char* cnh_last_error(void);
 /* ---- DetectionLoss (losses/centernet.py:7-95,98-133,192-223) ---------------------------
  * cnh_detloss_fused: ONE cooperative launch = sigmoid+clamp, penalty-reduced focal loss,
  * masked gather-L1 heads, all gradients (upstream gradient 1.0), scalars and totals.
- * Small problems keep the raw heat-map gradient in registers across the grid barrier
- * (16 B per heat-map element of HBM traffic); large ones pre-count num_pos (20 B). */
+ * Heat-map chunks are staged in shared memory by TMA bulk copies.  Problems that fit one wave
+ * of CTAs keep the raw heat-map gradient in shared memory across the grid barrier (16 B per
+ * heat-map element of HBM traffic); larger ones pre-count num_pos over the target and skip
+ * its all-zero 4 KB sub-blocks in the second pass (16 B for sparse targets, <= 20 B). */
 size_t cnh_detloss_workspace_bytes(const cnh_detloss_args* a);
+/* 1 if cnh_detloss_fused would run this problem as a single wave (the schedule
+ * cnh_detloss_fused_peers requires), else 0.  Needs a current CUDA device. */
+int cnh_detloss_single_wave(const cnh_detloss_args* a);
 int cnh_detloss_fused(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
                       cnh_stream_t stream);
 /* Sharded, fused exchange (one process per GPU, peer-mapped mailboxes over NVLink/NVSwitch): the same
  * single launch as cnh_detloss_fused; the finaliser CTA stores this rank's normalisers and exact
  * totals into every peer's mailbox (st.release.sys), waits for the peers' (ld.acquire.sys), and
  * releases the local CTAs with the GLOBAL normalisers -- no collective library call on the step path.
- * Every rank must issue the call (it spins until all peers have arrived).  Requires the STASH
- * schedule (small per-rank problems); returns CNH_E_UNSUPPORTED otherwise (use count/main below).
+ * Every rank must issue the call (it spins until all peers have arrived).  Requires the single-wave
+ * schedule (cnh_detloss_single_wave() == 1); returns CNH_E_UNSUPPORTED otherwise (use count/main below).
  * mailbox[r]: device pointer, valid on THIS device, to rank r's mailbox (CNH_MAILBOX_BYTES, zeroed
  * once, symmetric allocation); mailbox[rank] is the local one. */
 #define CNH_MAX_PEERS 8
@@ -132,7 +137,11 @@ typedef struct cnh_peers {
 int cnh_detloss_fused_peers(const cnh_detloss_args* a, const cnh_peers* peers, void* workspace,
                             size_t workspace_bytes, cnh_stream_t stream);
 /* Sharded (one process per GPU) schedule: count -> all-reduce(norm_out) -> main ->
- * all-reduce(totals) -> finalize.  Gradients are final after cnh_detloss_main. */
+ * all-reduce(totals) -> finalize.  Gradients are final after cnh_detloss_main.
+ * cnh_detloss_count also leaves, in the workspace, one sparsity word per 4096-element chunk of hm_gt
+ * (which 4 KB sub-blocks hold anything but zeros); a cnh_detloss_main on the SAME workspace and the
+ * SAME hm_gt pointer consumes them (all-zero sub-blocks of the target are not re-read) and clears
+ * them.  Do not modify hm_gt between the two calls. */
 int cnh_detloss_count(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
                       cnh_stream_t stream);
 int cnh_detloss_main(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,

@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --maxfail=10 --timeout=300 -x > gpurun_out/pytest_t3.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/pytest_t3.log
+timeout 300 python tools/stage_times.py cfg2 2>&1 | head -18 | cut -c1-200
+timeout 600 python tools/prof_kernels.py cfg2 2>&1 | grep -E "fused_stash|full_step"
+echo "--- no coop"
+CNH_NO_COOP=1 timeout 600 python tools/prof_kernels.py cfg2 2>&1 | grep -E "fused_stash|full_step"

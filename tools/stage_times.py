@@ -37,7 +37,17 @@ lib.cnh_debug_set_buffer(dbg.data_ptr())
 for rep in range(2):
     dbg.zero_(); torch.cuda.synchronize()
     d.loss_only(rep)
-    show(f"detloss {name} rep{rep}", 8)
+    show(f"detloss {name} rep{rep}", 15)
+    t = dbg.cpu(); used = (t[:, 0] != 0) & (t[:, 1] != 0)
+    if used.any():
+        t0 = t[used, 0].min(); sm = t[used, 15]; done = (t[used, 1] - t0).float() / 1e3; start = (t[used, 0] - t0).float() / 1e3
+        per = {}
+        for s_, d_, st_ in zip(sm.tolist(), done.tolist(), start.tolist()): per.setdefault(s_, []).append((round(st_, 2), round(d_, 2)))
+        by = {}
+        for s_, v in per.items(): by.setdefault(len(v), []).append(max(d for _, d in v))
+        for k_, v in sorted(by.items()): print(f"  SMs with {k_} CTAs: {len(v)}; chunk-done max per SM: min {min(v):.2f} median {sorted(v)[len(v)//2]:.2f} max {max(v):.2f}")
+        worst = sorted(per.items(), key=lambda kv: -max(d for _, d in kv[1]))[:4]
+        print("  slowest SMs (start, done):", worst)
     dbg.zero_(); torch.cuda.synchronize()
     L.check(lib.cnh_decode(C.byref(d.dec_args[rep]), d.ws_dec.data_ptr(), d.ws_dec.numel(), L.stream_ptr()), "d")
     show(f"decode {name} rep{rep}", 12)
