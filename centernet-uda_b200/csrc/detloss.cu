@@ -71,7 +71,9 @@ struct __align__(128) Stage {
 struct WsHeader {
   unsigned parity;
   unsigned done;
+  unsigned next;                              // streaming schedules: next chunk ticket
   unsigned epoch;                             // launches that used the peer exchange so far
+  unsigned next0;                             // streaming schedules: next chunk-group ticket of the count phase
   unsigned flags_chunks;                      // COUNT left valid sparsity words for this many chunks ...
   unsigned long long flags_gt;                // ... of this target tensor
   unsigned long long bar[2][1 + CNH_MAX_HEADS];  // single wave [parity]: [0] chunk CTAs: arrivals << 32 | num_pos;
@@ -137,6 +139,27 @@ __device__ __forceinline__ void acc_add_counted(long long* acc, int q, float v) 
   const long long f = __double2ll_rn((double)v * 1099511627776.0);        // 2^40
   atomicAdd(reinterpret_cast<unsigned long long*>(acc + q), (unsigned long long)((f >> 32) + (1ll << kCntHi)));
   atomicAdd(reinterpret_cast<unsigned long long*>(acc + kQ + q), (unsigned long long)((f & 0xffffffffll) + (1ll << kCntLo)));
+}
+// A CTA's partial totals.  Its lo word is carry-normalised first (lo < 2^32, the carry moves to hi: same
+// value), so that the sum of the lo words of up to 2^16 contributions stays below the counter bits.
+__device__ __forceinline__ void acc_add_pair(long long* acc, int q, long long hi, long long lo) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc + q), (unsigned long long)(hi + (lo >> 32)));
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc + kQ + q), (unsigned long long)(lo & 0xffffffffll));
+}
+__device__ __forceinline__ void acc_add_pair_counted(long long* acc, int q, long long hi, long long lo) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc + q), (unsigned long long)(hi + (lo >> 32) + (1ll << kCntHi)));
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc + kQ + q), (unsigned long long)((lo & 0xffffffffll) + (1ll << kCntLo)));
+}
+// published totals are canonical: 0 <= lo < 2^32 for the fixed-point sums (q = 0, 2+3h, 3+3h)
+__device__ __forceinline__ void canonicalise_totals(long long* t) {
+  const int qs[7] = {0, 2, 3, 5, 6, 8, 9};
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const int q = qs[i];
+    const long long lo = t[kQ + q];
+    t[q] += lo >> 32;
+    t[kQ + q] = lo & 0xffffffffll;
+  }
 }
 __device__ __forceinline__ void acc_add_int(long long* acc, int q, long long n) {
   atomicAdd(reinterpret_cast<unsigned long long*>(acc + kQ + q), (unsigned long long)n);
@@ -280,27 +303,6 @@ __device__ __forceinline__ int block_sum_compute(int v, int* red) {
   return t;
 }
 
-__device__ __forceinline__ void block_reduce2(float& s, int& n, float* red_f, int* red_i) {
-  s = warp_sum(s);
-  n = warp_sum(n);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  sync_compute();
-  if (lane == 0) {
-    red_f[warp] = s;
-    red_i[warp] = n;
-  }
-  sync_compute();
-  float ts = red_f[0];
-  int tn = red_i[0];
-#pragma unroll
-  for (int w = 1; w < kWarps; ++w) {
-    ts += red_f[w];
-    tn += red_i[w];
-  }
-  s = ts;
-  n = tn;
-}
-
 // ---- one chunk: shared-memory stage -> probability, loss terms, gradient ---------------------------
 struct ChunkRef {
   long long base;          // element offset of the chunk in the heat-map tensors
@@ -323,7 +325,10 @@ __device__ __forceinline__ void issue_chunk(const cnh_detloss_args& a, const Chu
 #pragma unroll
   for (int v = 0; v < kSubs; ++v) {
     const int left = r.n - v * kSub;
-    if (left <= 0) break;
+    if (left <= 0) {                          // short chunk: keep the phases of all four barriers in step
+      mbar_arrive(bar + v);
+      continue;
+    }
     const unsigned bytes = (unsigned)(left < kSub ? left : kSub) * 4u;
     const bool has_g = (gmask >> v) & 1u;
     mbar_expect_tx(bar + v, has_g ? 2u * bytes : bytes);
@@ -347,14 +352,27 @@ __device__ __forceinline__ void fill_stage_sync(const cnh_detloss_args& a, const
   sync_compute();
 }
 
+// Thread-local loss accumulators.  A thread's partial sum over its 16 elements of a chunk (a float,
+// fixed order) is converted to 2^-40 fixed point and split into (hi, lo) at once; from there on everything
+// is integer addition, so the totals do not depend on which CTA, wave or GPU processed which chunk.
+struct LossAcc {
+  long long hi, lo;
+  int npos;
+};
+__device__ __forceinline__ void loss_acc_add(LossAcc& la, float v) {
+  const long long f = __double2ll_rn((double)v * 1099511627776.0);        // 2^40
+  la.hi += f >> 32;
+  la.lo += f & 0xffffffffll;
+}
+
 // Consume one staged chunk: the probability goes straight to HBM; the gradient too when its scale is
-// known (NEED_GRAD && !KEEP), or (KEEP, single wave) it replaces the logits in the stage, unscaled.  Adds the chunk's loss sum to acc (COUNTED: self-validating words of the single-wave
-// schedule); returns its num_pos (every thread).  Ends with a barrier of the compute warps after the last
-// read of the stage.
-template <bool NEED_GRAD, bool COUNTED, bool FAST, bool VEC, bool KEEP = false>
-__device__ __forceinline__ int process_chunk(const cnh_detloss_args& a, long long* acc, const ChunkRef& r, Stage& st,
-                                             u64* bar, unsigned parity, unsigned gmask, float scale,
-                                             float* red_f, int* red_i) {
+// known (NEED_GRAD && !KEEP), or (KEEP, single wave) it replaces the logits in the stage, unscaled.
+// Loss terms and num_pos go to the thread-local accumulators.  No barrier inside: a thread only
+// touches its own slots of the stage (WAIT: the stage is filled by bulk copies, wait for each sub-block).
+template <bool NEED_GRAD, bool FAST, bool WAIT, bool KEEP>
+__device__ __forceinline__ void process_chunk(const cnh_detloss_args& a, const ChunkRef& r, Stage& st, u64* bar,
+                                              unsigned parity, unsigned gmask, float scale, LossAcc& la) {
+  constexpr bool VEC = WAIT;                  // bulk-copied stages imply 16-byte aligned tensors and n % 4 == 0
   float* __restrict__ pp = a.prob + r.base;
   float* __restrict__ gq = NEED_GRAD ? a.grad_hm + r.base : nullptr;
   float sum = 0.f;
@@ -363,9 +381,9 @@ __device__ __forceinline__ int process_chunk(const cnh_detloss_args& a, long lon
   for (int v = 0; v < kSubs; ++v) {
     if (v * kSub >= r.n) break;
     const int off = v * kSub + threadIdx.x * 4;
-    if (VEC) mbar_wait(bar + v, parity);
+    if (WAIT) mbar_wait(bar + v, parity);
     float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool live = !VEC || off < r.n;      // VEC: n % 4 == 0, a float4 is all in or all out
+    const bool live = !VEC || off < r.n;      // VEC: a float4 is all in or all out
     if (live) {
       x4 = *reinterpret_cast<const float4*>(st.x + off);
       if ((gmask >> v) & 1u) g4 = *reinterpret_cast<const float4*>(st.g + off);
@@ -374,7 +392,7 @@ __device__ __forceinline__ int process_chunk(const cnh_detloss_args& a, long lon
     }
     const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, gs[4] = {g4.x, g4.y, g4.z, g4.w};
     // positives are rare (one pixel per object): a warp whose targets are all < 1 takes the
-    // select-free path (same bits, ~30 % fewer instructions)
+    // select-free packed path (same bits, about half the instructions)
     const bool special = !(gs[0] < 1.0f) || !(gs[1] < 1.0f) || !(gs[2] < 1.0f) || !(gs[3] < 1.0f);
     float ps[4], gr[4];
     if (__any_sync(0xffffffffu, special)) {
@@ -416,12 +434,37 @@ __device__ __forceinline__ int process_chunk(const cnh_detloss_args& a, long lon
     }
     if (NEED_GRAD && KEEP) *reinterpret_cast<float4*>(st.x + off) = make_float4(gr[0], gr[1], gr[2], gr[3]);
   }
-  if (FAST) sum = __fmul_rn(sum, kLn2F);      // log2 -> natural log, once per thread
-  block_reduce2(sum, npos, red_f, red_i);
-  if (threadIdx.x == 0) {
-    if (COUNTED) acc_add_counted(acc, 0, sum); else acc_add_fixed(acc, 0, sum);
+  if (FAST) sum = __fmul_rn(sum, kLn2F);      // log2 -> natural log, once per thread and chunk
+  loss_acc_add(la, sum);
+  la.npos += npos;
+}
+
+// Sum the thread-local accumulators over the 8 compute warps (integers: exact, any order).  Thread 0 returns the totals.
+__device__ __forceinline__ void block_reduce_loss(LossAcc& la, long long* red_l, int* red_i) {
+  la.hi = warp_sum(la.hi);
+  la.lo = warp_sum(la.lo);
+  la.npos = warp_sum(la.npos);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  sync_compute();
+  if (lane == 0) {
+    red_l[2 * warp] = la.hi;
+    red_l[2 * warp + 1] = la.lo;
+    red_i[warp] = la.npos;
   }
-  return npos;
+  sync_compute();
+  if (threadIdx.x == 0) {
+    long long h = 0, l = 0;
+    int n = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      h += red_l[2 * w];
+      l += red_l[2 * w + 1];
+      n += red_i[w];
+    }
+    la.hi = h;
+    la.lo = l;
+    la.npos = n;
+  }
 }
 
 // Single wave, after the grid barrier: raw gradient (left in the stage by process_chunk<KEEP>) * scale -> HBM.
@@ -809,12 +852,11 @@ __device__ void scalars_from_totals(const cnh_detloss_args& a, const long long* 
 // Read the live accumulator set (written by other CTAs: through L2), publish it to a.totals,
 // compute the scalars.  Threads 0..23 load one word each; thread 0 finishes.
 __device__ void finalize_from_acc(const cnh_detloss_args& a, const long long* acc, long long* sh_tot) {
-  if (threadIdx.x < CNH_TOTALS) {
-    const long long v = __ldcg(acc + threadIdx.x);
-    sh_tot[threadIdx.x] = v;
-    if (a.totals != nullptr) a.totals[threadIdx.x] = v;
-  }
+  if (threadIdx.x < CNH_TOTALS) sh_tot[threadIdx.x] = __ldcg(acc + threadIdx.x);
   __syncthreads();
+  if (threadIdx.x == 0) canonicalise_totals(sh_tot);
+  __syncthreads();
+  if (threadIdx.x < CNH_TOTALS && a.totals != nullptr) a.totals[threadIdx.x] = sh_tot[threadIdx.x];
   if (threadIdx.x == 0 && a.scalars != nullptr) scalars_from_totals(a, sh_tot, a.scalars);
 }
 
@@ -845,7 +887,7 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Stage* const stages = reinterpret_cast<Stage*>(smem_raw);
   __shared__ u64 mbar[kMaxStages * kStashBars];
-  __shared__ float red_f[kWarps];
+  __shared__ long long red_l[2 * kWarps];
   __shared__ int red_i[kWarps];
   __shared__ long long sh_tot[CNH_TOTALS];
   __shared__ int sh_norm[1 + CNH_MAX_HEADS];
@@ -922,14 +964,15 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
     if (tid == 0) atomicAdd(bar_chunk, (1ull << 32) | (unsigned long long)(unsigned)npos);
     // ---- pass 2a, before the barrier resolves: probabilities to HBM, loss sums, raw gradient into the
     // stage (the logits arrive while the other CTAs are still counting)
-    long long* acc = g.hdr->acc[par];                        // (thread 0 only: the others never touch it)
+    LossAcc la = {0ll, 0ll, 0};
 #pragma unroll 1
     for (int r = 0; r < S; ++r) {
       const int chunk = bid + r * W;
       if (chunk >= g.n_chunks) break;
-      process_chunk<true, true, FAST, VEC, true>(a, acc, chunk_ref(g, chunk), stages[r], &mbar[r * kStashBars + kSubs], 0u, 0xfu,
-                                                 0.f, red_f, red_i);
+      process_chunk<true, FAST, VEC, true>(a, chunk_ref(g, chunk), stages[r], &mbar[r * kStashBars + kSubs], 0u, 0xfu, 0.f, la);
     }
+    block_reduce_loss(la, red_l, red_i);
+    if (tid == 0) acc_add_pair_counted(g.hdr->acc[par], 0, la.hi, la.lo);   // one contribution per worker CTA
     dbg_stamp(g.dbg, 4);
     // zero-fill of this CTA's pieces of the regression gradient planes; warp 8 scatters after it
     for (int o = bid; o < g.n_items; o += W) l1_zero_fill_block(a, g, decode_item(a, g, o));
@@ -1061,7 +1104,7 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
       const int qi = tid % 7, lo = tid / 7;                  // 7 sums (focal, then l1 / angle per head) x (hi, lo)
       const int h = (qi - 1) >> 1, is_ang = (qi - 1) & 1;
       const int q = qi == 0 ? 0 : 2 + 3 * h + is_ang;
-      long long expect = g.n_chunks;
+      long long expect = W;                                  // focal: one contribution per worker CTA
       if (qi > 0) {
         expect = 0;
         if (h < a.n_heads) {
@@ -1089,6 +1132,8 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
     } else if (tid == 14 + CNH_MAX_HEADS) {
       sh_tot[kQ + 1] = (long long)(unsigned)sh_norm[0];      // num_pos
     }
+    __syncthreads();
+    if (tid == 0) canonicalise_totals(sh_tot);
     __syncthreads();
     dbg_stamp(g.dbg, 3);
     if (g.world > 1) {
@@ -1123,45 +1168,70 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
 }
 
 // ================================================================================================
-// Streaming schedules (PRECOUNT / MAIN / COUNT / FWD): persistent CTAs, chunks through a TMA ring.
+// Streaming schedules (PRECOUNT / MAIN / COUNT / FWD): persistent CTAs of 9 warps.
+//   warp 8 (producer): draws chunk tickets from a global counter (dynamic scheduling: SMs do not get
+//           the same share of the memory system, a static split ends with a 20 % tail), waits for a free
+//           stage of the ring, issues the chunk's bulk copies.  The ticket for the next issue is drawn one
+//           step ahead, so its round trip is never waited for.
+//   warps 0-7 (consumers): sub-block by sub-block as they land; probability + gradient straight to HBM;
+//           loss terms into thread-local exact accumulators; one arrival per warp frees the stage.
+//           No block barrier and no atomic per chunk.
 // ================================================================================================
 template <int MODE, bool FAST, bool VEC>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kStashThreads, 2)
 detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Stage* const stages = reinterpret_cast<Stage*>(smem_raw);
-  __shared__ u64 mbar[kMaxStages * kSubs];
-  __shared__ float red_f[kWarps];
+  __shared__ u64 full[kMaxStages * kSubs];
+  __shared__ u64 empty[kMaxStages];
+  __shared__ long long red_l[2 * kWarps];
   __shared__ int red_i[kWarps];
   __shared__ long long sh_tot[CNH_TOTALS];
-  __shared__ unsigned sh_ticket;
+  __shared__ unsigned sh_ticket, sh_parity;
   __shared__ unsigned sh_mask[kMaxStages];
+  __shared__ int sh_chunk[kMaxStages];
   const int bid = blockIdx.x, grid = gridDim.x;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool consumer = warp < kWarps;
   constexpr bool kGrad = (MODE == M_PRECOUNT || MODE == M_MAIN);
   const int S = g.n_stages;
-  long long* acc = g.hdr->acc[0];               // ticket modes leave the set zeroed: parity stays what it is
 
   dbg_stamp(g.dbg, 0);
-  if (MODE != M_COUNT && VEC && tid == 0) {
-    for (int i = 0; i < S * kSubs; ++i) mbar_init(&mbar[i], 1);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid == 0) {
+    if (MODE != M_COUNT && VEC) {
+      for (int i = 0; i < S * kSubs; ++i) mbar_init(&full[i], 1);
+      for (int i = 0; i < S; ++i) mbar_init(&empty[i], kWarps);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    sh_parity = __ldcg(&g.hdr->parity) & 1u;   // ticket modes leave their set zeroed: parity stays what it is
   }
-  // accumulator set of the live parity
-  __shared__ unsigned sh_parity;
-  if (tid == 0) sh_parity = __ldcg(&g.hdr->parity) & 1u;
   __syncthreads();
-  acc = g.hdr->acc[sh_parity];
+  long long* acc = g.hdr->acc[sh_parity];
 
   float scale = 0.f;
   float inv_denom[CNH_MAX_HEADS] = {0.f, 0.f, 0.f};
   if (MODE == M_PRECOUNT || MODE == M_COUNT) {
     // ---- phase 0: normalisers and sparsity words from the targets only --------------------------
     int npos = 0;
-    for (int c = bid; c < g.n_chunks; c += kCountUnroll * grid) npos += count_chunks<VEC>(a, g, c, grid);
-    npos = block_sum(npos, red_i);
-    if (tid == 0 && npos) acc_add_int(acc, 1, npos);
-    for (int u = (grid - 1 - bid) * kWarps + warp; u < g.n_count; u += grid * kWarps) count_unit_warp(a, acc, u);
+    if (consumer) {
+      // groups of kCountUnroll consecutive chunks, drawn dynamically (ticket for the next group requested
+      // before this group's loads are consumed)
+      const unsigned n_groups = (unsigned)((g.n_chunks + kCountUnroll - 1) / kCountUnroll);
+      unsigned t_next = 0;
+      if (tid == 0) t_next = atomicAdd(&g.hdr->next0, 1u);
+      for (;;) {
+        if (tid == 0) sh_ticket = t_next;
+        sync_compute();
+        const unsigned t = sh_ticket;
+        sync_compute();
+        if (t >= n_groups) break;
+        if (tid == 0) t_next = atomicAdd(&g.hdr->next0, 1u);
+        npos += count_chunks<VEC>(a, g, (int)t * kCountUnroll, 1);
+      }
+      npos = block_sum_compute(npos, red_i);
+      if (tid == 0 && npos) acc_add_int(acc, 1, npos);
+      for (int u = (grid - 1 - bid) * kWarps + warp; u < g.n_count; u += grid * kWarps) count_unit_warp(a, acc, u);
+    }
     dbg_stamp(g.dbg, 1);
   }
   if (MODE == M_PRECOUNT) {
@@ -1179,57 +1249,109 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
     for (int h = 0; h < CNH_MAX_HEADS; ++h) inv_denom[h] = 1.f / ((float)a.norm[1 + h] + 1e-4f);
   }
   if (MODE != M_COUNT) {
-    // ---- the streaming pass (reverse chunk order after a pre-count: L2 reuse) ---------------------
-    // sparsity words: PRECOUNT wrote them in phase 0; MAIN may use the ones a preceding COUNT left
-    // for this very target; FWD has none.  Whoever reads a word clears it (self-cleaning workspace).
-    bool sparse_ok = (MODE == M_PRECOUNT) && VEC;
-    if (MODE == M_MAIN && VEC)
-      sparse_ok = __ldcg(&g.hdr->flags_chunks) == (unsigned)g.n_chunks &&
-                  __ldcg(&g.hdr->flags_gt) == (unsigned long long)(uintptr_t)a.hm_gt;
-    const int my_n = bid < g.n_chunks ? (g.n_chunks - bid + grid - 1) / grid : 0;
-    auto chunk_at = [&](int i) { return (MODE == M_PRECOUNT) ? g.n_chunks - 1 - (bid + i * grid) : bid + i * grid; };
-    auto issue = [&](int i) {                                  // thread 0 only
-      const int chunk = chunk_at(i), s = i % S;
-      unsigned m = 0xfu;
-      if (sparse_ok) {
-        m = __ldcg(g.sparse + chunk);
-        g.sparse[chunk] = 0u;
-      }
-      sh_mask[s] = m;
-      issue_chunk(a, chunk_ref(g, chunk), stages[s], &mbar[s * kSubs], m);
-    };
-    if (VEC && tid == 0)
-      for (int i = 0; i < S && i < my_n; ++i) issue(i);
-    if (!VEC && tid < kMaxStages) sh_mask[tid] = 0xfu;
-    __syncthreads();
-    int npos = 0;
-#pragma unroll 1
-    for (int i = 0; i < my_n; ++i) {
-      const int s = i % S;
-      const ChunkRef cr = chunk_ref(g, chunk_at(i));
-      if (!VEC) fill_stage_sync(a, cr, stages[s]);
-      // (the mask word was written by thread 0 before its arrive on the stage's barriers; the wait
-      //  inside process_chunk acquires it -- read it after the first wait)
-      if (VEC) mbar_wait(&mbar[s * kSubs], (unsigned)((i / S) & 1));
-      const unsigned m = sh_mask[s];
-      npos += process_chunk<kGrad, false, FAST, VEC>(a, acc, cr, stages[s], &mbar[s * kSubs], (unsigned)((i / S) & 1), m,
-                                                     scale, red_f, red_i);
-      if (VEC && tid == 0 && i + S < my_n) issue(i + S);       // every thread is past its last read of stage s
-    }
-    if (MODE != M_PRECOUNT && tid == 0 && npos) acc_add_int(acc, 1, npos);   // PRECOUNT counted in phase 0
-    dbg_stamp(g.dbg, 3);
-    const int n_other = g.n_items + (MODE == M_PRECOUNT ? 0 : g.n_count);
-    for (int o = (grid - 1 - bid) * kWarps + warp; o < n_other; o += grid * kWarps) {
-      if (o < g.n_items) {
-        const ItemRef r = decode_item(a, g, o);
-        if (kGrad) {
-          const float inv = r.h == 0 ? inv_denom[0] : (r.h == 1 ? inv_denom[1] : inv_denom[2]);
-          l1_item_warp<true, true, true, false, FAST>(a, g, acc, r, inv);
+    // ---- the streaming pass -----------------------------------------------------------------------
+    // ticket t -> chunk: reverse order after a pre-count (the tail of the target is still in L2)
+    auto chunk_of = [&](int t) { return (MODE == M_PRECOUNT) ? g.n_chunks - 1 - t : t; };
+    LossAcc la = {0ll, 0ll, 0};
+    // regression units first (the last CTAs get them): the chunk tickets are dynamic, a CTA that is busy
+    // here simply draws fewer chunks -- nothing is left to do after the streaming loop
+    if (consumer) {
+      const int n_other = g.n_items + (MODE == M_PRECOUNT ? 0 : g.n_count);
+      for (int o = (grid - 1 - bid) * kWarps + warp; o < n_other; o += grid * kWarps) {
+        if (o < g.n_items) {
+          const ItemRef r = decode_item(a, g, o);
+          if (kGrad) {
+            const float inv = r.h == 0 ? inv_denom[0] : (r.h == 1 ? inv_denom[1] : inv_denom[2]);
+            l1_item_warp<true, true, true, false, FAST>(a, g, acc, r, inv);
+          } else {
+            l1_item_warp<false, true, false, false, FAST>(a, g, acc, r, 0.f);
+          }
         } else {
-          l1_item_warp<false, true, false, false, FAST>(a, g, acc, r, 0.f);
+          count_unit_warp(a, acc, o - g.n_items);
         }
-      } else {
-        count_unit_warp(a, acc, o - g.n_items);
+      }
+    }
+    if (!VEC) {
+      // shapes the TMA unit cannot move: static split, every consumer thread copies (correctness path)
+      if (consumer)
+        for (int c = bid; c < g.n_chunks; c += grid) {
+          const ChunkRef cr = chunk_ref(g, chunk_of(c));
+          fill_stage_sync(a, cr, stages[0]);
+          process_chunk<kGrad, FAST, false, false>(a, cr, stages[0], full, 0u, 0xfu, scale, la);
+        }
+    } else if (!consumer) {
+      // ---- producer ----
+      if (lane == 0) {
+        // sparsity words: PRECOUNT wrote them in phase 0; MAIN may use the ones a preceding COUNT left
+        // for this very target; FWD has none.  Whoever reads a word clears it (self-cleaning workspace).
+        bool sparse_ok = (MODE == M_PRECOUNT);
+        if (MODE == M_MAIN)
+          sparse_ok = __ldcg(&g.hdr->flags_chunks) == (unsigned)g.n_chunks &&
+                      __ldcg(&g.hdr->flags_gt) == (unsigned long long)(uintptr_t)a.hm_gt;
+        // software pipeline: the ticket for issue j+2 and the sparsity word for issue j+1 are requested
+        // while issue j is prepared -- no round trip of the (loaded) memory system is ever waited for
+        auto load_mask = [&](unsigned t) -> unsigned {
+          unsigned m = 0xfu;
+          if (sparse_ok && t < (unsigned)g.n_chunks)
+            asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(m) : "l"(g.sparse + chunk_of((int)t)));
+          return m;
+        };
+        unsigned t_a = atomicAdd(&g.hdr->next, 1u);
+        unsigned t_b = atomicAdd(&g.hdr->next, 1u);
+        unsigned m_a = load_mask(t_a);
+        for (int j = 0;; ++j) {
+          const int s = j % S;
+          const unsigned t_c = atomicAdd(&g.hdr->next, 1u);
+          const unsigned m_b = load_mask(t_b);
+          if (t_b < (unsigned)g.n_chunks) {                                  // next issue's chunk: start it towards L2 now
+            const ChunkRef nr = chunk_ref(g, chunk_of((int)t_b));
+            const unsigned bytes = (unsigned)nr.n * 4u;
+            l2_prefetch_bulk(a.hm_logits + nr.base, bytes);
+            if (!sparse_ok) l2_prefetch_bulk(a.hm_gt + nr.base, bytes);
+          }
+          long long tw0 = 0;
+          if (g.dbg != nullptr) tw0 = clock_ns();
+          if (j >= S) mbar_wait(&empty[s], (unsigned)(((j / S) - 1) & 1));   // every consumer warp is done with the stage
+          if (g.dbg != nullptr) g.dbg[(long long)bid * 16 + 10] += clock_ns() - tw0;
+          if (t_a >= (unsigned)g.n_chunks) {                                 // out of work: wake the consumers
+            sh_chunk[s] = -1;
+            mbar_arrive(&full[s * kSubs]);
+            break;
+          }
+          const int chunk = chunk_of((int)t_a);
+          if (sparse_ok) g.sparse[chunk] = 0u;
+          sh_chunk[s] = chunk;
+          sh_mask[s] = m_a;
+          issue_chunk(a, chunk_ref(g, chunk), stages[s], &full[s * kSubs], m_a);
+          t_a = t_b;
+          t_b = t_c;
+          m_a = m_b;
+        }
+      }
+    } else {
+      // ---- consumers ----
+#pragma unroll 1
+      for (int i = 0;; ++i) {
+        const int s = i % S;
+        const unsigned ph = (unsigned)((i / S) & 1);
+        long long tw0 = 0;
+        if (g.dbg != nullptr && tid == 0) tw0 = clock_ns();
+        mbar_wait(&full[s * kSubs], ph);                     // acquires sh_chunk / sh_mask of this fill
+        if (g.dbg != nullptr && tid == 0) { g.dbg[(long long)bid * 16 + 8] += clock_ns() - tw0; g.dbg[(long long)bid * 16 + 9] += 1; }
+        const int chunk = sh_chunk[s];
+        if (chunk < 0) break;
+        const unsigned m = sh_mask[s];
+        process_chunk<kGrad, FAST, true, false>(a, chunk_ref(g, chunk), stages[s], &full[s * kSubs], ph, m, scale, la);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+    }
+    dbg_stamp(g.dbg, 3);
+    if (consumer) {
+      block_reduce_loss(la, red_l, red_i);
+      if (tid == 0) {
+        acc_add_pair(acc, 0, la.hi, la.lo);
+        if (MODE != M_PRECOUNT && la.npos) acc_add_int(acc, 1, la.npos);     // PRECOUNT counted in phase 0
       }
     }
   }
@@ -1256,7 +1378,11 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   }
   __syncthreads();
   if (tid < CNH_TOTALS) acc[tid] = 0ll;
-  if (tid == 0) g.hdr->done = 0;
+  if (tid == 0) {
+    g.hdr->done = 0;
+    g.hdr->next = 0;
+    g.hdr->next0 = 0;
+  }
   dbg_stamp(g.dbg, 4);
 }
 
@@ -1416,7 +1542,7 @@ static int launch(const void* kernel, bool cooperative, int grid, int stages, co
 
 // STASH plan: the smallest number of stages per CTA with which one wave holds every chunk
 static bool plan_stash(const void* kernel, Geo& g) {
-  if (g.n_chunks > kMaxCounted || g.n_items > kMaxCounted) return false;   // contribution counters are 16 bits
+  if (g.n_items > kMaxCounted) return false;                 // contribution counters are 16 bits
   for (int S = 1; S <= kMaxStages; ++S) {
     const long long cap = (long long)resident_ctas(kernel, S, kStashThreads) - 1;     // one CTA is the finaliser
     if (cap >= 1 && cap * S >= g.n_chunks) {
@@ -1431,7 +1557,7 @@ static bool plan_stash(const void* kernel, Geo& g) {
 static int stream_grid(const void* kernel, const Geo& g, long long warp_units, int stages = kStreamStages) {
   long long want = g.n_chunks + (warp_units + kWarps - 1) / kWarps;
   if (want < 1) want = 1;
-  int cap = resident_ctas(kernel, stages);
+  int cap = resident_ctas(kernel, stages, kStashThreads);
   if (cap < 1) cap = 1;
   return (int)(want < cap ? want : cap);
 }
@@ -1468,7 +1594,7 @@ static int detloss_fused_impl(const cnh_detloss_args* a, const cnh_peers* peers,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->grad_hm == nullptr) {
     const void* k = pick_stream<M_FWD>(fast, vec);
-    return launch(k, false, stream_grid(k, g, g.n_items + g.n_count), kStreamStages, a, g, st);
+    return launch(k, false, stream_grid(k, g, g.n_items + g.n_count), kStreamStages, a, g, st, kStashThreads);
   }
   const void* ks = pick_stash(fast, vec);
   if (!(a->flags & CNH_FLAG_NO_STASH) && plan_stash(ks, g)) {
@@ -1479,7 +1605,7 @@ static int detloss_fused_impl(const cnh_detloss_args* a, const cnh_peers* peers,
               "detloss_fused_peers: problem too large for the single-wave schedule (%d chunks); use count/main", g.n_chunks);
   g.n_stages = kStreamStages;
   const void* kp = pick_stream<M_PRECOUNT>(fast, vec);
-  return launch(kp, true, stream_grid(kp, g, g.n_items + g.n_count), kStreamStages, a, g, st);
+  return launch(kp, true, stream_grid(kp, g, g.n_items + g.n_count), kStreamStages, a, g, st, kStashThreads);
 }
 
 extern "C" int cnh_detloss_fused(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
@@ -1505,7 +1631,7 @@ extern "C" int cnh_detloss_count(const cnh_detloss_args* a, void* workspace, siz
               "detloss_count: workspace %zu < %zu bytes", workspace_bytes, ws_bytes(a));
   const Geo g = make_geo(a, workspace);
   const void* k = pick_stream<M_COUNT>(true, use_vec(a, g));
-  return launch(k, false, stream_grid(k, g, g.n_count, 0), 0, a, g, static_cast<cudaStream_t>(stream));
+  return launch(k, false, stream_grid(k, g, g.n_count, 0), 0, a, g, static_cast<cudaStream_t>(stream), kStashThreads);
 }
 
 extern "C" int cnh_detloss_main(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
@@ -1519,7 +1645,7 @@ extern "C" int cnh_detloss_main(const cnh_detloss_args* a, void* workspace, size
   const Geo g = make_geo(a, workspace);
   const void* k = pick_stream<M_MAIN>(!(a->flags & CNH_FLAG_ACCURATE_MATH), use_vec(a, g));
   return launch(k, false, stream_grid(k, g, g.n_items + g.n_count), kStreamStages, a, g,
-                static_cast<cudaStream_t>(stream));
+                static_cast<cudaStream_t>(stream), kStashThreads);
 }
 
 extern "C" int cnh_detloss_finalize(const cnh_detloss_args* a, const int64_t* totals, cnh_stream_t stream) {

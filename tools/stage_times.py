@@ -37,9 +37,14 @@ lib.cnh_debug_set_buffer(dbg.data_ptr())
 for rep in range(2):
     dbg.zero_(); torch.cuda.synchronize()
     d.loss_only(rep)
-    show(f"detloss {name} rep{rep}", 15)
+    show(f"detloss {name} rep{rep}", 8)
     t = dbg.cpu(); used = (t[:, 0] != 0) & (t[:, 1] != 0)
-    if used.any():
+    if name == "cfg5":
+        u2 = t[:, 9] > 0
+        print("  consumer blocked on full (us) median/max:", (t[u2, 8].float() / 1e3).median().item(), (t[u2, 8].float() / 1e3).max().item(),
+              "| chunks per CTA min/median/max:", (t[u2, 9] - 1).min().item(), (t[u2, 9] - 1).median().item(), (t[u2, 9] - 1).max().item(),
+              "| producer blocked on empty (us) median:", (t[u2, 10].float() / 1e3).median().item())
+    if used.any() and name != "cfg5":
         t0 = t[used, 0].min(); sm = t[used, 15]; done = (t[used, 1] - t0).float() / 1e3; start = (t[used, 0] - t0).float() / 1e3
         per = {}
         for s_, d_, st_ in zip(sm.tolist(), done.tolist(), start.tolist()): per.setdefault(s_, []).append((round(st_, 2), round(d_, 2)))
