@@ -29,9 +29,18 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace cnh {
+
+// Barrier over the first 256 threads of the CTA (warps 0-7).  The selection helpers below are written for
+// 256 threads; in the 256-thread kernels this is a full-CTA barrier, in the 1024-thread cluster kernel the
+// other warps wait at the next __syncthreads().
+__device__ __forceinline__ void group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 constexpr int kCols = 128;                // max tile columns
 constexpr int kPadL = 4;                  // left halo padded to 4 floats: interior is 16B aligned
@@ -92,9 +101,9 @@ __device__ __forceinline__ unsigned block_suffix_excl(unsigned v, unsigned* warp
     const unsigned t = __shfl_down_sync(0xffffffffu, incl, o);
     if (lane + o < 32) incl += t;
   }
-  __syncthreads();                        // warp_tot may still be read from a previous use
+  group_sync();                        // warp_tot may still be read from a previous use
   if (lane == 0) warp_tot[warp] = incl;
-  __syncthreads();
+  group_sync();
   unsigned higher = 0;
   total = 0;
 #pragma unroll
@@ -142,7 +151,7 @@ __device__ __noinline__ void find_kth_bin(SM& s, unsigned need) {
       acc += c[j];
     }
   }
-  __syncthreads();
+  group_sync();
 }
 
 // Threshold from the sample's global coarse histogram: score bits of the lower edge of the highest
@@ -168,7 +177,7 @@ __device__ __noinline__ unsigned global_threshold(const unsigned* ghist, unsigne
       acc += c[j];
     }
   }
-  __syncthreads();
+  group_sync();
   return s.sh_thr;
 }
 
@@ -182,11 +191,11 @@ __device__ u64 radix_select_kth(ForEach for_each, int need, SM& s) {
   unsigned remaining = (unsigned)need;
   for (int shift = 56; shift >= 0; shift -= 8) {
     for (int i = threadIdx.x; i < 256; i += kThreads) s.hist[i] = 0;
-    __syncthreads();
+    group_sync();
     for_each([&](u64 k) {
       if ((k & mask) == prefix) atomicAdd(&s.hist[(unsigned)(k >> shift) & 255u], 1u);
     });
-    __syncthreads();
+    group_sync();
     if (threadIdx.x < 32) {
       // lane owns bins [8*lane, 8*lane+8); find the highest digit d with count(>= d) >= remaining
       const int lane = threadIdx.x;
@@ -213,12 +222,12 @@ __device__ u64 radix_select_kth(ForEach for_each, int need, SM& s) {
         s.sh_flag = (s.hist[d] == remaining - acc) ? 1u : 0u;   // whole bin taken: done
       }
     }
-    __syncthreads();
+    group_sync();
     prefix = s.sh_prefix;
     remaining = s.sh_need;
     mask |= (u64)255u << shift;
     const bool done = s.sh_flag != 0u;
-    __syncthreads();
+    group_sync();
     if (done) break;
   }
   return prefix;   // lower digits zero: every key of the last bin is >= prefix
@@ -255,55 +264,113 @@ __device__ __noinline__ bool is_candidate_global(const cnh_decode_args& a, int b
   return m == v;
 }
 
-// ---- stage 2: merge one sample (run by the CTA whose ticket completed it) ---------------------
-typedef DecSmemT<kMergeKeyCap> MergeSmem;
-__device__ void merge_sample(const cnh_decode_args& a, const DecGeo& g, MergeSmem& s, int b) {
-  constexpr int kKeyCap = MergeSmem::kKeyCap;
+// ---- threshold-first scan of one staged tile (rows x cols, halo included in `tile`) -------------
+// warp w of kNWarps owns rows [w*kRows/kNWarps, (w+1)*kRows/kNWarps), lane owns columns [4*lane, 4*lane+4).  Peaks with score >= thr
+// are appended to keys (counter *key_cnt, shared memory) and counted in the packed fine histogram s.hist.
+// plane_flat0 = c*H*W; (y0, x0) = tile origin in the plane.
+template <int kRows, int kNWarps, class SM>
+__device__ __forceinline__ void scan_tile(SM& s, u64* keys, unsigned* key_cnt, const float* tile, int BW, int rows,
+                                          int cols, unsigned thr, unsigned plane_flat0, int y0, int x0, int W) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float thr_f = __uint_as_float(thr);
+  constexpr int kRowsPerWarp = kRows / kNWarps;
+  float cv[kRowsPerWarp][4];
+  unsigned flags = 0;                     // bit 4*rr + e
+#pragma unroll
+  for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+    const int r = warp * kRowsPerWarp + rr;
+    const float* row = tile + (r + 1) * BW + kPadL;
+    const float4 v = *reinterpret_cast<const float4*>(row + 4 * lane);
+    cv[rr][0] = v.x; cv[rr][1] = v.y; cv[rr][2] = v.z; cv[rr][3] = v.w;
+    const bool row_ok = r < rows;
+    unsigned pass = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      pass |= (row_ok && (4 * lane + e < cols) && cv[rr][e] > 0.f && cv[rr][e] >= thr_f) ? (1u << e) : 0u;
+    const unsigned hit = __ballot_sync(0xffffffffu, pass != 0u);
+    if (hit == 0u) continue;                                       // nothing in this row can matter
+    if (__popc(hit) <= 6) {
+      // sparse row (the steady state once the threshold has tightened): each lane tests its own
+      // few pixels against their 8 neighbours straight from shared memory
+      if (pass) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (pass & (1u << e)) {
+            const float* p = row + 4 * lane + e;
+            const float m = fmaxf(fmaxf(fmaxf(p[-BW - 1], p[-BW]), fmaxf(p[-BW + 1], p[-1])),
+                                  fmaxf(fmaxf(p[1], p[BW - 1]), fmaxf(p[BW], p[BW + 1])));
+            if (cv[rr][e] >= m) flags |= 1u << (4 * rr + e);
+          }
+      }
+      continue;
+    }
+    // dense row: 3x3 maximum for the whole row, rows r-1, r, r+1 (tile rows r, r+1, r+2),
+    // neighbours by shuffle
+    float m[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int dr = 0; dr < 3; ++dr) {
+      const float* rw = tile + (r + dr) * BW + kPadL;
+      const float4 u = (dr == 1) ? v : *reinterpret_cast<const float4*>(rw + 4 * lane);
+      float left = __shfl_up_sync(0xffffffffu, u.w, 1);
+      float right = __shfl_down_sync(0xffffffffu, u.x, 1);
+      if (lane == 0) left = rw[-1];
+      if (lane == 31) right = rw[4 * 32];
+      m[0] = fmaxf(m[0], fmaxf(fmaxf(left, u.x), u.y));
+      m[1] = fmaxf(m[1], fmaxf(fmaxf(u.x, u.y), u.z));
+      m[2] = fmaxf(m[2], fmaxf(fmaxf(u.y, u.z), u.w));
+      m[3] = fmaxf(m[3], fmaxf(fmaxf(u.z, u.w), right));
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if ((pass & (1u << e)) && cv[rr][e] == m[e]) flags |= 1u << (4 * rr + e);
+  }
+  // one warp-aggregated append for the warp's rows
+  const int mine = __popc(flags);
+  if (__ballot_sync(0xffffffffu, mine != 0) != 0u) {
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned base = 0;
+    if (lane == 31) base = atomicAdd(key_cnt, (unsigned)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    unsigned pos = base + (unsigned)(incl - mine);
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+      const unsigned flat0 = plane_flat0 +
+                             (unsigned)(y0 + warp * kRowsPerWarp + rr) * (unsigned)W + (unsigned)(x0 + 4 * lane);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (flags & (1u << (4 * rr + e))) {
+          const unsigned bits = __float_as_uint(cv[rr][e]);
+          keys[pos++] = ((u64)bits << 32) | (u64)(0xffffffffu - (flat0 + e));
+          hist_add(s.hist, fine_bin(bits));
+        }
+    }
+  }
+}
+
+// ---- final selection, sort, filler, gather and box assembly of one sample -------------------------
+// keys[0..m): candidate keys in shared memory, a superset of the sample's top-K, with s.hist holding their
+// packed fine histogram (only read when m > kThreads); if m > key_cap the list in `keys` is partial and
+// overflow_keys(f) must call f(key) for every candidate (each thread a disjoint subset, all threads
+// participating).  Uses s.stage as `sorted` and aliases s.hist as `sel`; s.cnt2 must be 0.
+template <class SM, class Overflow>
+__device__ __forceinline__ void select_sort_emit(const cnh_decode_args& a, const DecGeo& g, SM& s, int b,
+                                                 const u64* keys, int m, int key_cap, Overflow overflow_keys) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K;
-  unsigned* ghist = g.ghist + (long long)b * kCoarseBins;
-  const u64* cand = g.cand + (long long)b * g.tiles_per_sample * g.slot;
   u64* const sel = reinterpret_cast<u64*>(s.hist);
   u64* const sorted = s.stage;
-  dbg_stamp(g.dbg, 5);
-  for (int j = 0; j < kFineBins / 2 / kThreads; ++j) s.hist[tid + j * kThreads] = 0u;
-  if (tid == 0) { s.cnt = 0; s.cnt2 = 0; }
-  asm volatile("griddepcontrol.wait;" ::: "memory");     // PDL: the tile kernel's writes are visible from here
-  const unsigned nc = __ldcg(&g.state[b].cand_cnt);                         // same round trip as the histogram
-  const unsigned thr_final = global_threshold(ghist, (unsigned)K, s);        // barriers inside
-  dbg_stamp(g.dbg, 6);
-  // survivors (score >= final threshold) -> shared memory keys + fine histogram; dense list, 8
-  // independent loads in flight per thread
-  auto for_each_survivor = [&](auto f) {
-    constexpr int kB = 8;
-    for (unsigned e0 = 0; e0 < nc; e0 += kB * kThreads) {
-      u64 k[kB];
-#pragma unroll
-      for (int j = 0; j < kB; ++j) {
-        const unsigned e = e0 + j * kThreads + tid;
-        k[j] = (e < nc) ? __ldcg(cand + e) : 0ull;
-      }
-#pragma unroll
-      for (int j = 0; j < kB; ++j) {
-        if (e0 + j * kThreads >= nc) break;                                 // block-uniform
-        f(e0 + j * kThreads + tid < nc && (unsigned)(k[j] >> 32) >= thr_final, k[j]);
-      }
-    }
-  };
-  for_each_survivor([&](bool ok, u64 k) {
-    append_if(ok, k, s.keys, &s.cnt, (unsigned)kKeyCap);
-    if (ok) hist_add(s.hist, fine_bin((unsigned)(k >> 32)));
-  });
-  __syncthreads();
-  dbg_stamp(g.dbg, 7);
-  const int m = (int)s.cnt;                  // survivors (may exceed kKeyCap: then s.keys is partial)
   int got = 0;                               // keys to sort; the first min(got, K) ranks are real detections
   const u64* sort_src = sel;
-  if (m <= kMaxK) {
-    sort_src = s.keys;                       // few enough: rank-sort the survivors directly
+  if (m <= kThreads || m <= K) {
+    sort_src = keys;                         // one key per thread (bitonic) or nothing to cut: sort the survivors directly
     got = m;
-  } else if (m <= kKeyCap) {
-    const u64* keys = s.keys;
+  } else if (m <= key_cap) {
     find_kth_bin(s, (unsigned)K);            // ends with a barrier: the histogram is dead afterwards
     const unsigned keep_n = s.sh_above + s.sh_inbin;
     if (keep_n <= (unsigned)kMaxK) {
@@ -326,25 +393,25 @@ __device__ void merge_sample(const cnh_decode_args& a, const DecGeo& g, MergeSme
   } else {
     // more survivors than shared memory holds (heavy ties): exact radix select straight from the
     // sample's candidate list in global memory
-    const u64 T = radix_select_kth([&](auto f) { for_each_survivor([&](bool ok, u64 k) { if (ok) f(k); }); }, K, s);
-    for_each_survivor([&](bool ok, u64 k) { append_if(ok && k >= T, k, sel, &s.cnt2, (unsigned)kMaxK); });
+    const u64 T = radix_select_kth(overflow_keys, K, s);
+    overflow_keys([&](u64 k) { append_if(k >= T, k, sel, &s.cnt2, (unsigned)kMaxK); });
     got = K;
   }
-  __syncthreads();
+  group_sync();
   dbg_stamp(g.dbg, 8);
   if (got <= kThreads) {
     // <= 256 keys: one key per thread, bitonic sort (descending; padding 0 sorts last).  Exchange
     // distances below 32 are warp shuffles, the rest go through shared memory.
     u64 k = (tid < got) ? sort_src[tid] : 0ull;
-    __syncthreads();                                       // sort_src may alias `sorted`'s neighbours: settle reads
+    group_sync();                                       // sort_src may alias `sorted`'s neighbours: settle reads
     for (int size = 2; size <= kThreads; size <<= 1) {
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
         u64 other;
         if (stride >= 32) {
           sorted[tid] = k;
-          __syncthreads();
+          group_sync();
           other = sorted[tid ^ stride];
-          __syncthreads();
+          group_sync();
         } else {
           other = __shfl_xor_sync(0xffffffffu, k, stride);
         }
@@ -383,7 +450,7 @@ __device__ void merge_sample(const cnh_decode_args& a, const DecGeo& g, MergeSme
   }
   dbg_stamp(g.dbg, 11);
   if (g.dbg && tid == 0) { g.dbg[(long long)blockIdx.x * 16 + 12] = m; g.dbg[(long long)blockIdx.x * 16 + 13] = got; }
-  __syncthreads();
+  group_sync();
   if (got > K) got = K;
   // fewer than K peaks: zero-score filler at the lowest flat indices that are not candidates
   if (got < K) {
@@ -394,16 +461,16 @@ __device__ void merge_sample(const cnh_decode_args& a, const DecGeo& g, MergeSme
       const bool fill = (f < total) && !is_candidate_global(a, b, f, g.HW);
       const unsigned bal = __ballot_sync(0xffffffffu, fill);
       if (lane == 0) s.warp_tot[warp] = (unsigned)__popc(bal);
-      __syncthreads();
+      group_sync();
       unsigned before = 0, all = 0;
       for (int w = 0; w < kWarps; ++w) { if (w < warp) before += s.warp_tot[w]; all += s.warp_tot[w]; }
       const unsigned pos = (unsigned)have + before + (unsigned)__popc(bal & ((1u << lane) - 1u));
       if (fill && pos < (unsigned)K) sorted[pos] = (u64)(0xffffffffu - (unsigned)f);   // score bits 0
       have += (int)all;
-      __syncthreads();
+      group_sync();
     }
   }
-  __syncthreads();
+  group_sync();
   dbg_stamp(g.dbg, 9);
   // ---- gather + box assembly (backends/decode.py:44-74) -----------------------------------------
   const int ncol = a.rotated ? 7 : 6;
@@ -449,6 +516,49 @@ __device__ void merge_sample(const cnh_decode_args& a, const DecGeo& g, MergeSme
       }
     }
   }
+}
+
+// ---- stage 2: merge one sample (run by the CTA whose ticket completed it) ---------------------
+typedef DecSmemT<kMergeKeyCap> MergeSmem;
+__device__ void merge_sample(const cnh_decode_args& a, const DecGeo& g, MergeSmem& s, int b) {
+  constexpr int kKeyCap = MergeSmem::kKeyCap;
+  const int tid = threadIdx.x;
+  const int K = a.K;
+  unsigned* ghist = g.ghist + (long long)b * kCoarseBins;
+  const u64* cand = g.cand + (long long)b * g.tiles_per_sample * g.slot;
+  dbg_stamp(g.dbg, 5);
+  for (int j = 0; j < kFineBins / 2 / kThreads; ++j) s.hist[tid + j * kThreads] = 0u;
+  if (tid == 0) { s.cnt = 0; s.cnt2 = 0; }
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // PDL: the tile kernel's writes are visible from here
+  const unsigned nc = __ldcg(&g.state[b].cand_cnt);                         // same round trip as the histogram
+  const unsigned thr_final = global_threshold(ghist, (unsigned)K, s);        // barriers inside
+  dbg_stamp(g.dbg, 6);
+  // survivors (score >= final threshold) -> shared memory keys + fine histogram; dense list, 8
+  // independent loads in flight per thread
+  auto for_each_survivor = [&](auto f) {
+    constexpr int kB = 8;
+    for (unsigned e0 = 0; e0 < nc; e0 += kB * kThreads) {
+      u64 k[kB];
+#pragma unroll
+      for (int j = 0; j < kB; ++j) {
+        const unsigned e = e0 + j * kThreads + tid;
+        k[j] = (e < nc) ? __ldcg(cand + e) : 0ull;
+      }
+#pragma unroll
+      for (int j = 0; j < kB; ++j) {
+        if (e0 + j * kThreads >= nc) break;                                 // block-uniform
+        f(e0 + j * kThreads + tid < nc && (unsigned)(k[j] >> 32) >= thr_final, k[j]);
+      }
+    }
+  };
+  for_each_survivor([&](bool ok, u64 k) {
+    append_if(ok, k, s.keys, &s.cnt, (unsigned)kKeyCap);
+    if (ok) hist_add(s.hist, fine_bin((unsigned)(k >> 32)));
+  });
+  __syncthreads();
+  dbg_stamp(g.dbg, 7);
+  select_sort_emit(a, g, s, b, s.keys, (int)s.cnt, kKeyCap,
+                   [&](auto f) { for_each_survivor([&](bool ok, u64 k) { if (ok) f(k); }); });
   dbg_stamp(g.dbg, 10);
   // ---- leave the per-sample state zeroed for the next launch ---------------------------------
   __syncthreads();
@@ -474,7 +584,7 @@ decode_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_a
   DecSmem& s = *reinterpret_cast<DecSmem*>(smem_raw);
   float* const ring = reinterpret_cast<float*>(smem_raw + sizeof(DecSmem));
   const int S = g.n_stages;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int K = a.K;
   const int BW = g.box_w;
   // this CTA's contiguous tile range
@@ -581,88 +691,7 @@ decode_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_a
     if (t == lo) dbg_stamp(g.dbg, 1);
     if (dbg_it) dbg_stamp(g.dbg, 7);
 
-    // ---- threshold-first scan: warp w owns rows {2w, 2w+1}, lane owns columns [4*lane, 4*lane+4) ----
-    {
-      const float thr_f = __uint_as_float(thr);
-      constexpr int kRowsPerWarp = kRows / kWarps;
-      float cv[kRowsPerWarp][4];
-      unsigned flags = 0;                     // bit 4*rr + e
-#pragma unroll
-      for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-        const int r = warp * kRowsPerWarp + rr;
-        const float* row = tile + (r + 1) * BW + kPadL;
-        const float4 v = *reinterpret_cast<const float4*>(row + 4 * lane);
-        cv[rr][0] = v.x; cv[rr][1] = v.y; cv[rr][2] = v.z; cv[rr][3] = v.w;
-        const bool row_ok = r < rows;
-        unsigned pass = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          pass |= (row_ok && (4 * lane + e < cols) && cv[rr][e] > 0.f && cv[rr][e] >= thr_f) ? (1u << e) : 0u;
-        const unsigned hit = __ballot_sync(0xffffffffu, pass != 0u);
-        if (hit == 0u) continue;                                       // nothing in this row can matter
-        if (__popc(hit) <= 6) {
-          // sparse row (the steady state once the threshold has tightened): each lane tests its own
-          // few pixels against their 8 neighbours straight from shared memory
-          if (pass) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (pass & (1u << e)) {
-                const float* p = row + 4 * lane + e;
-                const float m = fmaxf(fmaxf(fmaxf(p[-BW - 1], p[-BW]), fmaxf(p[-BW + 1], p[-1])),
-                                      fmaxf(fmaxf(p[1], p[BW - 1]), fmaxf(p[BW], p[BW + 1])));
-                if (cv[rr][e] >= m) flags |= 1u << (4 * rr + e);
-              }
-          }
-          continue;
-        }
-        // dense row: 3x3 maximum for the whole row, rows r-1, r, r+1 (tile rows r, r+1, r+2),
-        // neighbours by shuffle
-        float m[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int dr = 0; dr < 3; ++dr) {
-          const float* rw = tile + (r + dr) * BW + kPadL;
-          const float4 u = (dr == 1) ? v : *reinterpret_cast<const float4*>(rw + 4 * lane);
-          float left = __shfl_up_sync(0xffffffffu, u.w, 1);
-          float right = __shfl_down_sync(0xffffffffu, u.x, 1);
-          if (lane == 0) left = rw[-1];
-          if (lane == 31) right = rw[4 * 32];
-          m[0] = fmaxf(m[0], fmaxf(fmaxf(left, u.x), u.y));
-          m[1] = fmaxf(m[1], fmaxf(fmaxf(u.x, u.y), u.z));
-          m[2] = fmaxf(m[2], fmaxf(fmaxf(u.y, u.z), u.w));
-          m[3] = fmaxf(m[3], fmaxf(fmaxf(u.z, u.w), right));
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if ((pass & (1u << e)) && cv[rr][e] == m[e]) flags |= 1u << (4 * rr + e);
-      }
-      // one warp-aggregated append for the warp's rows
-      const int mine = __popc(flags);
-      if (__ballot_sync(0xffffffffu, mine != 0) != 0u) {
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        unsigned base = 0;
-        if (lane == 31) base = atomicAdd(&s.cnt, (unsigned)total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        unsigned pos = base + (unsigned)(incl - mine);
-#pragma unroll
-        for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-          const unsigned flat0 = (unsigned)c * (unsigned)g.HW +
-                                 (unsigned)(y0 + warp * kRowsPerWarp + rr) * (unsigned)a.W + (unsigned)(x0 + 4 * lane);
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (flags & (1u << (4 * rr + e))) {
-              const unsigned bits = __float_as_uint(cv[rr][e]);
-              s.keys[pos++] = ((u64)bits << 32) | (u64)(0xffffffffu - (flat0 + e));
-              hist_add(s.hist, fine_bin(bits));
-            }
-        }
-      }
-    }
+    scan_tile<kRows, kWarps>(s, s.keys, &s.cnt, tile, BW, rows, cols, thr, (unsigned)c * (unsigned)g.HW, y0, x0, a.W);
     if (dbg_it) dbg_stamp(g.dbg, 8);
     __syncthreads();                          // tile[buf] is free; keys / histogram complete
     const int n = (int)s.cnt;
@@ -750,6 +779,279 @@ decode_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const cnh_decode_a
   flush(cur_b);
 }
 
+// ---- lean scan for the cluster kernel: peaks >= thr of one staged tile -> keys, no histogram ---------
+// The tile is staged WITHOUT halo columns: rows of W floats (W <= 128, row stride W), first row = the row above
+// the tile; rows outside the image hold 0.  One row per warp, lane owns columns [4*lane, 4*lane+4); colmask
+// (4 bits) masks the lane's columns beyond W (those lanes read the following row: harmless).  3x3 maximum =
+// vertical max of three LDS.128, then horizontal max with the neighbours' edge columns by shuffle; the
+// columns left of 0 and right of W-1 are the max-pool padding (0 is neutral: heat >= 0).
+__device__ __forceinline__ void scan_rows_lean(u64* keys, unsigned* key_cnt, const float* tile, int W, unsigned colmask,
+                                               bool last_lane, unsigned thr, unsigned flat_row0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* row = tile + (warp + 1) * W + 4 * lane;
+  const float4 mid = *reinterpret_cast<const float4*>(row);
+  const float thr_eff = fmaxf(__uint_as_float(thr), __uint_as_float(1u));      // >= thr and > 0
+  unsigned pass = (mid.x >= thr_eff ? 1u : 0u) | (mid.y >= thr_eff ? 2u : 0u) | (mid.z >= thr_eff ? 4u : 0u) |
+                  (mid.w >= thr_eff ? 8u : 0u);
+  pass &= colmask;
+  if (__ballot_sync(0xffffffffu, pass != 0u) == 0u) return;                      // nothing in this row can matter
+  const float4 up = *reinterpret_cast<const float4*>(row - W);
+  const float4 dn = *reinterpret_cast<const float4*>(row + W);
+  const float v0 = fmaxf(fmaxf(up.x, mid.x), dn.x), v1 = fmaxf(fmaxf(up.y, mid.y), dn.y);
+  const float v2 = fmaxf(fmaxf(up.z, mid.z), dn.z), v3 = fmaxf(fmaxf(up.w, mid.w), dn.w);
+  float left = __shfl_up_sync(0xffffffffu, v3, 1), right = __shfl_down_sync(0xffffffffu, v0, 1);
+  if (lane == 0) left = 0.f;
+  if (last_lane) right = 0.f;
+  const float h0 = fmaxf(fmaxf(left, v0), v1), h1 = fmaxf(fmaxf(v0, v1), v2);
+  const float h2 = fmaxf(fmaxf(v1, v2), v3), h3 = fmaxf(fmaxf(v2, v3), right);
+  const unsigned flags = pass & ((mid.x == h0 ? 1u : 0u) | (mid.y == h1 ? 2u : 0u) | (mid.z == h2 ? 4u : 0u) |
+                                 (mid.w == h3 ? 8u : 0u));
+  const unsigned any = __ballot_sync(0xffffffffu, flags != 0u);
+  if (any == 0u) return;
+  const int mine = __popc(flags);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    incl += (lane >= o) ? v : 0;
+  }
+  unsigned base = 0;
+  if (lane == 31) base = atomicAdd(key_cnt, (unsigned)incl);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  u64* dst = keys + base + (unsigned)(incl - mine);
+  const unsigned nflat = 0xffffffffu - (flat_row0 + 4u * (unsigned)lane);       // ~flat of the lane's first column
+  if (flags & 1u) *dst++ = ((u64)__float_as_uint(mid.x) << 32) | (u64)nflat;
+  if (flags & 2u) *dst++ = ((u64)__float_as_uint(mid.y) << 32) | (u64)(nflat - 1u);
+  if (flags & 4u) *dst++ = ((u64)__float_as_uint(mid.z) << 32) | (u64)(nflat - 2u);
+  if (flags & 8u) *dst++ = ((u64)__float_as_uint(mid.w) << 32) | (u64)(nflat - 3u);
+}
+
+// ---- cluster path: one thread-block cluster per sample, ONE launch, no global scratch ------------------
+// The CS CTAs of a cluster split the sample's tiles (tile t -> CTA t % CS), each walking its share
+// with a TMA ring and keeping a running candidate set in shared memory: whenever the set outgrows
+// K + kSlack keys it is cut back to the bins >= that of its K-th score (exact radix select on heavy
+// ties) and the cut becomes the pruning threshold of the following tiles.  At the end every CTA
+// pushes its <= K + kSlack keys into the leader's shared memory through DSMEM (one remote atomic for
+// the slice, then remote stores), a cluster barrier publishes them, and the leader runs the final
+// selection, sort, filler, gather and box assembly.  Versus the two-kernel path: no candidate lists,
+// histograms or tickets in global memory, no second launch, nothing to leave zeroed.
+constexpr int kClRows = 32;
+constexpr int kClTileFloats = (kClRows + 2) * kCols + 128;   // 34 rows of <= 128 floats + slack for masked lanes
+constexpr int kClTile = kClRows * kCols;   // most peaks one tile can add
+constexpr int kClCap = 2 * kClTile;        // running candidate set: cut back whenever it exceeds kClTile
+constexpr int kClStages = 4;               // TMA ring depth
+constexpr int kClThreads = 1024;           // 32 warps: one tile row per warp in the scan
+static_assert(kClThreads / 32 == kClRows, "scan_rows_lean: one tile row per warp");
+struct __align__(128) ClSmem {              // followed by the TMA ring and the leader's inbox
+  u64 stage[kClCap];                       // the set (the scan appends to it); final stage: `sorted`
+  unsigned hist[kFineBins / 2];            // packed fine histogram of the set, built per cut; final stage: `sel`
+  u64 mbar[kClStages];
+  u64 sh_prefix;
+  unsigned cnt;                            // size of the set
+  unsigned cnt2;
+  unsigned sh_need;
+  unsigned sh_flag;
+  unsigned sh_thr;
+  unsigned sh_bin;
+  unsigned sh_above;
+  unsigned sh_inbin;
+  unsigned sh_base;
+  unsigned fin_cnt;                        // leader: keys received from the cluster
+  unsigned warp_tot[kWarps];
+};
+static_assert(kClCap >= kMaxK, "stage also holds the sorted output");
+
+__global__ void __launch_bounds__(kClThreads, 1)
+decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_constant__ DecGeo g) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int b = (int)(blockIdx.x / (unsigned)CS);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ClSmem& s = *reinterpret_cast<ClSmem*>(smem_raw);
+  float* const ring = reinterpret_cast<float*>(smem_raw + sizeof(ClSmem));
+  u64* const inbox = reinterpret_cast<u64*>(smem_raw + sizeof(ClSmem) + (size_t)kClStages * kClTileFloats * sizeof(float));
+  const int tid = threadIdx.x;
+  const bool group0 = tid < kThreads;                       // warps 0-7 run the 256-thread selection helpers
+  const int K = a.K, W = a.W, H = a.H;
+  const unsigned slot = (unsigned)g.slot;
+  const int n_my = rank < g.tiles_per_sample ? (g.tiles_per_sample - rank + CS - 1) / CS : 0;
+  const float* const sample = a.heat + (long long)b * a.C * g.HW;
+  dbg_stamp(g.dbg, 0);
+
+  // Tile t of the sample = rows [32*ty, 32*ty+32) of class plane c, t = c*tiles_y + ty (W <= 128: one tile
+  // column).  This CTA walks t = rank, rank+CS, ...; every thread keeps two cursors, advanced without
+  // divisions: the tile being scanned and the tile being prefetched kClStages ahead.
+  struct Cursor { int c, ty; };
+  auto advance = [&](Cursor& q, int by) {
+    q.ty += by;
+    while (q.ty >= g.tiles_y) { q.ty -= g.tiles_y; ++q.c; }
+  };
+  // Stage tile q into ring slot buf: the rows of the tile plus one halo row above and below are contiguous
+  // in global memory (one bulk copy, SASS UBLKCP); halo/tail rows outside the image are zero-filled by the
+  // CTA's threads (max-pool padding: 0 is neutral because heat >= 0).  Called by ALL threads.
+  auto stage_tile = [&](const Cursor& q, int buf) {
+    float* dst = ring + (size_t)buf * kClTileFloats;
+    const int y0 = q.ty * kClRows;
+    const int ylo = max(y0 - 1, 0), yhi = min(y0 + kClRows + 1, H);       // image rows [ylo, yhi) are copied
+    const int r_lo = ylo - (y0 - 1), r_hi = yhi - (y0 - 1);               // -> tile rows [r_lo, r_hi) of 34
+    for (int i = tid; i < r_lo * W; i += kClThreads) dst[i] = 0.f;
+    for (int i = r_hi * W + tid; i < (kClRows + 2) * W; i += kClThreads) dst[i] = 0.f;
+    if (tid == 0) {
+      const unsigned bytes = (unsigned)((yhi - ylo) * W) * 4u;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // earlier generic accesses of the slot
+      mbar_expect_tx(&s.mbar[buf], bytes);
+      bulk_load_1d(dst + r_lo * W, sample + (long long)q.c * g.HW + (long long)ylo * W, bytes, &s.mbar[buf]);
+    }
+  };
+
+  asm volatile("griddepcontrol.wait;" ::: "memory");        // PDL: the producer of `heat` has completed
+  if (tid == 0) {
+    s.cnt = 0;
+    s.cnt2 = 0;
+    s.fin_cnt = 0;
+    for (int i = 0; i < kClStages; ++i) mbar_init(&s.mbar[i], 1);
+  }
+  __syncthreads();
+  Cursor cur = {0, 0}, pre = {0, 0};
+  advance(cur, rank);
+  pre = cur;
+  for (int j = 0; j < kClStages && j < n_my; ++j) { stage_tile(pre, j); advance(pre, CS); }
+  cluster.barrier_arrive();                                 // every CTA's inbox counter is initialised
+
+  // In-place compaction of stage[0..n) by the whole CTA, 1024 keys per step: a step's keys are in registers
+  // before anything is written, and writes only go below the step's first key.  Leaves the new size in s.cnt.
+  auto compact_all = [&](const unsigned n, auto pred) {
+    if (tid == 0) s.cnt2 = 0;
+    for (unsigned i0 = 0; i0 < n; i0 += kClThreads) {
+      const unsigned i = i0 + tid;
+      const u64 k = (i < n) ? s.stage[i] : 0ull;
+      const bool keep = (i < n) && pred(k);
+      __syncthreads();
+      append_if(keep, k, s.stage, &s.cnt2, (unsigned)kClCap);
+    }
+    __syncthreads();
+    if (tid == 0) s.cnt = s.cnt2;
+  };
+  // packed fine histogram of stage[0..n) (built only when a cut needs it)
+  auto build_hist = [&](const unsigned n) {
+    for (int w = tid; w < kFineBins / 2; w += kClThreads) s.hist[w] = 0u;
+    __syncthreads();
+    for (unsigned i = tid; i < n; i += kClThreads) hist_add(s.hist, fine_bin((unsigned)(s.stage[i] >> 32)));
+    __syncthreads();
+  };
+  // K-th key of the set, exactly (heavy ties inside one histogram bin); clobbers s.hist.  Everyone gets T.
+  auto exact_cut_key = [&](const unsigned n) {
+    if (group0) {
+      const u64 T = radix_select_kth([&](auto f) { for (unsigned i = tid; i < n; i += kThreads) f(s.stage[i]); }, K, s);
+      if (tid == 0) s.sh_prefix = T;
+    }
+    __syncthreads();
+    return s.sh_prefix;
+  };
+
+  unsigned thr = 0;                                         // pruning threshold, score bits (uniform)
+  const int lane_col = 4 * (tid & 31);
+  const unsigned colmask = W - lane_col >= 4 ? 15u : (W - lane_col <= 0 ? 0u : ((1u << (W - lane_col)) - 1u));
+  const bool last_lane = lane_col + 4 >= W;                 // the column right of this lane's is outside the image
+  for (int j = 0; j < n_my; ++j) {
+    const int buf = j & (kClStages - 1), phase = (j >> 2) & 1;
+    static_assert(kClStages == 4, "phase = (j >> log2 stages) & 1");
+    float* tile = ring + (size_t)buf * kClTileFloats;
+    const int c = cur.c, y0 = cur.ty * kClRows;
+    mbar_wait(&s.mbar[buf], (unsigned)phase);
+    if (a.apply_sigmoid) {                                  // export.py:31-33: logits in, clamp(sigmoid) fused
+      const int r_lo = max(y0 - 1, 0) - (y0 - 1), r_hi = min(y0 + kClRows + 1, H) - (y0 - 1);
+      for (int i = r_lo * W + tid; i < r_hi * W; i += kClThreads) tile[i] = clamp_prob(1.0f / (1.0f + expf(-tile[i])));
+      __syncthreads();
+    }
+    if (j == 0) dbg_stamp(g.dbg, 1);
+    scan_rows_lean(s.stage, &s.cnt, tile, W, colmask, last_lane, thr,
+                   (unsigned)c * (unsigned)g.HW + (unsigned)(y0 + (tid >> 5)) * (unsigned)W);
+    __syncthreads();                                        // tile[buf] is free; the set is complete
+    if (j == 0) dbg_stamp(g.dbg, 5);
+    if (j == 1) dbg_stamp(g.dbg, 6);
+    if (j == n_my - 1) dbg_stamp(g.dbg, 7);
+    advance(cur, CS);
+    if (j + kClStages < n_my) { stage_tile(pre, buf); advance(pre, CS); }   // refill the ring
+    const unsigned n = s.cnt;
+    // Cut the set back to (a superset of) its top K when the next tile might overflow it and, on long walks,
+    // after tiles 1, 2, 4, 8, ... so that the pruning threshold tightens early.
+    const bool more = j + 1 < n_my;
+    if (!more || !(n > (unsigned)kClTile || (n_my >= 12 && n > slot && ((j + 1) & j) == 0))) continue;
+    build_hist(n);
+    if (group0) find_kth_bin(s, (unsigned)K);
+    __syncthreads();
+    const unsigned keep_n = s.sh_above + s.sh_inbin;
+    const int tbin = (int)s.sh_bin;
+    unsigned thr_new;
+    if (keep_n <= (unsigned)kClTile) {
+      compact_all(n, [&](u64 k) { return fine_bin((unsigned)(k >> 32)) >= tbin; });
+      thr_new = __float_as_uint((float)tbin * (1.0f / (float)kFineBins));
+    } else {                                                // a plateau of ties fills the cut bin: exact selection
+      const u64 T = exact_cut_key(n);
+      compact_all(n, [&](u64 k) { return k >= T; });
+      thr_new = (unsigned)(T >> 32);
+    }
+    if (thr_new > thr) thr = thr_new;
+    __syncthreads();
+  }
+  dbg_stamp(g.dbg, 2);
+
+  // ---- final cut fused with the push into the leader's inbox (DSMEM) --------------------------------
+  const unsigned n = s.cnt;
+  int mode = 0, tbin = 0;                                   // 0: send everything, 1: bins >= tbin, 2: keys >= T
+  u64 T = 0;
+  unsigned send_n = n;
+  if (n > slot) {
+    build_hist(n);
+    if (group0) find_kth_bin(s, (unsigned)K);
+    __syncthreads();
+    send_n = s.sh_above + s.sh_inbin;
+    tbin = (int)s.sh_bin;
+    mode = 1;
+    if (send_n > slot) {
+      T = exact_cut_key(n);
+      send_n = (unsigned)K;
+      mode = 2;
+    }
+  }
+  cluster.barrier_wait();                                   // the leader's fin_cnt is initialised
+  unsigned* const r_cnt = cluster.map_shared_rank(&s.fin_cnt, 0);
+  u64* const r_inbox = cluster.map_shared_rank(inbox, 0);
+  if (tid == 0) {
+    s.sh_base = send_n ? atomicAdd(r_cnt, send_n) : 0u;     // one remote atomic reserves the CTA's slice
+    s.cnt2 = 0;
+  }
+  __syncthreads();
+  {
+    u64* const dst = r_inbox + s.sh_base;
+    for (unsigned i0 = 0; i0 < n; i0 += kClThreads) {
+      const unsigned i = i0 + tid;
+      const u64 k = (i < n) ? s.stage[i] : 0ull;
+      const bool keep = (i < n) && (mode == 0 || (mode == 1 ? fine_bin((unsigned)(k >> 32)) >= tbin : k >= T));
+      append_if(keep, k, dst, &s.cnt2, send_n);
+    }
+  }
+  cluster.sync();                                           // release/acquire: the inbox is complete
+  if (rank != 0) return;
+  dbg_stamp(g.dbg, 3);
+
+  // ---- leader: final selection + sort + gather ---------------------------------------------------------
+  const int m = (int)*reinterpret_cast<volatile unsigned*>(&s.fin_cnt);
+  if (m > kThreads && m > K) {                              // the selection needs the histogram of the inbox
+    for (int w = tid; w < kFineBins / 2; w += kClThreads) s.hist[w] = 0u;
+    __syncthreads();
+    for (int i = tid; i < m; i += kClThreads) hist_add(s.hist, fine_bin((unsigned)(inbox[i] >> 32)));
+  }
+  if (tid == 0) s.cnt2 = 0;
+  __syncthreads();
+  if (!group0) return;
+  select_sort_emit(a, g, s, b, inbox, m, CS * (int)slot,
+                   [&](auto f) { for (int i = tid; i < m; i += kThreads) f(inbox[i]); });
+  dbg_stamp(g.dbg, 4);
+}
+
 // ---- host ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -820,9 +1122,97 @@ static size_t decode_ws_bytes(const cnh_decode_args* a) {
          (size_t)a->B * g.tiles_per_sample * g.slot * sizeof(u64);
 }
 
+constexpr int kClusterUnavailable = -999;
+constexpr int kClMaxSmem = 227 * 1024;
+
+// co-resident clusters of cs CTAs at one CTA per SM on device `dev` (cached; -1 = unavailable)
+static int active_clusters(int dev, int cs) {
+  static int max_clusters[64][9] = {};            // 0 = not queried
+  if (max_clusters[dev][cs] == 0) {
+    cudaLaunchConfig_t q;
+    memset(&q, 0, sizeof(q));
+    q.gridDim = dim3((unsigned)cs * 64u);
+    q.blockDim = dim3(kClThreads);
+    q.dynamicSmemBytes = kClMaxSmem - 1024;        // conservative: one CTA per SM
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = (unsigned)cs;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    q.attrs = qa;
+    q.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, decode_cluster_kernel, &q) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = -1;
+    }
+    max_clusters[dev][cs] = n;
+  }
+  return max_clusters[dev][cs];
+}
+
+// Largest cluster size <= 8 whose B clusters are co-resident, else 1 (samples then run in waves).
+// (On a B200 fifteen 8-CTA clusters fit at one CTA per SM, so a batch of 16 runs as 16 clusters of 7.)
+static int pick_cluster_size(int B, int tiles_per_sample, int dev) {
+  for (int cs = 8; cs > 1; --cs) {
+    if (cs > tiles_per_sample) continue;
+    if ((long long)B <= (long long)active_clusters(dev, cs)) return cs;
+  }
+  return active_clusters(dev, 1) < 1 ? -1 : 1;
+}
+
+static int launch_cluster(const cnh_decode_args* a, void* workspace, int dev, cudaStream_t st) {
+  constexpr int kMaxSmem = kClMaxSmem;
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64) return kClusterUnavailable;
+  if (!attr_set[dev]) {
+    if (cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess) {
+      cudaGetLastError();
+      return kClusterUnavailable;
+    }
+    attr_set[dev] = true;
+  }
+  DecGeo g = make_geo(a, workspace, kClRows);
+  const int cs = pick_cluster_size(a->B, g.tiles_per_sample, dev);
+  if (cs < 1) return kClusterUnavailable;
+  g.n_stages = kClStages;
+  g.use_tma = 1;
+  const size_t smem = sizeof(ClSmem) + (size_t)kClStages * kClTileFloats * sizeof(float) + (size_t)cs * g.slot * sizeof(u64);
+  if (smem > (size_t)kMaxSmem) return kClusterUnavailable;
+  static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3((unsigned)a->B * (unsigned)cs);
+  lc.blockDim = dim3(kClThreads);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = use_pdl ? 2 : 1;
+  CNH_CUDA(cudaLaunchKernelEx(&lc, decode_cluster_kernel, *a, g));
+  CNH_CUDA(cudaGetLastError());
+  return CNH_OK;
+}
+
 }  // namespace cnh
 
 using namespace cnh;
+
+// not part of the public ABI (tools/): cluster size the one-launch path would use * 1000 + co-resident 8-CTA clusters
+extern "C" int cnh_debug_decode_cluster(const cnh_decode_args* a) {
+  int dev = 0;
+  if (validate(a) != CNH_OK || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClMaxSmem);
+  DecGeo g = make_geo(a, nullptr, kClRows);
+  const int cs = pick_cluster_size(a->B, g.tiles_per_sample, dev);
+  return (cs < 0 ? 0 : cs) * 1000 + active_clusters(dev, 8);
+}
 
 extern "C" size_t cnh_decode_workspace_bytes(const cnh_decode_args* a) {
   if (validate(a) != CNH_OK) return 0;
@@ -833,6 +1223,16 @@ extern "C" int cnh_decode(const cnh_decode_args* a, void* workspace, size_t work
   if (int rc = validate(a)) return rc;
   CNH_REQUIRE(workspace != nullptr && workspace_bytes >= cnh_decode_workspace_bytes(a), CNH_E_WORKSPACE,
               "decode: workspace %zu < %zu bytes", workspace_bytes, cnh_decode_workspace_bytes(a));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EncodeTiledFn enc = encode_fn();
+  const bool tma_ok = enc != nullptr && a->W % 4 == 0 && aligned16(a->heat);
+  int dev = 0;
+  CNH_CUDA(cudaGetDevice(&dev));
+  // ---- cluster path (one launch, no global scratch) when a tile's rows are contiguous and 16-byte aligned ----
+  if (a->W <= kCols && a->W % 4 == 0 && aligned16(a->heat) && getenv("CNH_DECODE_TWO_KERNEL") == nullptr) {
+    const int rc = launch_cluster(a, workspace, dev, st);
+    if (rc != kClusterUnavailable) return rc;
+  }
   // ---- configuration: 32-row tiles + single buffer when every CTA gets at most one tile (small
   // problems: latency matters), else 16-row tiles walked by persistent CTAs with a 4-deep TMA ring.
   struct Cfg { int rows, stages; const void* kernel; size_t smem; int ctas_per_sm; };
@@ -840,8 +1240,6 @@ extern "C" int cnh_decode(const cnh_decode_args* a, void* workspace, size_t work
       {32, 1, (const void*)decode_tiles_kernel<32>, sizeof(DecSmemT<32 * kCols>) + 1 * sizeof(float) * tile_floats(32), 0},
       {16, 4, (const void*)decode_tiles_kernel<16>, sizeof(DecSmemT<16 * kCols>) + 4 * sizeof(float) * tile_floats(16), 0}};
   static bool attr_set[64] = {false};
-  int dev = 0;
-  CNH_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     for (Cfg& c : cfgs) CNH_CUDA(cudaFuncSetAttribute(c.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     CNH_CUDA(cudaFuncSetAttribute(decode_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
@@ -864,8 +1262,7 @@ extern "C" int cnh_decode(const cnh_decode_args* a, void* workspace, size_t work
   CNH_REQUIRE(g.n_tiles < (1ll << 31), CNH_E_SHAPE, "decode: too many tiles");
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  EncodeTiledFn enc = encode_fn();
-  if (enc != nullptr && a->W % 4 == 0 && aligned16(a->heat)) {
+  if (tma_ok) {
     const cuuint64_t dims[3] = {(cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B * (cuuint64_t)a->C};
     const cuuint64_t strides[2] = {(cuuint64_t)a->W * 4, (cuuint64_t)a->W * (cuuint64_t)a->H * 4};
     const cuuint32_t box[3] = {(cuuint32_t)g.box_w, (cuuint32_t)(cfg.rows + 2), 1};
@@ -877,7 +1274,6 @@ extern "C" int cnh_decode(const cnh_decode_args* a, void* workspace, size_t work
   }
   long long grid = (long long)cfg.ctas_per_sm * sms;          // persistent: every CTA walks a tile range
   if (grid > g.n_tiles) grid = g.n_tiles;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     void* params[3] = {&tmap, const_cast<cnh_decode_args*>(a), &g};
     CNH_CUDA(cudaLaunchKernel(cfg.kernel, dim3((unsigned)grid), dim3(kThreads), params, cfg.smem, st));

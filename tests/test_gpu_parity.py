@@ -204,6 +204,17 @@ def test_large_problem_precount_schedule():
 # ---------------------------------------------------------------------------------------------
 # decode
 # ---------------------------------------------------------------------------------------------
+@pytest.fixture(params=["cluster", "two_kernel"])
+def decode_path(request, monkeypatch):
+    """csrc/decode.cu has a one-launch cluster path (TMA-stageable maps) and the persistent tile kernel +
+    merge kernel path (everything else); the environment switch forces the latter everywhere."""
+    if request.param == "two_kernel":
+        monkeypatch.setenv("CNH_DECODE_TWO_KERNEL", "1")
+    else:
+        monkeypatch.delenv("CNH_DECODE_TWO_KERNEL", raising=False)
+    return request.param
+
+
 def run_decode(heat, wh, reg, kps, K, rotated):
     from backends.decode import decode_detection
     res = decode_detection(heat.cuda(), wh.cuda(), None if reg is None else reg.cuda(),
@@ -231,7 +242,7 @@ def assert_decode_exact(heat, wh, reg, kps, K, rotated):
 
 
 @pytest.mark.parametrize("name", golden_names("decode_"))
-def test_decode_vs_reference_fixture(name):
+def test_decode_vs_reference_fixture(name, decode_path):
     g = load_golden(name)
     heat, wh = torch.from_numpy(g["heat"]), torch.from_numpy(g["wh"])
     reg = torch.from_numpy(g["reg"]) if "reg" in g else None
@@ -257,8 +268,13 @@ def test_decode_vs_reference_fixture(name):
     (2, 2, 17, 23, 11, True, True, 0, 2.0),           # odd everything
     (2, 1, 64, 64, 1024, False, True, 0, 2.0),        # K at the supported maximum, > #peaks
     (2, 4, 128, 128, 150, False, True, 0, 8.0),       # saturated logits: thousands of ties at 1-1e-4
+    (40, 2, 64, 128, 30, False, True, 0, 2.0),        # more samples than 8-CTA clusters fit: cluster of 2
+    (150, 1, 32, 64, 10, False, True, 0, 2.0),        # more samples than SMs: clusters of 1, two waves
+    (1, 40, 128, 128, 150, False, True, 0, 1.0),      # one cluster walks 160 tiles: repeated cuts
+    (3, 12, 96, 128, 1000, False, True, 0, 3.0),      # large K: wide inbox, rank sort
+    (2, 9, 128, 128, 200, False, True, 0, 30.0),      # nearly everything saturated: plateaus of ties in every tile
 ])
-def test_decode_vs_oracle(B, C, H, W, K, rotated, use_reg, nk, sigma):
+def test_decode_vs_oracle(B, C, H, W, K, rotated, use_reg, nk, sigma, decode_path):
     g = torch.Generator().manual_seed(B * 1000 + C * 100 + H + W + K)
     heat = oracle.sigmoid_clamp(torch.randn(B, C, H, W, generator=g) * sigma - 2.19)
     wh = torch.rand(B, 3 if rotated else 2, H, W, generator=g) * 40

@@ -55,7 +55,7 @@ for rep in range(2):
         print("  slowest SMs (start, done):", worst)
     dbg.zero_(); torch.cuda.synchronize()
     L.check(lib.cnh_decode(C.byref(d.dec_args[rep]), d.ws_dec.data_ptr(), d.ws_dec.numel(), L.stream_ptr()), "d")
-    show(f"decode {name} rep{rep}", 12)
+    show(f"decode {name} rep{rep}", 16)
     t = dbg.cpu(); used = t[:, 0] != 0
     mg = t[:batch]; print("  merge m/got:", mg[:, 12].tolist()[:8], mg[:, 13].tolist()[:8])
     used = used & (torch.arange(t.shape[0]) >= batch)
@@ -64,3 +64,5 @@ for rep in range(2):
           "| final thr (as prob) min/median", torch.tensor(t[used, 14].int().tolist(), dtype=torch.int32).view(torch.float32).min().item(),
           torch.tensor(t[used, 14].int().tolist(), dtype=torch.int32).view(torch.float32).median().item())
 lib.cnh_debug_set_buffer(None)
+lib.cnh_debug_decode_cluster.argtypes = [C.c_void_p]
+print("decode cluster size*1000 + co-resident 8-CTA clusters:", lib.cnh_debug_decode_cluster(C.byref(d.dec_args[0])))
