@@ -826,6 +826,62 @@ __device__ __forceinline__ void scan_rows_lean(u64* keys, unsigned* key_cnt, con
   if (flags & 8u) *dst++ = ((u64)__float_as_uint(mid.w) << 32) | (u64)(nflat - 3u);
 }
 
+// Four rows per warp (the 256-thread group scan: four tiles of a round are scanned concurrently, one per
+// group of 8 warps).  Same test as scan_rows_lean with a rolling three-row window (6 LDS.128 for 4 rows);
+// the scores of flagged pixels are re-read from shared memory when the keys are written.  Appends are
+// bounded by `cap`: the counter may run past it (the caller detects that and rescans the round serially).
+__device__ __forceinline__ void scan_rows4(u64* keys, unsigned* key_cnt, unsigned cap, const float* tile, int W,
+                                           unsigned colmask, bool last_lane, unsigned thr, unsigned flat_tile0, int gwarp) {
+  const int lane = threadIdx.x & 31;
+  const float* base_row = tile + (4 * gwarp) * W + 4 * lane;                      // staged row above the warp's first row
+  const float thr_eff = fmaxf(__uint_as_float(thr), __uint_as_float(1u));      // >= thr and > 0
+  float4 up = *reinterpret_cast<const float4*>(base_row);
+  float4 mid = *reinterpret_cast<const float4*>(base_row + W);
+  unsigned flags = 0;                                                             // bit 4*rr + e
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const float4 dn = *reinterpret_cast<const float4*>(base_row + (rr + 2) * W);
+    unsigned pass = (mid.x >= thr_eff ? 1u : 0u) | (mid.y >= thr_eff ? 2u : 0u) | (mid.z >= thr_eff ? 4u : 0u) |
+                    (mid.w >= thr_eff ? 8u : 0u);
+    pass &= colmask;
+    if (__ballot_sync(0xffffffffu, pass != 0u) != 0u) {
+      const float v0 = fmaxf(fmaxf(up.x, mid.x), dn.x), v1 = fmaxf(fmaxf(up.y, mid.y), dn.y);
+      const float v2 = fmaxf(fmaxf(up.z, mid.z), dn.z), v3 = fmaxf(fmaxf(up.w, mid.w), dn.w);
+      float left = __shfl_up_sync(0xffffffffu, v3, 1), right = __shfl_down_sync(0xffffffffu, v0, 1);
+      if (lane == 0) left = 0.f;
+      if (last_lane) right = 0.f;
+      const float h0 = fmaxf(fmaxf(left, v0), v1), h1 = fmaxf(fmaxf(v0, v1), v2);
+      const float h2 = fmaxf(fmaxf(v1, v2), v3), h3 = fmaxf(fmaxf(v2, v3), right);
+      const unsigned f = pass & ((mid.x == h0 ? 1u : 0u) | (mid.y == h1 ? 2u : 0u) | (mid.z == h2 ? 4u : 0u) |
+                                 (mid.w == h3 ? 8u : 0u));
+      flags |= f << (4 * rr);
+    }
+    up = mid;
+    mid = dn;
+  }
+  if (__ballot_sync(0xffffffffu, flags != 0u) == 0u) return;
+  const int mine = __popc(flags);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    incl += (lane >= o) ? v : 0;
+  }
+  unsigned base = 0;
+  if (lane == 31) base = atomicAdd(key_cnt, (unsigned)incl);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  unsigned pos = base + (unsigned)(incl - mine);
+  const unsigned flat_lane0 = flat_tile0 + (unsigned)(4 * gwarp) * (unsigned)W + 4u * (unsigned)lane;
+  while (flags) {
+    const int bit = __ffs(flags) - 1;
+    flags &= flags - 1u;
+    const int rr = bit >> 2, e = bit & 3;
+    const float v = base_row[(rr + 1) * W + e];
+    if (pos < cap) keys[pos] = ((u64)__float_as_uint(v) << 32) | (u64)(0xffffffffu - (flat_lane0 + (unsigned)(rr * W + e)));
+    ++pos;
+  }
+}
+
 // ---- cluster path: one thread-block cluster per sample, ONE launch, no global scratch ------------------
 // The CS CTAs of a cluster split the sample's tiles (tile t -> CTA t % CS), each walking its share
 // with a TMA ring and keeping a running candidate set in shared memory: whenever the set outgrows
@@ -839,10 +895,11 @@ constexpr int kClRows = 32;
 constexpr int kClTileFloats = (kClRows + 2) * kCols + 128;   // 34 rows of <= 128 floats + slack for masked lanes
 constexpr int kClTile = kClRows * kCols;   // most peaks one tile can add
 constexpr int kClCap = 2 * kClTile;        // running candidate set: cut back whenever it exceeds kClTile
-constexpr int kClStages = 4;               // TMA ring depth
+constexpr int kClGroups = 4;               // tiles scanned concurrently (one per group of 8 warps) = one round
+constexpr int kClStages = 2 * kClGroups;   // ring depth: the round being scanned + the round in flight
 constexpr int kClThreads = 1024;           // 32 warps: one tile row per warp in the scan
 static_assert(kClThreads / 32 == kClRows, "scan_rows_lean: one tile row per warp");
-struct __align__(128) ClSmem {              // followed by the TMA ring and the leader's inbox
+struct __align__(128) ClSmem {              // followed by the TMA ring (the leader's doubles as the inbox)
   u64 stage[kClCap];                       // the set (the scan appends to it); final stage: `sorted`
   unsigned hist[kFineBins / 2];            // packed fine histogram of the set, built per cut; final stage: `sel`
   u64 mbar[kClStages];
@@ -870,7 +927,7 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ClSmem& s = *reinterpret_cast<ClSmem*>(smem_raw);
   float* const ring = reinterpret_cast<float*>(smem_raw + sizeof(ClSmem));
-  u64* const inbox = reinterpret_cast<u64*>(smem_raw + sizeof(ClSmem) + (size_t)kClStages * kClTileFloats * sizeof(float));
+  u64* const inbox = reinterpret_cast<u64*>(ring);          // the leader's ring becomes the inbox once every CTA has scanned
   const int tid = threadIdx.x;
   const bool group0 = tid < kThreads;                       // warps 0-7 run the 256-thread selection helpers
   const int K = a.K, W = a.W, H = a.H;
@@ -883,21 +940,29 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   // column).  This CTA walks t = rank, rank+CS, ...; every thread keeps two cursors, advanced without
   // divisions: the tile being scanned and the tile being prefetched kClStages ahead.
   struct Cursor { int c, ty; };
-  auto advance = [&](Cursor& q, int by) {
-    q.ty += by;
-    while (q.ty >= g.tiles_y) { q.ty -= g.tiles_y; ++q.c; }
+  struct Stride { int c, ty; };                             // a tile-index step split by tiles_y, computed once
+  auto stride_of = [&](int by) { Stride d; d.c = by / g.tiles_y; d.ty = by - d.c * g.tiles_y; return d; };
+  auto advance = [&](Cursor& q, const Stride& d) {
+    q.c += d.c;
+    q.ty += d.ty;
+    if (q.ty >= g.tiles_y) { q.ty -= g.tiles_y; ++q.c; }
   };
+  auto cursor_at = [&](int t) { Cursor q; q.c = t / g.tiles_y; q.ty = t - q.c * g.tiles_y; return q; };
+  const Stride step1 = stride_of(CS), step_round = stride_of(kClGroups * CS);
   // Stage tile q into ring slot buf: the rows of the tile plus one halo row above and below are contiguous
   // in global memory (one bulk copy, SASS UBLKCP); halo/tail rows outside the image are zero-filled by the
-  // CTA's threads (max-pool padding: 0 is neutral because heat >= 0).  Called by ALL threads.
+  // calling warp (max-pool padding: 0 is neutral because heat >= 0).  Called by ONE warp.
   auto stage_tile = [&](const Cursor& q, int buf) {
     float* dst = ring + (size_t)buf * kClTileFloats;
+    const int lane = tid & 31;
     const int y0 = q.ty * kClRows;
     const int ylo = max(y0 - 1, 0), yhi = min(y0 + kClRows + 1, H);       // image rows [ylo, yhi) are copied
     const int r_lo = ylo - (y0 - 1), r_hi = yhi - (y0 - 1);               // -> tile rows [r_lo, r_hi) of 34
-    for (int i = tid; i < r_lo * W; i += kClThreads) dst[i] = 0.f;
-    for (int i = r_hi * W + tid; i < (kClRows + 2) * W; i += kClThreads) dst[i] = 0.f;
-    if (tid == 0) {
+    if (r_lo > 0 || r_hi < kClRows + 2) {
+      for (int i = lane; i < r_lo * W; i += 32) dst[i] = 0.f;
+      for (int i = r_hi * W + lane; i < (kClRows + 2) * W; i += 32) dst[i] = 0.f;
+    }
+    if (lane == 0) {
       const unsigned bytes = (unsigned)((yhi - ylo) * W) * 4u;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // earlier generic accesses of the slot
       mbar_expect_tx(&s.mbar[buf], bytes);
@@ -913,33 +978,38 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
     for (int i = 0; i < kClStages; ++i) mbar_init(&s.mbar[i], 1);
   }
   __syncthreads();
-  Cursor cur = {0, 0}, pre = {0, 0};
-  advance(cur, rank);
-  pre = cur;
-  for (int j = 0; j < kClStages && j < n_my; ++j) { stage_tile(pre, j); advance(pre, CS); }
-  cluster.barrier_arrive();                                 // every CTA's inbox counter is initialised
+  const int gq = tid >> 8, gwarp = (tid >> 5) & 7;           // scan group (one tile of the round each) and warp in it
+  const int wid = tid >> 5;
+  // warp w < kClStages stages ring slot w: tiles w, w + kClStages, ... of this CTA's walk (j = w + 8k)
+  Cursor pre = cursor_at(rank + min(wid, kClStages - 1) * CS);
+  const Stride step_ring = stride_of(kClStages * CS);
+  if (wid < kClStages && wid < n_my) stage_tile(pre, wid);
+  advance(pre, step_ring);
+  Cursor mine = cursor_at(rank + gq * CS);                  // the tile this thread's group scans in the current round
 
-  // In-place compaction of stage[0..n) by the whole CTA, 1024 keys per step: a step's keys are in registers
-  // before anything is written, and writes only go below the step's first key.  Leaves the new size in s.cnt.
-  auto compact_all = [&](const unsigned n, auto pred) {
+  // In-place compaction of arr[0..n) by the whole CTA, 1024 keys per step: a step's keys are in registers
+  // before anything is written, and writes only go below the step's first key.  New size -> *out_cnt.
+  auto compact_arr = [&](u64* arr, const unsigned n, unsigned* out_cnt, auto pred) {
     if (tid == 0) s.cnt2 = 0;
     for (unsigned i0 = 0; i0 < n; i0 += kClThreads) {
       const unsigned i = i0 + tid;
-      const u64 k = (i < n) ? s.stage[i] : 0ull;
+      const u64 k = (i < n) ? arr[i] : 0ull;
       const bool keep = (i < n) && pred(k);
       __syncthreads();
-      append_if(keep, k, s.stage, &s.cnt2, (unsigned)kClCap);
+      append_if(keep, k, arr, &s.cnt2, n);
     }
     __syncthreads();
-    if (tid == 0) s.cnt = s.cnt2;
+    if (tid == 0) *out_cnt = s.cnt2;
   };
+  auto compact_all = [&](const unsigned n, auto pred) { compact_arr(s.stage, n, &s.cnt, pred); };
   // packed fine histogram of stage[0..n) (built only when a cut needs it)
-  auto build_hist = [&](const unsigned n) {
+  auto build_hist_of = [&](const u64* arr, const unsigned n) {
     for (int w = tid; w < kFineBins / 2; w += kClThreads) s.hist[w] = 0u;
     __syncthreads();
-    for (unsigned i = tid; i < n; i += kClThreads) hist_add(s.hist, fine_bin((unsigned)(s.stage[i] >> 32)));
+    for (unsigned i = tid; i < n; i += kClThreads) hist_add(s.hist, fine_bin((unsigned)(arr[i] >> 32)));
     __syncthreads();
   };
+  auto build_hist = [&](const unsigned n) { build_hist_of(s.stage, n); };
   // K-th key of the set, exactly (heavy ties inside one histogram bin); clobbers s.hist.  Everyone gets T.
   auto exact_cut_key = [&](const unsigned n) {
     if (group0) {
@@ -954,31 +1024,8 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   const int lane_col = 4 * (tid & 31);
   const unsigned colmask = W - lane_col >= 4 ? 15u : (W - lane_col <= 0 ? 0u : ((1u << (W - lane_col)) - 1u));
   const bool last_lane = lane_col + 4 >= W;                 // the column right of this lane's is outside the image
-  for (int j = 0; j < n_my; ++j) {
-    const int buf = j & (kClStages - 1), phase = (j >> 2) & 1;
-    static_assert(kClStages == 4, "phase = (j >> log2 stages) & 1");
-    float* tile = ring + (size_t)buf * kClTileFloats;
-    const int c = cur.c, y0 = cur.ty * kClRows;
-    mbar_wait(&s.mbar[buf], (unsigned)phase);
-    if (a.apply_sigmoid) {                                  // export.py:31-33: logits in, clamp(sigmoid) fused
-      const int r_lo = max(y0 - 1, 0) - (y0 - 1), r_hi = min(y0 + kClRows + 1, H) - (y0 - 1);
-      for (int i = r_lo * W + tid; i < r_hi * W; i += kClThreads) tile[i] = clamp_prob(1.0f / (1.0f + expf(-tile[i])));
-      __syncthreads();
-    }
-    if (j == 0) dbg_stamp(g.dbg, 1);
-    scan_rows_lean(s.stage, &s.cnt, tile, W, colmask, last_lane, thr,
-                   (unsigned)c * (unsigned)g.HW + (unsigned)(y0 + (tid >> 5)) * (unsigned)W);
-    __syncthreads();                                        // tile[buf] is free; the set is complete
-    if (j == 0) dbg_stamp(g.dbg, 5);
-    if (j == 1) dbg_stamp(g.dbg, 6);
-    if (j == n_my - 1) dbg_stamp(g.dbg, 7);
-    advance(cur, CS);
-    if (j + kClStages < n_my) { stage_tile(pre, buf); advance(pre, CS); }   // refill the ring
-    const unsigned n = s.cnt;
-    // Cut the set back to (a superset of) its top K when the next tile might overflow it and, on long walks,
-    // after tiles 1, 2, 4, 8, ... so that the pruning threshold tightens early.
-    const bool more = j + 1 < n_my;
-    if (!more || !(n > (unsigned)kClTile || (n_my >= 12 && n > slot && ((j + 1) & j) == 0))) continue;
+  // Cut the set back to (a superset of) its top K; the cut becomes the pruning threshold.
+  auto cut = [&](const unsigned n) {
     build_hist(n);
     if (group0) find_kth_bin(s, (unsigned)K);
     __syncthreads();
@@ -995,14 +1042,68 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
     }
     if (thr_new > thr) thr = thr_new;
     __syncthreads();
+  };
+  auto tile_rows = [&](int y0, int& r_lo, int& r_hi) {      // staged rows that hold image rows
+    r_lo = max(y0 - 1, 0) - (y0 - 1);
+    r_hi = min(y0 + kClRows + 1, H) - (y0 - 1);
+  };
+
+  const int n_rounds = (n_my + kClGroups - 1) / kClGroups;
+  for (int r = 0; r < n_rounds; ++r) {
+    const int half = (r & 1) * kClGroups, phase = (r >> 1) & 1;
+    const int in_round = min(kClGroups, n_my - r * kClGroups);
+    const unsigned n_before = s.cnt;                        // <= kClTile (invariant)
+    if (gq < in_round) {
+      const Cursor q = mine;
+      const int y0 = q.ty * kClRows;
+      float* tile = ring + (size_t)(half + gq) * kClTileFloats;
+      mbar_wait(&s.mbar[half + gq], (unsigned)phase);
+      if (a.apply_sigmoid) {                                // export.py:31-33: logits in, clamp(sigmoid) fused
+        int r_lo, r_hi;
+        tile_rows(y0, r_lo, r_hi);
+        for (int i = r_lo * W + (tid & 255); i < r_hi * W; i += 256) tile[i] = clamp_prob(1.0f / (1.0f + expf(-tile[i])));
+        asm volatile("bar.sync %0, 256;" ::"r"(2 + gq) : "memory");
+      }
+      scan_rows4(s.stage, &s.cnt, (unsigned)kClCap, tile, W, colmask, last_lane, thr,
+                 (unsigned)q.c * (unsigned)g.HW + (unsigned)y0 * (unsigned)W, gwarp);
+    }
+    __syncthreads();                                        // the round's tiles are scanned
+    if (r == 0) dbg_stamp(g.dbg, 1);
+    unsigned n = s.cnt;
+    if (n > (unsigned)kClCap) {
+      // plateaus: the round found more peaks than the buffer holds.  Rescan its tiles one at a time with
+      // the whole CTA (one row per warp), cutting in between.
+      __syncthreads();
+      if (tid == 0) s.cnt = n_before;
+      __syncthreads();
+      Cursor q = cursor_at(rank + r * kClGroups * CS);
+      for (int t = 0; t < in_round; ++t, advance(q, step1)) {
+        scan_rows_lean(s.stage, &s.cnt, ring + (size_t)(half + t) * kClTileFloats, W, colmask, last_lane, thr,
+                       (unsigned)q.c * (unsigned)g.HW + (unsigned)(q.ty * kClRows + (tid >> 5)) * (unsigned)W);
+        __syncthreads();
+        n = s.cnt;
+        if (n > (unsigned)kClTile) { cut(n); n = s.cnt; }
+      }
+    }
+    advance(mine, step_round);
+    if (wid >= half && wid < half + kClGroups) {            // refill the freed half of the ring: round r + 2
+      if ((r + 2) * kClGroups + (wid - half) < n_my) stage_tile(pre, wid);
+      advance(pre, step_ring);
+    }
+    // Cut when the next round might overflow the invariant and, on long walks, after rounds 1, 2, 4, 8, ...
+    // so that the pruning threshold tightens early.
+    if (r + 1 < n_rounds && (n > (unsigned)kClTile || (n_rounds >= 4 && n > slot && ((r + 1) & r) == 0))) cut(n);
   }
   dbg_stamp(g.dbg, 2);
+  cluster.barrier_arrive();                                 // this CTA no longer reads its ring (the leader's is the inbox)
 
   // ---- final cut fused with the push into the leader's inbox (DSMEM) --------------------------------
   const unsigned n = s.cnt;
   int mode = 0, tbin = 0;                                   // 0: send everything, 1: bins >= tbin, 2: keys >= T
   u64 T = 0;
   unsigned send_n = n;
+  // What travels to the leader is at most K + kSlack keys per CTA (measured: letting the leader cut the
+  // raw sets of a whole cluster is slower than one cut per CTA in parallel).
   if (n > slot) {
     build_hist(n);
     if (group0) find_kth_bin(s, (unsigned)K);
@@ -1016,7 +1117,9 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
       mode = 2;
     }
   }
-  cluster.barrier_wait();                                   // the leader's fin_cnt is initialised
+  dbg_stamp(g.dbg, 5);
+  cluster.barrier_wait();                                   // every CTA, the leader included, is done with its ring
+  dbg_stamp(g.dbg, 6);
   unsigned* const r_cnt = cluster.map_shared_rank(&s.fin_cnt, 0);
   u64* const r_inbox = cluster.map_shared_rank(inbox, 0);
   if (tid == 0) {
@@ -1033,21 +1136,40 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
       append_if(keep, k, dst, &s.cnt2, send_n);
     }
   }
+  dbg_stamp(g.dbg, 7);
   cluster.sync();                                           // release/acquire: the inbox is complete
   if (rank != 0) return;
   dbg_stamp(g.dbg, 3);
 
-  // ---- leader: final selection + sort + gather ---------------------------------------------------------
-  const int m = (int)*reinterpret_cast<volatile unsigned*>(&s.fin_cnt);
-  if (m > kThreads && m > K) {                              // the selection needs the histogram of the inbox
-    for (int w = tid; w < kFineBins / 2; w += kClThreads) s.hist[w] = 0u;
+  // ---- leader: final selection (all warps) + sort + gather (warps 0-7) -------------------------------------
+  int m = (int)*reinterpret_cast<volatile unsigned*>(&s.fin_cnt);
+  if (m > kThreads && m > K) {
+    build_hist_of(inbox, (unsigned)m);
+    if (group0) find_kth_bin(s, (unsigned)K);
     __syncthreads();
-    for (int i = tid; i < m; i += kClThreads) hist_add(s.hist, fine_bin((unsigned)(inbox[i] >> 32)));
+    const unsigned keep_n = s.sh_above + s.sh_inbin;
+    const int tbin2 = (int)s.sh_bin;
+    if (keep_n <= (unsigned)kMaxK) {                        // (else: ties, select_sort_emit selects exactly)
+      // the histogram stays valid for select_sort_emit: it only looks at the bins from the top down to tbin2
+      compact_arr(inbox, (unsigned)m, &s.fin_cnt, [&](u64 k) { return fine_bin((unsigned)(k >> 32)) >= tbin2; });
+      __syncthreads();
+      m = (int)keep_n;
+    }
   }
   if (tid == 0) s.cnt2 = 0;
   __syncthreads();
   if (!group0) return;
-  select_sort_emit(a, g, s, b, inbox, m, CS * (int)slot,
+  if (m <= kThreads && tid < m) {                           // start the gather's cache lines on their way before sorting
+    const unsigned flat = 0xffffffffu - (unsigned)(inbox[tid] & 0xffffffffu);
+    const unsigned pix = flat % (unsigned)g.HW;
+    if (a.reg) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.reg + ((long long)b * 2 + 0) * g.HW + pix));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.reg + ((long long)b * 2 + 1) * g.HW + pix));
+    }
+    for (int d = 0; d < (a.rotated ? 3 : 2); ++d)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.wh + ((long long)b * a.D + d) * g.HW + pix));
+  }
+  select_sort_emit(a, g, s, b, inbox, m, kClStages * kClTileFloats / 2,
                    [&](auto f) { for (int i = tid; i < m; i += kThreads) f(inbox[i]); });
   dbg_stamp(g.dbg, 4);
 }
@@ -1177,7 +1299,8 @@ static int launch_cluster(const cnh_decode_args* a, void* workspace, int dev, cu
   if (cs < 1) return kClusterUnavailable;
   g.n_stages = kClStages;
   g.use_tma = 1;
-  const size_t smem = sizeof(ClSmem) + (size_t)kClStages * kClTileFloats * sizeof(float) + (size_t)cs * g.slot * sizeof(u64);
+  const size_t smem = sizeof(ClSmem) + (size_t)kClStages * kClTileFloats * sizeof(float);
+  static_assert((size_t)kClStages * kClTileFloats * sizeof(float) >= (size_t)8 * kStageCap * sizeof(u64), "the ring holds the inbox");
   if (smem > (size_t)kMaxSmem) return kClusterUnavailable;
   static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
   cudaLaunchConfig_t lc;

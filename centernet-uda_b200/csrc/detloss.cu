@@ -901,6 +901,9 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
   const int n_other = g.n_items + g.n_count;
   constexpr unsigned long long kCountMask = (1ull << 40) - 1ull;
 
+  // PDL: a dependent launched with programmatic stream serialisation (cnh_scale_inplace, cnh_decode) may be
+  // placed on the SMs now; it still blocks in griddepcontrol.wait until this grid has completed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   dbg_stamp(g.dbg, 0);
   // every thread that touches the accumulators reads the header itself (all lanes of warps 0 and 8 load
   // the same two words: one request, no shuffle that would make the warp wait before it has issued the rest)
@@ -1196,6 +1199,7 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   constexpr bool kGrad = (MODE == M_PRECOUNT || MODE == M_MAIN);
   const int S = g.n_stages;
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: see detloss_stash_kernel
   dbg_stamp(g.dbg, 0);
   if (tid == 0) {
     if (MODE != M_COUNT && VEC) {
@@ -1395,6 +1399,7 @@ detloss_finalize_kernel(const cnh_detloss_args a, const long long* __restrict__ 
 // Launched with programmatic stream serialisation: the launch overlaps the tail of the loss kernel.
 __global__ void __launch_bounds__(kThreads)
 scale_inplace_kernel(const cnh_scale_args s) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next PDL launch (decode) may be placed now
   asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int t = 0; t < s.n_tensors; ++t) {
     const float f = (s.fa[t] ? __ldg(s.fa[t]) : 0.f) + (s.fb[t] ? __ldg(s.fb[t]) : 0.f);
@@ -1406,7 +1411,16 @@ scale_inplace_kernel(const cnh_scale_args s) {
     if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
       const long long n4 = n >> 2;
       float4* p4 = reinterpret_cast<float4*>(p);
-      for (long long k = i; k < n4; k += stride) {
+      long long k = i;
+      for (; k + 3 * stride < n4; k += 4 * stride) {       // four independent 16-byte loads in flight per thread
+        float4 v0 = p4[k], v1 = p4[k + stride], v2 = p4[k + 2 * stride], v3 = p4[k + 3 * stride];
+        v0.x *= f; v0.y *= f; v0.z *= f; v0.w *= f;
+        v1.x *= f; v1.y *= f; v1.z *= f; v1.w *= f;
+        v2.x *= f; v2.y *= f; v2.z *= f; v2.w *= f;
+        v3.x *= f; v3.y *= f; v3.z *= f; v3.w *= f;
+        p4[k] = v0; p4[k + stride] = v1; p4[k + 2 * stride] = v2; p4[k + 3 * stride] = v3;
+      }
+      for (; k < n4; k += stride) {
         float4 v = p4[k];
         v.x *= f; v.y *= f; v.z *= f; v.w *= f;
         p4[k] = v;
@@ -1669,7 +1683,7 @@ extern "C" int cnh_scale_inplace(const cnh_scale_args* s, cnh_stream_t stream) {
   }
   if (s->n_tensors == 0 || most == 0) return CNH_OK;
   long long want = (most / 4 + kThreads - 1) / kThreads;
-  const int cap = sm_count() * 8;
+  const int cap = sm_count() * 2;               // the usual case (factor 1.0) is a no-op: keep the launch small
   const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
   static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
   cudaLaunchConfig_t lc;
