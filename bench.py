@@ -373,9 +373,11 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     value = batch * world * steps / (ms_total * 1e-3)
 
     # ---- e2e: plugin API, pinned host inputs, H2D + D2H inside the timed region ------------------------
-    e2e = None
+    e2e = e2e_boxes = None
     if not args.no_e2e:
         e2e = run_e2e(cfg, batch, rank, world, dev, steps, warmup)
+        if world == 1 and not cfg.angle:
+            e2e_boxes = run_e2e(cfg, batch, rank, world, dev, steps, warmup, from_boxes=True)
 
     if rank != 0:
         return
@@ -416,6 +418,7 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
         "step_hbm_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
         "roofline": roof,
         "e2e": e2e,
+        "e2e_boxes": e2e_boxes,
         "gpu_launches": dstep.launches_per_step * steps,
         "clocks": clk,
     }
@@ -427,9 +430,10 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_e2e(cfg, batch, rank, world, dev, steps, warmup):
+def run_e2e(cfg, batch, rank, world, dev, steps, warmup, from_boxes=False):
     from cnhead import synthetic, sharded
     from cnhead.feeder import HostFeeder
+    from cnhead import functional as F
     from losses.centernet import DetectionLoss
     from backends.decode import decode_detection
     kw = synthetic.loss_kwargs(cfg)
@@ -438,8 +442,19 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup):
     host = []
     for i in range(n_host):
         d = synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, seed_offset=20 + i, sample_offset=rank * batch)
+        bt = d["batch"]
+        if from_boxes:
+            # the host ships object lists (boxes in heat-map pixels, classes, counts) and the
+            # targets are rasterised on the device; the boxes are rebuilt from the synthetic targets.
+            cx = (bt["ind"] % cfg.width).float() + bt["reg"][..., 0]
+            cy = (bt["ind"] // cfg.width).float() + bt["reg"][..., 1]
+            w, h = bt["wh"][..., 0], bt["wh"][..., 1]
+            g = torch.Generator().manual_seed(77 + i)
+            bt = {"boxes": torch.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], dim=-1).contiguous(),
+                  "classes": torch.randint(0, cfg.classes, bt["ind"].shape, generator=g, dtype=torch.int32),
+                  "n_obj": bt["reg_mask"].sum(1).to(torch.int32)}
         host.append(({k: v.pin_memory() for k, v in d["output"].items()},
-                     {k: v.pin_memory() for k, v in d["batch"].items()}))
+                     {k: v.pin_memory() for k, v in bt.items()}))
     h2d = sum(v.numel() * v.element_size() for grp in host[0] for v in grp.values())
     dets_host = torch.empty(batch, cfg.K, 7 if cfg.rotated else 6).pin_memory()
     loss_host = torch.empty(1).pin_memory()
@@ -455,6 +470,8 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup):
         o, b = feeder.get()
         out = {k: v.detach().requires_grad_(True) for k, v in o.items()}
         work = dict(out)
+        if from_boxes:
+            b = F.raster_targets(b["boxes"], b["classes"], b["n_obj"], cfg.classes, cfg.height, cfg.width)
         loss, stats = crit(work, b)
         loss.backward()
         dets = decode_detection(work["hm"], work["wh"].detach(), work["reg"].detach(), K=cfg.K, rotated=cfg.rotated)
@@ -482,6 +499,8 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup):
             "d2h_bytes_per_step": d2h, "ms_per_step": ms / e2e_steps, "steps": e2e_steps,
             "h2d_GBps": h2d / (ms / e2e_steps * 1e-3) / 1e9,
             "api": "cnhead.feeder.HostFeeder (double-buffered H2D from pinned memory on a copy stream) + "
+                   + ("cnhead.functional.raster_targets (targets rasterised on the device from object lists) + "
+                      if from_boxes else "") +
                    "losses.centernet.DetectionLoss + loss.backward() + backends.decode.decode_detection + D2H of "
                    "loss and detections, stream-synchronised every step"}
 

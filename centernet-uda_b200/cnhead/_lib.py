@@ -57,7 +57,15 @@ class DecodeArgs(C.Structure):
                 ("D", C.c_int32), ("nk", C.c_int32), ("rotated", C.c_int32),
                 ("heat", C.c_void_p), ("wh", C.c_void_p), ("reg", C.c_void_p), ("kps", C.c_void_p),
                 ("dets", C.c_void_p), ("inds_out", C.c_void_p), ("kps_out", C.c_void_p),
-                ("apply_sigmoid", C.c_int32), ("box_scale", C.c_float)]
+                ("apply_sigmoid", C.c_int32), ("box_scale", C.c_float),
+                ("counts_out", C.c_void_p), ("score_threshold", C.c_float), ("_pad", C.c_int32)]
+
+
+class RasterArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("M", C.c_int32),
+                ("min_overlap_num", C.c_int32), ("min_overlap_den", C.c_int32), ("_pad", C.c_int32),
+                ("boxes", C.c_void_p), ("classes", C.c_void_p), ("n_obj", C.c_void_p), ("hm", C.c_void_p),
+                ("wh", C.c_void_p), ("reg", C.c_void_p), ("ind", C.c_void_p), ("reg_mask", C.c_void_p)]
 
 
 _lib = None
@@ -109,6 +117,8 @@ def lib() -> C.CDLL:
         L.cnh_decode_workspace_bytes.argtypes = [C.POINTER(DecodeArgs)]
         L.cnh_decode.restype = C.c_int
         L.cnh_decode.argtypes = [C.POINTER(DecodeArgs), vp, sz, st]
+        L.cnh_raster_targets.restype = C.c_int
+        L.cnh_raster_targets.argtypes = [C.POINTER(RasterArgs), st]
         _lib = L
     return _lib
 

@@ -248,7 +248,12 @@ def bce_const(y: torch.Tensor, label: float) -> torch.Tensor:
 # decode
 # ----------------------------------------------------------------------------------------------
 def decode(heat, wh, reg=None, kps=None, K=100, rotated=False, apply_sigmoid=False, box_scale=1.0,
-           return_inds=False):
+           return_inds=False, score_threshold=None):
+    """backends/decode.py:35-76 in one launch.  Extras over the reference signature (its callers' epilogues,
+    SURVEY 8f N1/N4): ``apply_sigmoid`` (export.py:31-33), ``box_scale`` (uda/base.py:90 ``down_ratio``),
+    ``return_inds`` (flat peak indices) and ``score_threshold`` -> an extra int32 ``[B]`` tensor with the number
+    of rows per sample whose score reaches it (rows are sorted, so they are the first ones;
+    evaluation/coco.py:266-267).  Returns dets[, kps][, inds][, counts]."""
     heat = L.require(heat.detach(), "heat")
     wh = L.require(wh.detach(), "wh")
     reg = L.require(reg.detach(), "reg") if reg is not None else None
@@ -272,6 +277,10 @@ def decode(heat, wh, reg=None, kps=None, K=100, rotated=False, apply_sigmoid=Fal
     a.dets, a.inds_out, a.kps_out = dets.data_ptr(), L.ptr(inds), L.ptr(kout)
     a.apply_sigmoid = 1 if apply_sigmoid else 0
     a.box_scale = float(box_scale)
+    counts = None
+    if score_threshold is not None:
+        counts = torch.empty(B, dtype=torch.int32, device=heat.device)
+        a.counts_out, a.score_threshold = counts.data_ptr(), float(score_threshold)
     nbytes = L.lib().cnh_decode_workspace_bytes(C.byref(a))
     if nbytes == 0:
         L.check(-2, "decode")
@@ -282,4 +291,38 @@ def decode(heat, wh, reg=None, kps=None, K=100, rotated=False, apply_sigmoid=Fal
         res += (kout,)
     if return_inds:
         res += (inds,)
+    if counts is not None:
+        res += (counts,)
     return res[0] if len(res) == 1 else res
+
+
+# ----------------------------------------------------------------------------------------------
+# target rasteriser (the step before the loss)
+# ----------------------------------------------------------------------------------------------
+def raster_targets(boxes, classes, n_obj, num_classes, height, width) -> Dict[str, torch.Tensor]:
+    """datasets/coco.py:168-215 on the device: from ``boxes [B,M,4]`` fp32 (x1,y1,x2,y2 in heat-map pixels),
+    ``classes [B,M]`` int32 and ``n_obj [B]`` int32 to the batch dict DetectionLoss consumes --
+    ``{'hm' [B,C,H,W], 'reg_mask' [B,M] u8, 'ind' [B,M] i64, 'wh' [B,M,2], 'reg' [B,M,2]}``.
+    The host then ships B*M*20 bytes per step instead of the 4*B*C*H*W-byte heat-map target."""
+    boxes = L.require(boxes, "boxes")
+    classes = L.require(classes, "classes", torch.int32)
+    n_obj = L.require(n_obj, "n_obj", torch.int32)
+    if boxes.dim() != 3 or boxes.shape[2] != 4:
+        raise RuntimeError(f"cnhead: boxes must be [B,M,4], got {tuple(boxes.shape)}")
+    B, M = boxes.shape[:2]
+    if tuple(classes.shape) != (B, M) or tuple(n_obj.shape) != (B,):
+        raise RuntimeError("cnhead: classes must be [B,M] and n_obj [B]")
+    dev = boxes.device
+    out = {"hm": torch.empty(B, num_classes, height, width, dtype=torch.float32, device=dev),
+           "reg_mask": torch.empty(B, M, dtype=torch.uint8, device=dev),
+           "ind": torch.empty(B, M, dtype=torch.int64, device=dev),
+           "wh": torch.empty(B, M, 2, dtype=torch.float32, device=dev),
+           "reg": torch.empty(B, M, 2, dtype=torch.float32, device=dev)}
+    a = L.RasterArgs()
+    a.B, a.C, a.H, a.W, a.M = B, int(num_classes), int(height), int(width), M
+    a.min_overlap_num, a.min_overlap_den = 7, 10            # utils/image.py:8 default, the only value callers use
+    a.boxes, a.classes, a.n_obj = boxes.data_ptr(), classes.data_ptr(), n_obj.data_ptr()
+    a.hm, a.wh, a.reg = out["hm"].data_ptr(), out["wh"].data_ptr(), out["reg"].data_ptr()
+    a.ind, a.reg_mask = out["ind"].data_ptr(), out["reg_mask"].data_ptr()
+    L.check(L.lib().cnh_raster_targets(C.byref(a), L.stream_ptr()), "raster_targets")
+    return out

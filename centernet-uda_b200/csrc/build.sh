@@ -8,10 +8,10 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
        -I"$HERE/../../include" -I"$HERE" "$@")
 pids=()
-for f in api detloss softmax_stat decode; do
+for f in api detloss softmax_stat decode raster; do
   "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/obj/$f.o" &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -shared -o "$OUT/libcnhead_sm100.so" "$HERE"/obj/{api,detloss,softmax_stat,decode}.o -cudart static
+"$NVCC" -shared -o "$OUT/libcnhead_sm100.so" "$HERE"/obj/{api,detloss,softmax_stat,decode,raster}.o -cudart static
 echo "built $OUT/libcnhead_sm100.so"

@@ -474,6 +474,16 @@ __device__ __forceinline__ void select_sort_emit(const cnh_decode_args& a, const
   dbg_stamp(g.dbg, 9);
   // ---- gather + box assembly (backends/decode.py:44-74) -----------------------------------------
   const int ncol = a.rotated ? 7 : 6;
+  if (a.counts_out) {                        // rows with score >= threshold: a prefix of the sorted list
+    if (tid == 0) s.cnt2 = 0;
+    group_sync();
+    int mine = 0;
+    for (int r = tid; r < K; r += kThreads) mine += (__uint_as_float((unsigned)(sorted[r] >> 32)) >= a.score_threshold) ? 1 : 0;
+    mine = warp_sum(mine);
+    if (lane == 0 && mine) atomicAdd(&s.cnt2, (unsigned)mine);
+    group_sync();
+    if (tid == 0) a.counts_out[b] = (int)s.cnt2;
+  }
   for (int r = tid; r < K; r += kThreads) {
     const u64 k = sorted[r];
     const float score = __uint_as_float((unsigned)(k >> 32));

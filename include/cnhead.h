@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CNH_VERSION 100 /* major*100 + minor */
+#define CNH_VERSION 101 /* major*100 + minor */
 
 typedef void* cnh_stream_t; /* cudaStream_t */
 
@@ -188,7 +188,11 @@ int cnh_bce_const(const float* y, float* grad, float* loss_out, int64_t n, float
  * reg [B,2,H,W] or NULL (+0.5); kps [B,2*nk,H,W] or NULL.
  * dets [B,K,6] = (x1,y1,x2,y2,score,class) or, rotated, [B,K,7] = (x,y,w,h,angle,score,class),
  * sorted by score descending, ties broken by LOWER flat index c*H*W + y*W + x.
- * inds_out (nullable) [B,K] int64 receives that flat index; kps_out (nullable) [B,K,nk,2]. */
+ * inds_out (nullable) [B,K] int64 receives that flat index; kps_out (nullable) [B,K,nk,2].
+ * Two launch shapes, chosen by the library: when a tile's rows are contiguous and 16-byte aligned
+ * (W <= 128, W % 4 == 0) ONE launch of thread-block clusters (a cluster per sample, candidates exchanged
+ * through distributed shared memory, no global scratch); otherwise a persistent tile kernel + a merge
+ * kernel that use the workspace. */
 typedef struct cnh_decode_args {
   int32_t B, C, H, W, K, D, nk, rotated;
   const float* heat;
@@ -200,10 +204,37 @@ typedef struct cnh_decode_args {
   float* kps_out;
   int32_t apply_sigmoid;   /* 1: heat holds raw logits; clamp(sigmoid) fused in (export.py:31-33) */
   float box_scale;         /* multiply the 4 box columns (uda/base.py:90 down_ratio); 1.0 = off   */
+  int32_t* counts_out;     /* nullable [B]: detections with score >= score_threshold -- a prefix of the
+                              sorted rows (the filter of evaluation/coco.py:266-267, folded in)     */
+  float score_threshold;
+  int32_t _pad;
 } cnh_decode_args;
 size_t cnh_decode_workspace_bytes(const cnh_decode_args* a);
 int cnh_decode(const cnh_decode_args* a, void* workspace, size_t workspace_bytes,
                cnh_stream_t stream);
+
+/* ---- target rasteriser (datasets/coco.py:168-215, utils/image.py:8-57) -----------
+ * Builds the dense targets of DetectionLoss on the device from per-sample object lists.
+ * boxes [B,M,4] fp32 (x1,y1,x2,y2) in HEAT-MAP pixels (i.e. after the dataset's resize to the output
+ * grid, coco.py:189-196), classes [B,M] int32, n_obj [B] int32 (only the first n_obj[b] slots of sample
+ * b are read).  Out: hm [B,C,H,W] (zero-filled, then one gaussian per object max-blended into its class
+ * plane, exact 1.0 at the integer centre), wh [B,M,2], reg [B,M,2], ind [B,M] int64, reg_mask [B,M] u8;
+ * slots without a valid object are zero, as in the reference.  Arithmetic is the reference's float64
+ * sequence; min_overlap is passed as a ratio of integers (7/10: the reference's 0.7 literal). */
+typedef struct cnh_raster_args {
+  int32_t B, C, H, W, M;
+  int32_t min_overlap_num, min_overlap_den;
+  int32_t _pad;
+  const float* boxes;
+  const int32_t* classes;
+  const int32_t* n_obj;
+  float* hm;
+  float* wh;
+  float* reg;
+  int64_t* ind;
+  uint8_t* reg_mask;
+} cnh_raster_args;
+int cnh_raster_targets(const cnh_raster_args* a, cnh_stream_t stream);
 
 #ifdef __cplusplus
 }

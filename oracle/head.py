@@ -294,3 +294,69 @@ def self_information_backward(logits: torch.Tensor, upstream: torch.Tensor):
     out = self_information_map(x)
     out.backward(upstream)
     return out.detach(), x.grad
+
+
+# --------------------------------------------------------------------------- #
+# target rasteriser (the step before the path)
+# --------------------------------------------------------------------------- #
+def gaussian_radius(det_size, min_overlap=0.7):
+    """utils/image.py:8-28: smallest of the three CornerNet roots (each divided by 2, as the reference does)."""
+    import numpy as np
+    height, width = det_size
+    b1 = height + width
+    c1 = width * height * (1 - min_overlap) / (1 + min_overlap)
+    r1 = (b1 + np.sqrt(b1 ** 2 - 4 * 1 * c1)) / 2
+    b2 = 2 * (height + width)
+    c2 = (1 - min_overlap) * width * height
+    r2 = (b2 + np.sqrt(b2 ** 2 - 4 * 4 * c2)) / 2
+    a3 = 4 * min_overlap
+    b3 = -2 * min_overlap * (height + width)
+    c3 = (min_overlap - 1) * width * height
+    r3 = (b3 + np.sqrt(b3 ** 2 - 4 * a3 * c3)) / 2
+    return min(r1, r2, r3)
+
+
+def draw_gaussian(plane, cx, cy, radius):
+    """utils/image.py:31-57: max-blend the (2r+1)^2 gaussian, sigma = (2r+1)/6, clipped at the borders."""
+    import numpy as np
+    diameter = 2 * radius + 1
+    sigma = diameter / 6
+    m = (diameter - 1.) / 2.
+    y, x = np.ogrid[-m:m + 1, -m:m + 1]
+    g = np.exp(-(x * x + y * y) / (2 * sigma * sigma))
+    g[g < np.finfo(g.dtype).eps * g.max()] = 0
+    h, w = plane.shape
+    left, right = min(cx, radius), min(w - cx, radius + 1)
+    top, bottom = min(cy, radius), min(h - cy, radius + 1)
+    view = plane[cy - top:cy + bottom, cx - left:cx + right]
+    part = g[radius - top:radius + bottom, radius - left:radius + right]
+    if min(part.shape) > 0 and min(view.shape) > 0:
+        np.maximum(view, part, out=view)
+
+
+def raster_targets(boxes, classes, n_obj, num_classes, height, width):
+    """datasets/coco.py:168-215 for boxes already in heat-map pixels: numpy arrays in, the batch dict out."""
+    import numpy as np
+    B, M = classes.shape
+    hm = np.zeros((B, num_classes, height, width), dtype=np.float32)
+    wh = np.zeros((B, M, 2), dtype=np.float32)
+    reg = np.zeros((B, M, 2), dtype=np.float32)
+    ind = np.zeros((B, M), dtype=np.int64)
+    mask = np.zeros((B, M), dtype=np.uint8)
+    for b in range(B):
+        for k in range(int(n_obj[b])):
+            bbox = np.array(boxes[b, k], dtype=np.float64)
+            bbox[[0, 2]] = np.clip(bbox[[0, 2]], 0, width - 1)          # :199-200
+            bbox[[1, 3]] = np.clip(bbox[[1, 3]], 0, height - 1)
+            h, w = bbox[3] - bbox[1], bbox[2] - bbox[0]
+            cls = int(classes[b, k])
+            if h > 0 and w > 0 and 0 <= cls < num_classes:
+                radius = max(0, int(gaussian_radius((np.ceil(h), np.ceil(w)))))
+                ct = np.array([(bbox[0] + bbox[2]) / 2, (bbox[1] + bbox[3]) / 2], dtype=np.float32)
+                ct_int = ct.astype(np.int32)
+                draw_gaussian(hm[b, cls], int(ct_int[0]), int(ct_int[1]), radius)
+                wh[b, k] = 1. * w, 1. * h
+                ind[b, k] = ct_int[1] * width + ct_int[0]
+                reg[b, k] = ct - ct_int
+                mask[b, k] = 1
+    return {"hm": hm, "reg_mask": mask, "ind": ind, "wh": wh, "reg": reg}

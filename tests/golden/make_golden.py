@@ -216,6 +216,49 @@ def main():
         draw_umich_gaussian(hm, (cx, cy), r)
     save("raster_gaussians", hm=hm, boxes=np.array(boxes, dtype=np.float64), radii=np.array(radii))
 
+    # ---- full target rasterisation of a batch (row N2) ----------------------------------------
+    # datasets/coco.py cannot be imported here (imgaug / pycocotools are missing), so the per-object
+    # statements of COCO.__getitem__ (datasets/coco.py:168-174, 191-215) are executed around the
+    # reference's own gaussian_radius / draw_umich_gaussian, on boxes already in output-grid pixels.
+    rng = np.random.RandomState(7)
+    B, C, H, W, M = 3, 4, 48, 64, 12
+    n_obj = np.array([12, 5, 0], dtype=np.int32)
+    boxes = np.zeros((B, M, 4), dtype=np.float32)
+    classes = rng.randint(0, C, size=(B, M)).astype(np.int32)
+    for b in range(B):
+        for k in range(M):
+            x1, y1 = rng.uniform(-6, W - 2), rng.uniform(-6, H - 2)
+            boxes[b, k] = (x1, y1, x1 + rng.uniform(0.3, 40), y1 + rng.uniform(0.3, 30))
+    boxes[0, 3] = (10.0, 5.0, 10.0, 9.0)              # zero width: skipped
+    boxes[0, 4] = (61.5, 40.0, 80.0, 60.0)            # clipped at the right/bottom border
+    boxes[0, 5] = boxes[0, 6]                         # duplicate object
+    classes[0, 5] = classes[0, 6]
+    boxes[1, 0] = (0.0, 0.0, 63.0, 47.0)              # the whole map
+    hm = np.zeros((B, C, H, W), dtype=np.float32)
+    wh = np.zeros((B, M, 2), dtype=np.float32)
+    reg = np.zeros((B, M, 2), dtype=np.float32)
+    ind = np.zeros((B, M), dtype=np.int64)
+    reg_mask = np.zeros((B, M), dtype=np.uint8)
+    for b in range(B):
+        for k in range(n_obj[b]):
+            bbox = np.array([boxes[b, k, 0], boxes[b, k, 1], boxes[b, k, 2], boxes[b, k, 3]], dtype=np.float64)
+            cls_id = int(classes[b, k])
+            bbox[[0, 2]] = np.clip(bbox[[0, 2]], 0, W - 1)
+            bbox[[1, 3]] = np.clip(bbox[[1, 3]], 0, H - 1)
+            h, w = bbox[3] - bbox[1], bbox[2] - bbox[0]
+            if h > 0 and w > 0:
+                radius = gaussian_radius((np.ceil(h), np.ceil(w)))
+                radius = max(0, int(radius))
+                ct = np.array([(bbox[0] + bbox[2]) / 2, (bbox[1] + bbox[3]) / 2], dtype=np.float32)
+                ct_int = ct.astype(np.int32)
+                draw_umich_gaussian(hm[b, cls_id], ct_int, radius)
+                wh[b, k] = 1. * w, 1. * h
+                ind[b, k] = ct_int[1] * W + ct_int[0]
+                reg[b, k] = ct - ct_int
+                reg_mask[b, k] = 1
+    save("raster_targets", boxes=boxes, classes=classes, n_obj=n_obj, hm=hm, wh=wh, reg=reg, ind=ind,
+         reg_mask=reg_mask, C=C)
+
 
 if __name__ == "__main__":
     main()

@@ -30,14 +30,15 @@ def test_header_declares_the_expected_entry_points():
     names = declared_symbols()
     for must in ("cnh_detloss_fused", "cnh_detloss_count", "cnh_detloss_main", "cnh_detloss_finalize",
                  "cnh_scale_inplace", "cnh_softmax_loss", "cnh_entropy_map_fwd", "cnh_entropy_map_bwd",
-                 "cnh_bce_const", "cnh_decode", "cnh_decode_workspace_bytes", "cnh_version", "cnh_last_error"):
+                 "cnh_bce_const", "cnh_decode", "cnh_decode_workspace_bytes", "cnh_raster_targets", "cnh_version",
+                 "cnh_last_error"):
         assert must in names
 
 
 def test_library_exports_every_declared_symbol(library):
     for name in declared_symbols():
         assert hasattr(library, name), name
-    assert library.cnh_version() == 100
+    assert library.cnh_version() == 101
 
 
 def test_struct_layouts_match_header():
@@ -45,10 +46,12 @@ def test_struct_layouts_match_header():
     # sizes follow from the C declarations (LP64): checked against a C compiler
     src = r'''
     #include <stdio.h>
+    #include <stddef.h>
     #include "cnhead.h"
     int main(void) {
-      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(cnh_head), sizeof(cnh_detloss_args), sizeof(cnh_scale_args),
-             sizeof(cnh_decode_args), offsetof(cnh_detloss_args, heads), offsetof(cnh_decode_args, apply_sigmoid));
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(cnh_head), sizeof(cnh_detloss_args), sizeof(cnh_scale_args),
+             sizeof(cnh_decode_args), offsetof(cnh_detloss_args, heads), offsetof(cnh_decode_args, apply_sigmoid),
+             offsetof(cnh_decode_args, counts_out), sizeof(cnh_raster_args), offsetof(cnh_raster_args, boxes));
       return 0;
     }'''
     import tempfile
@@ -58,7 +61,8 @@ def test_struct_layouts_match_header():
                         os.path.join(d, "t")], check=True)
         out = subprocess.run([os.path.join(d, "t")], check=True, capture_output=True, text=True).stdout.split()
     got = [C.sizeof(L.Head), C.sizeof(L.DetLossArgs), C.sizeof(L.ScaleArgs), C.sizeof(L.DecodeArgs),
-           L.DetLossArgs.heads.offset, L.DecodeArgs.apply_sigmoid.offset]
+           L.DetLossArgs.heads.offset, L.DecodeArgs.apply_sigmoid.offset, L.DecodeArgs.counts_out.offset,
+           C.sizeof(L.RasterArgs), L.RasterArgs.boxes.offset]
     assert [int(v) for v in out] == got
 
 
@@ -72,6 +76,8 @@ def test_argument_errors_are_reported_without_a_gpu(library):
     assert library.cnh_decode_workspace_bytes(C.byref(d)) == 0
     assert b"K=17" in library.cnh_last_error()
     assert library.cnh_bce_const(None, None, None, 4, 1.0, None) == -1
+    r = L.RasterArgs()
+    assert library.cnh_raster_targets(C.byref(r), None) == -2 and b"raster_targets" in library.cnh_last_error()
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -318,6 +318,87 @@ def test_decode_fused_sigmoid_and_scale():
     assert rel_err(dets.cpu()[same], ref[same]) <= TOL
 
 
+def test_decode_epilogue_threshold_scale_and_async_fetch(decode_path):
+    """uda/base.py:73-94 + evaluation/coco.py:266-267: boxes * down_ratio, host copy, score filter."""
+    from cnhead.epilogue import DetectionsFetcher
+    g = torch.Generator().manual_seed(11)
+    heat = oracle.sigmoid_clamp(torch.randn(5, 6, 128, 128, generator=g) * 2 - 2.19)
+    wh, reg = torch.rand(5, 2, 128, 128, generator=g) * 30, torch.rand(5, 2, 128, 128, generator=g)
+    ref, _ = oracle.decode_stable(heat, wh, reg, K=150)
+    thr = float(ref[0, 40, 4])                                   # an actual score: the comparison is >=
+    fetch = DetectionsFetcher(150, down_ratio=4.0, score_threshold=thr)
+    pend = [fetch.launch(heat.cuda(), wh.cuda(), reg.cuda()) for _ in range(3)]   # more launches than slots in flight
+    res = pend[-1].result()
+    want = ref.clone()
+    want[..., :4] *= 4.0
+    assert np.array_equal(res['pred_scores'], ref[..., 4].numpy())
+    assert np.array_equal(res['pred_classes'], ref[..., 5].numpy().astype(np.int32))
+    assert rel_err(torch.from_numpy(res['pred_boxes']), want[..., :4]) <= TOL
+    assert np.array_equal(res['counts'], (ref[..., 4] >= thr).sum(1).numpy().astype(np.int32))
+    assert res['counts'][0] == 41
+
+
+# ---------------------------------------------------------------------------------------------
+# target rasteriser (SURVEY 8f N2)
+# ---------------------------------------------------------------------------------------------
+def run_raster(boxes, classes, n_obj, C, H, W):
+    from cnhead import functional as F
+    out = F.raster_targets(torch.from_numpy(boxes).cuda(), torch.from_numpy(classes).cuda(),
+                           torch.from_numpy(n_obj).cuda(), C, H, W)
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def test_raster_targets_vs_reference_fixture():
+    g = load_golden("raster_targets")
+    out = run_raster(g["boxes"], g["classes"], g["n_obj"], int(g["C"]), g["hm"].shape[2], g["hm"].shape[3])
+    for k in ("hm", "wh", "reg", "ind", "reg_mask"):
+        assert np.array_equal(out[k], g[k]), k                   # bit-exact, float64 gaussians included
+
+
+@pytest.mark.parametrize("B,C,H,W,M,hi", [(16, 6, 128, 128, 150, 20), (4, 80, 128, 128, 150, 60), (2, 3, 96, 200, 40, 40)])
+def test_raster_targets_vs_oracle(B, C, H, W, M, hi):
+    rng = np.random.RandomState(B * 100 + C)
+    n_obj = rng.randint(0, hi + 1, size=B).astype(np.int32)
+    boxes = np.zeros((B, M, 4), dtype=np.float32)
+    x1, y1 = rng.uniform(-8, W, size=(B, M)), rng.uniform(-8, H, size=(B, M))
+    boxes[..., 0], boxes[..., 1] = x1, y1
+    boxes[..., 2], boxes[..., 3] = x1 + rng.uniform(0, 70, size=(B, M)), y1 + rng.uniform(0, 70, size=(B, M))
+    classes = rng.randint(0, C, size=(B, M)).astype(np.int32)
+    ref = oracle.raster_targets(boxes, classes, n_obj, C, H, W)
+    out = run_raster(boxes, classes, n_obj, C, H, W)
+    for k in ("wh", "reg", "ind", "reg_mask"):
+        assert np.array_equal(out[k], ref[k]), k
+    # the gaussians are float64 exp() rounded to fp32: CUDA's and glibc's exp may differ in the last bit of
+    # the double, which survives the rounding to fp32 only on a tie -- allow at most a handful of 1-ulp cells
+    diff = out["hm"] != ref["hm"]
+    assert diff.mean() <= 1e-6, int(diff.sum())
+    assert np.abs(out["hm"].view(np.int32).astype(np.int64) - ref["hm"].view(np.int32)).max() <= 1
+    assert np.array_equal(out["hm"] == 1.0, ref["hm"] == 1.0)       # positives (gt == 1) are exact
+
+
+def test_rastered_targets_feed_the_loss():
+    """boxes -> device targets -> DetectionLoss equals the loss on the host-rasterised batch."""
+    from cnhead import synthetic
+    from losses.centernet import DetectionLoss
+    cfg = synthetic.CONFIGS["cfg2"]
+    data = synthetic.make_inputs(cfg, batch=4, hm_sigma=1.0)
+    rng = np.random.RandomState(3)
+    B, M, C, H, W = 4, cfg.max_objects, cfg.classes, cfg.height, cfg.width
+    n_obj = np.array([7, 1, 20, 0], dtype=np.int32)
+    boxes = np.zeros((B, M, 4), dtype=np.float32)
+    x1, y1 = rng.uniform(0, W - 10, size=(B, M)), rng.uniform(0, H - 10, size=(B, M))
+    boxes[..., 0], boxes[..., 1], boxes[..., 2], boxes[..., 3] = x1, y1, x1 + rng.uniform(4, 60, size=(B, M)), y1 + rng.uniform(4, 60, size=(B, M))
+    classes = rng.randint(0, C, size=(B, M)).astype(np.int32)
+    host = {k: torch.from_numpy(v) for k, v in oracle.raster_targets(boxes, classes, n_obj, C, H, W).items()}
+    from cnhead import functional as F
+    devb = F.raster_targets(torch.from_numpy(boxes).cuda(), torch.from_numpy(classes).cuda(), torch.from_numpy(n_obj).cuda(), C, H, W)
+    kw = synthetic.loss_kwargs(cfg)
+    with torch.no_grad():
+        l_dev, _ = DetectionLoss(**kw)(dev(data["output"]), devb)
+    rl, _, _, _ = oracle.detection_loss_with_grads(data["output"], host, **kw)
+    assert rel_err(l_dev, rl) <= TOL
+
+
 def test_decode_K_larger_than_plane_raises():
     from backends.decode import decode_detection
     with pytest.raises(RuntimeError):

@@ -93,3 +93,12 @@ def test_dropin_shadowing_of_a_reference_checkout():
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([PKG, REF]))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_host_feeder_and_fetcher_refuse_to_run_without_cuda():
+    """the staging helpers are plumbing around the CUDA path: no CPU mode"""
+    from cnhead.feeder import HostFeeder
+    with pytest.raises(RuntimeError, match="CUDA"):
+        HostFeeder("cpu")
+    with pytest.raises(ValueError):
+        HostFeeder("cuda", depth=0)

@@ -115,3 +115,12 @@ def test_rasteriser_matches_reference():
         assert r == int(r_ref)
         splat_gaussian(hm, int(cx), int(cy), r)
     assert np.array_equal(hm, g["hm"])
+
+
+def test_raster_targets_matches_reference():
+    """datasets/coco.py:168-215 around the reference's gaussian_radius / draw_umich_gaussian (fixture)."""
+    g = load_golden("raster_targets")
+    out = oracle.raster_targets(g["boxes"], g["classes"], g["n_obj"], int(g["C"]), g["hm"].shape[2], g["hm"].shape[3])
+    for k in ("hm", "wh", "reg", "ind", "reg_mask"):
+        assert np.array_equal(out[k], g[k]), k
+    assert out["reg_mask"].sum() == 16 and out["hm"].max() == 1.0
