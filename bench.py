@@ -12,7 +12,10 @@ its backward, and decode_detection of the same head tensors.
            rotating buffer sets that together exceed the L2 (HBM-cold), timed with CUDA events.
   e2e    : the same step through the reference-facing plugin API (losses.centernet.DetectionLoss,
            loss.backward(), backends.decode.decode_detection) with PINNED HOST inputs: H2D copy of the
-           head maps and targets, D2H read of the loss and the detections inside the timed region.
+           head maps and targets (cnhead.feeder.HostFeeder: step i+1's copy rides a copy stream under
+           step i), D2H read of the loss and the detections inside the timed region, stream-synchronised
+           every step.  e2e_boxes: same, with the targets rasterised on the device from object lists
+           (cnhead.functional.raster_targets) -- the host ships boxes instead of the dense heat-map target.
   roofline: the dominant kernel (fused detection-loss launch) timed alone with CUDA events.
   cpu_baseline / --impl reference: the oracle port of the reference's PyTorch path on the host cores.
 Rank 0 prints ONE JSON line.
@@ -54,6 +57,8 @@ def parse():
 
 def workload_name(cfg, batch):
     extra = " + rotated/periodic angle head" if cfg.angle else ""
+    if cfg.target_domain:
+        extra += " + EntropyLoss and MaxSquareLoss fwd+bwd on a target-domain batch"
     return (f"{cfg.name}: batch {batch} per GPU, {cfg.classes} classes, {cfg.height}x{cfg.width} heat maps, "
             f"DetectionLoss fwd+bwd + decode K={cfg.K}{extra}")
 
@@ -182,9 +187,16 @@ class BufferSet:
         mode = L.ANGLE_NONE if not cfg.angle else (L.ANGLE_PERIODIC if cfg.periodic else L.ANGLE_SIGMOID)
         self.heads = [F.HeadSpec(self.wh, self.wh_t, self.mask, 0.1, 1.0, mode),
                       F.HeadSpec(self.reg, self.reg_t, self.mask, 1.0)]
+        self.tdom = None
+        if cfg.target_domain:                      # cfg4: target-domain logits for EntropyLoss + MaxSquareLoss
+            self.tdom = data["target"]["hm"].to(dev)
+            self.tgrads = [torch.empty_like(self.tdom), torch.empty_like(self.tdom)]
+            self.tloss = torch.zeros(2, device=dev)
 
     def nbytes(self):
         ts = [self.hm, self.wh, self.reg, self.gt, self.prob] + self.grads
+        if self.tdom is not None:
+            ts += [self.tdom] + self.tgrads
         return sum(t.numel() * t.element_size() for t in ts)
 
 
@@ -222,6 +234,21 @@ class DeviceStep:
         self.ws_dec = torch.zeros(self.lib.cnh_decode_workspace_bytes(C.byref(self.dec_args[0])) + 256,
                                   dtype=torch.uint8, device=dev)
         self.launches_per_step = 3 if world == 1 else 5
+        self.uda_scale, self.ws_soft = [], None
+        if cfg.target_domain:
+            s0 = sets[0]
+            N, Cc, H, W = s0.tdom.shape
+            self.uda_dims = (N, Cc, H, W, N * world)
+            self.ws_soft = [torch.zeros(self.lib.cnh_softmax_workspace_bytes(N, Cc, H, W) + 256, dtype=torch.uint8, device=dev)
+                            for _ in range(2)]
+            for s in sets:
+                sc = L.ScaleArgs()
+                sc.n_tensors = 2
+                for i, t in enumerate(s.tgrads):
+                    sc.data[i], sc.count[i] = t.data_ptr(), t.numel()
+                    sc.fa[i], sc.fb[i] = s.ones.data_ptr(), None
+                self.uda_scale.append(sc)
+            self.launches_per_step += 3
         self.box = None
         if world > 1 and self.sharded.peers_schedule_fits(sets[0].hm):
             try:
@@ -257,6 +284,13 @@ class DeviceStep:
         L.check(self.lib.cnh_scale_inplace(C.byref(self.scale_args[i]), st), "scale")            # backward
         L.check(self.lib.cnh_decode(C.byref(self.dec_args[i]), self.ws_dec.data_ptr(), self.ws_dec.numel(), st),
                 "decode")
+        if self.ws_soft is not None:               # cfg4: EntropyLoss and MaxSquareLoss fwd+bwd on the target batch
+            N, Cc, H, W, n_total = self.uda_dims
+            for j, mode in enumerate((L.SOFTMAX_ENTROPY, L.SOFTMAX_MAX_SQUARE)):
+                L.check(self.lib.cnh_softmax_loss(s.tdom.data_ptr(), s.tgrads[j].data_ptr(), s.tloss[j:].data_ptr(), N, Cc,
+                                                  H, W, n_total, mode, 0.0, self.ws_soft[j].data_ptr(),
+                                                  self.ws_soft[j].numel(), st), "softmax_loss")
+            L.check(self.lib.cnh_scale_inplace(C.byref(self.uda_scale[i]), st), "scale")         # their backward
 
 
 def barrier(world):

@@ -81,11 +81,23 @@ def main():
         for i in range(n_sets):      # norm must hold valid values for main
             count(i)
         torch.cuda.synchronize()
+        uda = []
+        if cfg.target_domain:
+            N, Cc, H, W, n_total = d.uda_dims
+            def soft(j, mode):
+                def f(i):
+                    s_ = sets[i]
+                    L.check(lib.cnh_softmax_loss(s_.tdom.data_ptr(), s_.tgrads[j].data_ptr(), s_.tloss[j:].data_ptr(), N, Cc, H, W,
+                                                 n_total, mode, 0.0, d.ws_soft[j].data_ptr(), d.ws_soft[j].numel(), L.stream_ptr()), "s")
+                return f
+            uda = [("entropy_fwd_bwd", soft(0, L.SOFTMAX_ENTROPY), batch * 8 * cfg.classes * hw),
+                   ("max_square_fwd_bwd", soft(1, L.SOFTMAX_MAX_SQUARE), batch * 8 * cfg.classes * hw)]
         for tag, fn, nbytes in (("fused_stash", fused(0), loss_bytes), ("fused_precount", fused(2), loss_bytes),
                                 ("fused_stash_accurate", fused(1), loss_bytes), ("fwd_only", fwd_only, loss_bytes * 12 // 16),
                                 ("count", count, batch * 4 * cfg.classes * hw), ("main", main_, loss_bytes),
                                 ("scale_noop", scale, 0), ("decode", decode, dec_bytes),
-                                ("torch_copy_hm", copy, batch * 8 * cfg.classes * hw), ("full_step", d.step, batch * cfg.bytes_per_sample())):
+                                ("torch_copy_hm", copy, batch * 8 * cfg.classes * hw), *uda,
+                                ("full_step", d.step, batch * cfg.bytes_per_sample())):
             us = timed(fn, n_sets)
             us_eager = timed(fn, n_sets, graph=False) if tag in ("fused_stash", "decode", "full_step") else None
             res[tag] = {"us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1), "frac": round(nbytes / us / 1e3 / PEAK, 3),
