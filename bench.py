@@ -253,7 +253,9 @@ class DeviceStep:
         if world > 1 and self.sharded.peers_schedule_fits(sets[0].hm):
             try:
                 self.box = self.sharded.PeerMailbox.get(group)
-                self.launches_per_step = 3
+                self.launches_per_step = 4
+                self.side = torch.cuda.Stream(device=dev)
+                self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
             except Exception as e:                      # noqa: BLE001
                 print(f"[bench] peer mailboxes unavailable ({e!r}); using the NCCL schedule", file=sys.stderr)
 
@@ -271,6 +273,7 @@ class DeviceStep:
             L.check(self.lib.cnh_detloss_fused(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), st), "fused")
         elif self.box is not None:
             a.scalars = s.scalars.data_ptr()
+            a.flags |= L.FLAG_DEFER_TOTALS            # the loss VALUE is completed next to scale + decode (below)
             L.check(self.lib.cnh_detloss_fused_peers(C.byref(a), C.byref(self.box.c), self.ws_loss.data_ptr(),
                                                      self.ws_loss.numel(), st), "fused_peers")
         else:
@@ -281,9 +284,22 @@ class DeviceStep:
             self.sharded.reduce_totals(s.totals, self.group)
             a.scalars = s.scalars.data_ptr()
             L.check(self.lib.cnh_detloss_finalize(C.byref(a), s.totals.data_ptr(), st), "finalize")
+        forked = self.world > 1 and self.box is not None
+        if forked:
+            # fork: the totals' exchange (post, NVLink round trip, sum, scalars: one warp) runs on a side stream
+            # next to the backward scale and the decode; joined before the step ends
+            main = torch.cuda.current_stream()
+            self.ev_fork.record(main)
+            self.side.wait_event(self.ev_fork)
+            with torch.cuda.stream(self.side):
+                L.check(self.lib.cnh_detloss_peers_finalize(C.byref(a), C.byref(self.box.c), self.ws_loss.data_ptr(),
+                                                            self.ws_loss.numel(), L.stream_ptr()), "peers_finalize")
+                self.ev_join.record(self.side)
         L.check(self.lib.cnh_scale_inplace(C.byref(self.scale_args[i]), st), "scale")            # backward
         L.check(self.lib.cnh_decode(C.byref(self.dec_args[i]), self.ws_dec.data_ptr(), self.ws_dec.numel(), st),
                 "decode")
+        if forked:
+            torch.cuda.current_stream().wait_event(self.ev_join)
         if self.ws_soft is not None:               # cfg4: EntropyLoss and MaxSquareLoss fwd+bwd on the target batch
             N, Cc, H, W, n_total = self.uda_dims
             for j, mode in enumerate((L.SOFTMAX_ENTROPY, L.SOFTMAX_MAX_SQUARE)):
@@ -377,12 +393,13 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     steps, warmup = args.steps, max(3, args.warmup)
 
     # rotating buffer sets: together > 2x L2 so every step reads its inputs from HBM
-    probe = BufferSet(synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, sample_offset=rank * batch), cfg, dev)
+    rank_data = rank
+    probe = BufferSet(synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, sample_offset=rank_data * batch), cfg, dev)
     n_sets = max(2, min(16, -(-2 * L2_BYTES // probe.nbytes())))
     if probe.nbytes() > L2_BYTES:
         n_sets = 2
     sets = [probe] + [BufferSet(synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, seed_offset=1 + i,
-                                                      sample_offset=rank * batch), cfg, dev)
+                                                      sample_offset=rank_data * batch), cfg, dev)
                       for i in range(n_sets - 1)]
     dstep = DeviceStep(sets, cfg, world, group)
     side = torch.cuda.Stream(device=dev)
@@ -445,8 +462,9 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
                          f"({n_sets * probe.nbytes() / 2**20:.0f} MiB > 126 MiB L2): HBM-cold every step",
                    "launch": "CUDA graph replay" if graphs else "eager stream launches",
                    "parallelism": "single GPU" if world == 1 else
-                   (f"batch-sharded dp{world}, normalisers/totals exchanged inside the fused kernel through "
-                    f"NVLink-mapped peer mailboxes ({dstep.box.how})" if dstep.box is not None else
+                   (f"batch-sharded dp{world}, normalisers exchanged inside the fused kernel through NVLink-mapped "
+                    f"peer mailboxes ({dstep.box.how}), totals traded by a 1-warp launch on a side stream next to decode"
+                    if dstep.box is not None else
                     f"batch-sharded dp{world}, NCCL all-reduce of normalisers")},
         "step_algorithmic_bytes": step_bytes,
         "step_hbm_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,

@@ -20,7 +20,7 @@ MAX_HEADS = 3
 TOTALS = 24
 SCALARS = 8
 ANGLE_NONE, ANGLE_SIGMOID, ANGLE_PERIODIC = 0, 1, 2
-FLAG_ACCURATE_MATH, FLAG_NO_STASH = 1, 2
+FLAG_ACCURATE_MATH, FLAG_NO_STASH, FLAG_DEFER_TOTALS = 1, 2, 4
 SOFTMAX_ENTROPY, SOFTMAX_ENTROPY_ETA, SOFTMAX_MAX_SQUARE = 0, 1, 2
 
 
@@ -99,6 +99,8 @@ def lib() -> C.CDLL:
         L.cnh_detloss_single_wave.argtypes = [C.POINTER(DetLossArgs)]
         L.cnh_detloss_fused_peers.restype = C.c_int
         L.cnh_detloss_fused_peers.argtypes = [C.POINTER(DetLossArgs), C.POINTER(Peers), vp, sz, st]
+        L.cnh_detloss_peers_finalize.restype = C.c_int
+        L.cnh_detloss_peers_finalize.argtypes = [C.POINTER(DetLossArgs), C.POINTER(Peers), vp, sz, st]
         L.cnh_detloss_finalize.restype = C.c_int
         L.cnh_detloss_finalize.argtypes = [C.POINTER(DetLossArgs), vp, st]
         L.cnh_scale_inplace.restype = C.c_int

@@ -115,7 +115,7 @@ class _PeersDetectionLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, meta, hm, *maps):
-        gt, ind, specs, hm_weight, group = meta
+        gt, ind, specs, hm_weight, group, deferred = meta
         heads = [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode, s.elementwise_mask)
                  for m, s in zip(maps, specs)]
         box = PeerMailbox.get(group)
@@ -127,8 +127,16 @@ class _PeersDetectionLossFn(torch.autograd.Function):
         a = F.fill_detloss_args(hm, gt, ind, heads, hm_weight, prob, grads, scalars, totals,
                                 b_global=hm.shape[0] * box.world)
         ws = L.workspace("detloss_peers", L.lib().cnh_detloss_workspace_bytes(C.byref(a)), dev)
+        if deferred:
+            # the launch waits for the peers' normalisers only; their totals (the loss VALUE) are received
+            # by a second, tiny launch -- a caller that queues other work in between (bench.py: decode)
+            # hides that NVLink round trip; here it follows at once
+            a.flags |= L.FLAG_DEFER_TOTALS
         L.check(L.lib().cnh_detloss_fused_peers(C.byref(a), C.byref(box.c), ws.data_ptr(), ws.numel(),
                                                 L.stream_ptr()), "detloss_fused_peers")
+        if deferred:
+            L.check(L.lib().cnh_detloss_peers_finalize(C.byref(a), C.byref(box.c), ws.data_ptr(), ws.numel(),
+                                                       L.stream_ptr()), "detloss_peers_finalize")
         ctx.grads = grads
         ctx.used = False
         ctx.mark_non_differentiable(prob, totals)
@@ -178,8 +186,9 @@ class _ShardedDetectionLossFn(torch.autograd.Function):
 
 def detection_loss_sharded(hm, gt, ind, heads: Sequence[F.HeadSpec], hm_weight=1.0, group=None,
                            exchange: str = "auto"):
-    """exchange: 'peers' (in-kernel NVLink mailboxes), 'nccl' (count -> all-reduce -> main), or 'auto'
-    (peers when the per-rank problem fits the register-stash schedule)."""
+    """exchange: 'peers' (in-kernel NVLink mailboxes), 'peers_deferred' (same, the totals received by a
+    second launch), 'nccl' (count -> all-reduce -> main), or 'auto' (peers when the per-rank problem fits the
+    single-wave schedule)."""
     hm = L.require(hm, "output['hm']")
     gt = L.require(gt, "batch['hm']")
     ind = L.require(ind, "batch['ind']", torch.int64)
@@ -206,9 +215,11 @@ def detection_loss_sharded(hm, gt, ind, heads: Sequence[F.HeadSpec], hm_weight=1
                     "detloss_finalize")
         return scalars, prob, totals
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    use_peers = world > 1 and (exchange == "peers" or (exchange == "auto" and peers_schedule_fits(hm)))
-    fn = _PeersDetectionLossFn if use_peers else _ShardedDetectionLossFn
-    return fn.apply((gt, ind, specs, float(hm_weight), group), hm, *maps)
+    use_peers = world > 1 and (exchange in ("peers", "peers_deferred") or (exchange == "auto" and peers_schedule_fits(hm)))
+    if use_peers:
+        return _PeersDetectionLossFn.apply((gt, ind, specs, float(hm_weight), group, exchange == "peers_deferred"),
+                                           hm, *maps)
+    return _ShardedDetectionLossFn.apply((gt, ind, specs, float(hm_weight), group), hm, *maps)
 
 
 def make_sharded_loss(base_cls):

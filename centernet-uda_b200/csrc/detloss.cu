@@ -83,9 +83,13 @@ struct WsHeader {
 constexpr size_t kHeaderBytes = (sizeof(WsHeader) + 255) / 256 * 256;
 
 // One mailbox slot per (parity, source rank), 32 words:
-//   [0]     (tag << 32) | num_pos of the source rank   -- sent first, all the heat-map gradient needs
-//   [1..24] the source rank's exact totals (counts included)
-//   [31]    tag, stored (release.sys) after the totals
+//   [0]      (tag << 32) | num_pos of the source rank   -- sent first, with [25..27]: all the gradients need
+//   [1..24]  the source rank's exact totals (counts included)
+//   [25..27] (tag << 32) | mask count of head 0..2 of the source rank
+//   [31]     tag, stored (release.sys) after the totals
+// Words 0 and 25..27 validate themselves (payload and tag in one 64-bit store), so they are plain relaxed
+// system-scope stores: no fence sits on the path of the normalisers.  (A release.sys store there waits for
+// the SM's outstanding probability stores: measured +4 us per step at N = 2.)
 constexpr int kSlotWords = 32;
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
@@ -93,6 +97,14 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -118,6 +130,7 @@ struct Geo {
   int chunk_ctas;          // STASH: worker CTAs (the grid has one more: the finaliser)
   int x_delay_ns;          // STASH: pause between issuing the target and the logit copies
   int world, rank;         // peer exchange (world == 1: none)
+  int defer_totals;        // peers: post the totals and return; cnh_detloss_peers_finalize receives and sums
   unsigned long long* mailbox[CNH_MAX_PEERS];
   WsHeader* hdr;
   unsigned* sparse;        // [n_chunks] bit v: sub-block v of the chunk's target is not all zero
@@ -987,7 +1000,7 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
         unsigned total = 0;
         for (int r = 0; r < g.world; ++r) {
           unsigned long long v;
-          do { v = ld_acquire_sys(box + (size_t)r * kSlotWords); } while ((v >> 32) != tag);
+          do { v = ld_relaxed_sys(box + (size_t)r * kSlotWords); } while ((v >> 32) != tag);
           total += (unsigned)(v & 0xffffffffull);
         }
         sh_norm[0] = (int)total;
@@ -1044,15 +1057,18 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
     asm volatile("bar.sync 2, %0;" ::"n"(kStashThreads) : "memory");
     if (first < g.n_items) {
       if (lane == 0) {
-        if (g.world > 1) {                                   // the mask counts of every rank arrive with the totals
+        if (g.world > 1) {                                   // the mask counts of every rank arrive with its num_pos
           const unsigned long long tag = (unsigned long long)epoch + 1ull;
           const unsigned long long* box = g.mailbox[g.rank] + (size_t)(tag & 1ull) * CNH_MAX_PEERS * kSlotWords;
           long long cnt[CNH_MAX_HEADS] = {0, 0, 0};
           for (int r = 0; r < g.world; ++r) {
             const unsigned long long* slot = box + (size_t)r * kSlotWords;
-            while (ld_acquire_sys(slot + 31) != tag) { }
 #pragma unroll
-            for (int h = 0; h < CNH_MAX_HEADS; ++h) cnt[h] += (long long)__ldcv(slot + 1 + kQ + 4 + 3 * h);
+            for (int h = 0; h < CNH_MAX_HEADS; ++h) {                      // self-validating words of the first message
+              unsigned long long v;
+              do { v = ld_relaxed_sys(slot + 25 + h); } while ((v >> 32) != tag);
+              cnt[h] += (long long)(v & 0xffffffffull);
+            }
           }
 #pragma unroll
           for (int h = 0; h < CNH_MAX_HEADS; ++h) sh_norm[1 + h] = (int)cnt[h];
@@ -1097,11 +1113,25 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
     if (tid < CNH_TOTALS) g.hdr->acc[par ^ 1u][tid] = 0ll;
     if (tid < 1 + CNH_MAX_HEADS) g.hdr->bar[par ^ 1u][tid] = 0ull;
     if (tid == 0) sh_norm[0] = (int)wait_for(&g.hdr->bar[par][0], W);
+    if (g.world > 1 && tid >= 1 && tid <= CNH_MAX_HEADS) {   // mask counts (tiny units, long since arrived)
+      int c = 0;
+      if (tid - 1 < a.n_heads) {
+        unsigned long long v;
+        do { v = ld_acquire_u64(&g.hdr->bar[par][tid]); } while ((int)(v >> 40) < a.B);
+        c = (int)(v & kCountMask);
+      }
+      sh_norm[tid] = c;
+    }
     __syncthreads();
-    // first, and alone on the critical path: this rank's num_pos inside the tag word of every peer's slot
-    if (g.world > 1 && tid < g.world)
-      st_release_sys(g.mailbox[tid] + ((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords,
-                     (tag << 32) | (unsigned long long)(unsigned)sh_norm[0]);
+    // first, and alone on the critical path: this rank's num_pos inside the tag word of every peer's slot,
+    // preceded by its mask counts (the regression gradients of the peers wait for nothing else)
+    if (g.world > 1 && tid < g.world) {
+      unsigned long long* slot = g.mailbox[tid] + ((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords;
+      st_relaxed_sys(slot, (tag << 32) | (unsigned long long)(unsigned)sh_norm[0]);
+#pragma unroll
+      for (int h = 0; h < CNH_MAX_HEADS; ++h)
+        st_relaxed_sys(slot + 25 + h, (tag << 32) | (unsigned long long)(unsigned)sh_norm[1 + h]);
+    }
     // every sum word validates itself: poll until it holds the expected number of contributions
     if (tid < 14) {
       const int qi = tid % 7, lo = tid / 7;                  // 7 sums (focal, then l1 / angle per head) x (hi, lo)
@@ -1139,6 +1169,14 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
     if (tid == 0) canonicalise_totals(sh_tot);
     __syncthreads();
     dbg_stamp(g.dbg, 3);
+    if (g.world > 1 && g.defer_totals) {
+      // deferred: this rank's totals stay local; cnh_detloss_peers_finalize posts them, receives the peers'
+      // and sums.  (Posting them here costs the launch the NVLink write acknowledgements at its very end:
+      // measured 4.5 us per step at N = 2, all of it in front of the next kernel of the stream.)
+      if (tid < CNH_TOTALS) a.totals[tid] = sh_tot[tid];
+      if (tid == 0) { g.hdr->epoch = (unsigned)tag; g.hdr->parity = par ^ 1u; }
+      return;
+    }
     if (g.world > 1) {
       // ---- the rest of the exchange: exact totals (counts included), then the second tag --------
       if (tid < g.world * CNH_TOTALS) {                      // thread = (destination rank, word)
@@ -1395,6 +1433,40 @@ detloss_finalize_kernel(const cnh_detloss_args a, const long long* __restrict__ 
   if (threadIdx.x == 0) scalars_from_totals(a, totals, a.scalars);
 }
 
+// Deferred half of the peer exchange (one warp): post this rank's totals of the LAST cnh_detloss_fused_peers
+// launch on this workspace (tag = hdr->epoch; a.totals holds them) into every peer's mailbox, wait for the
+// peers', sum (exact integers) and produce the global totals + scalars.
+__global__ void __launch_bounds__(32)
+detloss_peers_finalize_kernel(const cnh_detloss_args a, const Geo g) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  __shared__ long long sh_tot[CNH_TOTALS];
+  const int tid = threadIdx.x;
+  const unsigned long long tag = (unsigned long long)g.hdr->epoch;
+  const unsigned mpar = (unsigned)(tag & 1ull);
+  if (tid < CNH_TOTALS) {
+    const unsigned long long mine = (unsigned long long)a.totals[tid];
+    for (int r = 0; r < g.world; ++r)
+      g.mailbox[r][((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords + 1 + tid] = mine;
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (tid < g.world) {
+    st_release_sys(g.mailbox[tid] + ((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords + 31, tag);
+    const unsigned long long* slot = g.mailbox[g.rank] + ((size_t)mpar * CNH_MAX_PEERS + tid) * kSlotWords;
+    while (ld_acquire_sys(slot + 31) != tag) { }
+  }
+  __syncwarp();
+  if (tid < CNH_TOTALS) {
+    long long sum = 0;
+    for (int r = 0; r < g.world; ++r)
+      sum += (long long)__ldcv(g.mailbox[g.rank] + ((size_t)mpar * CNH_MAX_PEERS + r) * kSlotWords + 1 + tid);
+    sh_tot[tid] = sum;
+    a.totals[tid] = sum;
+  }
+  __syncwarp();
+  if (tid == 0 && a.scalars != nullptr) scalars_from_totals(a, sh_tot, a.scalars);
+}
+
 // g *= factor (factor read from device scalars); nothing to do when factor == 1.
 // Launched with programmatic stream serialisation: the launch overlaps the tail of the loss kernel.
 __global__ void __launch_bounds__(kThreads)
@@ -1495,6 +1567,7 @@ static Geo make_geo(const cnh_detloss_args* a, void* ws) {
   static const int x_delay = getenv("CNH_X_DELAY_NS") ? atoi(getenv("CNH_X_DELAY_NS")) : 0;
   g.x_delay_ns = x_delay;
   g.world = 1;
+  g.defer_totals = 0;
   g.rank = 0;
   for (int i = 0; i < CNH_MAX_PEERS; ++i) g.mailbox[i] = nullptr;
   g.hdr = static_cast<WsHeader*>(ws);
@@ -1602,6 +1675,8 @@ static int detloss_fused_impl(const cnh_detloss_args* a, const cnh_peers* peers,
     g.world = peers->world;
     g.rank = peers->rank;
     for (int i = 0; i < peers->world; ++i) g.mailbox[i] = static_cast<unsigned long long*>(peers->mailbox[i]);
+    g.defer_totals = (a->flags & CNH_FLAG_DEFER_TOTALS) ? 1 : 0;
+    CNH_REQUIRE(!g.defer_totals || a->totals != nullptr, CNH_E_NULL, "detloss_fused_peers: CNH_FLAG_DEFER_TOTALS needs a->totals");
     CNH_REQUIRE(a->grad_hm != nullptr, CNH_E_UNSUPPORTED, "detloss_fused_peers: forward-only runs need no exchange before the loss value; use cnh_detloss_fused + an all-reduce of totals");
   }
   const bool fast = !(a->flags & CNH_FLAG_ACCURATE_MATH), vec = use_vec(a, g);
@@ -1635,6 +1710,37 @@ extern "C" int cnh_detloss_fused_peers(const cnh_detloss_args* a, const cnh_peer
   for (int i = 0; i < peers->world; ++i)
     CNH_REQUIRE(peers->mailbox[i] != nullptr, CNH_E_NULL, "detloss_fused_peers: mailbox[%d] is NULL", i);
   return detloss_fused_impl(a, peers, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cnh_detloss_peers_finalize(const cnh_detloss_args* a, const cnh_peers* peers, void* workspace,
+                                          size_t workspace_bytes, cnh_stream_t stream) {
+  if (int rc = validate(a, false)) return rc;
+  CNH_REQUIRE(peers != nullptr && peers->world > 1 && peers->world <= CNH_MAX_PEERS && peers->rank >= 0 &&
+              peers->rank < peers->world, CNH_E_SHAPE, "detloss_peers_finalize: bad peers");
+  CNH_REQUIRE(a->totals != nullptr, CNH_E_NULL, "detloss_peers_finalize: a->totals (this rank's totals in, global totals out) is NULL");
+  CNH_REQUIRE(workspace != nullptr && workspace_bytes >= ws_bytes(a), CNH_E_WORKSPACE,
+              "detloss_peers_finalize: workspace %zu < %zu bytes", workspace_bytes, ws_bytes(a));
+  Geo g = make_geo(a, workspace);
+  g.world = peers->world;
+  g.rank = peers->rank;
+  for (int i = 0; i < peers->world; ++i) {
+    CNH_REQUIRE(peers->mailbox[i] != nullptr, CNH_E_NULL, "detloss_peers_finalize: mailbox[%d] is NULL", i);
+    g.mailbox[i] = static_cast<unsigned long long*>(peers->mailbox[i]);
+  }
+  static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(1);
+  lc.blockDim = dim3(32);
+  lc.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = use_pdl ? 1 : 0;
+  CNH_CUDA(cudaLaunchKernelEx(&lc, detloss_peers_finalize_kernel, *a, g));
+  CNH_CUDA(cudaGetLastError());
+  return CNH_OK;
 }
 
 extern "C" int cnh_detloss_count(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,

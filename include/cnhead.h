@@ -55,7 +55,8 @@ enum {
 /* flags */
 enum {
   CNH_FLAG_ACCURATE_MATH = 1, /* expf/logf/IEEE divide instead of ex2/lg2/rcp.approx */
-  CNH_FLAG_NO_STASH = 2       /* force the two-pass (pre-count) schedule             */
+  CNH_FLAG_NO_STASH = 2,      /* force the two-pass (pre-count) schedule             */
+  CNH_FLAG_DEFER_TOTALS = 4   /* cnh_detloss_fused_peers: see cnh_detloss_peers_finalize */
 };
 
 /* One masked gather-L1 regression head (replaces RegL1Loss / PeriodicRegL1Loss /
@@ -136,6 +137,14 @@ typedef struct cnh_peers {
 } cnh_peers;
 int cnh_detloss_fused_peers(const cnh_detloss_args* a, const cnh_peers* peers, void* workspace,
                             size_t workspace_bytes, cnh_stream_t stream);
+/* With CNH_FLAG_DEFER_TOTALS the fused launch only trades the normalisers (what the gradients need),
+ * leaves THIS rank's exact totals in a->totals and writes no scalars; this one-warp launch -- any time
+ * later, and complete BEFORE the next cnh_detloss_fused_peers on the workspace starts -- posts them to the
+ * peers, waits for theirs, sums, and writes the global a->totals / a->scalars.  It may run on another
+ * stream next to decode (bench.py does): the NVLink round trip of the totals and the write
+ * acknowledgements then cost the step nothing (measured at N = 2: 33.8 -> 27 us). */
+int cnh_detloss_peers_finalize(const cnh_detloss_args* a, const cnh_peers* peers, void* workspace,
+                               size_t workspace_bytes, cnh_stream_t stream);
 /* Sharded (one process per GPU) schedule: count -> all-reduce(norm_out) -> main ->
  * all-reduce(totals) -> finalize.  Gradients are final after cnh_detloss_main.
  * cnh_detloss_count also leaves, in the workspace, one sparsity word per 4096-element chunk of hm_gt

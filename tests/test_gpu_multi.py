@@ -43,7 +43,7 @@ def _worker(rank, world, port, cfg_name, exchange, out):
         work = dict(o)
         loss, stats = crit(work, b)
         loss.backward()
-        if exchange == "peers":                       # the kernel can be re-launched on the same mailboxes
+        if exchange.startswith("peers"):              # the kernel can be re-launched on the same mailboxes
             for _ in range(3):
                 o2 = {k: v[sl].cuda().requires_grad_(True) for k, v in whole["output"].items()}
                 l2, _s = crit(dict(o2), b)
@@ -81,7 +81,7 @@ def _worker(rank, world, port, cfg_name, exchange, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("exchange", ["nccl", "peers"])
+@pytest.mark.parametrize("exchange", ["nccl", "peers", "peers_deferred"])
 @pytest.mark.parametrize("cfg_name", ["cfg2", "cfg3"])
 def test_sharded_loss_two_gpus(cfg_name, exchange):
     world = 2
