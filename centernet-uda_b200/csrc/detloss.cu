@@ -991,8 +991,11 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
     if (tid == 0) acc_add_pair_counted(g.hdr->acc[par], 0, la.hi, la.lo);   // one contribution per worker CTA
     dbg_stamp(g.dbg, 4);
     // zero-fill of this CTA's pieces of the regression gradient planes; warp 8 scatters after it
-    for (int o = bid; o < g.n_items; o += W) l1_zero_fill_block(a, g, decode_item(a, g, o));
+    const bool want_grad = a.grad_hm != nullptr;             // forward only (validation): no stores after the barrier
+    if (want_grad)
+      for (int o = bid; o < g.n_items; o += W) l1_zero_fill_block(a, g, decode_item(a, g, o));
     asm volatile("bar.arrive 2, %0;" ::"n"(kStashThreads) : "memory");
+    if (!want_grad) return;
     if (tid == 0) {
       if (g.world > 1) {                                     // sharded: num_pos of every rank, straight from the mailbox
         const unsigned long long tag = (unsigned long long)epoch + 1ull;
@@ -1055,6 +1058,7 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
     if (dbg8) g.dbg[(long long)bid * 16 + 2] = clock_ns();
     // ---- regression gradients: need the batch-wide mask counts and this CTA's zero-fill -----------------
     asm volatile("bar.sync 2, %0;" ::"n"(kStashThreads) : "memory");
+    if (a.grad_hm == nullptr) return;                        // forward only: the loss terms are all there is
     if (first < g.n_items) {
       if (lane == 0) {
         if (g.world > 1) {                                   // the mask counts of every rank arrive with its num_pos
@@ -1681,11 +1685,17 @@ static int detloss_fused_impl(const cnh_detloss_args* a, const cnh_peers* peers,
   }
   const bool fast = !(a->flags & CNH_FLAG_ACCURATE_MATH), vec = use_vec(a, g);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const void* ks = pick_stash(fast, vec);
   if (a->grad_hm == nullptr) {
+    // forward only (torch.no_grad() validation): the single wave when it fits (its CTAs simply stop after the
+    // loss terms; measured 17.6 -> see DESIGN at cfg2), else the streaming kernel
+    if (!(a->flags & CNH_FLAG_NO_STASH) && plan_stash(ks, g)) {
+      static const bool no_coop_f = (getenv("CNH_NO_COOP") != nullptr);
+      return launch(ks, !no_coop_f, g.chunk_ctas + 1, g.n_stages, a, g, st, kStashThreads);
+    }
     const void* k = pick_stream<M_FWD>(fast, vec);
     return launch(k, false, stream_grid(k, g, g.n_items + g.n_count), kStreamStages, a, g, st, kStashThreads);
   }
-  const void* ks = pick_stash(fast, vec);
   if (!(a->flags & CNH_FLAG_NO_STASH) && plan_stash(ks, g)) {
     static const bool no_coop = (getenv("CNH_NO_COOP") != nullptr);      // experiment: plain launch of the single wave
     return launch(ks, !no_coop, g.chunk_ctas + 1, g.n_stages, a, g, st, kStashThreads);
