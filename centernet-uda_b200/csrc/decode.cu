@@ -836,25 +836,28 @@ __device__ __forceinline__ void scan_rows_lean(u64* keys, unsigned* key_cnt, con
   if (flags & 8u) *dst++ = ((u64)__float_as_uint(mid.w) << 32) | (u64)(nflat - 3u);
 }
 
-// Four rows per warp (the 256-thread group scan: four tiles of a round are scanned concurrently, one per
-// group of 8 warps).  Same test as scan_rows_lean with a rolling three-row window (6 LDS.128 for 4 rows);
+// RW rows per warp (the 256-thread group scan: four tiles of a round are scanned concurrently, one per
+// group of 8 warps; RW = tile rows / 8).  Same test as scan_rows_lean with a rolling three-row window (6 LDS.128 for 4 rows);
 // the scores of flagged pixels are re-read from shared memory when the keys are written.  Appends are
 // bounded by `cap`: the counter may run past it (the caller detects that and rescans the round serially).
-__device__ __forceinline__ void scan_rows4(u64* keys, unsigned* key_cnt, unsigned cap, const float* tile, int W,
-                                           unsigned colmask, bool last_lane, unsigned thr, unsigned flat_tile0, int gwarp) {
+template <int RW>
+__device__ __forceinline__ void scan_rows_group(u64* keys, unsigned* key_cnt, unsigned cap, const float* tile, int W,
+                                                unsigned colmask, bool last_lane, unsigned thr, unsigned flat_tile0, int gwarp) {
   const int lane = threadIdx.x & 31;
-  const float* base_row = tile + (4 * gwarp) * W + 4 * lane;                      // staged row above the warp's first row
+  const float* base_row = tile + (RW * gwarp) * W + 4 * lane;                     // staged row above the warp's first row
   const float thr_eff = fmaxf(__uint_as_float(thr), __uint_as_float(1u));      // >= thr and > 0
   float4 up = *reinterpret_cast<const float4*>(base_row);
   float4 mid = *reinterpret_cast<const float4*>(base_row + W);
   unsigned flags = 0;                                                             // bit 4*rr + e
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
+  for (int rr = 0; rr < RW; ++rr) {
     const float4 dn = *reinterpret_cast<const float4*>(base_row + (rr + 2) * W);
-    unsigned pass = (mid.x >= thr_eff ? 1u : 0u) | (mid.y >= thr_eff ? 2u : 0u) | (mid.z >= thr_eff ? 4u : 0u) |
-                    (mid.w >= thr_eff ? 8u : 0u);
-    pass &= colmask;
-    if (__ballot_sync(0xffffffffu, pass != 0u) != 0u) {
+    // row-level early-out on the lane's maximum (3 instructions); the per-pixel bits only when a lane passes
+    const bool any = colmask != 0u && fmaxf(fmaxf(mid.x, mid.y), fmaxf(mid.z, mid.w)) >= thr_eff;
+    if (__ballot_sync(0xffffffffu, any) != 0u) {
+      unsigned pass = (mid.x >= thr_eff ? 1u : 0u) | (mid.y >= thr_eff ? 2u : 0u) | (mid.z >= thr_eff ? 4u : 0u) |
+                      (mid.w >= thr_eff ? 8u : 0u);
+      pass &= colmask;
       const float v0 = fmaxf(fmaxf(up.x, mid.x), dn.x), v1 = fmaxf(fmaxf(up.y, mid.y), dn.y);
       const float v2 = fmaxf(fmaxf(up.z, mid.z), dn.z), v3 = fmaxf(fmaxf(up.w, mid.w), dn.w);
       float left = __shfl_up_sync(0xffffffffu, v3, 1), right = __shfl_down_sync(0xffffffffu, v0, 1);
@@ -881,7 +884,7 @@ __device__ __forceinline__ void scan_rows4(u64* keys, unsigned* key_cnt, unsigne
   if (lane == 31) base = atomicAdd(key_cnt, (unsigned)incl);
   base = __shfl_sync(0xffffffffu, base, 31);
   unsigned pos = base + (unsigned)(incl - mine);
-  const unsigned flat_lane0 = flat_tile0 + (unsigned)(4 * gwarp) * (unsigned)W + 4u * (unsigned)lane;
+  const unsigned flat_lane0 = flat_tile0 + (unsigned)(RW * gwarp) * (unsigned)W + 4u * (unsigned)lane;
   while (flags) {
     const int bit = __ffs(flags) - 1;
     flags &= flags - 1u;
@@ -901,18 +904,26 @@ __device__ __forceinline__ void scan_rows4(u64* keys, unsigned* key_cnt, unsigne
 // the slice, then remote stores), a cluster barrier publishes them, and the leader runs the final
 // selection, sort, filler, gather and box assembly.  Versus the two-kernel path: no candidate lists,
 // histograms or tickets in global memory, no second launch, nothing to leave zeroed.
-constexpr int kClRows = 32;
-constexpr int kClTileFloats = (kClRows + 2) * kCols + 128;   // 34 rows of <= 128 floats + slack for masked lanes
-constexpr int kClTile = kClRows * kCols;   // most peaks one tile can add
-constexpr int kClCap = 2 * kClTile;        // running candidate set: cut back whenever it exceeds kClTile
 constexpr int kClGroups = 4;               // tiles scanned concurrently (one per group of 8 warps) = one round
-constexpr int kClStages = 2 * kClGroups;   // ring depth: the round being scanned + the round in flight
-constexpr int kClThreads = 1024;           // 32 warps: one tile row per warp in the scan
-static_assert(kClThreads / 32 == kClRows, "scan_rows_lean: one tile row per warp");
-struct __align__(128) ClSmem {              // followed by the TMA ring (the leader's doubles as the inbox)
-  u64 stage[kClCap];                       // the set (the scan appends to it); final stage: `sorted`
+constexpr int kClThreads = 1024;
+// Two shapes of the same kernel.  R = 32: tiles of 32 rows, ring of 2 rounds -- the fewest rounds, for short
+// walks (latency-bound, cfg2).  R = 16: tiles of 16 rows, ring of 4 rounds -- twice the rounds of copies in
+// flight, for long walks (cfg5: a round lasts about one copy latency, so bytes in flight are throughput).
+template <int R>
+struct ClCfg {
+  static constexpr int kRows = R;
+  static constexpr int kDepth = R == 32 ? 2 : 4;                 // rounds in the ring
+  static constexpr int kStages = kDepth * kClGroups;             // ring slots
+  static constexpr int kTileFloats = (R + 2) * kCols + 128;      // R + 2 rows of <= 128 floats + slack for masked lanes
+  static constexpr int kTile = R * kCols;                        // most peaks one tile can add
+  static constexpr int kCap = R == 32 ? 2 * kTile : 3 * kTile;   // running candidate set; cut whenever it exceeds kTile
+  static constexpr int kRowsPerWarp = R / kWarps;                // group scan: 8 warps per tile
+};
+template <int R>
+struct __align__(128) ClSmemT {             // followed by the TMA ring (the leader's doubles as the inbox)
+  u64 stage[ClCfg<R>::kCap];               // the set (the scan appends to it); final stage: `sorted`
   unsigned hist[kFineBins / 2];            // packed fine histogram of the set, built per cut; final stage: `sel`
-  u64 mbar[kClStages];
+  u64 mbar[ClCfg<R>::kStages];
   u64 sh_prefix;
   unsigned cnt;                            // size of the set
   unsigned cnt2;
@@ -926,8 +937,9 @@ struct __align__(128) ClSmem {              // followed by the TMA ring (the lea
   unsigned fin_cnt;                        // leader: keys received from the cluster
   unsigned warp_tot[kWarps];
 };
-static_assert(kClCap >= kMaxK, "stage also holds the sorted output");
+static_assert(ClCfg<32>::kCap >= kMaxK && ClCfg<16>::kCap >= kMaxK, "stage also holds the sorted output");
 
+template <int R>
 __global__ void __launch_bounds__(kClThreads, 1)
 decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_constant__ DecGeo g) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -935,6 +947,10 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   const int rank = (int)cluster.block_rank();
   const int b = (int)(blockIdx.x / (unsigned)CS);
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  typedef ClCfg<R> Cfg;
+  constexpr int kClRows = Cfg::kRows, kClStages = Cfg::kStages, kClTileFloats = Cfg::kTileFloats;
+  constexpr int kClTile = Cfg::kTile, kClCap = Cfg::kCap, kDepth = Cfg::kDepth;
+  typedef ClSmemT<R> ClSmem;
   ClSmem& s = *reinterpret_cast<ClSmem*>(smem_raw);
   float* const ring = reinterpret_cast<float*>(smem_raw + sizeof(ClSmem));
   u64* const inbox = reinterpret_cast<u64*>(ring);          // the leader's ring becomes the inbox once every CTA has scanned
@@ -996,6 +1012,7 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   if (wid < kClStages && wid < n_my) stage_tile(pre, wid);
   advance(pre, step_ring);
   Cursor mine = cursor_at(rank + gq * CS);                  // the tile this thread's group scans in the current round
+  Cursor round0 = cursor_at(rank);                          // first tile of the current round (uniform)
 
   // In-place compaction of arr[0..n) by the whole CTA, 1024 keys per step: a step's keys are in registers
   // before anything is written, and writes only go below the step's first key.  New size -> *out_cnt.
@@ -1060,7 +1077,7 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
 
   const int n_rounds = (n_my + kClGroups - 1) / kClGroups;
   for (int r = 0; r < n_rounds; ++r) {
-    const int half = (r & 1) * kClGroups, phase = (r >> 1) & 1;
+    const int half = (r % kDepth) * kClGroups, phase = (r / kDepth) & 1;
     const int in_round = min(kClGroups, n_my - r * kClGroups);
     const unsigned n_before = s.cnt;                        // <= kClTile (invariant)
     if (gq < in_round) {
@@ -1074,7 +1091,7 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
         for (int i = r_lo * W + (tid & 255); i < r_hi * W; i += 256) tile[i] = clamp_prob(1.0f / (1.0f + expf(-tile[i])));
         asm volatile("bar.sync %0, 256;" ::"r"(2 + gq) : "memory");
       }
-      scan_rows4(s.stage, &s.cnt, (unsigned)kClCap, tile, W, colmask, last_lane, thr,
+      scan_rows_group<Cfg::kRowsPerWarp>(s.stage, &s.cnt, (unsigned)kClCap, tile, W, colmask, last_lane, thr,
                  (unsigned)q.c * (unsigned)g.HW + (unsigned)y0 * (unsigned)W, gwarp);
     }
     __syncthreads();                                        // the round's tiles are scanned
@@ -1086,18 +1103,20 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
       __syncthreads();
       if (tid == 0) s.cnt = n_before;
       __syncthreads();
-      Cursor q = cursor_at(rank + r * kClGroups * CS);
+      Cursor q = round0;
       for (int t = 0; t < in_round; ++t, advance(q, step1)) {
-        scan_rows_lean(s.stage, &s.cnt, ring + (size_t)(half + t) * kClTileFloats, W, colmask, last_lane, thr,
-                       (unsigned)q.c * (unsigned)g.HW + (unsigned)(q.ty * kClRows + (tid >> 5)) * (unsigned)W);
+        if ((tid >> 5) < kClRows)                             // one row per warp
+          scan_rows_lean(s.stage, &s.cnt, ring + (size_t)(half + t) * kClTileFloats, W, colmask, last_lane, thr,
+                         (unsigned)q.c * (unsigned)g.HW + (unsigned)(q.ty * kClRows + (tid >> 5)) * (unsigned)W);
         __syncthreads();
         n = s.cnt;
         if (n > (unsigned)kClTile) { cut(n); n = s.cnt; }
       }
     }
     advance(mine, step_round);
-    if (wid >= half && wid < half + kClGroups) {            // refill the freed half of the ring: round r + 2
-      if ((r + 2) * kClGroups + (wid - half) < n_my) stage_tile(pre, wid);
+    advance(round0, step_round);
+    if (wid >= half && wid < half + kClGroups) {            // refill the freed slots of the ring: round r + kDepth
+      if ((r + kDepth) * kClGroups + (wid - half) < n_my) stage_tile(pre, wid);
       advance(pre, step_ring);
     }
     // Cut when the next round might overflow the invariant and, on long walks, after rounds 1, 2, 4, 8, ...
@@ -1274,7 +1293,7 @@ static int active_clusters(int dev, int cs) {
     q.attrs = qa;
     q.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, decode_cluster_kernel, &q) != cudaSuccess || n < 1) {
+    if (cudaOccupancyMaxActiveClusters(&n, decode_cluster_kernel<32>, &q) != cudaSuccess || n < 1) {
       cudaGetLastError();
       n = -1;
     }
@@ -1293,25 +1312,15 @@ static int pick_cluster_size(int B, int tiles_per_sample, int dev) {
   return active_clusters(dev, 1) < 1 ? -1 : 1;
 }
 
-static int launch_cluster(const cnh_decode_args* a, void* workspace, int dev, cudaStream_t st) {
-  constexpr int kMaxSmem = kClMaxSmem;
-  static bool attr_set[64] = {false};
-  if (dev < 0 || dev >= 64) return kClusterUnavailable;
-  if (!attr_set[dev]) {
-    if (cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess) {
-      cudaGetLastError();
-      return kClusterUnavailable;
-    }
-    attr_set[dev] = true;
-  }
-  DecGeo g = make_geo(a, workspace, kClRows);
-  const int cs = pick_cluster_size(a->B, g.tiles_per_sample, dev);
-  if (cs < 1) return kClusterUnavailable;
-  g.n_stages = kClStages;
+template <int R>
+static int launch_cluster_rows(const cnh_decode_args* a, const DecGeo& g0, int cs, cudaStream_t st) {
+  typedef ClCfg<R> Cfg;
+  DecGeo g = g0;
+  g.n_stages = Cfg::kStages;
   g.use_tma = 1;
-  const size_t smem = sizeof(ClSmem) + (size_t)kClStages * kClTileFloats * sizeof(float);
-  static_assert((size_t)kClStages * kClTileFloats * sizeof(float) >= (size_t)8 * kStageCap * sizeof(u64), "the ring holds the inbox");
-  if (smem > (size_t)kMaxSmem) return kClusterUnavailable;
+  const size_t smem = sizeof(ClSmemT<R>) + (size_t)Cfg::kStages * Cfg::kTileFloats * sizeof(float);
+  static_assert((size_t)Cfg::kStages * Cfg::kTileFloats * sizeof(float) >= (size_t)8 * kStageCap * sizeof(u64), "the ring holds the inbox");
+  static_assert(sizeof(ClSmemT<R>) + (size_t)Cfg::kStages * Cfg::kTileFloats * sizeof(float) <= (size_t)kClMaxSmem, "shared memory");
   static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
@@ -1328,9 +1337,37 @@ static int launch_cluster(const cnh_decode_args* a, void* workspace, int dev, cu
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = use_pdl ? 2 : 1;
-  CNH_CUDA(cudaLaunchKernelEx(&lc, decode_cluster_kernel, *a, g));
+  CNH_CUDA(cudaLaunchKernelEx(&lc, decode_cluster_kernel<R>, *a, g));
   CNH_CUDA(cudaGetLastError());
   return CNH_OK;
+}
+
+static bool cluster_attrs(int dev) {
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64) return false;
+  if (!attr_set[dev]) {
+    if (cudaFuncSetAttribute(decode_cluster_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClMaxSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClMaxSmem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    attr_set[dev] = true;
+  }
+  return true;
+}
+
+// 32-row tiles by default.  The 16-row / four-round shape exists for experiments (CNH_DECODE_ROWS=16) and is
+// covered by the parity tests; measured at the cfg5 shard it is SLOWER (58 vs 44 us): a round is bounded by
+// its fixed cost (scan issue + barrier), not by the bytes in flight -- mbarrier waits return at once.
+static int launch_cluster(const cnh_decode_args* a, void* workspace, int dev, cudaStream_t st) {
+  if (!cluster_attrs(dev)) return kClusterUnavailable;
+  DecGeo g32 = make_geo(a, workspace, 32);
+  const int cs = pick_cluster_size(a->B, g32.tiles_per_sample, dev);
+  if (cs < 1) return kClusterUnavailable;
+  const char* force = getenv("CNH_DECODE_ROWS");            // tests: force one shape
+  const bool rows16 = force != nullptr && atoi(force) == 16;
+  if (!rows16) return launch_cluster_rows<32>(a, g32, cs, st);
+  return launch_cluster_rows<16>(a, make_geo(a, workspace, 16), cs, st);
 }
 
 }  // namespace cnh
@@ -1341,8 +1378,8 @@ using namespace cnh;
 extern "C" int cnh_debug_decode_cluster(const cnh_decode_args* a) {
   int dev = 0;
   if (validate(a) != CNH_OK || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
-  cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClMaxSmem);
-  DecGeo g = make_geo(a, nullptr, kClRows);
+  if (!cluster_attrs(dev)) return -1;
+  DecGeo g = make_geo(a, nullptr, 32);
   const int cs = pick_cluster_size(a->B, g.tiles_per_sample, dev);
   return (cs < 0 ? 0 : cs) * 1000 + active_clusters(dev, 8);
 }

@@ -204,14 +204,17 @@ def test_large_problem_precount_schedule():
 # ---------------------------------------------------------------------------------------------
 # decode
 # ---------------------------------------------------------------------------------------------
-@pytest.fixture(params=["cluster", "two_kernel"])
+@pytest.fixture(params=["cluster", "cluster_rows16", "cluster_rows32", "two_kernel"])
 def decode_path(request, monkeypatch):
-    """csrc/decode.cu has a one-launch cluster path (TMA-stageable maps) and the persistent tile kernel +
-    merge kernel path (everything else); the environment switch forces the latter everywhere."""
+    """csrc/decode.cu has a one-launch cluster path (contiguous, aligned tile rows; in two shapes: 32-row
+    tiles for short walks, 16-row tiles with a deeper ring for long ones) and the persistent tile kernel +
+    merge kernel path (everything else); environment switches force each of them everywhere."""
+    monkeypatch.delenv("CNH_DECODE_TWO_KERNEL", raising=False)
+    monkeypatch.delenv("CNH_DECODE_ROWS", raising=False)
     if request.param == "two_kernel":
         monkeypatch.setenv("CNH_DECODE_TWO_KERNEL", "1")
-    else:
-        monkeypatch.delenv("CNH_DECODE_TWO_KERNEL", raising=False)
+    elif request.param.startswith("cluster_rows"):
+        monkeypatch.setenv("CNH_DECODE_ROWS", request.param[len("cluster_rows"):])
     return request.param
 
 
