@@ -131,7 +131,17 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"cnhead.{what} failed (code {rc}): {msg.decode() if msg else ''}")
 
 
+try:                                                    # raw handle without building Stream objects (~10x cheaper)
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+    _cur_device = torch._C._cuda_getDevice
+except AttributeError:                                  # pragma: no cover -- older torch
+    _raw_stream = _cur_device = None
+
+
 def stream_ptr() -> int:
+    """cudaStream_t of the calling thread's current stream on the current device."""
+    if _raw_stream is not None:
+        return _raw_stream(_cur_device())
     return torch.cuda.current_stream().cuda_stream
 
 
