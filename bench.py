@@ -505,8 +505,10 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup, from_boxes=False):
             bt = {"boxes": torch.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], dim=-1).contiguous(),
                   "classes": torch.randint(0, cfg.classes, bt["ind"].shape, generator=g, dtype=torch.int32),
                   "n_obj": bt["reg_mask"].sum(1).to(torch.int32)}
-        host.append(({k: v.pin_memory() for k, v in d["output"].items()},
-                     {k: v.pin_memory() for k, v in bt.items()}))
+        host.append((d["output"], bt))
+    # pinned host staging carved from one large page-locked arena (steady 50 GB/s H2D; separate small
+    # pin_memory() allocations copy at 20-40 GB/s depending on the box: tools/h2d_probe.py)
+    host = HostFeeder.pinned_sets(host)
     h2d = sum(v.numel() * v.element_size() for grp in host[0] for v in grp.values())
     dets_host = torch.empty(batch, cfg.K, 7 if cfg.rotated else 6).pin_memory()
     loss_host = torch.empty(1).pin_memory()

@@ -112,14 +112,14 @@ class _DetectionLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_scalars, _g_prob, _g_totals):
-        if ctx.grads is None:
-            raise RuntimeError("cnhead: DetectionLoss was run without gradients")
         if ctx.used:
             raise RuntimeError("cnhead: the fused DetectionLoss graph can be backpropagated only once "
                                "(its gradients were produced by the forward launch); run forward again")
+        if ctx.grads is None:
+            raise RuntimeError("cnhead: DetectionLoss was run without gradients")
         ctx.used = True
-        grads = ctx.grads
-        g = L.require(g_scalars, "grad_output")
+        grads, ctx.grads = ctx.grads, None      # hand over the only reference: AccumulateGrad then keeps the
+        g = L.require(g_scalars, "grad_output")  # tensors as .grad instead of cloning them (3 copy launches)
         s = L.ScaleArgs()
         s.n_tensors = len(grads)
         base = g.data_ptr()
@@ -129,7 +129,9 @@ class _DetectionLossFn(torch.autograd.Function):
             s.fa[i] = base                      # d/d(total loss)
             s.fb[i] = base + 4 * (1 + i)        # d/d(hm_loss | head-i loss) if a stat is differentiated
         L.check(L.lib().cnh_scale_inplace(C.byref(s), L.stream_ptr()), "scale_inplace")
-        out = [None] + [gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[1:])]
+        needs = ctx.needs_input_grad[1:]
+        out = [None] + [gr if need else None for gr, need in zip(grads, needs)]
+        del grads
         return tuple(out)
 
 
@@ -186,7 +188,8 @@ class _SoftmaxLossFn(torch.autograd.Function):
         s.n_tensors = 1
         s.data[0], s.count[0], s.fa[0], s.fb[0] = ctx.grad.data_ptr(), ctx.grad.numel(), g.data_ptr(), None
         L.check(L.lib().cnh_scale_inplace(C.byref(s), L.stream_ptr()), "scale_inplace")
-        return ctx.grad, None, None, None
+        grad, ctx.grad = ctx.grad, None         # sole reference -> no clone in AccumulateGrad
+        return grad, None, None, None
 
 
 def softmax_loss(x: torch.Tensor, mode: int, eta: Optional[float] = None, n_total: int = 0) -> torch.Tensor:

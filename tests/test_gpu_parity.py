@@ -402,6 +402,28 @@ def test_rastered_targets_feed_the_loss():
     assert rel_err(l_dev, rl) <= TOL
 
 
+def test_host_feeder_round_trip_from_a_pinned_arena():
+    """cnhead.feeder: double-buffered H2D staging hands out exactly what was put, in order."""
+    from cnhead.feeder import HostFeeder
+    g = torch.Generator().manual_seed(1)
+    sets = [({"hm": torch.randn(2, 3, 8, 8, generator=g)}, {"ind": torch.randint(0, 64, (2, 5), generator=g),
+                                                             "mask": torch.randint(0, 2, (2, 5), generator=g).to(torch.uint8)})
+            for _ in range(3)]
+    host = HostFeeder.pinned_sets(sets)
+    assert all(t.is_pinned() for st in host for d in st for t in d.values())
+    f = HostFeeder(torch.device("cuda", 0), depth=2)
+    f.put(*host[0])
+    for i in range(3):
+        if i + 1 < 3:
+            f.put(*host[i + 1])
+        o, b = f.get()
+        assert torch.equal(o["hm"].cpu(), sets[i][0]["hm"]) and torch.equal(b["ind"].cpu(), sets[i][1]["ind"])
+        assert torch.equal(b["mask"].cpu(), sets[i][1]["mask"])
+        f.release()
+    with pytest.raises(RuntimeError):
+        f.get()
+
+
 def test_decode_K_larger_than_plane_raises():
     from backends.decode import decode_detection
     with pytest.raises(RuntimeError):

@@ -12,7 +12,8 @@ kw = synthetic.loss_kwargs(cfg); crit = DetectionLoss(**kw)
 host = []
 for i in range(4):
     d = synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, seed_offset=20 + i)
-    host.append(({k: v.pin_memory() for k, v in d["output"].items()}, {k: v.pin_memory() for k, v in d["batch"].items()}))
+    host.append((d["output"], d["batch"]))
+host = HostFeeder.pinned_sets(host)
 dets_host = torch.empty(batch, cfg.K, 6).pin_memory(); loss_host = torch.empty(1).pin_memory()
 feeder = HostFeeder(dev, depth=2)
 T = {}
@@ -37,6 +38,26 @@ t0 = time.perf_counter()
 for i in range(n): step(i, True)
 tot = time.perf_counter() - t0
 print(f"per step {tot / n * 1e6:.0f} us:", {k: round(v / n * 1e6, 1) for k, v in T.items()})
+class _Noop(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x): return x.sum()
+    @staticmethod
+    def backward(ctx, g): return None
+xs = torch.zeros(4, device=dev, requires_grad=True)
+def engine_floor(n=300):
+    ys = [_Noop.apply(xs) for _ in range(n)]
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for y in ys: y.backward()
+    return (time.perf_counter() - t0) / n * 1e6
+print(f"autograd engine floor (no-op Function, CUDA scalar): {engine_floor():.0f} us per backward()")
+if hasattr(torch.autograd, "set_multithreading_enabled"):
+    torch.autograd.set_multithreading_enabled(False)
+    print(f"  with torch.autograd.set_multithreading_enabled(False): {engine_floor():.0f} us")
+    T.clear(); t0 = time.perf_counter()
+    for i in range(n): step(i, True)
+    tot = time.perf_counter() - t0
+    print(f"per step {tot / n * 1e6:.0f} us (single-threaded autograd):", {k: round(v / n * 1e6, 1) for k, v in T.items()})
+    torch.autograd.set_multithreading_enabled(True)
 pr = cProfile.Profile(); pr.enable()
 for i in range(200): step(i)
 pr.disable()

@@ -1,22 +1,8 @@
-import os, glob, torch
+"""Pinned H2D bandwidth of the step's tensors: separate allocations vs slices of one large pinned arena,
+touched or untouched (IOMMU / page-size effects differ between boxes)."""
+import torch
 torch.cuda.init()
 dev = torch.device("cuda")
-p = torch.cuda.get_device_properties(0)
-pci = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
-try: gnode = int(open(f"/sys/bus/pci/devices/{pci}/numa_node").read())
-except Exception as e: gnode = repr(e)
-print("gpu pci", pci, "numa node", gnode, "allowed cpus", len(os.sched_getaffinity(0)), sorted(os.sched_getaffinity(0))[:4], "...")
-def cpulist(s):
-    out = set()
-    for part in s.strip().split(","):
-        if not part: continue
-        a, _, b = part.partition("-")
-        out |= set(range(int(a), int(b or a) + 1))
-    return out
-nodes = {}
-for d in sorted(glob.glob("/sys/devices/system/node/node[0-9]*")):
-    nodes[int(d.rsplit("node", 1)[1])] = cpulist(open(d + "/cpulist").read())
-print("nodes:", {k: len(v) for k, v in nodes.items()})
 sizes = [6291456, 2097152, 2097152, 6291456, 19200, 2400, 19200, 19200]
 def bw(host_list, dev_list, n=100):
     s = torch.cuda.Stream()
@@ -29,15 +15,24 @@ def bw(host_list, dev_list, n=100):
         for _ in range(n):
             for h, d in zip(host_list, dev_list): d.copy_(h, non_blocking=True)
         e1.record(); torch.cuda.synchronize()
-    return sum(h.numel() for h in host_list) * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    return round(sum(h.numel() for h in host_list) * n / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1)
 ds = [torch.empty(n, dtype=torch.uint8, device=dev) for n in sizes]
-allowed = os.sched_getaffinity(0)
-for node, cpus in nodes.items():
-    use = cpus & allowed
-    if not use: print("node", node, "no allowed cpus"); continue
-    os.sched_setaffinity(0, use)
-    hs = [torch.empty(n, dtype=torch.uint8).pin_memory() for n in sizes]
-    for h in hs: h.fill_(1)
-    print("node", node, "cpus", len(use), "H2D 8 tensors:", round(bw(hs, ds), 1), "GB/s")
-    del hs
-os.sched_setaffinity(0, allowed)
+def carve(arena):
+    out, off = [], 0
+    for n in sizes:
+        out.append(arena[off:off + n]); off += (n + 4095) // 4096 * 4096
+    return out
+for rep in range(2):
+    sep = [torch.empty(n, dtype=torch.uint8).pin_memory() for n in sizes]
+    print("separate, untouched      :", bw(sep, ds), "GB/s")
+    for h in sep: h.fill_(1)
+    print("separate, touched        :", bw(sep, ds), "GB/s")
+    src = [torch.randint(0, 255, (n,), dtype=torch.uint8) for n in sizes]
+    sep2 = [t.pin_memory() for t in src]
+    print("separate, t.pin_memory() :", bw(sep2, ds), "GB/s")
+    for mb in (32, 256):
+        arena = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+        print(f"arena {mb:3d} MiB, untouched :", bw(carve(arena), ds), "GB/s")
+        arena.fill_(1)
+        print(f"arena {mb:3d} MiB, touched   :", bw(carve(arena), ds), "GB/s")
+        del arena
