@@ -996,6 +996,7 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
     }
   };
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next PDL launch (the next step's loss) may be placed
   asm volatile("griddepcontrol.wait;" ::: "memory");        // PDL: the producer of `heat` has completed
   if (tid == 0) {
     s.cnt = 0;

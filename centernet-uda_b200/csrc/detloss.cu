@@ -917,6 +917,9 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
   // PDL: a dependent launched with programmatic stream serialisation (cnh_scale_inplace, cnh_decode) may be
   // placed on the SMs now; it still blocks in griddepcontrol.wait until this grid has completed.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // ... and this launch may itself have been placed early (programmatic serialisation behind cnh_decode):
+  // nothing is read or written before the grid in front of it has completed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   dbg_stamp(g.dbg, 0);
   // every thread that touches the accumulators reads the header itself (all lanes of warps 0 and 8 load
   // the same two words: one request, no shuffle that would make the warp wait before it has issued the rest)
@@ -1242,6 +1245,7 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   const int S = g.n_stages;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: see detloss_stash_kernel
+  asm volatile("griddepcontrol.wait;" ::: "memory");                // (cooperative launches carry the PDL attribute)
   dbg_stamp(g.dbg, 0);
   if (tid == 0) {
     if (MODE != M_COUNT && VEC) {
@@ -1624,9 +1628,31 @@ static int launch(const void* kernel, bool cooperative, int grid, int stages, co
                   cudaStream_t stream, int threads = kThreads) {
   void* params[2] = {const_cast<cnh_detloss_args*>(a), const_cast<Geo*>(&g)};
   const size_t smem = (size_t)stages * sizeof(Stage);
-  if (cooperative)
+  if (cooperative) {
+    // cooperative (co-residency for the grid barrier) + programmatic stream serialisation: the launch latency
+    // and the CTA ramp-up hide under the tail of the kernel in front (decode of the previous step); the kernel
+    // starts with griddepcontrol.wait.  Falls back to the plain cooperative launch if the driver refuses.
+    static bool pdl_ok = (getenv("CNH_NO_PDL") == nullptr);
+    if (pdl_ok) {
+      cudaLaunchConfig_t lc;
+      memset(&lc, 0, sizeof(lc));
+      lc.gridDim = dim3(grid);
+      lc.blockDim = dim3(threads);
+      lc.dynamicSmemBytes = smem;
+      lc.stream = stream;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = attr;
+      lc.numAttrs = 2;
+      if (cudaLaunchKernelExC(&lc, kernel, params) == cudaSuccess) return CNH_OK;
+      cudaGetLastError();
+      pdl_ok = false;
+    }
     CNH_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(threads), params, smem, stream));
-  else
+  } else
     CNH_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), params, smem, stream));
   return CNH_OK;
 }
