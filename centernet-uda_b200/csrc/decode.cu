@@ -353,6 +353,10 @@ __device__ __forceinline__ void scan_tile(SM& s, u64* keys, unsigned* key_cnt, c
   }
 }
 
+template <class SM>
+__device__ __forceinline__ void emit_sorted(const cnh_decode_args& a, const DecGeo& g, SM& s, int b, int got,
+                                            const float* payload, int n_payload);
+
 // ---- final selection, sort, filler, gather and box assembly of one sample -------------------------
 // keys[0..m): candidate keys in shared memory, a superset of the sample's top-K, with s.hist holding their
 // packed fine histogram (only read when m > kThreads); if m > key_cap the list in `keys` is partial and
@@ -361,7 +365,7 @@ __device__ __forceinline__ void scan_tile(SM& s, u64* keys, unsigned* key_cnt, c
 template <class SM, class Overflow>
 __device__ __forceinline__ void select_sort_emit(const cnh_decode_args& a, const DecGeo& g, SM& s, int b,
                                                  const u64* keys, int m, int key_cap, Overflow overflow_keys) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int K = a.K;
   u64* const sel = reinterpret_cast<u64*>(s.hist);
   u64* const sorted = s.stage;
@@ -451,6 +455,18 @@ __device__ __forceinline__ void select_sort_emit(const cnh_decode_args& a, const
   dbg_stamp(g.dbg, 11);
   if (g.dbg && tid == 0) { g.dbg[(long long)blockIdx.x * 16 + 12] = m; g.dbg[(long long)blockIdx.x * 16 + 13] = got; }
   group_sync();
+  emit_sorted(a, g, s, b, got, nullptr, 0);
+}
+
+// ---- the tail of select_sort_emit: s.stage[0..got) sorted descending -> filler, counts, gather, boxes -------------
+// payload (nullable, shared memory): for rank r < n_payload the gathered values {reg x, reg y, w, h, angle} at
+// payload[5*r ..], loaded while the keys were being sorted (the cluster leader does); other ranks gather here.
+template <class SM>
+__device__ __forceinline__ void emit_sorted(const cnh_decode_args& a, const DecGeo& g, SM& s, int b, int got,
+                                            const float* payload, int n_payload) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = a.K;
+  u64* const sorted = s.stage;
   if (got > K) got = K;
   // fewer than K peaks: zero-score filler at the lowest flat indices that are not candidates
   if (got < K) {
@@ -492,15 +508,16 @@ __device__ __forceinline__ void select_sort_emit(const cnh_decode_args& a, const
     const int pix = (int)(flat - (unsigned)cls * (unsigned)g.HW);
     const int yy = pix / a.W, xx = pix - yy * a.W;
     float xs = (float)xx, ys = (float)yy;
+    const bool pre = r < n_payload;           // gathered while sorting
     if (a.reg) {
-      xs += a.reg[((long long)b * 2 + 0) * g.HW + pix];
-      ys += a.reg[((long long)b * 2 + 1) * g.HW + pix];
+      xs += pre ? payload[5 * r + 0] : a.reg[((long long)b * 2 + 0) * g.HW + pix];
+      ys += pre ? payload[5 * r + 1] : a.reg[((long long)b * 2 + 1) * g.HW + pix];
     } else {
       xs += 0.5f;
       ys += 0.5f;
     }
-    const float w = a.wh[((long long)b * a.D + 0) * g.HW + pix];
-    const float h = a.wh[((long long)b * a.D + 1) * g.HW + pix];
+    const float w = pre ? payload[5 * r + 2] : a.wh[((long long)b * a.D + 0) * g.HW + pix];
+    const float h = pre ? payload[5 * r + 3] : a.wh[((long long)b * a.D + 1) * g.HW + pix];
     float* out = a.dets + ((long long)b * K + r) * ncol;
     const float sc = a.box_scale;
     if (!a.rotated) {
@@ -508,7 +525,7 @@ __device__ __forceinline__ void select_sort_emit(const cnh_decode_args& a, const
       if (sc != 1.0f) { x1 *= sc; y1 *= sc; x2 *= sc; y2 *= sc; }
       out[0] = x1; out[1] = y1; out[2] = x2; out[3] = y2; out[4] = score; out[5] = (float)cls;
     } else {
-      const float av = a.wh[((long long)b * a.D + 2) * g.HW + pix];
+      const float av = pre ? payload[5 * r + 4] : a.wh[((long long)b * a.D + 2) * g.HW + pix];
       const float ang = clamp_prob(1.0f / (1.0f + expf(-av))) * 360.0f - 180.0f;
       float bx = xs, by = ys, bw = w, bh = h;
       if (sc != 1.0f) { bx *= sc; by *= sc; bw *= sc; bh *= sc; }
@@ -1188,6 +1205,48 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   }
   if (tid == 0) s.cnt2 = 0;
   __syncthreads();
+  if (m <= kThreads) {
+    // the usual case: <= 256 keys left.  Rank sort by the whole CTA (keys are unique: position = number of
+    // larger keys), four lanes per key each scanning a quarter of the list.  The key's reg / wh values are
+    // loaded BEFORE the scan (their latency hides under it) and land in shared memory at the key's rank.
+    const int i = tid >> 2, part = tid & 3;
+    const u64 k = (i < m) ? inbox[i] : 0ull;
+    float pv[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool loader = i < m && part == 0;
+    if (loader) {
+      const unsigned pix = (0xffffffffu - (unsigned)(k & 0xffffffffu)) % (unsigned)g.HW;
+      if (a.reg) {
+        pv[0] = __ldg(a.reg + ((long long)b * 2 + 0) * g.HW + pix);
+        pv[1] = __ldg(a.reg + ((long long)b * 2 + 1) * g.HW + pix);
+      }
+      pv[2] = __ldg(a.wh + ((long long)b * a.D + 0) * g.HW + pix);
+      pv[3] = __ldg(a.wh + ((long long)b * a.D + 1) * g.HW + pix);
+      if (a.rotated) pv[4] = __ldg(a.wh + ((long long)b * a.D + 2) * g.HW + pix);
+    }
+    int rank = 0;
+    if (i < m) {
+      int j = part;
+      for (; j + 12 < m; j += 16) {                         // four independent loads in flight
+        const u64 k0 = inbox[j], k1 = inbox[j + 4], k2 = inbox[j + 8], k3 = inbox[j + 12];
+        rank += (k0 > k) + (k1 > k) + (k2 > k) + (k3 > k);
+      }
+      for (; j < m; j += 4) rank += (inbox[j] > k);
+    }
+    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+    float* const payload = reinterpret_cast<float*>(s.hist);      // the histogram is dead: 256 ranks x 5 floats
+    if (loader) {
+      s.stage[rank] = k;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) payload[5 * rank + c] = pv[c];
+    }
+    __syncthreads();
+    if (!group0) return;
+    dbg_stamp(g.dbg, 11);
+    emit_sorted(a, g, s, b, m, payload, m);
+    dbg_stamp(g.dbg, 4);
+    return;
+  }
   if (!group0) return;
   if (m <= kThreads && tid < m) {                           // start the gather's cache lines on their way before sorting
     const unsigned flat = 0xffffffffu - (unsigned)(inbox[tid] & 0xffffffffu);
