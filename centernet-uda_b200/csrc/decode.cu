@@ -1397,8 +1397,10 @@ static int launch_cluster_rows(const cnh_decode_args* a, const DecGeo& g0, int c
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = use_pdl ? 2 : 1;
-  CNH_CUDA(cudaLaunchKernelEx(&lc, decode_cluster_kernel<R>, *a, g));
-  CNH_CUDA(cudaGetLastError());
+  if (cudaLaunchKernelEx(&lc, decode_cluster_kernel<R>, *a, g) != cudaSuccess) {
+    cudaGetLastError();                                  // e.g. a partitioned device that cannot co-schedule the
+    return kClusterUnavailable;                          // cluster: the caller takes the two-kernel path
+  }
   return CNH_OK;
 }
 
