@@ -999,20 +999,21 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
       for (int o = bid; o < g.n_items; o += W) l1_zero_fill_block(a, g, decode_item(a, g, o));
     asm volatile("bar.arrive 2, %0;" ::"n"(kStashThreads) : "memory");
     if (!want_grad) return;
-    if (tid == 0) {
-      if (g.world > 1) {                                     // sharded: num_pos of every rank, straight from the mailbox
-        const unsigned long long tag = (unsigned long long)epoch + 1ull;
+    if (g.world > 1) {
+      if (warp == 0) {                                       // sharded: num_pos of every rank, straight from the mailbox;
+        const unsigned long long tag = (unsigned long long)epoch + 1ull;     // one lane per source rank polls in parallel
         const unsigned long long* box = g.mailbox[g.rank] + (size_t)(tag & 1ull) * CNH_MAX_PEERS * kSlotWords;
-        unsigned total = 0;
-        for (int r = 0; r < g.world; ++r) {
+        int mine = 0;
+        if (lane < g.world) {
           unsigned long long v;
-          do { v = ld_relaxed_sys(box + (size_t)r * kSlotWords); } while ((v >> 32) != tag);
-          total += (unsigned)(v & 0xffffffffull);
+          do { v = ld_relaxed_sys(box + (size_t)lane * kSlotWords); } while ((v >> 32) != tag);
+          mine = (int)(unsigned)(v & 0xffffffffull);
         }
-        sh_norm[0] = (int)total;
-      } else {
-        sh_norm[0] = (int)wait_for(bar_chunk, W);
+        mine = warp_sum(mine);
+        if (lane == 0) sh_norm[0] = mine;
       }
+    } else if (tid == 0) {
+      sh_norm[0] = (int)wait_for(bar_chunk, W);
     }
     sync_compute();
     dbg_stamp(g.dbg, 3);
@@ -1063,23 +1064,21 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
     asm volatile("bar.sync 2, %0;" ::"n"(kStashThreads) : "memory");
     if (a.grad_hm == nullptr) return;                        // forward only: the loss terms are all there is
     if (first < g.n_items) {
-      if (lane == 0) {
-        if (g.world > 1) {                                   // the mask counts of every rank arrive with its num_pos
-          const unsigned long long tag = (unsigned long long)epoch + 1ull;
-          const unsigned long long* box = g.mailbox[g.rank] + (size_t)(tag & 1ull) * CNH_MAX_PEERS * kSlotWords;
-          long long cnt[CNH_MAX_HEADS] = {0, 0, 0};
-          for (int r = 0; r < g.world; ++r) {
-            const unsigned long long* slot = box + (size_t)r * kSlotWords;
+      if (g.world > 1) {                                     // the mask counts of every rank arrive with its num_pos:
+        const unsigned long long tag = (unsigned long long)epoch + 1ull;   // lane = (source rank, head) polls in parallel
+        const unsigned long long* box = g.mailbox[g.rank] + (size_t)(tag & 1ull) * CNH_MAX_PEERS * kSlotWords;
+        const int r = lane >> 2, h = lane & 3;               // 8 ranks x 4 (3 heads used)
+        int mine = 0;
+        if (r < g.world && h < CNH_MAX_HEADS) {
+          unsigned long long v;
+          do { v = ld_relaxed_sys(box + (size_t)r * kSlotWords + 25 + h); } while ((v >> 32) != tag);   // self-validating words
+          mine = (int)(unsigned)(v & 0xffffffffull);
+        }
 #pragma unroll
-            for (int h = 0; h < CNH_MAX_HEADS; ++h) {                      // self-validating words of the first message
-              unsigned long long v;
-              do { v = ld_relaxed_sys(slot + 25 + h); } while ((v >> 32) != tag);
-              cnt[h] += (long long)(v & 0xffffffffull);
-            }
-          }
-#pragma unroll
-          for (int h = 0; h < CNH_MAX_HEADS; ++h) sh_norm[1 + h] = (int)cnt[h];
-        } else {
+        for (int o = 4; o < 32; o <<= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);    // sum over ranks, per head
+        if (lane < CNH_MAX_HEADS) sh_norm[1 + lane] = mine;
+      } else if (lane == 0) {
+        {
           const bool all_heads = first + step < g.n_items || !kept;
           for (int h = 0; h < a.n_heads; ++h) {
             if (!all_heads && h != kr.h) continue;
