@@ -1029,6 +1029,8 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   const Stride step_ring = stride_of(kClStages * CS);
   if (wid < kClStages && wid < n_my) stage_tile(pre, wid);
   advance(pre, step_ring);
+  __syncthreads();                                          // the staging warps' zero-filled halo rows (generic stores: the
+                                                            // mbarrier only covers the bulk copy) before anyone scans
   Cursor mine = cursor_at(rank + gq * CS);                  // the tile this thread's group scans in the current round
   Cursor round0 = cursor_at(rank);                          // first tile of the current round (uniform)
 
