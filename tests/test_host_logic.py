@@ -102,3 +102,33 @@ def test_host_feeder_and_fetcher_refuse_to_run_without_cuda():
         HostFeeder("cpu")
     with pytest.raises(ValueError):
         HostFeeder("cuda", depth=0)
+
+
+def test_host_feeder_span_detection():
+    """HostFeeder ships a set as one copy only when it is a dense, aligned run of slices of ONE storage."""
+    from cnhead.feeder import HostFeeder
+    buf = torch.empty(1 << 16, dtype=torch.uint8)
+
+    def carve(t, off):
+        n = t.numel() * t.element_size()
+        out = buf[off:off + n].view(t.dtype).view(t.shape)
+        out.copy_(t)
+        return out
+
+    a, b, c = torch.randn(2, 3, 8, 8), torch.randint(0, 64, (2, 5)), torch.ones(2, 5, dtype=torch.uint8)
+    ha, hb, hc = carve(a, 4096), carve(b, 8192), carve(c, 12288)
+    lo, span, layout = HostFeeder._span(({"hm": ha}, {"ind": hb, "mask": hc}))
+    assert lo == 4096 and span == 8192 + 10
+    assert layout == ((0, torch.float32, (2, 3, 8, 8)), (4096, torch.int64, (2, 5)), (8192, torch.uint8, (2, 5)))
+    # separate storages, a misaligned slice, or a sparse span: per-tensor copies instead
+    assert HostFeeder._span(({"hm": a}, {"ind": b})) is None
+    assert HostFeeder._span(({"hm": ha}, {"mask": buf[12289:12299]})) is None
+    big = torch.empty(1 << 22, dtype=torch.uint8)
+    assert HostFeeder._span(({"x": big[:16]}, {"y": big[(1 << 22) - 16:]})) is None
+    assert HostFeeder._span(({"hm": ha.transpose(2, 3)},)) is None
+
+
+def test_pinned_arena_layout_arithmetic():
+    from cnhead.feeder import PinnedArena
+    ts = [torch.empty(3, 5), torch.empty(7, dtype=torch.int64), torch.empty(1, dtype=torch.uint8)]
+    assert PinnedArena.bytes_for(ts) == 3 * 4096 and PinnedArena.MIN_BYTES >= 256 << 20
