@@ -18,6 +18,14 @@ its backward, and decode_detection of the same head tensors.
            (cnhead.functional.raster_targets) -- the host ships boxes instead of the dense heat-map target.
   roofline: the dominant kernel (fused detection-loss launch) timed alone with CUDA events.
   cpu_baseline / --impl reference: the oracle port of the reference's PyTorch path on the host cores.
+  cfg5   : (every N) the same step on BASELINE config 5's per-GPU shard (16 x 80 x 128^2 of the 128-sample
+           COCO-scale batch): ms_per_step, step_hbm_frac, per-kernel {us, frac}; at N > 1 the schedule
+           north_star names (count -> all-reduce -> main -> all-reduce -> finalize over NCCL) with the
+           all-reduce time.
+  shapes : step_hbm_frac of the other named shapes (cfg1, cfg3, cfg4), short runs.
+  sharded_parity (N > 1, outside the timed region): one sharded step per schedule is compared with a
+           single-device launch over the all-gathered batch -- scalars, probabilities, heat-map gradients and
+           detections must be bit-identical, else the run fails (rc != 0).
 Rank 0 prints ONE JSON line.
 """
 import argparse
@@ -52,6 +60,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg5 / shapes blocks and the sharded parity check")
     return ap.parse_args()
 
 
@@ -61,6 +70,14 @@ def workload_name(cfg, batch):
         extra += " + EntropyLoss and MaxSquareLoss fwd+bwd on a target-domain batch"
     return (f"{cfg.name}: batch {batch} per GPU, {cfg.classes} classes, {cfg.height}x{cfg.width} heat maps, "
             f"DetectionLoss fwd+bwd + decode K={cfg.K}{extra}")
+
+
+def config_dict(cfg, batch, world):
+    """`config` of the JSON line -- the SAME dict in both arms (the reference arm runs `our arm's config`)."""
+    return {"workload": workload_name(cfg, batch), "global_batch": batch * world,
+            "l2": "GPU arm: rotating buffer sets that together exceed twice the 126 MiB L2, HBM-cold every step "
+                  "(sets larger than the L2 rotate in pairs); CPU arm: one batch in host memory",
+            "parallelism": "single device" if world == 1 else f"batch-sharded dp{world}, one process per GPU"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -145,20 +162,20 @@ def time_cpu(cfg, batch, steps, warmup, budget_s=None):
     return batch * done / dt, dt / done * 1e3, done, torch.get_num_threads()
 
 
-def run_reference(args, cfg, batch, rank):
+def run_reference(args, cfg, batch, rank, world):
     if rank != 0:
         return
-    steps = max(1, args.steps)
-    value, ms, done, cores = time_cpu(cfg, batch, steps, max(1, min(args.warmup, 3)), budget_s=150.0)
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    value, ms, done, cores = time_cpu(cfg, batch, steps, warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(cfg, batch), "device": "cpu"},
+        "config": config_dict(cfg, batch, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{done} steps of one {cfg.name} batch ({batch} samples) on the host: oracle port of "
                                    f"the reference's PyTorch-CPU DetectionLoss fwd+bwd + decode (the Python reference "
-                                   f"cannot travel to the GPU box)"},
+                                   f"cannot travel to the GPU box); one CPU process whatever --gpus says"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -201,9 +218,13 @@ class BufferSet:
 
 
 class DeviceStep:
-    """the launches of one step through the C ABI on device-resident buffers."""
+    """the launches of one step through the C ABI on device-resident buffers.
 
-    def __init__(self, sets, cfg, world, group):
+    schedule: 'single' (one GPU), 'peers' (sharded: normalisers exchanged INSIDE the fused launch through
+    NVLink-mapped mailboxes; the totals by a one-warp launch forked next to decode) or 'nccl' (sharded:
+    count -> all-reduce -> main -> all-reduce (forked next to decode) -> finalize)."""
+
+    def __init__(self, sets, cfg, world, group, schedule="auto"):
         import ctypes as C
         from cnhead import _lib as L, functional as F, sharded
         self.C, self.L, self.sharded, self.world, self.group, self.cfg = C, L, sharded, world, group, cfg
@@ -233,7 +254,6 @@ class DeviceStep:
                                    dtype=torch.uint8, device=dev)
         self.ws_dec = torch.zeros(self.lib.cnh_decode_workspace_bytes(C.byref(self.dec_args[0])) + 256,
                                   dtype=torch.uint8, device=dev)
-        self.launches_per_step = 3 if world == 1 else 5
         self.uda_scale, self.ws_soft = [], None
         if cfg.target_domain:
             s0 = sets[0]
@@ -248,30 +268,77 @@ class DeviceStep:
                     sc.data[i], sc.count[i] = t.data_ptr(), t.numel()
                     sc.fa[i], sc.fb[i] = s.ones.data_ptr(), None
                 self.uda_scale.append(sc)
-            self.launches_per_step += 3
         self.box = None
-        if world > 1 and self.sharded.peers_schedule_fits(sets[0].hm):
-            try:
-                self.box = self.sharded.PeerMailbox.get(group)
-                self.launches_per_step = 4
-                self.side = torch.cuda.Stream(device=dev)
-                self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
-            except Exception as e:                      # noqa: BLE001
-                print(f"[bench] peer mailboxes unavailable ({e!r}); using the NCCL schedule", file=sys.stderr)
+        self.schedule = "single"
+        if world > 1:
+            self.schedule = "nccl"
+            self.side = torch.cuda.Stream(device=dev)
+            self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
+            self.single_wave = bool(self.lib.cnh_detloss_single_wave(C.byref(self.loss_args[0])))
+            if schedule in ("auto", "peers"):
+                try:
+                    self.box = self.sharded.PeerMailbox.get(group)
+                    self.schedule = "peers"
+                except Exception as e:                      # noqa: BLE001
+                    print(f"[bench] peer mailboxes unavailable ({e!r}); using the NCCL schedule", file=sys.stderr)
+            # every rank must take the same branch
+            flag = torch.tensor([1 if self.schedule == "peers" else 0], device=dev)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                self.schedule, self.box = "nccl", None
+        self.launches_per_step = {"single": 3, "peers": 4, "nccl": 5}[self.schedule] + (3 if cfg.target_domain else 0)
 
+    def describe(self):
+        if self.schedule == "single":
+            return "single GPU: fused loss launch + backward scale + decode"
+        if self.schedule == "peers":
+            where = ("single wave: the finaliser CTA posts, the chunk CTAs poll" if self.single_wave else
+                     "pre-count schedule: CTA 0 posts after the count phase's grid barrier, every CTA polls")
+            return (f"normalisers exchanged inside the fused loss launch through NVLink-mapped peer mailboxes "
+                    f"({self.box.how}; {where}); totals traded by a 1-warp launch on a side stream next to decode")
+        return ("cnh_detloss_count -> ncclAllReduce(4 doubles) -> cnh_detloss_main -> [side stream: "
+                "ncclAllReduce(24 int64 exact totals) -> cnh_detloss_finalize] next to backward scale + decode")
+
+    # ---- pieces (also timed alone) -------------------------------------------------------------------------
     def loss_only(self, i):
         C, L = self.C, self.L
         a = self.loss_args[i]
         L.check(self.lib.cnh_detloss_fused(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), L.stream_ptr()),
                 "detloss_fused")
 
+    def count_only(self, i):
+        C, L = self.C, self.L
+        a = self.loss_args[i]
+        L.check(self.lib.cnh_detloss_count(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), L.stream_ptr()), "count")
+
+    def main_only(self, i):
+        C, L = self.C, self.L
+        a = self.loss_args[i]
+        keep, a.scalars = a.scalars, None
+        L.check(self.lib.cnh_detloss_main(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), L.stream_ptr()), "main")
+        a.scalars = keep
+
+    def allreduce_only(self, i):
+        s = self.sets[i]
+        self.sharded.exchange_normalisers(s.norm, self.group)
+        self.sharded.reduce_totals(s.totals, self.group)
+
+    def scale_only(self, i):
+        self.L.check(self.lib.cnh_scale_inplace(self.C.byref(self.scale_args[i]), self.L.stream_ptr()), "scale")
+
+    def decode_only(self, i):
+        L = self.L
+        L.check(self.lib.cnh_decode(self.C.byref(self.dec_args[i]), self.ws_dec.data_ptr(), self.ws_dec.numel(),
+                                    L.stream_ptr()), "decode")
+
+    # ---- the step -------------------------------------------------------------------------------------------
     def step(self, i):
         C, L = self.C, self.L
         st = L.stream_ptr()
         a, s = self.loss_args[i], self.sets[i]
-        if self.world == 1:
+        if self.schedule == "single":
             L.check(self.lib.cnh_detloss_fused(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), st), "fused")
-        elif self.box is not None:
+        elif self.schedule == "peers":
             a.scalars = s.scalars.data_ptr()
             a.flags |= L.FLAG_DEFER_TOTALS            # the loss VALUE is completed next to scale + decode (below)
             L.check(self.lib.cnh_detloss_fused_peers(C.byref(a), C.byref(self.box.c), self.ws_loss.data_ptr(),
@@ -281,24 +348,25 @@ class DeviceStep:
             L.check(self.lib.cnh_detloss_count(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), st), "count")
             self.sharded.exchange_normalisers(s.norm, self.group)
             L.check(self.lib.cnh_detloss_main(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), st), "main")
-            self.sharded.reduce_totals(s.totals, self.group)
             a.scalars = s.scalars.data_ptr()
-            L.check(self.lib.cnh_detloss_finalize(C.byref(a), s.totals.data_ptr(), st), "finalize")
-        forked = self.world > 1 and self.box is not None
-        if forked:
-            # fork: the totals' exchange (post, NVLink round trip, sum, scalars: one warp) runs on a side stream
+        if self.schedule != "single":
+            # fork: what only the loss VALUE needs (the totals' exchange and the scalars) runs on a side stream
             # next to the backward scale and the decode; joined before the step ends
             main = torch.cuda.current_stream()
             self.ev_fork.record(main)
             self.side.wait_event(self.ev_fork)
             with torch.cuda.stream(self.side):
-                L.check(self.lib.cnh_detloss_peers_finalize(C.byref(a), C.byref(self.box.c), self.ws_loss.data_ptr(),
-                                                            self.ws_loss.numel(), L.stream_ptr()), "peers_finalize")
+                if self.schedule == "peers":
+                    L.check(self.lib.cnh_detloss_peers_finalize(C.byref(a), C.byref(self.box.c), self.ws_loss.data_ptr(),
+                                                                self.ws_loss.numel(), L.stream_ptr()), "peers_finalize")
+                else:
+                    self.sharded.reduce_totals(s.totals, self.group)
+                    L.check(self.lib.cnh_detloss_finalize(C.byref(a), s.totals.data_ptr(), L.stream_ptr()), "finalize")
                 self.ev_join.record(self.side)
         L.check(self.lib.cnh_scale_inplace(C.byref(self.scale_args[i]), st), "scale")            # backward
         L.check(self.lib.cnh_decode(C.byref(self.dec_args[i]), self.ws_dec.data_ptr(), self.ws_dec.numel(), st),
                 "decode")
-        if forked:
+        if self.schedule != "single":
             torch.cuda.current_stream().wait_event(self.ev_join)
         if self.ws_soft is not None:               # cfg4: EntropyLoss and MaxSquareLoss fwd+bwd on the target batch
             N, Cc, H, W, n_total = self.uda_dims
@@ -315,26 +383,26 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
+def aligned_start(world, dev):
+    """barrier + synchronize, then (N > 1) every rank leaves at the same wall-clock instant: with 20-step timed
+    regions (0.6 ms) the tens of microseconds by which ranks leave an NCCL barrier apart would otherwise be
+    charged to the first step's in-kernel rendezvous.  One node: the ranks share the system clock."""
+    barrier(world)
+    if world == 1:
+        return
+    t = torch.tensor([time.time() + 0.003], dtype=torch.float64, device=dev)
+    torch.distributed.broadcast(t, 0)
+    t0 = float(t.item())
+    while time.time() < t0:
+        pass
+
+
 def max_over_ranks(ms, world, dev):
     if world == 1:
         return ms
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     return float(t.item())
-
-
-def timed_loop(fn, steps, warmup, world, dev):
-    """W untimed + exactly K timed calls of fn(i), bracketed by barrier + synchronize; device time, max over ranks."""
-    for i in range(warmup):
-        fn(i)
-    barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        fn(warmup + i)
-    e1.record()
-    barrier(world)
-    return max_over_ranks(e0.elapsed_time(e1), world, dev)
 
 
 class GraphRunner:
@@ -375,7 +443,7 @@ class GraphRunner:
 
     def timed(self, steps, warmup, world, dev):
         self.run(warmup)
-        barrier(world)
+        aligned_start(world, dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         self.run(steps)
@@ -384,63 +452,228 @@ class GraphRunner:
         return max_over_ranks(e0.elapsed_time(e1), world, dev)
 
 
-def run_ours(args, cfg, batch, rank, local_rank, world):
-    from cnhead import synthetic
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device for --impl ours"
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    group = None
-    steps, warmup = args.steps, max(3, args.warmup)
-
-    # rotating buffer sets: together > 2x L2 so every step reads its inputs from HBM
-    rank_data = rank
-    probe = BufferSet(synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, sample_offset=rank_data * batch), cfg, dev)
-    n_sets = max(2, min(16, -(-2 * L2_BYTES // probe.nbytes())))
-    if probe.nbytes() > L2_BYTES:
-        n_sets = 2
-    sets = [probe] + [BufferSet(synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, seed_offset=1 + i,
-                                                      sample_offset=rank_data * batch), cfg, dev)
-                      for i in range(n_sets - 1)]
-    dstep = DeviceStep(sets, cfg, world, group)
-    side = torch.cuda.Stream(device=dev)
-
-    # ---- value: device-resident, graph-replayed ------------------------------------------------------
-    use_graph = not args.no_graph
-    with torch.cuda.stream(side):
-        for i in range(n_sets):                      # warm every kernel / tensor map before capture
-            dstep.step(i)
-            dstep.loss_only(i)
-        torch.cuda.synchronize()
-        run_step = GraphRunner(dstep.step, n_sets, side, use_graph, rank)
-        run_loss = GraphRunner(dstep.loss_only, n_sets, side, use_graph and world == 1, rank)
-        clocks = Clocks(local_rank)
-        clocks.start()
-        ms_total = run_step.timed(steps, warmup, world, dev)
-        # ---- roofline: the dominant kernel alone, same buffers, CUDA events on its stream -------------------
-        ms_kernel = run_loss.timed(steps, warmup, 1, dev) / steps if world == 1 else None
-        clk = clocks.stop()
-    graphs = run_step.graphs
-    ms_step = ms_total / steps
-    value = batch * world * steps / (ms_total * 1e-3)
-
-    # ---- e2e: plugin API, pinned host inputs, H2D + D2H inside the timed region ------------------------
-    e2e = e2e_boxes = None
-    if not args.no_e2e:
-        e2e = run_e2e(cfg, batch, rank, world, dev, steps, warmup)
-        if world == 1 and not cfg.angle:
-            e2e_boxes = run_e2e(cfg, batch, rank, world, dev, steps, warmup, from_boxes=True)
-
-    if rank != 0:
-        return
+def hbm_peak():
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy), of measured" if "hbm_gbs" in peaks else "6650 GB/s fallback"
-    hw = cfg.height * cfg.width
-    loss_bytes = batch * (16 * cfg.classes * hw + 4 * (cfg.wh_channels + 2) * hw)
+    if "hbm_gbs" in peaks:
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy), of measured"
+    return 6650.0, "6650 GB/s fallback (B200_PROFILING.md), of fallback"
+
+
+class Workload:
+    """buffer sets + launches + graphs of one named shape on this rank."""
+
+    def __init__(self, cfg, batch, rank, world, dev, use_graph=True, schedule="auto"):
+        from cnhead import synthetic
+        self.cfg, self.batch, self.rank, self.world, self.dev = cfg, batch, rank, world, dev
+        mk = lambda i: BufferSet(synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, seed_offset=i,   # noqa: E731
+                                                       sample_offset=rank * batch), cfg, dev)
+        probe = mk(0)
+        # rotating buffer sets: together > 2x L2 so every step reads its inputs from HBM
+        n_sets = max(2, min(16, -(-2 * L2_BYTES // probe.nbytes())))
+        if probe.nbytes() > L2_BYTES:
+            n_sets = 2
+        self.sets = [probe] + [mk(1 + i) for i in range(n_sets - 1)]
+        self.n_sets, self.set_bytes = n_sets, probe.nbytes()
+        self.dstep = DeviceStep(self.sets, cfg, world, None, schedule)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.use_graph = use_graph
+        self.runners = {}
+        hw = cfg.height * cfg.width
+        self.loss_bytes = batch * (16 * cfg.classes * hw + 4 * (cfg.wh_channels + 2) * hw)
+        self.dec_bytes = batch * 4 * cfg.classes * hw
+        self.step_bytes = batch * cfg.bytes_per_sample()
+        with torch.cuda.stream(self.stream):
+            for i in range(n_sets):                      # warm every kernel / tensor map before capture
+                self.dstep.step(i)
+            torch.cuda.synchronize()
+
+    def runner(self, name, collective=False):
+        if name not in self.runners:
+            fn = getattr(self.dstep, name)
+            with torch.cuda.stream(self.stream):
+                for i in range(self.n_sets):
+                    fn(i)
+                torch.cuda.synchronize()
+                self.runners[name] = GraphRunner(fn, self.n_sets, self.stream, self.use_graph, self.rank)
+        return self.runners[name]
+
+    def time(self, name, steps, warmup, collective):
+        """ms per call of dstep.<name>; `collective`: every rank runs it in lockstep (max over ranks)."""
+        r = self.runner(name)
+        with torch.cuda.stream(self.stream):
+            ms = r.timed(steps, warmup, self.world if collective else 1, self.dev)
+        return ms / steps
+
+    def launch_mode(self):
+        r = self.runners.get("step")
+        return "CUDA graph replay" if (r is not None and r.graphs) else "eager stream launches"
+
+    def close(self):
+        self.runners.clear()
+        self.sets = None
+        self.dstep = None
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
+
+def kernel_block(w, steps, warmup, peak):
+    """per-kernel {us, frac} of one workload's launches, each timed alone (graph replay, HBM-cold rotation)."""
+    out = {}
+
+    def put(tag, name, nbytes, collective=False):
+        us = w.time(name, steps, warmup, collective) * 1e3
+        out[tag] = {"us": round(us, 2), "frac": round(nbytes / (us * 1e-6) / 1e9 / peak, 3) if nbytes else None}
+
+    sched = w.dstep.schedule
+    if sched == "single":
+        put("loss_fused", "loss_only", w.loss_bytes)
+    if sched == "nccl":
+        hw = w.cfg.height * w.cfg.width
+        put("loss_count", "count_only", w.batch * 4 * w.cfg.classes * hw)
+        put("loss_main", "main_only", w.loss_bytes)
+        put("allreduce_pair", "allreduce_only", 0, collective=True)
+    put("scale_noop", "scale_only", 0)
+    put("decode", "decode_only", w.dec_bytes)
+    return out
+
+
+def workload_block(cfg, batch, rank, world, dev, steps, warmup, use_graph, peak, kernels=True, schedule="auto"):
+    """one named shape: step time (max over ranks), whole-job heatmaps/s, step_hbm_frac, per-kernel timings."""
+    w = Workload(cfg, batch, rank, world, dev, use_graph, schedule)
+    ms = w.time("step", steps, warmup, True)
+    blk = {"workload": workload_name(cfg, batch), "ms_per_step": ms, "value": batch * world / (ms * 1e-3), "unit": UNIT,
+           "steps": steps, "warmup": warmup, "step_algorithmic_bytes": w.step_bytes,
+           "step_hbm_frac": w.step_bytes / (ms * 1e-3) / 1e9 / peak, "schedule": w.dstep.describe(),
+           "launch": w.launch_mode(), "buffer_sets": f"{w.n_sets} x {w.set_bytes / 2**20:.0f} MiB",
+           "gpu_launches_per_step": w.dstep.launches_per_step}
+    if kernels:
+        blk["kernels"] = kernel_block(w, max(20, steps // 2), warmup, peak)
+    return blk, w
+
+
+def sharded_parity(w, rank, world, dev):
+    """N > 1, outside any timed region: this rank's sharded step (set 0) against ONE single-device launch over the
+    all-gathered batch.  Scalars, probabilities, heat-map gradients and detections must be bit-identical; the
+    regression gradients (float atomics on duplicate centres) within 1e-6.  Raises on mismatch."""
+    import ctypes as C
+    from cnhead import _lib as L, functional as F
+    dist = torch.distributed
+    s, d, cfg = w.sets[0], w.dstep, w.cfg
+    with torch.cuda.stream(w.stream):
+        d.step(0)
+    torch.cuda.synchronize()
+
+    def gather(t):
+        out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+
+    hm, wh, reg, gt, ind, mask, wh_t, reg_t = (gather(t) for t in (s.hm, s.wh, s.reg, s.gt, s.ind, s.mask, s.wh_t, s.reg_t))
+    torch.cuda.synchronize()
+    heads = [F.HeadSpec(wh, wh_t, mask, s.heads[0].weight, s.heads[0].angle_weight, s.heads[0].angle_mode),
+             F.HeadSpec(reg, reg_t, mask, s.heads[1].weight)]
+    prob = torch.empty_like(hm)
+    grads = [torch.empty_like(hm), torch.empty_like(wh), torch.empty_like(reg)]
+    scal = torch.zeros(L.SCALARS, device=dev)
+    tot = torch.zeros(L.TOTALS, dtype=torch.int64, device=dev)
+    a = F.fill_detloss_args(hm, gt, ind, heads, 1.0, prob, grads, scal, tot)
+    ws = torch.zeros(L.lib().cnh_detloss_workspace_bytes(C.byref(a)) + 256, dtype=torch.uint8, device=dev)
+    L.check(L.lib().cnh_detloss_fused(C.byref(a), ws.data_ptr(), ws.numel(), L.stream_ptr()), "fused (gathered batch)")
+    dets = F.decode(prob, wh, reg, K=cfg.K, rotated=cfg.rotated)
+    torch.cuda.synchronize()
+    sl = slice(rank * w.batch, (rank + 1) * w.batch)
+    res = {"schedule": d.schedule, "global_batch": int(hm.shape[0])}
+    checks = {"scalars": torch.equal(s.scalars[:6], scal[:6]), "totals": torch.equal(s.totals, tot),
+              "prob": torch.equal(s.prob, prob[sl]), "grad_hm": torch.equal(s.grads[0], grads[0][sl]),
+              "dets": torch.equal(s.dets, dets[sl])}
+    reg_rel = 0.0
+    for mine, ref in ((s.grads[1], grads[1][sl]), (s.grads[2], grads[2][sl])):
+        reg_rel = max(reg_rel, float((mine - ref).abs().max() / ref.abs().max().clamp_min(1e-30)))
+    ok = all(checks.values()) and reg_rel <= 1e-6
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res.update({k: ("bit-exact" if v else "MISMATCH") for k, v in checks.items()})
+    res["reg_grads_max_rel"] = reg_rel
+    res["loss"] = float(scal[0])
+    if int(flag.item()) != 1:
+        raise RuntimeError(f"sharded parity FAILED on some rank (rank {rank}: {res})")
+    return res
+
+
+def run_ours(args, cfg, batch, rank, local_rank, world):
+    from cnhead import synthetic
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device for --impl ours"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    steps, warmup = args.steps, max(3, args.warmup)
+    use_graph = not args.no_graph
+    peak, peak_src = hbm_peak()
+
+    # ---- value: device-resident, graph-replayed ------------------------------------------------------
+    w = Workload(cfg, batch, rank, world, dev, use_graph)
+    w.runner("step")
+    if world == 1:
+        w.runner("loss_only")
+    clocks = Clocks(local_rank)
+    clocks.start()
+    ms_step = w.time("step", steps, warmup, True)
+    # ---- roofline: the dominant kernel alone, same buffers, CUDA events on its stream -------------------
+    ms_kernel = w.time("loss_only", steps, warmup, False) if world == 1 else None
+    clk = clocks.stop()
+    value = batch * world / (ms_step * 1e-3)
+    launch_mode, schedule, n_sets, set_bytes = w.launch_mode(), w.dstep.describe(), w.n_sets, w.set_bytes
+    launches_per_step, loss_bytes, step_bytes = w.dstep.launches_per_step, w.loss_bytes, w.step_bytes
+    parity = {}
+    if world > 1 and not args.no_extra:
+        parity[cfg.name] = sharded_parity(w, rank, world, dev)
+    w.close()
+
+    # ---- e2e: plugin API, pinned host inputs, H2D + D2H inside the timed region ------------------------
+    # `e2e` (the headline leg): every input of the step from pinned host memory -- the head maps and, when the
+    # targets are rasterisable on the device (no angle channel), the object lists they are made from; else the
+    # dataset's dense targets.  e2e_dense_targets / e2e_targets_only: see run_e2e.
+    e2e = e2e_dense = e2e_tonly = None
+    if not args.no_e2e:
+        e2e_dense = run_e2e(cfg, batch, rank, world, dev, steps, warmup, "dense")
+        e2e = run_e2e(cfg, batch, rank, world, dev, steps, warmup, "boxes") if not cfg.angle else e2e_dense
+        e2e_tonly = run_e2e(cfg, batch, rank, world, dev, steps, warmup, "targets_only")
+
+    # ---- the other named shapes: BASELINE config 5's per-GPU shard at every N; cfg1 / cfg3 / cfg4 ------
+    extra = {}
+    if not args.no_extra:
+        x_steps, x_warm = 200, 20
+        if cfg.name != "cfg5":
+            c5 = synthetic.CONFIGS["cfg5"]
+            blk, w5 = workload_block(c5, 16, rank, world, dev, x_steps, x_warm, use_graph, peak)
+            if world > 1:
+                parity["cfg5"] = sharded_parity(w5, rank, world, dev)
+            sched5 = w5.dstep.schedule
+            w5.close()
+            if world > 1 and sched5 != "nccl":
+                # the schedule north_star names, measured beside the in-kernel exchange: one NCCL all-reduce of
+                # the normalisers between the count and the main launch, one of the exact totals next to decode
+                nb, wn = workload_block(c5, 16, rank, world, dev, x_steps, x_warm, use_graph, peak, schedule="nccl")
+                parity["cfg5_nccl"] = sharded_parity(wn, rank, world, dev)
+                wn.close()
+                blk["nccl_schedule"] = {k: nb[k] for k in ("ms_per_step", "value", "step_hbm_frac", "schedule", "launch",
+                                                           "kernels", "gpu_launches_per_step")}
+            extra["cfg5"] = blk
+        shapes = {}
+        for name in ("cfg1", "cfg3", "cfg4"):
+            if name == cfg.name:
+                continue
+            c = synthetic.CONFIGS[name]
+            blk, wx = workload_block(c, c.batch, rank, world, dev, x_steps, x_warm, use_graph, peak, kernels=False)
+            wx.close()
+            shapes[name] = {k: blk[k] for k in ("workload", "ms_per_step", "value", "step_hbm_frac", "schedule")}
+        extra["shapes"] = shapes
+
+    if rank != 0:
+        return
     roof = None
     if ms_kernel:
         achieved = loss_bytes / (ms_kernel * 1e-3) / 1e9
@@ -452,28 +685,26 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
         roof = {"bound": "hbm", "kernel": "detloss_kernel (fused sigmoid-clamp-focal fwd+bwd + gather-L1 heads)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "bytes_per_launch": loss_bytes, "us_per_launch": ms_kernel * 1e3, "peak_source": peak_src}
-    step_bytes = batch * cfg.bytes_per_sample()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(cfg, batch), "global_batch": batch * world,
-                   "l2": f"rotating {n_sets} buffer sets of {probe.nbytes() / 2**20:.1f} MiB "
-                         f"({n_sets * probe.nbytes() / 2**20:.0f} MiB > 126 MiB L2): HBM-cold every step",
-                   "launch": "CUDA graph replay" if graphs else "eager stream launches",
-                   "parallelism": "single GPU" if world == 1 else
-                   (f"batch-sharded dp{world}, normalisers exchanged inside the fused kernel through NVLink-mapped "
-                    f"peer mailboxes ({dstep.box.how}), totals traded by a 1-warp launch on a side stream next to decode"
-                    if dstep.box is not None else
-                    f"batch-sharded dp{world}, NCCL all-reduce of normalisers")},
+        "config": config_dict(cfg, batch, world),
+        "run": {"buffer_sets": f"rotating {n_sets} buffer sets of {set_bytes / 2**20:.1f} MiB "
+                               f"({n_sets * set_bytes / 2**20:.0f} MiB > 126 MiB L2): HBM-cold every step",
+                "launch": launch_mode, "schedule": schedule},
         "step_algorithmic_bytes": step_bytes,
         "step_hbm_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
         "roofline": roof,
         "e2e": e2e,
-        "e2e_boxes": e2e_boxes,
-        "gpu_launches": dstep.launches_per_step * steps,
+        "e2e_dense_targets": e2e_dense,
+        "e2e_targets_only": e2e_tonly,
+        "gpu_launches": launches_per_step * steps,
         "clocks": clk,
     }
+    line.update(extra)
+    if parity:
+        line["sharded_parity"] = parity
     if not args.no_cpu_baseline and world == 1:
         v, ms, done, cores = time_cpu(cfg, batch, 60, 2, budget_s=12.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -482,7 +713,11 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_e2e(cfg, batch, rank, world, dev, steps, warmup, from_boxes=False):
+def run_e2e(cfg, batch, rank, world, dev, steps, warmup, mode="dense"):
+    """the step through the plugin API with HOST inputs.  mode: 'dense' -- head maps and the dataset's dense targets
+    from pinned host memory; 'boxes' -- head maps and object lists (the targets are rasterised on the device,
+    SURVEY 8f N2); 'targets_only' -- the head maps stay on the device, as they do behind the reference's backbone
+    (train.py:148-150 moves only the batch), and only the targets (object lists when rasterisable) come from the host."""
     from cnhead import synthetic, sharded
     from cnhead.feeder import HostFeeder
     from cnhead import functional as F
@@ -490,8 +725,10 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup, from_boxes=False):
     from backends.decode import decode_detection
     kw = synthetic.loss_kwargs(cfg)
     crit = DetectionLoss(**kw) if world == 1 else sharded.make_sharded_loss(DetectionLoss)(**kw)
+    from_boxes = mode == "boxes" or (mode == "targets_only" and not cfg.angle)
+    heads_on_device = mode == "targets_only"
     n_host = 4
-    host = []
+    host, dev_heads = [], []
     for i in range(n_host):
         d = synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, seed_offset=20 + i, sample_offset=rank * batch)
         bt = d["batch"]
@@ -505,7 +742,11 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup, from_boxes=False):
             bt = {"boxes": torch.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], dim=-1).contiguous(),
                   "classes": torch.randint(0, cfg.classes, bt["ind"].shape, generator=g, dtype=torch.int32),
                   "n_obj": bt["reg_mask"].sum(1).to(torch.int32)}
-        host.append((d["output"], bt))
+        if heads_on_device:
+            dev_heads.append({k: v.to(dev) for k, v in d["output"].items()})
+            host.append((bt,))
+        else:
+            host.append((d["output"], bt))
     # pinned host staging carved from one large page-locked arena (steady 50 GB/s H2D; separate small
     # pin_memory() allocations copy at 20-40 GB/s depending on the box: tools/h2d_probe.py)
     host = HostFeeder.pinned_sets(host)
@@ -521,7 +762,11 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup, from_boxes=False):
 
     def step(i):
         stage(i + 1)                                        # H2D of the NEXT step rides the copy engine under this one
-        o, b = feeder.get()
+        got = feeder.get()
+        if heads_on_device:
+            o, b = dev_heads[i % n_host], got[0]
+        else:
+            o, b = got
         out = {k: v.detach().requires_grad_(True) for k, v in o.items()}
         work = dict(out)
         if from_boxes:
@@ -540,7 +785,7 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup, from_boxes=False):
     for i in range(w):
         step(i)
     torch.cuda.current_stream().wait_stream(feeder.copy_stream)   # the primed copy of step w is outside the region
-    barrier(world)
+    aligned_start(world, dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(e2e_steps):                              # exactly K puts (H2D) and K gets/compute/D2H inside
@@ -549,9 +794,11 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup, from_boxes=False):
     e1.record()
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    what = {"dense": "head maps + dense targets", "boxes": "head maps + object lists",
+            "targets_only": "targets only (" + ("object lists" if from_boxes else "dense") + "); head maps device-resident"}[mode]
     return {"value": batch * world * e2e_steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "ms_per_step": ms / e2e_steps, "steps": e2e_steps,
-            "h2d_GBps": h2d / (ms / e2e_steps * 1e-3) / 1e9,
+            "h2d_GBps": h2d / (ms / e2e_steps * 1e-3) / 1e9, "host_inputs": what,
             "api": "cnhead.feeder.HostFeeder (double-buffered H2D from pinned memory on a copy stream) + "
                    + ("cnhead.functional.raster_targets (targets rasterised on the device from object lists) + "
                       if from_boxes else "") +
@@ -568,7 +815,7 @@ def main():
     cfg = synthetic.CONFIGS[args.config]
     batch = args.batch or (cfg.batch if cfg.name != "cfg5" else 16)
     if args.impl == "reference":
-        run_reference(args, cfg, batch, rank)
+        run_reference(args, cfg, batch, rank, world)
         return
     if world > 1:
         torch.cuda.set_device(local_rank)

@@ -40,11 +40,13 @@ class DetLossArgs(C.Structure):
 
 
 MAX_PEERS = 8
-MAILBOX_BYTES = 4096
+MAILBOX_BYTES = 8192
+E_PEER = -6
 
 
 class Peers(C.Structure):
-    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("mailbox", C.c_void_p * MAX_PEERS)]
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("mailbox", C.c_void_p * MAX_PEERS),
+                ("status", C.c_void_p), ("timeout_ms", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class ScaleArgs(C.Structure):

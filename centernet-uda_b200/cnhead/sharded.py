@@ -18,6 +18,7 @@ single-device launch, and gradients bit-identical on the heat map.  Decode needs
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -53,9 +54,14 @@ def shard_slice(batch: int, rank: int, world: int) -> slice:
 
 # ---- peer mailboxes: the exchange folded into the fused kernel -------------------------------------
 class PeerMailbox:
-    """One zeroed 4 KiB mailbox per rank, mapped into every peer's address space (NVLink / NVSwitch).
+    """One zeroed 8 KiB mailbox per rank, mapped into every peer's address space (NVLink / NVSwitch).
     `cnh_detloss_fused_peers` stores this rank's normalisers and exact totals into every peer's mailbox
-    and waits for theirs inside the kernel -- no collective call on the step path.
+    and waits for theirs inside the kernel -- no collective call on the step path.  The exchange counter
+    lives IN the mailbox, so the per-stream workspaces of the loss may come and go.
+
+    Waits on peers are bounded (``CNH_PEER_TIMEOUT_MS``, default 2000): a kernel that gives up writes a code
+    to ``status`` (a pinned host word), poisons its outputs with NaN, and every later call raises until
+    ``PeerMailbox.reset()`` has been called on every rank.
 
     Mapping: torch symmetric memory when available, CUDA IPC handles otherwise."""
 
@@ -95,12 +101,16 @@ class PeerMailbox:
                 self.ptrs.append(t.data_ptr())
             self._keep.append(buf)
             self.how = "cuda_ipc"
+        self.local = buf
+        self.status = torch.zeros(16, dtype=torch.int32).pin_memory()      # [0]: written by a kernel that timed out
         torch.cuda.synchronize()
         dist.barrier(group=group)                       # every mailbox is zeroed and mapped
         self.c = L.Peers()
         self.c.world, self.c.rank = self.world, self.rank
         for r, p in enumerate(self.ptrs):
             self.c.mailbox[r] = p
+        self.c.status = self.status.data_ptr()
+        self.c.timeout_ms = int(os.environ.get("CNH_PEER_TIMEOUT_MS", "2000"))
 
     @classmethod
     def get(cls, group=None):
@@ -108,6 +118,18 @@ class PeerMailbox:
         if key not in cls._cache:
             cls._cache[key] = cls(group)
         return cls._cache[key]
+
+    def timed_out(self) -> int:
+        """non-zero once a kernel gave up waiting for a peer (1: normalisers, 2: totals)"""
+        return int(self.status[0])
+
+    def reset(self) -> None:
+        """collective: after a timeout every rank zeroes its mailbox and status word and re-synchronises"""
+        torch.cuda.synchronize()
+        self.local.zero_()
+        self.status.zero_()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
 
 
 class _PeersDetectionLossFn(torch.autograd.Function):
@@ -145,11 +167,19 @@ class _PeersDetectionLossFn(torch.autograd.Function):
     backward = staticmethod(F._DetectionLossFn.backward)
 
 
-def peers_schedule_fits(hm: torch.Tensor) -> bool:
-    """the in-kernel exchange needs the single-wave schedule (every 4096-element chunk of the heat map has
-    its own shared-memory stage): 2 stages x 3 CTAs x 148 SMs on a B200; cnh_detloss_single_wave() is exact"""
-    b, c, h, w = hm.shape
-    return b * ((c * h * w + 4095) // 4096) <= 880
+def single_wave(hm: torch.Tensor, heads: Sequence[F.HeadSpec] = ()) -> bool:
+    """True when the fused loss runs this shard as ONE wave (every 4096-element chunk of the heat map has its own
+    shared-memory stage) -- asked of the library (`cnh_detloss_single_wave`), which knows the device's occupancy.
+    Either way the in-kernel peer exchange applies: larger shards trade the normalisers after the count phase."""
+    a = L.DetLossArgs()
+    a.B, a.C, a.H, a.W = hm.shape
+    a.M, a.n_heads = 0, 0
+    a.hm_logits = a.hm_gt = a.prob = hm.data_ptr()           # only the dimensions matter
+    return bool(L.lib().cnh_detloss_single_wave(C.byref(a)))
+
+
+def peers_schedule_fits(hm: torch.Tensor) -> bool:          # kept for callers of the round-1 name
+    return single_wave(hm)
 
 
 # ---- CUDA path --------------------------------------------------------------------------------------
@@ -187,8 +217,8 @@ class _ShardedDetectionLossFn(torch.autograd.Function):
 def detection_loss_sharded(hm, gt, ind, heads: Sequence[F.HeadSpec], hm_weight=1.0, group=None,
                            exchange: str = "auto"):
     """exchange: 'peers' (in-kernel NVLink mailboxes), 'peers_deferred' (same, the totals received by a
-    second launch), 'nccl' (count -> all-reduce -> main), or 'auto' (peers when the per-rank problem fits the
-    single-wave schedule)."""
+    second launch), 'nccl' (count -> all-reduce -> main), or 'auto' (peers when the peers' memory can be
+    mapped, else nccl)."""
     hm = L.require(hm, "output['hm']")
     gt = L.require(gt, "batch['hm']")
     ind = L.require(ind, "batch['ind']", torch.int64)
@@ -215,7 +245,12 @@ def detection_loss_sharded(hm, gt, ind, heads: Sequence[F.HeadSpec], hm_weight=1
                     "detloss_finalize")
         return scalars, prob, totals
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    use_peers = world > 1 and (exchange in ("peers", "peers_deferred") or (exchange == "auto" and peers_schedule_fits(hm)))
+    use_peers = world > 1 and exchange in ("peers", "peers_deferred", "auto")
+    if use_peers and exchange == "auto":
+        try:                                        # no peer mapping on this system (all ranks fail alike): NCCL
+            PeerMailbox.get(group)
+        except Exception:                           # noqa: BLE001
+            use_peers = False
     if use_peers:
         return _PeersDetectionLossFn.apply((gt, ind, specs, float(hm_weight), group, exchange == "peers_deferred"),
                                            hm, *maps)

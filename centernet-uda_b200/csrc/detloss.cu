@@ -113,6 +113,35 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   return v;
 }
 
+constexpr int kEpochWord = CNH_MAILBOX_EPOCH_WORD;   // local mailbox: number of exchanges completed on it
+static_assert(2 * CNH_MAX_PEERS * kSlotWords <= kEpochWord && (kEpochWord + 1) * 8 <= CNH_MAILBOX_BYTES, "mailbox layout");
+enum { kPeerTimeoutNormalisers = 1, kPeerTimeoutTotals = 2 };
+
+__device__ __forceinline__ long long now_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// Poll a self-validating word (tag in the upper half) with relaxed system-scope loads until it carries `tag`;
+// false when `deadline` (globaltimer) passes first.  The clock is read every 256 polls.
+__device__ __forceinline__ bool poll_tagged(const unsigned long long* p, unsigned long long tag, long long deadline,
+                                            unsigned long long& v) {
+  for (unsigned spins = 1;; ++spins) {
+    v = ld_relaxed_sys(p);
+    if ((v >> 32) == tag) return true;
+    if ((spins & 255u) == 0u && now_ns() > deadline) return false;
+  }
+}
+// Same for a word that IS the tag, with acquire semantics (the totals written before it become visible).
+__device__ __forceinline__ bool poll_acquire(const unsigned long long* p, unsigned long long tag, long long deadline) {
+  for (unsigned spins = 1;; ++spins) {
+    if (ld_acquire_sys(p) == tag) return true;
+    if ((spins & 255u) == 0u && now_ns() > deadline) return false;
+  }
+}
+__device__ __forceinline__ void report_peer_timeout(unsigned* status, unsigned code) {
+  if (status != nullptr) {
+    *reinterpret_cast<volatile unsigned*>(status) = code;
+    __threadfence_system();
+  }
+}
+
 struct Geo {
   int HW;
   long long CHW;
@@ -132,6 +161,8 @@ struct Geo {
   int world, rank;         // peer exchange (world == 1: none)
   int defer_totals;        // peers: post the totals and return; cnh_detloss_peers_finalize receives and sums
   unsigned long long* mailbox[CNH_MAX_PEERS];
+  unsigned* status;        // peers: pinned host word (nullable) that receives a non-zero code when a wait times out
+  long long timeout_ns;    // peers: bound of every wait on another rank
   WsHeader* hdr;
   unsigned* sparse;        // [n_chunks] bit v: sub-block v of the chunk's target is not all zero
   long long* dbg;
@@ -864,13 +895,14 @@ __device__ void scalars_from_totals(const cnh_detloss_args& a, const long long* 
 
 // Read the live accumulator set (written by other CTAs: through L2), publish it to a.totals,
 // compute the scalars.  Threads 0..23 load one word each; thread 0 finishes.
-__device__ void finalize_from_acc(const cnh_detloss_args& a, const long long* acc, long long* sh_tot) {
+// local_only: the totals are this SHARD's (a sharded launch): publish them, leave the scalars to the exchange.
+__device__ void finalize_from_acc(const cnh_detloss_args& a, const long long* acc, long long* sh_tot, bool local_only = false) {
   if (threadIdx.x < CNH_TOTALS) sh_tot[threadIdx.x] = __ldcg(acc + threadIdx.x);
   __syncthreads();
   if (threadIdx.x == 0) canonicalise_totals(sh_tot);
   __syncthreads();
   if (threadIdx.x < CNH_TOTALS && a.totals != nullptr) a.totals[threadIdx.x] = sh_tot[threadIdx.x];
-  if (threadIdx.x == 0 && a.scalars != nullptr) scalars_from_totals(a, sh_tot, a.scalars);
+  if (threadIdx.x == 0 && a.scalars != nullptr && !local_only) scalars_from_totals(a, sh_tot, a.scalars);
 }
 
 
@@ -926,8 +958,9 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
   unsigned par = 0, epoch = 0;
   if (warp == 0 || warp == kWarps) {
     par = __ldcg(&g.hdr->parity) & 1u;
-    epoch = __ldcg(&g.hdr->epoch);
+    if (g.world > 1) epoch = (unsigned)__ldcg(g.mailbox[g.rank] + kEpochWord);
   }
+  const long long deadline = g.world > 1 ? now_ns() + g.timeout_ns : 0ll;
   auto wait_for = [&](const unsigned long long* bar, int count) -> unsigned {
     unsigned long long v;
     do { v = ld_acquire_u64(bar); } while ((unsigned)(v >> 32) < (unsigned)count);
@@ -1004,13 +1037,18 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
         const unsigned long long tag = (unsigned long long)epoch + 1ull;     // one lane per source rank polls in parallel
         const unsigned long long* box = g.mailbox[g.rank] + (size_t)(tag & 1ull) * CNH_MAX_PEERS * kSlotWords;
         int mine = 0;
+        bool ok = true;
         if (lane < g.world) {
           unsigned long long v;
-          do { v = ld_relaxed_sys(box + (size_t)lane * kSlotWords); } while ((v >> 32) != tag);
-          mine = (int)(unsigned)(v & 0xffffffffull);
+          ok = poll_tagged(box + (size_t)lane * kSlotWords, tag, deadline, v);
+          mine = ok ? (int)(unsigned)(v & 0xffffffffull) : 0;
         }
+        ok = __all_sync(0xffffffffu, ok);
         mine = warp_sum(mine);
-        if (lane == 0) sh_norm[0] = mine;
+        if (lane == 0) {
+          sh_norm[0] = ok ? mine : -1;                       // -1: a peer never arrived -> NaN scale below
+          if (!ok && bid == 0) report_peer_timeout(g.status, kPeerTimeoutNormalisers);
+        }
       }
     } else if (tid == 0) {
       sh_norm[0] = (int)wait_for(bar_chunk, W);
@@ -1019,7 +1057,8 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
     dbg_stamp(g.dbg, 3);
     // ---- pass 2b: the gradient, scaled, from shared memory ------------------------------------------------
     const int npos_all = sh_norm[0];
-    const float scale = (npos_all == 0) ? -a.hm_weight : -a.hm_weight / (float)npos_all;
+    const float scale = (npos_all < 0) ? __int_as_float(0x7fc00000)
+                                       : ((npos_all == 0) ? -a.hm_weight : -a.hm_weight / (float)npos_all);
 #pragma unroll 1
     for (int r = 0; r < S; ++r) {
       const int chunk = bid + r * W;
@@ -1069,14 +1108,16 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
         const unsigned long long* box = g.mailbox[g.rank] + (size_t)(tag & 1ull) * CNH_MAX_PEERS * kSlotWords;
         const int r = lane >> 2, h = lane & 3;               // 8 ranks x 4 (3 heads used)
         int mine = 0;
+        bool ok = true;
         if (r < g.world && h < CNH_MAX_HEADS) {
           unsigned long long v;
-          do { v = ld_relaxed_sys(box + (size_t)r * kSlotWords + 25 + h); } while ((v >> 32) != tag);   // self-validating words
-          mine = (int)(unsigned)(v & 0xffffffffull);
+          ok = poll_tagged(box + (size_t)r * kSlotWords + 25 + h, tag, deadline, v);                    // self-validating words
+          mine = ok ? (int)(unsigned)(v & 0xffffffffull) : 0;
         }
+        ok = __all_sync(0xffffffffu, ok);
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);    // sum over ranks, per head
-        if (lane < CNH_MAX_HEADS) sh_norm[1 + lane] = mine;
+        if (lane < CNH_MAX_HEADS) sh_norm[1 + lane] = ok ? mine : -1;
       } else if (lane == 0) {
         {
           const bool all_heads = first + step < g.n_items || !kept;
@@ -1093,7 +1134,7 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
     if (dbg8) g.dbg[(long long)bid * 16 + 9] = clock_ns();
     for (int o = first; o < g.n_items; o += step) {
       const ItemRef r = (kept && o == first) ? kr : decode_item(a, g, o);
-      const float inv = 1.f / ((float)sh_norm[1 + r.h] + 1e-4f);
+      const float inv = sh_norm[1 + r.h] < 0 ? __int_as_float(0x7fc00000) : 1.f / ((float)sh_norm[1 + r.h] + 1e-4f);
       if (kept && o == first) {                              // slots kept in registers: no reload
         const cnh_head& hd = head_of(a, r.h);
         float* __restrict__ gplane = hd.grad + ((long long)r.b * hd.D + r.d) * g.HW;
@@ -1180,7 +1221,7 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
       // and sums.  (Posting them here costs the launch the NVLink write acknowledgements at its very end:
       // measured 4.5 us per step at N = 2, all of it in front of the next kernel of the stream.)
       if (tid < CNH_TOTALS) a.totals[tid] = sh_tot[tid];
-      if (tid == 0) { g.hdr->epoch = (unsigned)tag; g.hdr->parity = par ^ 1u; }
+      if (tid == 0) { g.mailbox[g.rank][kEpochWord] = tag; g.hdr->parity = par ^ 1u; }
       return;
     }
     if (g.world > 1) {
@@ -1193,9 +1234,11 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
       __syncthreads();
       if (tid < g.world) st_release_sys(g.mailbox[tid] + ((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords + 31, tag);
       // wait for every source rank's totals in the LOCAL mailbox, then sum (exact integers)
+      if (tid == 0) sh_hdr[0] = 1u;                          // every peer's totals arrived
+      __syncthreads();
       if (tid < g.world) {
         const unsigned long long* slot = g.mailbox[g.rank] + ((size_t)mpar * CNH_MAX_PEERS + tid) * kSlotWords;
-        while (ld_acquire_sys(slot + 31) != tag) { }
+        if (!poll_acquire(slot + 31, tag, deadline)) sh_hdr[0] = 0u;
       }
       __syncthreads();
       if (tid < CNH_TOTALS) {
@@ -1205,7 +1248,13 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
         sh_tot[tid] = sum;
       }
       __syncthreads();
-      if (tid == 0) g.hdr->epoch = (unsigned)tag;
+      if (tid == 0) g.mailbox[g.rank][kEpochWord] = tag;
+      if (sh_hdr[0] == 0u) {                                 // a peer never delivered: poisoned scalars, error word
+        if (tid == 0) report_peer_timeout(g.status, kPeerTimeoutTotals);
+        if (tid < CNH_SCALARS && a.scalars != nullptr) a.scalars[tid] = __int_as_float(0x7fc00000);
+        if (tid == 0) g.hdr->parity = par ^ 1u;
+        return;
+      }
     }
     if (tid < CNH_TOTALS && a.totals != nullptr) a.totals[tid] = sh_tot[tid];
     if (tid == 0 && a.scalars != nullptr) scalars_from_totals(a, sh_tot, a.scalars);
@@ -1235,6 +1284,8 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   __shared__ int red_i[kWarps];
   __shared__ long long sh_tot[CNH_TOTALS];
   __shared__ unsigned sh_ticket, sh_parity;
+  __shared__ long long sh_gnorm[4];           // peers: batch-wide mask counts of head 0..2, num_pos (-1: a peer timed out)
+  __shared__ unsigned long long sh_tag;
   __shared__ unsigned sh_mask[kMaxStages];
   __shared__ int sh_chunk[kMaxStages];
   const int bid = blockIdx.x, grid = gridDim.x;
@@ -1285,10 +1336,49 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   }
   if (MODE == M_PRECOUNT) {
     cg::this_grid().sync();
-    const long long npos = __ldcg(acc + kQ + 1);
-    scale = (npos == 0) ? -a.hm_weight : -a.hm_weight / (float)npos;
+    long long npos = __ldcg(acc + kQ + 1);
+    long long cnt[CNH_MAX_HEADS];
 #pragma unroll
-    for (int h = 0; h < CNH_MAX_HEADS; ++h) inv_denom[h] = 1.f / ((float)__ldcg(acc + kQ + 4 + 3 * h) + 1e-4f);
+    for (int h = 0; h < CNH_MAX_HEADS; ++h) cnt[h] = __ldcg(acc + kQ + 4 + 3 * h);
+    if (g.world > 1) {
+      // ---- sharded: the normalisers of every rank, traded through the peer-mapped mailboxes right here ----
+      // CTA 0 stores this shard's four words (self-validating: tag in the upper half, relaxed system-scope
+      // stores, no fence) into every peer's mailbox; warp 0 of EVERY CTA polls the local mailbox, one lane per
+      // (source rank, word), and sums over the ranks.  The totals follow in cnh_detloss_peers_finalize.
+      if (warp == 0) {
+        const unsigned long long tag = __ldcg(g.mailbox[g.rank] + kEpochWord) + 1ull;
+        const unsigned mpar = (unsigned)(tag & 1ull);
+        const long long deadline = now_ns() + g.timeout_ns;
+        const int r = lane >> 2, q = lane & 3;               // q = 0..2: mask count of head q (word 25 + q); 3: num_pos (word 0)
+        if (bid == 0 && r < g.world) {
+          const long long mine = q == 3 ? npos : (q == 0 ? cnt[0] : (q == 1 ? cnt[1] : cnt[2]));
+          unsigned long long* slot = g.mailbox[r] + ((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords;
+          st_relaxed_sys(slot + (q == 3 ? 0 : 25 + q), (tag << 32) | (unsigned long long)(unsigned)mine);
+        }
+        long long got = 0;
+        bool ok = true;
+        if (r < g.world) {
+          const unsigned long long* slot = g.mailbox[g.rank] + ((size_t)mpar * CNH_MAX_PEERS + r) * kSlotWords;
+          unsigned long long v;
+          ok = poll_tagged(slot + (q == 3 ? 0 : 25 + q), tag, deadline, v);
+          got = ok ? (long long)(unsigned)(v & 0xffffffffull) : 0ll;
+        }
+        ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) got += __shfl_xor_sync(0xffffffffu, got, o);      // sum over ranks, per word
+        if (lane < 4) sh_gnorm[lane] = ok ? got : -1ll;
+        if (lane == 0) sh_tag = tag;
+        if (!ok && bid == 0 && lane == 0) report_peer_timeout(g.status, kPeerTimeoutNormalisers);
+      }
+      __syncthreads();
+      npos = sh_gnorm[3];
+#pragma unroll
+      for (int h = 0; h < CNH_MAX_HEADS; ++h) cnt[h] = sh_gnorm[h];
+    }
+    const float kNaN = __int_as_float(0x7fc00000);
+    scale = npos < 0 ? kNaN : ((npos == 0) ? -a.hm_weight : -a.hm_weight / (float)npos);
+#pragma unroll
+    for (int h = 0; h < CNH_MAX_HEADS; ++h) inv_denom[h] = cnt[h] < 0 ? kNaN : 1.f / ((float)cnt[h] + 1e-4f);
     dbg_stamp(g.dbg, 2);
   }
   if (MODE == M_MAIN) {
@@ -1422,8 +1512,10 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
       g.hdr->flags_gt = (unsigned long long)(uintptr_t)a.hm_gt;
     }
   } else {
-    finalize_from_acc(a, acc, sh_tot);
+    finalize_from_acc(a, acc, sh_tot, /*local_only=*/MODE == M_PRECOUNT && g.world > 1);
     if (tid == 0 && MODE == M_MAIN) g.hdr->flags_chunks = 0u;
+    // sharded pre-count launch: the exchange is complete on this rank (cnh_detloss_peers_finalize trades the totals)
+    if (tid == 0 && MODE == M_PRECOUNT && g.world > 1) g.mailbox[g.rank][kEpochWord] = sh_tag;
   }
   __syncthreads();
   if (tid < CNH_TOTALS) acc[tid] = 0ll;
@@ -1448,8 +1540,9 @@ detloss_peers_finalize_kernel(const cnh_detloss_args a, const Geo g) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __shared__ long long sh_tot[CNH_TOTALS];
   const int tid = threadIdx.x;
-  const unsigned long long tag = (unsigned long long)g.hdr->epoch;
+  const unsigned long long tag = __ldcg(g.mailbox[g.rank] + kEpochWord);
   const unsigned mpar = (unsigned)(tag & 1ull);
+  const long long deadline = now_ns() + g.timeout_ns;
   if (tid < CNH_TOTALS) {
     const unsigned long long mine = (unsigned long long)a.totals[tid];
     for (int r = 0; r < g.world; ++r)
@@ -1457,12 +1550,18 @@ detloss_peers_finalize_kernel(const cnh_detloss_args a, const Geo g) {
   }
   __threadfence_system();
   __syncwarp();
+  bool ok = true;
   if (tid < g.world) {
     st_release_sys(g.mailbox[tid] + ((size_t)mpar * CNH_MAX_PEERS + g.rank) * kSlotWords + 31, tag);
     const unsigned long long* slot = g.mailbox[g.rank] + ((size_t)mpar * CNH_MAX_PEERS + tid) * kSlotWords;
-    while (ld_acquire_sys(slot + 31) != tag) { }
+    ok = poll_acquire(slot + 31, tag, deadline);
   }
-  __syncwarp();
+  ok = __all_sync(0xffffffffu, ok);
+  if (!ok) {                                                 // a peer never delivered: poisoned scalars, error word
+    if (tid == 0) report_peer_timeout(g.status, kPeerTimeoutTotals);
+    if (tid < CNH_SCALARS && a.scalars != nullptr) a.scalars[tid] = __int_as_float(0x7fc00000);
+    return;
+  }
   if (tid < CNH_TOTALS) {
     long long sum = 0;
     for (int r = 0; r < g.world; ++r)
@@ -1576,6 +1675,8 @@ static Geo make_geo(const cnh_detloss_args* a, void* ws) {
   g.world = 1;
   g.defer_totals = 0;
   g.rank = 0;
+  g.status = nullptr;
+  g.timeout_ns = 2000ll * 1000000ll;
   for (int i = 0; i < CNH_MAX_PEERS; ++i) g.mailbox[i] = nullptr;
   g.hdr = static_cast<WsHeader*>(ws);
   g.sparse = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + kHeaderBytes);
@@ -1693,6 +1794,29 @@ extern "C" int cnh_detloss_single_wave(const cnh_detloss_args* a) {
   return plan_stash(pick_stash(!(a->flags & CNH_FLAG_ACCURATE_MATH), use_vec(a, g)), g) ? 1 : 0;
 }
 
+static void geo_peers(Geo& g, const cnh_peers* peers) {
+  g.world = peers->world;
+  g.rank = peers->rank;
+  for (int i = 0; i < peers->world; ++i) g.mailbox[i] = static_cast<unsigned long long*>(peers->mailbox[i]);
+  g.status = peers->status;
+  g.timeout_ns = (long long)(peers->timeout_ms ? peers->timeout_ms : 2000u) * 1000000ll;
+}
+
+// an earlier launch on these mailboxes gave up waiting for a peer: refuse to go on (the exchange counters of the
+// ranks no longer agree)
+static int check_peer_status(const cnh_peers* peers, const char* who) {
+  if (peers->status != nullptr) {
+    const unsigned code = *reinterpret_cast<volatile const unsigned*>(peers->status);
+    CNH_REQUIRE(code == 0u, CNH_E_PEER,
+                "%s: an earlier peer exchange on these mailboxes timed out waiting for %s (code %u): a rank died or "
+                "skipped a step; re-create the mailboxes on every rank", who,
+                code == 1u ? "the normalisers" : "the totals", code);
+  }
+  return CNH_OK;
+}
+
+static int launch_peers_finalize(const cnh_detloss_args* a, const Geo& g, cudaStream_t stream);
+
 static int detloss_fused_impl(const cnh_detloss_args* a, const cnh_peers* peers, void* workspace,
                               size_t workspace_bytes, cnh_stream_t stream) {
   if (int rc = validate(a, true)) return rc;
@@ -1701,9 +1825,8 @@ static int detloss_fused_impl(const cnh_detloss_args* a, const cnh_peers* peers,
               "detloss_fused: workspace %zu < %zu bytes", workspace_bytes, ws_bytes(a));
   Geo g = make_geo(a, workspace);
   if (peers != nullptr && peers->world > 1) {
-    g.world = peers->world;
-    g.rank = peers->rank;
-    for (int i = 0; i < peers->world; ++i) g.mailbox[i] = static_cast<unsigned long long*>(peers->mailbox[i]);
+    if (int rc = check_peer_status(peers, "detloss_fused_peers")) return rc;
+    geo_peers(g, peers);
     g.defer_totals = (a->flags & CNH_FLAG_DEFER_TOTALS) ? 1 : 0;
     CNH_REQUIRE(!g.defer_totals || a->totals != nullptr, CNH_E_NULL, "detloss_fused_peers: CNH_FLAG_DEFER_TOTALS needs a->totals");
     CNH_REQUIRE(a->grad_hm != nullptr, CNH_E_UNSUPPORTED, "detloss_fused_peers: forward-only runs need no exchange before the loss value; use cnh_detloss_fused + an all-reduce of totals");
@@ -1725,11 +1848,35 @@ static int detloss_fused_impl(const cnh_detloss_args* a, const cnh_peers* peers,
     static const bool no_coop = (getenv("CNH_NO_COOP") != nullptr);      // experiment: plain launch of the single wave
     return launch(ks, !no_coop, g.chunk_ctas + 1, g.n_stages, a, g, st, kStashThreads);
   }
-  CNH_REQUIRE(g.world == 1, CNH_E_UNSUPPORTED,
-              "detloss_fused_peers: problem too large for the single-wave schedule (%d chunks); use count/main", g.n_chunks);
   g.n_stages = kStreamStages;
   const void* kp = pick_stream<M_PRECOUNT>(fast, vec);
+  if (g.world > 1) {
+    // sharded pre-count launch: the normalisers are traded after the count phase's grid barrier; the totals always
+    // by the one-warp finalize launch (here, unless the caller defers it to overlap it with other work)
+    CNH_REQUIRE(a->totals != nullptr, CNH_E_NULL, "detloss_fused_peers: a->totals is NULL");
+    const int want_finalize = !g.defer_totals;
+    g.defer_totals = 1;
+    if (int rc = launch(kp, true, stream_grid(kp, g, g.n_items + g.n_count), kStreamStages, a, g, st, kStashThreads)) return rc;
+    return want_finalize ? launch_peers_finalize(a, g, st) : CNH_OK;
+  }
   return launch(kp, true, stream_grid(kp, g, g.n_items + g.n_count), kStreamStages, a, g, st, kStashThreads);
+}
+
+static int launch_peers_finalize(const cnh_detloss_args* a, const Geo& g, cudaStream_t stream) {
+  static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(1);
+  lc.blockDim = dim3(32);
+  lc.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = use_pdl ? 1 : 0;
+  CNH_CUDA(cudaLaunchKernelEx(&lc, detloss_peers_finalize_kernel, *a, g));
+  CNH_CUDA(cudaGetLastError());
+  return CNH_OK;
 }
 
 extern "C" int cnh_detloss_fused(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
@@ -1755,27 +1902,12 @@ extern "C" int cnh_detloss_peers_finalize(const cnh_detloss_args* a, const cnh_p
   CNH_REQUIRE(a->totals != nullptr, CNH_E_NULL, "detloss_peers_finalize: a->totals (this rank's totals in, global totals out) is NULL");
   CNH_REQUIRE(workspace != nullptr && workspace_bytes >= ws_bytes(a), CNH_E_WORKSPACE,
               "detloss_peers_finalize: workspace %zu < %zu bytes", workspace_bytes, ws_bytes(a));
-  Geo g = make_geo(a, workspace);
-  g.world = peers->world;
-  g.rank = peers->rank;
-  for (int i = 0; i < peers->world; ++i) {
+  for (int i = 0; i < peers->world; ++i)
     CNH_REQUIRE(peers->mailbox[i] != nullptr, CNH_E_NULL, "detloss_peers_finalize: mailbox[%d] is NULL", i);
-    g.mailbox[i] = static_cast<unsigned long long*>(peers->mailbox[i]);
-  }
-  static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
-  cudaLaunchConfig_t lc;
-  memset(&lc, 0, sizeof(lc));
-  lc.gridDim = dim3(1);
-  lc.blockDim = dim3(32);
-  lc.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  lc.attrs = attr;
-  lc.numAttrs = use_pdl ? 1 : 0;
-  CNH_CUDA(cudaLaunchKernelEx(&lc, detloss_peers_finalize_kernel, *a, g));
-  CNH_CUDA(cudaGetLastError());
-  return CNH_OK;
+  if (int rc = check_peer_status(peers, "detloss_peers_finalize")) return rc;
+  Geo g = make_geo(a, workspace);
+  geo_peers(g, peers);
+  return launch_peers_finalize(a, g, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cnh_detloss_count(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CNH_VERSION 101 /* major*100 + minor */
+#define CNH_VERSION 102 /* major*100 + minor */
 
 typedef void* cnh_stream_t; /* cudaStream_t */
 
@@ -42,7 +42,8 @@ enum {
   CNH_E_SHAPE = -2,      /* unsupported / inconsistent dimensions         */
   CNH_E_ALIGN = -3,      /* pointer not aligned as required               */
   CNH_E_WORKSPACE = -4,  /* workspace too small                           */
-  CNH_E_UNSUPPORTED = -5 /* parameter combination not implemented         */
+  CNH_E_UNSUPPORTED = -5, /* parameter combination not implemented        */
+  CNH_E_PEER = -6         /* an earlier peer exchange timed out (see cnh_peers.status) */
 };
 
 /* angle handling of channel 2 of a 3-channel size head */
@@ -116,24 +117,33 @@ const char* cnh_last_error(void);
  * heat-map element of HBM traffic); larger ones pre-count num_pos over the target and skip
  * its all-zero 4 KB sub-blocks in the second pass (16 B for sparse targets, <= 20 B). */
 size_t cnh_detloss_workspace_bytes(const cnh_detloss_args* a);
-/* 1 if cnh_detloss_fused would run this problem as a single wave (the schedule
- * cnh_detloss_fused_peers requires), else 0.  Needs a current CUDA device. */
+/* 1 if cnh_detloss_fused would run this problem as a single wave, else 0 (the pre-count schedule).
+ * Needs a current CUDA device. */
 int cnh_detloss_single_wave(const cnh_detloss_args* a);
 int cnh_detloss_fused(const cnh_detloss_args* a, void* workspace, size_t workspace_bytes,
                       cnh_stream_t stream);
 /* Sharded, fused exchange (one process per GPU, peer-mapped mailboxes over NVLink/NVSwitch): the same
- * single launch as cnh_detloss_fused; the finaliser CTA stores this rank's normalisers and exact
- * totals into every peer's mailbox (st.release.sys), waits for the peers' (ld.acquire.sys), and
- * releases the local CTAs with the GLOBAL normalisers -- no collective library call on the step path.
- * Every rank must issue the call (it spins until all peers have arrived).  Requires the single-wave
- * schedule (cnh_detloss_single_wave() == 1); returns CNH_E_UNSUPPORTED otherwise (use count/main below).
- * mailbox[r]: device pointer, valid on THIS device, to rank r's mailbox (CNH_MAILBOX_BYTES, zeroed
- * once, symmetric allocation); mailbox[rank] is the local one. */
+ * launch as cnh_detloss_fused; the normalisers (num_pos, mask counts) of every rank are stored into every
+ * peer's mailbox and read from the local one INSIDE the kernel -- no collective library call on the step
+ * path.  Single wave: the finaliser CTA posts, the chunk CTAs poll.  Larger problems (pre-count schedule):
+ * CTA 0 posts after the count phase's grid barrier, every CTA polls before its streaming pass.
+ * Every rank must issue the call.  mailbox[r]: device pointer, valid on THIS device, to rank r's mailbox
+ * (CNH_MAILBOX_BYTES, zeroed once, symmetric allocation); mailbox[rank] is the local one.  The exchange
+ * counter lives in the local mailbox (word CNH_MAILBOX_EPOCH_WORD), so any workspace may be used with it.
+ * Waits on peers are BOUNDED: after timeout_ms (0 = 2000) without the peers' words a kernel stores a
+ * non-zero code to *status (nullable; PINNED HOST memory, zeroed by the caller: the kernel writes it through
+ * its unified address), poisons what it was about to produce (NaN gradient scale / NaN scalars) and
+ * terminates; every later peers call that sees *status != 0 returns CNH_E_PEER until the caller has
+ * re-created the mailboxes (all ranks) and cleared the word. */
 #define CNH_MAX_PEERS 8
-#define CNH_MAILBOX_BYTES 4096
+#define CNH_MAILBOX_BYTES 8192
+#define CNH_MAILBOX_EPOCH_WORD 512 /* uint64 index inside the local mailbox */
 typedef struct cnh_peers {
   int32_t world, rank;
   void* mailbox[CNH_MAX_PEERS];
+  uint32_t* status;      /* nullable: pinned host word, see above */
+  uint32_t timeout_ms;   /* 0 = default (2000)                    */
+  uint32_t _pad;
 } cnh_peers;
 int cnh_detloss_fused_peers(const cnh_detloss_args* a, const cnh_peers* peers, void* workspace,
                             size_t workspace_bytes, cnh_stream_t stream);

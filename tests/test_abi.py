@@ -38,7 +38,7 @@ def test_header_declares_the_expected_entry_points():
 def test_library_exports_every_declared_symbol(library):
     for name in declared_symbols():
         assert hasattr(library, name), name
-    assert library.cnh_version() == 101
+    assert library.cnh_version() == 102
 
 
 def test_struct_layouts_match_header():
@@ -49,9 +49,10 @@ def test_struct_layouts_match_header():
     #include <stddef.h>
     #include "cnhead.h"
     int main(void) {
-      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(cnh_head), sizeof(cnh_detloss_args), sizeof(cnh_scale_args),
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %d\n", sizeof(cnh_head), sizeof(cnh_detloss_args), sizeof(cnh_scale_args),
              sizeof(cnh_decode_args), offsetof(cnh_detloss_args, heads), offsetof(cnh_decode_args, apply_sigmoid),
-             offsetof(cnh_decode_args, counts_out), sizeof(cnh_raster_args), offsetof(cnh_raster_args, boxes));
+             offsetof(cnh_decode_args, counts_out), sizeof(cnh_raster_args), offsetof(cnh_raster_args, boxes),
+             sizeof(cnh_peers), offsetof(cnh_peers, status), CNH_MAILBOX_BYTES);
       return 0;
     }'''
     import tempfile
@@ -62,7 +63,8 @@ def test_struct_layouts_match_header():
         out = subprocess.run([os.path.join(d, "t")], check=True, capture_output=True, text=True).stdout.split()
     got = [C.sizeof(L.Head), C.sizeof(L.DetLossArgs), C.sizeof(L.ScaleArgs), C.sizeof(L.DecodeArgs),
            L.DetLossArgs.heads.offset, L.DecodeArgs.apply_sigmoid.offset, L.DecodeArgs.counts_out.offset,
-           C.sizeof(L.RasterArgs), L.RasterArgs.boxes.offset]
+           C.sizeof(L.RasterArgs), L.RasterArgs.boxes.offset, C.sizeof(L.Peers), L.Peers.status.offset,
+           L.MAILBOX_BYTES]
     assert [int(v) for v in out] == got
 
 

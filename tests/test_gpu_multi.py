@@ -32,7 +32,7 @@ def _worker(rank, world, port, cfg_name, exchange, out):
                             device_id=torch.device("cuda", rank))
     try:
         cfg = synthetic.CONFIGS[cfg_name]
-        B = 8
+        B = 8                                # cfg5: 4 x 80 x 128^2 per rank = 1280 chunks -> the pre-count schedule
         kw = synthetic.loss_kwargs(cfg)
         whole = synthetic.make_inputs(cfg, batch=B)
         sl = sharded.shard_slice(B, rank, world)
@@ -82,7 +82,7 @@ def _worker(rank, world, port, cfg_name, exchange, out):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 @pytest.mark.parametrize("exchange", ["nccl", "peers", "peers_deferred"])
-@pytest.mark.parametrize("cfg_name", ["cfg2", "cfg3"])
+@pytest.mark.parametrize("cfg_name", ["cfg2", "cfg3", "cfg5"])
 def test_sharded_loss_two_gpus(cfg_name, exchange):
     world = 2
     mgr = mp.Manager()

@@ -493,12 +493,57 @@ def test_advent_vs_reference_fixture(name):
     g = load_golden(name)
     y = torch.from_numpy(g["y"]).cuda().requires_grad_(True)
     l, st = AdventLoss()(y, int(g["label"]))
-    l2 = l * 1.0
-    l2 /= 2.0                                        # adversarial_entropy_minimization.py:122
-    l2.backward()
     assert rel_err(l.detach().cpu(), g["loss"]) <= TOL
+    l /= 2.0                                         # what the caller does, on the returned tensor itself
+    l.backward()                                     # (adversarial_entropy_minimization.py:122-123)
+    assert rel_err(l.detach().cpu() * 2.0, g["loss"]) <= TOL
     assert rel_err(y.grad.cpu() * 2.0, g["grad"]) <= TOL
     assert "advent_loss" in st
+
+
+# ---------------------------------------------------------------------------------------------
+# peer exchange: a rank that never arrives makes the kernel give up, not hang
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [0, 2])               # single wave / pre-count schedule
+def test_peer_exchange_times_out_instead_of_hanging(flags):
+    """world = 2 faked on ONE device: the second rank's mailbox is a local buffer nobody ever posts from.  The
+    launch must return within the timeout, poison its gradients (NaN scale), raise the status word, and the
+    next call on these mailboxes must be refused with CNH_E_PEER."""
+    import ctypes as C
+    import time
+    from cnhead import _lib as L, functional as F, synthetic
+    cfg = synthetic.CONFIGS["cfg2"]
+    data = synthetic.make_inputs(cfg, batch=2)
+    o = {k: v.cuda() for k, v in data["output"].items()}
+    b = {k: v.cuda() for k, v in data["batch"].items()}
+    heads = [F.HeadSpec(o["wh"], b["wh"], b["reg_mask"], 0.1), F.HeadSpec(o["reg"], b["reg"], b["reg_mask"], 1.0)]
+    prob = torch.empty_like(o["hm"])
+    grads = [torch.zeros_like(o["hm"]), torch.zeros_like(o["wh"]), torch.zeros_like(o["reg"])]
+    scal = torch.zeros(L.SCALARS, device="cuda")
+    tot = torch.zeros(L.TOTALS, dtype=torch.int64, device="cuda")
+    a = F.fill_detloss_args(o["hm"], b["hm"], b["ind"], heads, 1.0, prob, grads, scal, tot, flags=flags)
+    ws = torch.zeros(L.lib().cnh_detloss_workspace_bytes(C.byref(a)) + 256, dtype=torch.uint8, device="cuda")
+    boxes = [torch.zeros(L.MAILBOX_BYTES // 8, dtype=torch.int64, device="cuda") for _ in range(2)]
+    status = torch.zeros(16, dtype=torch.int32).pin_memory()
+    peers = L.Peers()
+    peers.world, peers.rank = 2, 0
+    peers.mailbox[0], peers.mailbox[1] = boxes[0].data_ptr(), boxes[1].data_ptr()
+    peers.status, peers.timeout_ms = status.data_ptr(), 100
+    torch.cuda.synchronize()
+    t0 = time.time()
+    rc = L.lib().cnh_detloss_fused_peers(C.byref(a), C.byref(peers), ws.data_ptr(), ws.numel(), L.stream_ptr())
+    assert rc == 0, L.lib().cnh_last_error()
+    torch.cuda.synchronize()
+    assert time.time() - t0 < 30.0
+    assert int(status[0]) in (1, 2)
+    assert torch.isnan(grads[0]).all(), "the heat-map gradient must be poisoned, not silently mis-normalised"
+    rc = L.lib().cnh_detloss_fused_peers(C.byref(a), C.byref(peers), ws.data_ptr(), ws.numel(), L.stream_ptr())
+    assert rc == L.E_PEER and b"timed out" in L.lib().cnh_last_error()
+    # the library is usable again on a clean single-device workspace
+    ws.zero_()
+    L.check(L.lib().cnh_detloss_fused(C.byref(a), ws.data_ptr(), ws.numel(), L.stream_ptr()), "fused")
+    torch.cuda.synchronize()
+    assert torch.isfinite(grads[0]).all() and torch.isfinite(scal).all()
 
 
 # ---------------------------------------------------------------------------------------------
