@@ -587,7 +587,11 @@ def sharded_parity(w, rank, world, dev):
     torch.cuda.synchronize()
     sl = slice(rank * w.batch, (rank + 1) * w.batch)
     res = {"schedule": d.schedule, "global_batch": int(hm.shape[0])}
-    checks = {"scalars": torch.equal(s.scalars[:6], scal[:6]), "totals": torch.equal(s.totals, tot),
+    def values(t):                      # the 12 exact quantities as Python integers, hi * 2^32 + lo (an all-reduced
+        t = t.tolist()                  # sum of carry-normalised pairs is compared by value)
+        return [(t[q] << 32) + t[12 + q] for q in range(12)]
+
+    checks = {"scalars": torch.equal(s.scalars[:6], scal[:6]), "totals": values(s.totals) == values(tot),
               "prob": torch.equal(s.prob, prob[sl]), "grad_hm": torch.equal(s.grads[0], grads[0][sl]),
               "dets": torch.equal(s.dets, dets[sl])}
     reg_rel = 0.0

@@ -154,6 +154,40 @@ __device__ __noinline__ void find_kth_bin(SM& s, unsigned need) {
   group_sync();
 }
 
+// Same over `hist` (e.g. the cluster-wide merge, counters saturating at 65535): s.sh_flag = 1 and
+// s.sh_bin / s.sh_above / s.sh_inbin as above when the histogram holds at least `need` keys, else s.sh_flag = 0.
+// Called by the first 256 threads; ends with their barrier.
+template <class SM>
+__device__ __noinline__ void find_kth_bin_in(SM& s, const unsigned* hist, unsigned need) {
+  const int tid = threadIdx.x;
+  unsigned c[16], v = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const unsigned w = hist[8 * tid + j];
+    c[2 * j] = w & 0xffffu;
+    c[2 * j + 1] = w >> 16;
+    v += c[2 * j] + c[2 * j + 1];
+  }
+  if (tid == 0) s.sh_flag = 0u;
+  unsigned total;
+  const unsigned excl = block_suffix_excl(v, s.warp_tot, total);     // barriers inside: the flag reset is ordered
+  if (excl < need && excl + v >= need) {
+    unsigned acc = excl;
+#pragma unroll
+    for (int j = 15; j >= 0; --j) {
+      if (acc + c[j] >= need) {
+        s.sh_bin = 16 * tid + j;
+        s.sh_above = acc;
+        s.sh_inbin = c[j];
+        s.sh_flag = 1u;
+        break;
+      }
+      acc += c[j];
+    }
+  }
+  group_sync();
+}
+
 // Threshold from the sample's global coarse histogram: score bits of the lower edge of the highest
 // coarse bin t with count(bins >= t) >= K, or 0 if fewer than K peaks are known.  Thread i owns
 // coarse bins [4i, 4i+4).  Result in s.sh_thr (also returned); ends with a barrier.
@@ -940,6 +974,7 @@ template <int R>
 struct __align__(128) ClSmemT {             // followed by the TMA ring (the leader's doubles as the inbox)
   u64 stage[ClCfg<R>::kCap];               // the set (the scan appends to it); final stage: `sorted`
   unsigned hist[kFineBins / 2];            // packed fine histogram of the set, built per cut; final stage: `sel`
+  unsigned hist_all[kFineBins / 2];        // the cluster's histograms merged (saturating 16-bit counters)
   u64 mbar[ClCfg<R>::kStages];
   u64 sh_prefix;
   unsigned cnt;                            // size of the set
@@ -1095,10 +1130,53 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
     r_hi = min(y0 + kClRows + 1, H) - (y0 - 1);
   };
 
-  const int n_rounds = (n_my + kClGroups - 1) / kClGroups;
+  // The cluster's histograms merged: every CTA builds the packed histogram of its set, a cluster barrier publishes
+  // them, and every CTA adds up all of them (512 threads x one 16-byte DSMEM load per peer, saturating 16-bit
+  // counters) into hist_all.  On return (CTA-uniform): s.sh_flag = "the cluster holds at least K keys", and then
+  // s.sh_bin / s.sh_above / s.sh_inbin describe the bin of the CLUSTER-WIDE K-th key -- the pruning threshold a
+  // CTA could only reach on its own after seeing the whole sample.  The caller must call cluster.barrier_wait()
+  // before s.hist is rebuilt (peers may still be reading it).
+  auto cluster_kth_bin = [&](const unsigned n) {
+    build_hist(n);
+    cluster.sync();
+    if (tid < kFineBins / 8) {
+      uint4 acc = reinterpret_cast<const uint4*>(s.hist)[tid];
+#pragma unroll 4
+      for (int c = 1; c < CS; ++c) {
+        const int peer = rank + c < CS ? rank + c : rank + c - CS;
+        const uint4 v = reinterpret_cast<const uint4*>(cluster.map_shared_rank(s.hist, peer))[tid];
+        acc.x = __vaddus2(acc.x, v.x);
+        acc.y = __vaddus2(acc.y, v.y);
+        acc.z = __vaddus2(acc.z, v.z);
+        acc.w = __vaddus2(acc.w, v.w);
+      }
+      reinterpret_cast<uint4*>(s.hist_all)[tid] = acc;
+    }
+    cluster.barrier_arrive();
+    __syncthreads();
+    if (group0) find_kth_bin_in(s, s.hist_all, (unsigned)K);
+    __syncthreads();
+  };
+  // Cluster-wide cut of the running sets (at rounds every CTA of the cluster agrees on).
+  auto cluster_cut = [&](const unsigned n) {
+    cluster_kth_bin(n);
+    if (s.sh_flag != 0u) {
+      const int tbin = (int)s.sh_bin;
+      const unsigned thr_new = __float_as_uint((float)tbin * (1.0f / (float)kFineBins));
+      compact_all(n, [&](u64 k) { return fine_bin((unsigned)(k >> 32)) >= tbin; });
+      if (thr_new > thr) thr = thr_new;
+    }
+    cluster.barrier_wait();
+    __syncthreads();
+  };
+
+  // every CTA of the cluster runs the same number of rounds (the last one may be empty for some): the cluster-wide
+  // cuts sit at rounds they all agree on
+  const int n_my_max = (g.tiles_per_sample + CS - 1) / CS;
+  const int n_rounds = (n_my_max + kClGroups - 1) / kClGroups;
   for (int r = 0; r < n_rounds; ++r) {
     const int half = (r % kDepth) * kClGroups, phase = (r / kDepth) & 1;
-    const int in_round = min(kClGroups, n_my - r * kClGroups);
+    const int in_round = max(0, min(kClGroups, n_my - r * kClGroups));
     const unsigned n_before = s.cnt;                        // <= kClTile (invariant)
     if (gq < in_round) {
       const Cursor q = mine;
@@ -1139,51 +1217,47 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
       if ((r + kDepth) * kClGroups + (wid - half) < n_my) stage_tile(pre, wid);
       advance(pre, step_ring);
     }
-    // Cut when the next round might overflow the invariant and, on long walks, after rounds 1, 2, 4, 8, ...
-    // so that the pruning threshold tightens early.
-    if (r + 1 < n_rounds && (n > (unsigned)kClTile || (n_rounds >= 4 && n > slot && ((r + 1) & r) == 0))) cut(n);
-  }
-  dbg_stamp(g.dbg, 2);
-  cluster.barrier_arrive();                                 // this CTA no longer reads its ring (the leader's is the inbox)
-
-  // ---- final cut fused with the push into the leader's inbox (DSMEM) --------------------------------
-  const unsigned n = s.cnt;
-  int mode = 0, tbin = 0;                                   // 0: send everything, 1: bins >= tbin, 2: keys >= T
-  u64 T = 0;
-  unsigned send_n = n;
-  // What travels to the leader is at most K + kSlack keys per CTA (measured: letting the leader cut the
-  // raw sets of a whole cluster is slower than one cut per CTA in parallel).
-  if (n > slot) {
-    build_hist(n);
-    if (group0) find_kth_bin(s, (unsigned)K);
-    __syncthreads();
-    send_n = s.sh_above + s.sh_inbin;
-    tbin = (int)s.sh_bin;
-    mode = 1;
-    if (send_n > slot) {
-      T = exact_cut_key(n);
-      send_n = (unsigned)K;
-      mode = 2;
+    // Cluster-wide cuts after rounds 0, 1, 3, 7, ... (the pruning threshold of the WHOLE sample so far, which
+    // tightens 'cluster size' times faster than a CTA's own); a local cut whenever the next round might
+    // otherwise overflow the set.
+    if (r + 1 < n_rounds) {
+      if (((r + 1) & r) == 0) { cluster_cut(n); n = s.cnt; }
+      if (n > (unsigned)kClTile) cut(n);
     }
   }
-  dbg_stamp(g.dbg, 5);
-  cluster.barrier_wait();                                   // every CTA, the leader included, is done with its ring
+  dbg_stamp(g.dbg, 2);
+
+  // ---- final cut, cluster-wide, then the push into the leader's inbox (DSMEM) -----------------------------
+  // Usually what travels is the cluster's top K plus the rest of the K-th key's histogram bin -- K + a few keys
+  // in total, which the leader rank-sorts at once.  Heavy ties (the bin holds thousands of keys): every CTA sends
+  // its own exact top K instead and the leader selects.
+  constexpr unsigned kFinalKeep = 4096;
+  {
+    const unsigned n = s.cnt;
+    cluster_kth_bin(n);                                     // (its cluster barrier: every CTA has finished scanning)
+    const bool found = s.sh_flag != 0u;
+    const unsigned keep_total = s.sh_above + s.sh_inbin;
+    const int tbin = (int)s.sh_bin;
+    dbg_stamp(g.dbg, 5);
+    cluster.barrier_wait();                                 // the histograms are dead; the leader's ring is the inbox now
+    __syncthreads();
+    if (found && keep_total <= kFinalKeep) {
+      compact_all(n, [&](u64 k) { return fine_bin((unsigned)(k >> 32)) >= tbin; });
+    } else if (found && n > (unsigned)K) {
+      const u64 T = exact_cut_key(n);
+      compact_all(n, [&](u64 k) { return k >= T; });
+    }
+    __syncthreads();
+  }
   dbg_stamp(g.dbg, 6);
   unsigned* const r_cnt = cluster.map_shared_rank(&s.fin_cnt, 0);
   u64* const r_inbox = cluster.map_shared_rank(inbox, 0);
-  if (tid == 0) {
-    s.sh_base = send_n ? atomicAdd(r_cnt, send_n) : 0u;     // one remote atomic reserves the CTA's slice
-    s.cnt2 = 0;
-  }
-  __syncthreads();
   {
+    const unsigned send_n = s.cnt;
+    if (tid == 0) s.sh_base = send_n ? atomicAdd(r_cnt, send_n) : 0u;     // one remote atomic reserves the CTA's slice
+    __syncthreads();
     u64* const dst = r_inbox + s.sh_base;
-    for (unsigned i0 = 0; i0 < n; i0 += kClThreads) {
-      const unsigned i = i0 + tid;
-      const u64 k = (i < n) ? s.stage[i] : 0ull;
-      const bool keep = (i < n) && (mode == 0 || (mode == 1 ? fine_bin((unsigned)(k >> 32)) >= tbin : k >= T));
-      append_if(keep, k, dst, &s.cnt2, send_n);
-    }
+    for (unsigned i = tid; i < send_n; i += kClThreads) dst[i] = s.stage[i];
   }
   dbg_stamp(g.dbg, 7);
   cluster.sync();                                           // release/acquire: the inbox is complete
@@ -1339,8 +1413,9 @@ constexpr int kClusterUnavailable = -999;
 constexpr int kClMaxSmem = 227 * 1024;
 
 // co-resident clusters of cs CTAs at one CTA per SM on device `dev` (cached; -1 = unavailable)
+constexpr int kMaxClusterSize = 16;                // 8 is the portable limit; 9..16 need the non-portable attribute
 static int active_clusters(int dev, int cs) {
-  static int max_clusters[64][9] = {};            // 0 = not queried
+  static int max_clusters[64][kMaxClusterSize + 1] = {};   // 0 = not queried
   if (max_clusters[dev][cs] == 0) {
     cudaLaunchConfig_t q;
     memset(&q, 0, sizeof(q));
@@ -1364,13 +1439,19 @@ static int active_clusters(int dev, int cs) {
   return max_clusters[dev][cs];
 }
 
-// Largest cluster size <= 8 whose B clusters are co-resident, else 1 (samples then run in waves).
-// (On a B200 fifteen 8-CTA clusters fit at one CTA per SM, so a batch of 16 runs as 16 clusters of 7.)
+// The cluster size whose B clusters are all co-resident (one CTA per SM) and cover the most SMs; ties go to the
+// smaller cluster (cheaper histogram merge).  Sizes 9..16 are non-portable: a GPC of the B200 holds two 9-CTA
+// clusters, so a batch of 16 can run as 16 x 9 = 144 CTAs where the portable sizes stop at 16 x 6 = 96.
+// CNH_DECODE_CS caps the size (experiments).  Nothing fits: 1 (samples then run in waves).
 static int pick_cluster_size(int B, int tiles_per_sample, int dev) {
-  for (int cs = 8; cs > 1; --cs) {
-    if (cs > tiles_per_sample) continue;
-    if ((long long)B <= (long long)active_clusters(dev, cs)) return cs;
+  static const int cap_env = getenv("CNH_DECODE_CS") ? atoi(getenv("CNH_DECODE_CS")) : 0;
+  const int cap = cap_env >= 1 && cap_env <= kMaxClusterSize ? cap_env : kMaxClusterSize;
+  int best = 0;
+  for (int cs = 2; cs <= cap; ++cs) {
+    if (cs > tiles_per_sample) break;
+    if ((long long)B <= (long long)active_clusters(dev, cs) && cs > best) best = cs;
   }
+  if (best) return best;
   return active_clusters(dev, 1) < 1 ? -1 : 1;
 }
 
@@ -1381,7 +1462,7 @@ static int launch_cluster_rows(const cnh_decode_args* a, const DecGeo& g0, int c
   g.n_stages = Cfg::kStages;
   g.use_tma = 1;
   const size_t smem = sizeof(ClSmemT<R>) + (size_t)Cfg::kStages * Cfg::kTileFloats * sizeof(float);
-  static_assert((size_t)Cfg::kStages * Cfg::kTileFloats * sizeof(float) >= (size_t)8 * kStageCap * sizeof(u64), "the ring holds the inbox");
+  static_assert((size_t)Cfg::kStages * Cfg::kTileFloats * sizeof(float) >= (size_t)kMaxClusterSize * kMaxK * sizeof(u64), "the ring holds the inbox");
   static_assert(sizeof(ClSmemT<R>) + (size_t)Cfg::kStages * Cfg::kTileFloats * sizeof(float) <= (size_t)kClMaxSmem, "shared memory");
   static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
   cudaLaunchConfig_t lc;
@@ -1415,6 +1496,10 @@ static bool cluster_attrs(int dev) {
       cudaGetLastError();
       return false;
     }
+    // clusters of 9..16 CTAs (non-portable); if the driver refuses, active_clusters() reports them unavailable
+    if (cudaFuncSetAttribute(decode_cluster_kernel<32>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_cluster_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+      cudaGetLastError();
     attr_set[dev] = true;
   }
   return true;
@@ -1446,6 +1531,13 @@ extern "C" int cnh_debug_decode_cluster(const cnh_decode_args* a) {
   DecGeo g = make_geo(a, nullptr, 32);
   const int cs = pick_cluster_size(a->B, g.tiles_per_sample, dev);
   return (cs < 0 ? 0 : cs) * 1000 + active_clusters(dev, 8);
+}
+
+// not part of the public ABI (tools/): co-resident clusters of `cs` CTAs of the decode kernel on the current device
+extern "C" int cnh_debug_active_clusters(int cs) {
+  int dev = 0;
+  if (cs < 1 || cs > kMaxClusterSize || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !cluster_attrs(dev)) return -1;
+  return active_clusters(dev, cs);
 }
 
 extern "C" size_t cnh_decode_workspace_bytes(const cnh_decode_args* a) {

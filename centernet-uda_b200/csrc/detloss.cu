@@ -1248,6 +1248,8 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
         sh_tot[tid] = sum;
       }
       __syncthreads();
+      if (tid == 0) canonicalise_totals(sh_tot);             // sums of canonical (hi, lo) pairs: carry again
+      __syncthreads();
       if (tid == 0) g.mailbox[g.rank][kEpochWord] = tag;
       if (sh_hdr[0] == 0u) {                                 // a peer never delivered: poisoned scalars, error word
         if (tid == 0) report_peer_timeout(g.status, kPeerTimeoutTotals);
@@ -1567,9 +1569,11 @@ detloss_peers_finalize_kernel(const cnh_detloss_args a, const Geo g) {
     for (int r = 0; r < g.world; ++r)
       sum += (long long)__ldcv(g.mailbox[g.rank] + ((size_t)mpar * CNH_MAX_PEERS + r) * kSlotWords + 1 + tid);
     sh_tot[tid] = sum;
-    a.totals[tid] = sum;
   }
   __syncwarp();
+  if (tid == 0) canonicalise_totals(sh_tot);                 // sums of canonical (hi, lo) pairs: carry again
+  __syncwarp();
+  if (tid < CNH_TOTALS) a.totals[tid] = sh_tot[tid];
   if (tid == 0 && a.scalars != nullptr) scalars_from_totals(a, sh_tot, a.scalars);
 }
 
