@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("CNH_LIB_PATH") or os.path.join(os.path.dirname(_HERE)
 MAX_HEADS = 3
 TOTALS = 24
 SCALARS = 8
-ANGLE_NONE, ANGLE_SIGMOID, ANGLE_PERIODIC = 0, 1, 2
+ANGLE_NONE, ANGLE_SIGMOID, ANGLE_PERIODIC, LIMB_SQRT, LIMB_L1 = 0, 1, 2, 3, 4
 FLAG_ACCURATE_MATH, FLAG_NO_STASH, FLAG_DEFER_TOTALS = 1, 2, 4
 SOFTMAX_ENTROPY, SOFTMAX_ENTROPY_ETA, SOFTMAX_MAX_SQUARE = 0, 1, 2
 
@@ -27,7 +27,7 @@ SOFTMAX_ENTROPY, SOFTMAX_ENTROPY_ETA, SOFTMAX_MAX_SQUARE = 0, 1, 2
 class Head(C.Structure):
     _fields_ = [("map", C.c_void_p), ("target", C.c_void_p), ("mask", C.c_void_p), ("grad", C.c_void_p),
                 ("D", C.c_int32), ("angle_mode", C.c_int32), ("elementwise_mask", C.c_int32),
-                ("weight", C.c_float), ("angle_weight", C.c_float), ("_pad", C.c_int32)]
+                ("weight", C.c_float), ("angle_weight", C.c_float), ("n_pairs", C.c_int32), ("pairs", C.c_void_p)]
 
 
 class DetLossArgs(C.Structure):

@@ -30,10 +30,11 @@ class HeadSpec:
     """One masked gather-L1 head: prediction map, target rows, mask and weights."""
 
     def __init__(self, fmap, target, mask, weight, angle_weight=1.0, angle_mode=L.ANGLE_NONE,
-                 elementwise_mask=False):
+                 elementwise_mask=False, pairs=None):
         self.fmap, self.target, self.mask = fmap, target, mask
         self.weight, self.angle_weight = float(weight), float(angle_weight)
         self.angle_mode, self.elementwise_mask = int(angle_mode), bool(elementwise_mask)
+        self.pairs = pairs          # LIMB_* modes: int32 [P,2] keypoint index pairs on the device (angle_weight = their weight)
 
 
 def _as_mask(t: torch.Tensor) -> torch.Tensor:
@@ -63,6 +64,8 @@ def fill_detloss_args(hm, gt, ind, heads: Sequence[HeadSpec], hm_weight, prob, g
         hd.angle_mode = h.angle_mode
         hd.elementwise_mask = 1 if h.elementwise_mask else 0
         hd.weight, hd.angle_weight = h.weight, h.angle_weight
+        pairs = getattr(h, "pairs", None)
+        hd.pairs, hd.n_pairs = (pairs.data_ptr(), pairs.shape[0]) if pairs is not None else (None, 0)
     a.scalars, a.totals = L.ptr(scalars), L.ptr(totals)
     a.norm, a.norm_out = L.ptr(norm), L.ptr(norm_out)
     return a
@@ -94,7 +97,7 @@ class _DetectionLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, hm, *maps):
         gt, ind, specs, hm_weight = meta
-        heads = [HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode, s.elementwise_mask)
+        heads = [HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode, s.elementwise_mask, s.pairs)
                  for m, s in zip(maps, specs)]
         need_grad = any(ctx.needs_input_grad[1:])
         prob = torch.empty_like(hm)
@@ -136,7 +139,23 @@ class _DetectionLossFn(torch.autograd.Function):
 
 
 class _Spec:
-    __slots__ = ("target", "mask", "weight", "angle_weight", "angle_mode", "elementwise_mask")
+    __slots__ = ("target", "mask", "weight", "angle_weight", "angle_mode", "elementwise_mask", "pairs")
+
+
+def _spec_of(h: "HeadSpec") -> "_Spec":
+    sp = _Spec()
+    sp.target = L.require(h.target, "head target")
+    sp.mask = _as_mask(h.mask)
+    sp.weight, sp.angle_weight = h.weight, h.angle_weight
+    sp.angle_mode, sp.elementwise_mask = h.angle_mode, h.elementwise_mask
+    sp.pairs = None
+    if h.angle_mode in (L.LIMB_SQRT, L.LIMB_L1):
+        if h.pairs is None:
+            raise RuntimeError("cnhead: a limb-length head needs its keypoint index pairs")
+        sp.pairs = L.require(h.pairs, "kp_indices", torch.int32)
+        if sp.pairs.dim() != 2 or sp.pairs.shape[1] != 2:
+            raise RuntimeError(f"cnhead: kp_indices must be [P,2], got {tuple(sp.pairs.shape)}")
+    return sp
 
 
 def detection_loss(hm: torch.Tensor, gt: torch.Tensor, ind: torch.Tensor, heads: Sequence[HeadSpec],
@@ -147,15 +166,10 @@ def detection_loss(hm: torch.Tensor, gt: torch.Tensor, ind: torch.Tensor, heads:
     ind = L.require(ind, "batch['ind']", torch.int64)
     specs, maps = [], []
     for h in heads:
-        sp = _Spec()
-        sp.target = L.require(h.target, "head target")
-        sp.mask = _as_mask(h.mask)
-        sp.weight, sp.angle_weight = h.weight, h.angle_weight
-        sp.angle_mode, sp.elementwise_mask = h.angle_mode, h.elementwise_mask
-        specs.append(sp)
+        specs.append(_spec_of(h))
         maps.append(L.require(h.fmap, "head map"))
     _check_heads(hm, gt, ind, [HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode,
-                                        s.elementwise_mask) for m, s in zip(maps, specs)])
+                                        s.elementwise_mask, s.pairs) for m, s in zip(maps, specs)])
     return _DetectionLossFn.apply((gt, ind, specs, float(hm_weight)), hm, *maps)
 
 

@@ -138,7 +138,7 @@ class _PeersDetectionLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, hm, *maps):
         gt, ind, specs, hm_weight, group, deferred = meta
-        heads = [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode, s.elementwise_mask)
+        heads = [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode, s.elementwise_mask, s.pairs)
                  for m, s in zip(maps, specs)]
         box = PeerMailbox.get(group)
         dev = hm.device
@@ -187,7 +187,7 @@ class _ShardedDetectionLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, hm, *maps):
         gt, ind, specs, hm_weight, group = meta
-        heads = [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode, s.elementwise_mask)
+        heads = [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode, s.elementwise_mask, s.pairs)
                  for m, s in zip(maps, specs)]
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         dev = hm.device
@@ -224,21 +224,16 @@ def detection_loss_sharded(hm, gt, ind, heads: Sequence[F.HeadSpec], hm_weight=1
     ind = L.require(ind, "batch['ind']", torch.int64)
     specs, maps = [], []
     for h in heads:
-        sp = F._Spec()
-        sp.target = L.require(h.target, "head target")
-        sp.mask = F._as_mask(h.mask)
-        sp.weight, sp.angle_weight = h.weight, h.angle_weight
-        sp.angle_mode, sp.elementwise_mask = h.angle_mode, h.elementwise_mask
-        specs.append(sp)
+        specs.append(F._spec_of(h))
         maps.append(L.require(h.fmap, "head map"))
     F._check_heads(hm, gt, ind, [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode,
-                                            s.elementwise_mask) for m, s in zip(maps, specs)])
+                                            s.elementwise_mask, s.pairs) for m, s in zip(maps, specs)])
     if not any(t.requires_grad for t in [hm] + maps) or not torch.is_grad_enabled():
         # validation: no gradients -> no normaliser exchange; only the loss value is reduced
         scalars, prob, totals = F.detection_loss(hm, gt, ind, heads, hm_weight)
         if reduce_totals(totals, group) is not None or (dist.is_initialized() and dist.get_world_size(group) > 1):
             a = F.fill_detloss_args(hm, gt, ind, [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight,
-                                                             s.angle_mode, s.elementwise_mask)
+                                                             s.angle_mode, s.elementwise_mask, s.pairs)
                                                   for m, s in zip(maps, specs)],
                                     hm_weight, prob, None, scalars, totals)
             L.check(L.lib().cnh_detloss_finalize(C.byref(a), totals.data_ptr(), L.stream_ptr()),
@@ -268,8 +263,6 @@ def make_sharded_loss(base_cls):
             self.exchange = exchange
 
         def forward(self, output, batch):
-            if self.with_keypoints and self.kp_indices is not None:
-                raise NotImplementedError("limb-length keypoint term is not sharded")
             heads = self._heads(output, batch)
             scalars, prob, totals = detection_loss_sharded(output['hm'], batch['hm'], batch['ind'], heads,
                                                          self.hm_weight, self.group, self.exchange)

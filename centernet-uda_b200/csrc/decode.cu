@@ -62,6 +62,8 @@ struct SampleState {                      // zero between launches
 
 struct DecGeo {
   int HW, rows, tiles_x, tiles_y, tiles_per_plane, tiles_per_sample, box_w, use_tma, slot, n_stages;
+  int pf_cycles;                          // cluster path: L2 prefetch distance in ring cycles (0 = off)
+  unsigned cut_mask;                      // cluster path: bit r set = cluster-wide cut after round r
   long long n_tiles;
   SampleState* state;                     // [B]                        zero between launches
   unsigned* ghist;                        // [B][kCoarseBins]           zero between launches
@@ -1030,6 +1032,13 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   // Stage tile q into ring slot buf: the rows of the tile plus one halo row above and below are contiguous
   // in global memory (one bulk copy, SASS UBLKCP); halo/tail rows outside the image are zero-filled by the
   // calling warp (max-pool padding: 0 is neutral because heat >= 0).  Called by ONE warp.
+  // start the rows of tile q on their way from HBM into L2 (no shared memory involved): issued pf_cycles ring
+  // cycles before the tile is staged, so that the bulk copy then finds them in L2.  Called by ONE lane.
+  auto prefetch_tile = [&](const Cursor& q) {
+    const int y0 = q.ty * kClRows;
+    const int ylo = max(y0 - 1, 0), yhi = min(y0 + kClRows + 1, H);
+    l2_prefetch_bulk(sample + (long long)q.c * g.HW + (long long)ylo * W, (unsigned)((yhi - ylo) * W) * 4u);
+  };
   auto stage_tile = [&](const Cursor& q, int buf) {
     float* dst = ring + (size_t)buf * kClTileFloats;
     const int lane = tid & 31;
@@ -1064,6 +1073,16 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   const Stride step_ring = stride_of(kClStages * CS);
   if (wid < kClStages && wid < n_my) stage_tile(pre, wid);
   advance(pre, step_ring);
+  // L2 prefetch cursor of the staging warps: tile (wid + 8 * (k + pf_cycles)) when tile (wid + 8 k) is staged
+  Cursor pf = pre;
+  int pf_j = wid + kClStages;                               // index (in this CTA's walk) of the tile `pf` points at
+  if (wid < kClStages && g.pf_cycles > 0) {
+    for (int c = 0; c < g.pf_cycles; ++c) {
+      if (pf_j < n_my && (tid & 31) == 0) prefetch_tile(pf);
+      advance(pf, step_ring);
+      pf_j += kClStages;
+    }
+  }
   __syncthreads();                                          // the staging warps' zero-filled halo rows (generic stores: the
                                                             // mbarrier only covers the bulk copy) before anyone scans
   Cursor mine = cursor_at(rank + gq * CS);                  // the tile this thread's group scans in the current round
@@ -1216,12 +1235,17 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
     if (wid >= half && wid < half + kClGroups) {            // refill the freed slots of the ring: round r + kDepth
       if ((r + kDepth) * kClGroups + (wid - half) < n_my) stage_tile(pre, wid);
       advance(pre, step_ring);
+      if (g.pf_cycles > 0) {
+        if (pf_j < n_my && (tid & 31) == 0) prefetch_tile(pf);
+        advance(pf, step_ring);
+        pf_j += kClStages;
+      }
     }
     // Cluster-wide cuts after rounds 0, 1, 3, 7, ... (the pruning threshold of the WHOLE sample so far, which
     // tightens 'cluster size' times faster than a CTA's own); a local cut whenever the next round might
     // otherwise overflow the set.
     if (r + 1 < n_rounds) {
-      if (((r + 1) & r) == 0) { cluster_cut(n); n = s.cnt; }
+      if (r < 32 && ((g.cut_mask >> r) & 1u)) { cluster_cut(n); n = s.cnt; }
       if (n > (unsigned)kClTile) cut(n);
     }
   }
@@ -1258,6 +1282,17 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
     __syncthreads();
     u64* const dst = r_inbox + s.sh_base;
     for (unsigned i = tid; i < send_n; i += kClThreads) dst[i] = s.stage[i];
+    // the usual few keys per CTA: start the cache lines the leader's gather will touch on their way into L2 now
+    // (the maps are HBM-cold; the leader's rank sort then waits an L2 hit instead of a DRAM round trip)
+    if (send_n <= 128u && (unsigned)tid < send_n) {
+      const unsigned pix = (0xffffffffu - (unsigned)(s.stage[tid] & 0xffffffffu)) % (unsigned)g.HW;
+      if (a.reg) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.reg + ((long long)b * 2 + 0) * g.HW + pix));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.reg + ((long long)b * 2 + 1) * g.HW + pix));
+      }
+      for (int d = 0; d < (a.rotated ? 3 : 2); ++d)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.wh + ((long long)b * a.D + d) * g.HW + pix));
+    }
   }
   dbg_stamp(g.dbg, 7);
   cluster.sync();                                           // release/acquire: the inbox is complete
@@ -1392,6 +1427,10 @@ static DecGeo make_geo(const cnh_decode_args* a, void* ws, int rows) {
   const int tw = a->W < kCols ? a->W : kCols;
   g.box_w = ((tw + 3) / 4) * 4 + 2 * kPadL;
   g.use_tma = 0;
+  static const int pf_env = getenv("CNH_DECODE_PF") ? atoi(getenv("CNH_DECODE_PF")) : 2;
+  static const unsigned cut_env = getenv("CNH_DECODE_CUTMASK") ? (unsigned)strtoul(getenv("CNH_DECODE_CUTMASK"), nullptr, 0) : 0x8bu;
+  g.pf_cycles = pf_env < 0 ? 0 : (pf_env > 8 ? 8 : pf_env);
+  g.cut_mask = cut_env;                    // default: after rounds 0, 1, 3, 7
   g.dbg = debug_buffer();
   g.slot = a->K + kSlack;
   char* p = static_cast<char*>(ws);

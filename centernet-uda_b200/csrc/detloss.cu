@@ -621,6 +621,13 @@ __device__ __forceinline__ const cnh_head& head_of(const cnh_detloss_args& a, in
   return h == 0 ? a.heads[0] : (h == 1 ? a.heads[1] : a.heads[2]);   // no local copy of the params
 }
 
+__device__ __host__ __forceinline__ bool head_has_angle(const cnh_head& hd) {
+  return hd.D == 3 && (hd.angle_mode == CNH_ANGLE_SIGMOID || hd.angle_mode == CNH_ANGLE_PERIODIC);
+}
+__device__ __host__ __forceinline__ bool head_has_limb(const cnh_head& hd) {
+  return hd.angle_mode == CNH_LIMB_SQRT || hd.angle_mode == CNH_LIMB_L1;
+}
+
 struct ItemRef {
   int h, b, d, p0, p1;
 };
@@ -709,6 +716,51 @@ __device__ __forceinline__ void l1_slot_math(const cnh_head& hd, bool is_angle, 
   gv = gcoef * m * (is_angle ? hd.angle_weight : hd.weight);
 }
 
+// Limb-length consistency term of a keypoint head (KPSL1Loss, losses/centernet.py:153-187) as seen from channel d
+// of one object slot whose centre is `idx`: for every pair (ka, kb) that contains keypoint d/2,
+//   pd = sqrt((pa-pb)^2 summed over x,y + 1e4)   (or |.|_1),   td likewise from the targets,   term = |pd - td|
+// with pa/pb/ta/tb the MASKED predictions / targets (pred *= mask; target *= mask, :147-148).  `val` receives the
+// terms this channel accounts for (each pair once: by the x channel of its first keypoint), `gcoef` the derivative of
+// the sum of terms with respect to the masked prediction of channel d.  Same operation order as the reference's fp32.
+__device__ __forceinline__ void limb_slot(const cnh_head& hd, const float* __restrict__ maps_b, const float* __restrict__ tgt_row,
+                                          const uint8_t* __restrict__ mask_row, int idx, int d, int HW, float& val, float& gcoef) {
+  const int j = d >> 1, c = d & 1;
+  val = 0.f;
+  gcoef = 0.f;
+  for (int p = 0; p < hd.n_pairs; ++p) {
+    const int ka = __ldg(hd.pairs + 2 * p), kb = __ldg(hd.pairs + 2 * p + 1);
+    if (ka != j && kb != j) continue;
+    float pa[2], pb[2], ta[2], tb[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int ca = 2 * ka + e, cb = 2 * kb + e;
+      const float ma = (float)__ldg(mask_row + ca), mb = (float)__ldg(mask_row + cb);
+      pa[e] = __fmul_rn(__ldg(maps_b + (long long)ca * HW + idx), ma);
+      pb[e] = __fmul_rn(__ldg(maps_b + (long long)cb * HW + idx), mb);
+      ta[e] = __fmul_rn(__ldg(tgt_row + ca), ma);
+      tb[e] = __fmul_rn(__ldg(tgt_row + cb), mb);
+    }
+    const float dxp = __fsub_rn(pa[0], pb[0]), dyp = __fsub_rn(pa[1], pb[1]);
+    const float dxt = __fsub_rn(ta[0], tb[0]), dyt = __fsub_rn(ta[1], tb[1]);
+    const float dc = c ? dyp : dxp;
+    float pd, td, dcoef;
+    if (hd.angle_mode == CNH_LIMB_L1) {
+      pd = __fadd_rn(fabsf(dxp), fabsf(dyp));
+      td = __fadd_rn(fabsf(dxt), fabsf(dyt));
+      dcoef = (dc > 0.f) ? 1.f : ((dc < 0.f) ? -1.f : 0.f);
+    } else {
+      pd = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dxp, dxp), __fmul_rn(dyp, dyp)), 1e4f));
+      td = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dxt, dxt), __fmul_rn(dyt, dyt)), 1e4f));
+      dcoef = __fdiv_rn(dc, pd);
+    }
+    const float diff = __fsub_rn(pd, td);
+    const float sg = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
+    if (ka == j && c == 0) val += fabsf(diff);
+    if (ka == j) gcoef += sg * dcoef;
+    if (kb == j) gcoef -= sg * dcoef;
+  }
+}
+
 // One warp, one item: zero-fill of the piece (ZERO), forward terms of the slots inside it (added to
 // acc), and either the scatter itself (SCATTER, inv_denom known) or the slots' (index, coefficient)
 // kept in registers for a scatter after the grid barrier (KEEP).  Every lane owns slots lane,
@@ -720,7 +772,8 @@ __device__ __forceinline__ void l1_item_warp(const cnh_detloss_args& a, const Ge
   const cnh_head& hd = head_of(a, r.h);
   const int lane = threadIdx.x & 31;
   const int D = hd.D;
-  const bool is_angle = (D == 3 && r.d == 2 && hd.angle_mode != CNH_ANGLE_NONE);
+  const bool is_angle = (r.d == 2 && head_has_angle(hd));
+  const bool limb = head_has_limb(hd);
   const float* __restrict__ plane = hd.map + ((long long)r.b * D + r.d) * g.HW;
   float* __restrict__ gplane = hd.grad ? hd.grad + ((long long)r.b * D + r.d) * g.HW : nullptr;
   float l1 = 0.f, ang = 0.f;
@@ -760,6 +813,14 @@ __device__ __forceinline__ void l1_item_warp(const cnh_detloss_args& a, const Ge
       if (idx[u] >= 0) {
         l1_slot_math<FAST>(hd, is_angle, pr[u], tg[u], mk[u], val, gv);
         if (FORWARD) { if (is_angle) ang += val; else l1 += val; }
+        if (limb) {                                              // keypoint head: + the limb-length term
+          const long long slot = (long long)r.b * a.M + (k0 + u * 32 + lane);
+          float lv, lg;
+          limb_slot(hd, hd.map + (long long)r.b * D * g.HW, hd.target + slot * D,
+                    hd.mask + (hd.elementwise_mask ? slot * D : slot), idx[u], r.d, g.HW, lv, lg);
+          if (FORWARD) ang += lv;
+          gv += lg * mk[u] * hd.angle_weight;
+        }
         if (SCATTER && gv != 0.f) atomicAdd(gplane + idx[u], gv * inv_denom);   // duplicate centres accumulate
       }
     }
@@ -768,8 +829,13 @@ __device__ __forceinline__ void l1_item_warp(const cnh_detloss_args& a, const Ge
     l1 = warp_sum(l1);
     ang = warp_sum(ang);
     if (lane == 0) {
-      if (COUNTED) {                                         // exactly one contribution per item, zero or not
-        acc_add_counted(acc, (is_angle ? 3 : 2) + 3 * r.h, is_angle ? ang : l1);
+      if (COUNTED) {                                         // exactly one contribution per item and word, zero or not
+        if (limb) {
+          acc_add_counted(acc, 2 + 3 * r.h, l1);
+          acc_add_counted(acc, 3 + 3 * r.h, ang);
+        } else {
+          acc_add_counted(acc, (is_angle ? 3 : 2) + 3 * r.h, is_angle ? ang : l1);
+        }
       } else {
         if (l1 != 0.f) acc_add_fixed(acc, 2 + 3 * r.h, l1);
         if (ang != 0.f) acc_add_fixed(acc, 3 + 3 * r.h, ang);
@@ -820,7 +886,7 @@ template <bool FAST>
 __device__ __forceinline__ void item_math(const cnh_detloss_args& a, long long* acc, const ItemRef& r, int (&idx)[kKeep],
                                           const float (&mk)[kKeep], const float (&tg)[kKeep], float (&pr)[kKeep]) {
   const cnh_head& hd = head_of(a, r.h);
-  const bool is_angle = (hd.D == 3 && r.d == 2 && hd.angle_mode != CNH_ANGLE_NONE);
+  const bool is_angle = (r.d == 2 && head_has_angle(hd));
   float l1 = 0.f, ang = 0.f;
 #pragma unroll
   for (int u = 0; u < kKeep; ++u) {
@@ -882,7 +948,7 @@ __device__ void scalars_from_totals(const cnh_detloss_args& a, const long long* 
       const cnh_head& hd = a.heads[h];
       const float denom = (float)q[4 + 3 * h] + 1e-4f;
       l = (float)q[2 + 3 * h] / denom * hd.weight;
-      if (hd.D == 3 && hd.angle_mode != CNH_ANGLE_NONE) l += (float)q[3 + 3 * h] / denom * hd.angle_weight;
+      if (head_has_angle(hd) || head_has_limb(hd)) l += (float)q[3 + 3 * h] / denom * hd.angle_weight;
       total += l;
     }
     out[2 + h] = l;
@@ -1189,8 +1255,8 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
         expect = 0;
         if (h < a.n_heads) {
           const cnh_head& hd = head_of(a, h);
-          const int ang_ch = (hd.D == 3 && hd.angle_mode != CNH_ANGLE_NONE) ? 1 : 0;
-          expect = (long long)a.B * g.ppp * (is_ang ? ang_ch : hd.D - ang_ch);
+          const int ang_ch = head_has_angle(hd) ? 1 : 0;       // items that contribute to the angle / limb word
+          expect = (long long)a.B * g.ppp * (is_ang ? (head_has_limb(hd) ? hd.D : ang_ch) : hd.D - ang_ch);
         }
       }
       long long clean = 0;
@@ -1631,8 +1697,11 @@ static int validate(const cnh_detloss_args* a, bool need_grad_ptrs) {
     CNH_REQUIRE(hd.map != nullptr, CNH_E_NULL, "detloss: head %d map is NULL", h);
     CNH_REQUIRE(a->M == 0 || (hd.target && hd.mask), CNH_E_NULL, "detloss: head %d target/mask is NULL", h);
     CNH_REQUIRE(hd.D > 0 && hd.D <= 1024, CNH_E_SHAPE, "detloss: head %d D=%d", h, hd.D);
-    CNH_REQUIRE(hd.angle_mode >= CNH_ANGLE_NONE && hd.angle_mode <= CNH_ANGLE_PERIODIC, CNH_E_UNSUPPORTED,
+    CNH_REQUIRE(hd.angle_mode >= CNH_ANGLE_NONE && hd.angle_mode <= CNH_LIMB_L1, CNH_E_UNSUPPORTED,
                 "detloss: head %d angle_mode=%d", h, hd.angle_mode);
+    if (head_has_limb(hd))
+      CNH_REQUIRE(hd.D % 2 == 0 && hd.n_pairs > 0 && hd.pairs != nullptr, CNH_E_SHAPE,
+                  "detloss: head %d limb term needs D = 2*nk (got %d) and a pairs table (n_pairs=%d)", h, hd.D, hd.n_pairs);
     CNH_REQUIRE(!(hd.angle_mode == CNH_ANGLE_PERIODIC && hd.D != 3), CNH_E_SHAPE,
                 "detloss: periodic angle loss needs a 3-channel head (got D=%d)", hd.D);
     if (need_grad_ptrs) {
@@ -1672,6 +1741,8 @@ static Geo make_geo(const cnh_detloss_args* a, void* ws) {
   g.n_count = a->B * a->n_heads;
   g.vec_planes = vec_planes ? 1 : 0;
   g.stash_slots = (a->M <= 32 * kKeep) ? 1 : 0;
+  for (int h = 0; h < a->n_heads; ++h)
+    if (head_has_limb(a->heads[h])) g.stash_slots = 0;       // the limb term lives in the generic item path only
   g.n_stages = kStreamStages;
   g.chunk_ctas = 0;
   static const int x_delay = getenv("CNH_X_DELAY_NS") ? atoi(getenv("CNH_X_DELAY_NS")) : 0;

@@ -39,11 +39,24 @@ class DetectionLoss(torch.nn.Module):
             raise RuntimeError("DetectionLoss(periodic=True) needs a 3-channel 'wh' head")
         heads = [_F.HeadSpec(wh, batch['wh'], batch['reg_mask'], self.wh_weight, self.angle_weight, mode),
                  _F.HeadSpec(output['reg'], batch['reg'], batch['reg_mask'], self.off_weight)]
-        if self.with_keypoints:                   # losses/centernet.py:143-151
-            heads.append(_F.HeadSpec(output['kps'], batch['kps'], batch['kp_reg_mask'],
+        if self.with_keypoints:                   # losses/centernet.py:143-151 (+ the limb-length term, :153-187)
+            kps = output['kps']
+            mode, pairs = _L.ANGLE_NONE, None
+            if self.kp_indices is not None:
+                mode = _L.LIMB_L1 if self.kp_distance_weight_l1 else _L.LIMB_SQRT
+                pairs = self._pairs_on(kps.device)
+            heads.append(_F.HeadSpec(kps, batch['kps'], batch['kp_reg_mask'],
                                      1.0 if self.kp_weight is None else self.kp_weight,
-                                     elementwise_mask=True))
+                                     angle_weight=self.kp_distance_weight, angle_mode=mode,
+                                     elementwise_mask=True, pairs=pairs))
         return heads
+
+    def _pairs_on(self, device):
+        """the reference's kps_weight_indices as an int32 [P,2] device table (cached per device)"""
+        cache = self.__dict__.setdefault('_pairs_cache', {})
+        if device not in cache:
+            cache[device] = self.kp_indices.to(device=device, dtype=torch.int32).contiguous()
+        return cache[device]
 
     def forward(self, output, batch):
         heads = self._heads(output, batch)
@@ -53,31 +66,9 @@ class DetectionLoss(torch.nn.Module):
         loss, hm_loss, wh_loss, off_loss = scalars[0], scalars[1], scalars[2], scalars[3]
         stats = {'centernet_loss': loss, 'hm_loss': hm_loss, 'wh_loss': wh_loss, 'off_loss': off_loss}
         if self.with_keypoints:
-            kp_loss = scalars[4]
-            if self.kp_indices is not None:        # limb-length term, O(B*M*pairs): losses/centernet.py:153-187
-                dist = self._limb_term(output['kps'], batch)
-                kp_loss = kp_loss + dist
-                loss = loss + dist
-                stats['centernet_loss'] = loss
-            stats['kp_loss'] = kp_loss
+            stats['kp_loss'] = scalars[4]           # main term + limb-length term, both from the fused launch
         self.last_totals = totals
         return loss, stats
-
-    def _limb_term(self, kps_map, batch):
-        ind, mask = batch['ind'], batch['kp_reg_mask'].float()
-        b, d = kps_map.shape[:2]
-        pred = kps_map.reshape(b, d, -1).gather(2, ind.unsqueeze(1).expand(-1, d, -1)).transpose(1, 2) * mask
-        tgt = batch['kps'] * mask
-        n, c, k2 = tgt.shape
-        pairs = self.kp_indices.to(ind.device)
-        p, t = pred.reshape(n, c, k2 // 2, 2), tgt.reshape(n, c, k2 // 2, 2)
-        pa, pb, ta, tb = p[:, :, pairs[:, 0]], p[:, :, pairs[:, 1]], t[:, :, pairs[:, 0]], t[:, :, pairs[:, 1]]
-        if self.kp_distance_weight_l1:
-            dp, dt = (pa - pb).abs().sum(-1), (ta - tb).abs().sum(-1)
-        else:
-            dp = (((pa - pb) ** 2).sum(-1) + 1e4) ** 0.5
-            dt = (((ta - tb) ** 2).sum(-1) + 1e4) ** 0.5
-        return (dp - dt).abs().sum() / (mask.sum() + 1e-4) * self.kp_distance_weight
 
 
 _reexport(__name__, __file__, globals())

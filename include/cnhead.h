@@ -46,11 +46,15 @@ enum {
   CNH_E_PEER = -6         /* an earlier peer exchange timed out (see cnh_peers.status) */
 };
 
-/* angle handling of channel 2 of a 3-channel size head */
+/* second term of a regression head: angle handling of channel 2 of a 3-channel size head, or the limb-length
+ * consistency term of a keypoint head (its weight is cnh_head.angle_weight in every case) */
 enum {
-  CNH_ANGLE_NONE = 0,    /* plain L1 on every channel (losses/centernet.py:128-131)          */
-  CNH_ANGLE_SIGMOID = 1, /* |sc(pred) - sc(target)|   (losses/centernet.py:112-126)           */
-  CNH_ANGLE_PERIODIC = 2 /* RAPiD periodic L1         (losses/centernet.py:192-223)           */
+  CNH_ANGLE_NONE = 0,     /* plain L1 on every channel (losses/centernet.py:128-131)          */
+  CNH_ANGLE_SIGMOID = 1,  /* |sc(pred) - sc(target)|   (losses/centernet.py:112-126)           */
+  CNH_ANGLE_PERIODIC = 2, /* RAPiD periodic L1         (losses/centernet.py:192-223)           */
+  CNH_LIMB_SQRT = 3,      /* keypoint head, D = 2*nk: + sum over pairs |sqrt(|pa-pb|^2 + 1e4) - sqrt(|ta-tb|^2 + 1e4)|
+                             (KPSL1Loss, losses/centernet.py:153-187; the 1e4 is the reference's literal)       */
+  CNH_LIMB_L1 = 4         /* same with |pa-pb|_1 (use_l1, losses/centernet.py:173-175)                            */
 };
 
 /* flags */
@@ -68,11 +72,12 @@ typedef struct cnh_head {
   const uint8_t* mask;   /* [B,M] or, if elementwise_mask, [B,M,D]                   */
   float* grad;           /* [B,D,H,W] out: dLoss/dmap (dense, zero-filled) or NULL   */
   int32_t D;
-  int32_t angle_mode;    /* CNH_ANGLE_*; only used when D == 3                       */
+  int32_t angle_mode;    /* CNH_ANGLE_* (used when D == 3) or CNH_LIMB_* (D = 2*nk)  */
   int32_t elementwise_mask;
   float weight;          /* wh_weight / off_weight / kp_weight                       */
-  float angle_weight;
-  int32_t _pad;
+  float angle_weight;    /* angle_weight, or kp_distance_weight for CNH_LIMB_*       */
+  int32_t n_pairs;       /* CNH_LIMB_*: rows of `pairs`                              */
+  const int32_t* pairs;  /* CNH_LIMB_*: [n_pairs,2] keypoint indices (device), the reference's kps_weight_indices */
 } cnh_head;
 
 #define CNH_MAX_HEADS 3
@@ -82,7 +87,7 @@ typedef struct cnh_head {
 /* totals (int64[CNH_TOTALS]): exact batch sums as (hi, lo) pairs, word q = hi, word 12+q = lo;
  * value = (hi * 2^32 + lo) * 2^-40 for the fixed-point sums, lo alone for the integer counts.
  *   q = 0 sum(pos_loss + neg_loss)   q = 1 num_pos (count)
- *   q = 2+3h sum|l1| of head h       q = 3+3h angle sum of head h    q = 4+3h sum(mask_expanded) (count)
+ *   q = 2+3h sum|l1| of head h       q = 3+3h angle / limb sum of head h    q = 4+3h sum(mask_expanded) (count)
  * Integer addition is associative: totals of batch shards may simply be added (all-reduce SUM)
  * and give bit-identical scalars to a single launch over the whole batch.
  * scalar block (float[CNH_SCALARS]):
