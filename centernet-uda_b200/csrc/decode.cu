@@ -57,19 +57,27 @@ constexpr int kStageCap = kMaxK + kSlack; // staging buffer (keys) per CTA
 struct SampleState {                      // zero between launches
   unsigned cand_cnt;
   unsigned thr_bits;
-  unsigned pad[2];
+  unsigned overflow;                      // streaming path: a candidate buffer ran over -> the cluster kernel redoes the sample
+  unsigned pad;
 };
 
 struct DecGeo {
   int HW, rows, tiles_x, tiles_y, tiles_per_plane, tiles_per_sample, box_w, use_tma, slot, n_stages;
-  int pf_cycles;                          // cluster path: L2 prefetch distance in ring cycles (0 = off)
-  unsigned cut_mask;                      // cluster path: bit r set = cluster-wide cut after round r
   long long n_tiles;
   SampleState* state;                     // [B]                        zero between launches
   unsigned* ghist;                        // [B][kCoarseBins]           zero between launches
   u64* cand;                              // [B][tiles_per_sample * slot]  dense per-sample lists
   long long* dbg;
+  // streaming path (decode_stream_kernel + decode_finish_kernel)
+  int G;                                  // CTAs per sample
+  int only_overflow;                      // cluster kernel launched as the fallback: samples without the flag exit at once
+  unsigned* shist;                        // [B][kSuperBins]  keys per 64 fine bins       zero between launches
+  unsigned* fhist;                        // [B][kFineBins]   keys per fine bin           zero between launches
+  unsigned* cta_cnt;                      // [B][G]           keys in every CTA's slice   zero between launches
+  u64* slices;                            // [B][G][kSliceCap] candidate keys, one private slice per CTA
 };
+constexpr int kSuperBins = 64;            // kFineBins / 64
+constexpr int kSliceCap = 4096;           // keys a CTA of the streaming path may forward
 
 constexpr int kMaxStages = 8;
 template <int KEYS>
@@ -148,40 +156,6 @@ __device__ __noinline__ void find_kth_bin(SM& s, unsigned need) {
         s.sh_bin = 16 * tid + j;
         s.sh_above = acc;
         s.sh_inbin = c[j];
-        break;
-      }
-      acc += c[j];
-    }
-  }
-  group_sync();
-}
-
-// Same over `hist` (e.g. the cluster-wide merge, counters saturating at 65535): s.sh_flag = 1 and
-// s.sh_bin / s.sh_above / s.sh_inbin as above when the histogram holds at least `need` keys, else s.sh_flag = 0.
-// Called by the first 256 threads; ends with their barrier.
-template <class SM>
-__device__ __noinline__ void find_kth_bin_in(SM& s, const unsigned* hist, unsigned need) {
-  const int tid = threadIdx.x;
-  unsigned c[16], v = 0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const unsigned w = hist[8 * tid + j];
-    c[2 * j] = w & 0xffffu;
-    c[2 * j + 1] = w >> 16;
-    v += c[2 * j] + c[2 * j + 1];
-  }
-  if (tid == 0) s.sh_flag = 0u;
-  unsigned total;
-  const unsigned excl = block_suffix_excl(v, s.warp_tot, total);     // barriers inside: the flag reset is ordered
-  if (excl < need && excl + v >= need) {
-    unsigned acc = excl;
-#pragma unroll
-    for (int j = 15; j >= 0; --j) {
-      if (acc + c[j] >= need) {
-        s.sh_bin = 16 * tid + j;
-        s.sh_above = acc;
-        s.sh_inbin = c[j];
-        s.sh_flag = 1u;
         break;
       }
       acc += c[j];
@@ -976,7 +950,6 @@ template <int R>
 struct __align__(128) ClSmemT {             // followed by the TMA ring (the leader's doubles as the inbox)
   u64 stage[ClCfg<R>::kCap];               // the set (the scan appends to it); final stage: `sorted`
   unsigned hist[kFineBins / 2];            // packed fine histogram of the set, built per cut; final stage: `sel`
-  unsigned hist_all[kFineBins / 2];        // the cluster's histograms merged (saturating 16-bit counters)
   u64 mbar[ClCfg<R>::kStages];
   u64 sh_prefix;
   unsigned cnt;                            // size of the set
@@ -1032,13 +1005,6 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   // Stage tile q into ring slot buf: the rows of the tile plus one halo row above and below are contiguous
   // in global memory (one bulk copy, SASS UBLKCP); halo/tail rows outside the image are zero-filled by the
   // calling warp (max-pool padding: 0 is neutral because heat >= 0).  Called by ONE warp.
-  // start the rows of tile q on their way from HBM into L2 (no shared memory involved): issued pf_cycles ring
-  // cycles before the tile is staged, so that the bulk copy then finds them in L2.  Called by ONE lane.
-  auto prefetch_tile = [&](const Cursor& q) {
-    const int y0 = q.ty * kClRows;
-    const int ylo = max(y0 - 1, 0), yhi = min(y0 + kClRows + 1, H);
-    l2_prefetch_bulk(sample + (long long)q.c * g.HW + (long long)ylo * W, (unsigned)((yhi - ylo) * W) * 4u);
-  };
   auto stage_tile = [&](const Cursor& q, int buf) {
     float* dst = ring + (size_t)buf * kClTileFloats;
     const int lane = tid & 31;
@@ -1059,6 +1025,9 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next PDL launch (the next step's loss) may be placed
   asm volatile("griddepcontrol.wait;" ::: "memory");        // PDL: the producer of `heat` has completed
+  // launched behind the streaming path as its fallback: only samples whose overflow flag is up are redone (every CTA
+  // of the cluster reads the same word, before anyone can have cleared it: the leader does so after the last barrier)
+  if (g.only_overflow && __ldcg(&g.state[b].overflow) == 0u) return;
   if (tid == 0) {
     s.cnt = 0;
     s.cnt2 = 0;
@@ -1073,16 +1042,6 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   const Stride step_ring = stride_of(kClStages * CS);
   if (wid < kClStages && wid < n_my) stage_tile(pre, wid);
   advance(pre, step_ring);
-  // L2 prefetch cursor of the staging warps: tile (wid + 8 * (k + pf_cycles)) when tile (wid + 8 k) is staged
-  Cursor pf = pre;
-  int pf_j = wid + kClStages;                               // index (in this CTA's walk) of the tile `pf` points at
-  if (wid < kClStages && g.pf_cycles > 0) {
-    for (int c = 0; c < g.pf_cycles; ++c) {
-      if (pf_j < n_my && (tid & 31) == 0) prefetch_tile(pf);
-      advance(pf, step_ring);
-      pf_j += kClStages;
-    }
-  }
   __syncthreads();                                          // the staging warps' zero-filled halo rows (generic stores: the
                                                             // mbarrier only covers the bulk copy) before anyone scans
   Cursor mine = cursor_at(rank + gq * CS);                  // the tile this thread's group scans in the current round
@@ -1149,53 +1108,10 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
     r_hi = min(y0 + kClRows + 1, H) - (y0 - 1);
   };
 
-  // The cluster's histograms merged: every CTA builds the packed histogram of its set, a cluster barrier publishes
-  // them, and every CTA adds up all of them (512 threads x one 16-byte DSMEM load per peer, saturating 16-bit
-  // counters) into hist_all.  On return (CTA-uniform): s.sh_flag = "the cluster holds at least K keys", and then
-  // s.sh_bin / s.sh_above / s.sh_inbin describe the bin of the CLUSTER-WIDE K-th key -- the pruning threshold a
-  // CTA could only reach on its own after seeing the whole sample.  The caller must call cluster.barrier_wait()
-  // before s.hist is rebuilt (peers may still be reading it).
-  auto cluster_kth_bin = [&](const unsigned n) {
-    build_hist(n);
-    cluster.sync();
-    if (tid < kFineBins / 8) {
-      uint4 acc = reinterpret_cast<const uint4*>(s.hist)[tid];
-#pragma unroll 4
-      for (int c = 1; c < CS; ++c) {
-        const int peer = rank + c < CS ? rank + c : rank + c - CS;
-        const uint4 v = reinterpret_cast<const uint4*>(cluster.map_shared_rank(s.hist, peer))[tid];
-        acc.x = __vaddus2(acc.x, v.x);
-        acc.y = __vaddus2(acc.y, v.y);
-        acc.z = __vaddus2(acc.z, v.z);
-        acc.w = __vaddus2(acc.w, v.w);
-      }
-      reinterpret_cast<uint4*>(s.hist_all)[tid] = acc;
-    }
-    cluster.barrier_arrive();
-    __syncthreads();
-    if (group0) find_kth_bin_in(s, s.hist_all, (unsigned)K);
-    __syncthreads();
-  };
-  // Cluster-wide cut of the running sets (at rounds every CTA of the cluster agrees on).
-  auto cluster_cut = [&](const unsigned n) {
-    cluster_kth_bin(n);
-    if (s.sh_flag != 0u) {
-      const int tbin = (int)s.sh_bin;
-      const unsigned thr_new = __float_as_uint((float)tbin * (1.0f / (float)kFineBins));
-      compact_all(n, [&](u64 k) { return fine_bin((unsigned)(k >> 32)) >= tbin; });
-      if (thr_new > thr) thr = thr_new;
-    }
-    cluster.barrier_wait();
-    __syncthreads();
-  };
-
-  // every CTA of the cluster runs the same number of rounds (the last one may be empty for some): the cluster-wide
-  // cuts sit at rounds they all agree on
-  const int n_my_max = (g.tiles_per_sample + CS - 1) / CS;
-  const int n_rounds = (n_my_max + kClGroups - 1) / kClGroups;
+  const int n_rounds = (n_my + kClGroups - 1) / kClGroups;
   for (int r = 0; r < n_rounds; ++r) {
     const int half = (r % kDepth) * kClGroups, phase = (r / kDepth) & 1;
-    const int in_round = max(0, min(kClGroups, n_my - r * kClGroups));
+    const int in_round = min(kClGroups, n_my - r * kClGroups);
     const unsigned n_before = s.cnt;                        // <= kClTile (invariant)
     if (gq < in_round) {
       const Cursor q = mine;
@@ -1235,68 +1151,57 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
     if (wid >= half && wid < half + kClGroups) {            // refill the freed slots of the ring: round r + kDepth
       if ((r + kDepth) * kClGroups + (wid - half) < n_my) stage_tile(pre, wid);
       advance(pre, step_ring);
-      if (g.pf_cycles > 0) {
-        if (pf_j < n_my && (tid & 31) == 0) prefetch_tile(pf);
-        advance(pf, step_ring);
-        pf_j += kClStages;
-      }
     }
-    // Cluster-wide cuts after rounds 0, 1, 3, 7, ... (the pruning threshold of the WHOLE sample so far, which
-    // tightens 'cluster size' times faster than a CTA's own); a local cut whenever the next round might
-    // otherwise overflow the set.
-    if (r + 1 < n_rounds) {
-      if (r < 32 && ((g.cut_mask >> r) & 1u)) { cluster_cut(n); n = s.cnt; }
-      if (n > (unsigned)kClTile) cut(n);
-    }
+    // Cut when the next round might overflow the invariant and, on long walks, after rounds 1, 2, 4, 8, ...
+    // so that the pruning threshold tightens early.
+    if (r + 1 < n_rounds && (n > (unsigned)kClTile || (n_rounds >= 4 && n > slot && ((r + 1) & r) == 0))) cut(n);
   }
   dbg_stamp(g.dbg, 2);
+  cluster.barrier_arrive();                                 // this CTA no longer reads its ring (the leader's is the inbox)
 
-  // ---- final cut, cluster-wide, then the push into the leader's inbox (DSMEM) -----------------------------
-  // Usually what travels is the cluster's top K plus the rest of the K-th key's histogram bin -- K + a few keys
-  // in total, which the leader rank-sorts at once.  Heavy ties (the bin holds thousands of keys): every CTA sends
-  // its own exact top K instead and the leader selects.
-  constexpr unsigned kFinalKeep = 4096;
-  {
-    const unsigned n = s.cnt;
-    cluster_kth_bin(n);                                     // (its cluster barrier: every CTA has finished scanning)
-    const bool found = s.sh_flag != 0u;
-    const unsigned keep_total = s.sh_above + s.sh_inbin;
-    const int tbin = (int)s.sh_bin;
-    dbg_stamp(g.dbg, 5);
-    cluster.barrier_wait();                                 // the histograms are dead; the leader's ring is the inbox now
+  // ---- final cut fused with the push into the leader's inbox (DSMEM) --------------------------------
+  const unsigned n = s.cnt;
+  int mode = 0, tbin = 0;                                   // 0: send everything, 1: bins >= tbin, 2: keys >= T
+  u64 T = 0;
+  unsigned send_n = n;
+  // What travels to the leader is at most K + kSlack keys per CTA (measured: letting the leader cut the
+  // raw sets of a whole cluster is slower than one cut per CTA in parallel).
+  if (n > slot) {
+    build_hist(n);
+    if (group0) find_kth_bin(s, (unsigned)K);
     __syncthreads();
-    if (found && keep_total <= kFinalKeep) {
-      compact_all(n, [&](u64 k) { return fine_bin((unsigned)(k >> 32)) >= tbin; });
-    } else if (found && n > (unsigned)K) {
-      const u64 T = exact_cut_key(n);
-      compact_all(n, [&](u64 k) { return k >= T; });
+    send_n = s.sh_above + s.sh_inbin;
+    tbin = (int)s.sh_bin;
+    mode = 1;
+    if (send_n > slot) {
+      T = exact_cut_key(n);
+      send_n = (unsigned)K;
+      mode = 2;
     }
-    __syncthreads();
   }
+  dbg_stamp(g.dbg, 5);
+  cluster.barrier_wait();                                   // every CTA, the leader included, is done with its ring
   dbg_stamp(g.dbg, 6);
   unsigned* const r_cnt = cluster.map_shared_rank(&s.fin_cnt, 0);
   u64* const r_inbox = cluster.map_shared_rank(inbox, 0);
+  if (tid == 0) {
+    s.sh_base = send_n ? atomicAdd(r_cnt, send_n) : 0u;     // one remote atomic reserves the CTA's slice
+    s.cnt2 = 0;
+  }
+  __syncthreads();
   {
-    const unsigned send_n = s.cnt;
-    if (tid == 0) s.sh_base = send_n ? atomicAdd(r_cnt, send_n) : 0u;     // one remote atomic reserves the CTA's slice
-    __syncthreads();
     u64* const dst = r_inbox + s.sh_base;
-    for (unsigned i = tid; i < send_n; i += kClThreads) dst[i] = s.stage[i];
-    // the usual few keys per CTA: start the cache lines the leader's gather will touch on their way into L2 now
-    // (the maps are HBM-cold; the leader's rank sort then waits an L2 hit instead of a DRAM round trip)
-    if (send_n <= 128u && (unsigned)tid < send_n) {
-      const unsigned pix = (0xffffffffu - (unsigned)(s.stage[tid] & 0xffffffffu)) % (unsigned)g.HW;
-      if (a.reg) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.reg + ((long long)b * 2 + 0) * g.HW + pix));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.reg + ((long long)b * 2 + 1) * g.HW + pix));
-      }
-      for (int d = 0; d < (a.rotated ? 3 : 2); ++d)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.wh + ((long long)b * a.D + d) * g.HW + pix));
+    for (unsigned i0 = 0; i0 < n; i0 += kClThreads) {
+      const unsigned i = i0 + tid;
+      const u64 k = (i < n) ? s.stage[i] : 0ull;
+      const bool keep = (i < n) && (mode == 0 || (mode == 1 ? fine_bin((unsigned)(k >> 32)) >= tbin : k >= T));
+      append_if(keep, k, dst, &s.cnt2, send_n);
     }
   }
   dbg_stamp(g.dbg, 7);
   cluster.sync();                                           // release/acquire: the inbox is complete
   if (rank != 0) return;
+  if (g.only_overflow && tid == 0) g.state[b].overflow = 0u;
   dbg_stamp(g.dbg, 3);
 
   // ---- leader: final selection (all warps) + sort + gather (warps 0-7) -------------------------------------
@@ -1374,6 +1279,303 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   dbg_stamp(g.dbg, 4);
 }
 
+// ================================================================================================
+// Streaming path (long walks: many tiles per SM, e.g. the 80-class COCO-scale shard).  Same skeleton as the
+// streaming detection-loss kernel: persistent CTAs of 9 warps, two per SM, NO block-wide barrier in steady state.
+//   warp 8 (producer): walks this CTA's tiles of ITS sample (tile t = j, j + G, ... for CTA j of the sample's G
+//           CTAs): waits for a free ring stage, forwards the candidates the consumers left in the stage's buffer
+//           to the CTA's private slice of the sample's candidate list in global memory (plain stores, no atomic
+//           round trip) while counting them into the sample's two-level global histogram (fire-and-forget REDs),
+//           refreshes the pruning threshold from that histogram (loads issued one tile ahead of their use), and
+//           issues the bulk copy (cp.async.bulk, SASS UBLKCP) of the next tile + halo rows.
+//   warps 0-7 (consumers): each scans 4 rows of the staged tile (threshold-first, 3x3 test from shared memory)
+//           and appends its peaks to the stage's buffer; one mbarrier arrival per warp frees the stage.
+// The histogram counts only keys already forwarded, so every threshold derived from it is valid (at least K real
+// peaks reach it) however far the CTAs of a sample have drifted apart.  decode_finish_kernel (one CTA per sample,
+// launched with programmatic stream serialisation) selects, sorts and emits.  A stage buffer or slice that runs
+// over (plateaus of ties: thousands of equal scores) raises the sample's overflow flag; the cluster kernel,
+// launched behind as a fallback that exits at once for every other sample, then redoes that sample exactly.
+// ================================================================================================
+constexpr int kStRows = 32;                               // tile rows
+constexpr int kStStages = 4;                              // ring depth
+constexpr int kStCap = 1024;                              // candidate keys per stage buffer
+constexpr int kStTileFloats = (kStRows + 2) * kCols + 128;   // + slack for the masked lanes of narrow maps
+constexpr int kStThreads = kThreads + 32;
+struct __align__(128) StSmem {
+  u64 cand[kStStages][kStCap];
+  u64 full[kStStages];
+  u64 empty[kStStages];
+  unsigned cnt[kStStages];
+  unsigned thr[kStStages];
+  int tile_c[kStStages];                                  // class plane of the staged tile, -1 = no more tiles
+  int tile_ty[kStStages];
+};
+constexpr size_t kStSmemBytes = sizeof(StSmem) + (size_t)kStStages * kStTileFloats * sizeof(float);
+
+__device__ __forceinline__ void red_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kStThreads, 2)
+decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_constant__ DecGeo g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StSmem& s = *reinterpret_cast<StSmem*>(smem_raw);
+  float* const ring = reinterpret_cast<float*>(smem_raw + sizeof(StSmem));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = (int)blockIdx.x / g.G, j = (int)blockIdx.x - b * g.G;
+  const int W = a.W, H = a.H, K = a.K;
+  const int n_mine = j < g.tiles_per_sample ? (g.tiles_per_sample - j + g.G - 1) / g.G : 0;
+  const float* const sample = a.heat + (long long)b * a.C * g.HW;
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");        // PDL: the producer of `heat` has completed
+  dbg_stamp(g.dbg, 0);
+  if (tid == 0) {
+    for (int i = 0; i < kStStages; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], kWarps);
+      s.cnt[i] = 0u;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kWarps) {
+    // ================= producer =================
+    unsigned* const shist = g.shist + (long long)b * kSuperBins;
+    unsigned* const fhist = g.fhist + (long long)b * kFineBins;
+    u64* const slice = g.slices + ((long long)b * g.G + j) * kSliceCap;
+    unsigned local_cnt = 0, thr = 0;
+    bool overflow = false;
+    // threshold refresh, pipelined over the producer's iterations: 0 idle -> 1 super-bin counts in flight ->
+    // 2 the fine bins of the K-th key's super bin in flight -> 0
+    int pending = 0, sb_sel = 0;
+    unsigned h0 = 0, h1 = 0, above_sb = 0;
+    int c = 0, ty = 0;                                       // cursor of the next tile to issue: t = j + i * G
+    { const int t0 = j; c = t0 / g.tiles_y; ty = t0 - c * g.tiles_y; }
+    const int dc = g.G / g.tiles_y, dty = g.G - dc * g.tiles_y;
+    for (int i = 0; i < n_mine + kStStages; ++i) {
+      const int st = i % kStStages;
+      if (i >= kStStages) {
+        // ---- stage st is free once the eight consumer warps have arrived: forward its candidates ----
+        mbar_wait(&s.empty[st], (unsigned)(((i / kStStages) - 1) & 1));
+        unsigned n = *reinterpret_cast<volatile unsigned*>(&s.cnt[st]);
+        if (n > (unsigned)kStCap) { overflow = true; n = (unsigned)kStCap; }
+        if (local_cnt + n > (unsigned)kSliceCap) { overflow = true; n = (unsigned)kSliceCap - local_cnt; }
+        for (unsigned k = lane; k < n; k += 32) {
+          const u64 key = s.cand[st][k];
+          slice[local_cnt + k] = key;
+          const int bin = fine_bin((unsigned)(key >> 32));
+          red_add_u32(fhist + bin, 1u);
+          red_add_u32(shist + (bin >> 6), 1u);
+        }
+        local_cnt += n;
+        __syncwarp();
+        if (lane == 0) s.cnt[st] = 0u;
+        // ---- threshold refresh ----
+        if (pending == 1) {
+          // lane owns super bins 2*lane, 2*lane+1; suffix sums from the top
+          const unsigned mine = h0 + h1;
+          unsigned incl = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += v;
+          }
+          const unsigned above = incl - mine;                // keys in super bins above this lane's pair
+          int sel = -1;
+          unsigned ab = 0;
+          if (above < (unsigned)K && incl >= (unsigned)K) {
+            if (above + h1 >= (unsigned)K) { sel = 2 * lane + 1; ab = above; }
+            else { sel = 2 * lane; ab = above + h1; }
+          }
+          const unsigned who = __ballot_sync(0xffffffffu, sel >= 0);
+          if (who != 0u) {
+            const int src = __ffs(who) - 1;
+            sb_sel = __shfl_sync(0xffffffffu, sel, src);
+            above_sb = __shfl_sync(0xffffffffu, ab, src);
+            const uint2 f = __ldcg(reinterpret_cast<const uint2*>(fhist + sb_sel * 64) + lane);
+            h0 = f.x;
+            h1 = f.y;
+            pending = 2;
+          } else {
+            pending = 0;                                     // fewer than K keys counted so far: no threshold yet
+          }
+        } else if (pending == 2) {
+          // lane owns fine bins sb_sel*64 + 2*lane, +1; the K-th key's bin: suffix sums from the top, offset above_sb
+          const unsigned mine = h0 + h1;
+          unsigned incl = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += v;
+          }
+          const unsigned above = above_sb + incl - mine;
+          int sel = -1;
+          if (above < (unsigned)K && above + mine >= (unsigned)K) sel = (above + h1 >= (unsigned)K) ? 2 * lane + 1 : 2 * lane;
+          const unsigned who = __ballot_sync(0xffffffffu, sel >= 0);
+          if (who != 0u) {
+            const int fb = sb_sel * 64 + __shfl_sync(0xffffffffu, sel, __ffs(who) - 1);
+            const unsigned t_new = __float_as_uint((float)fb * (1.0f / (float)kFineBins));
+            if (t_new > thr) thr = t_new;
+          }
+          pending = 0;
+        }
+        if (pending == 0 && i < n_mine) {
+          const uint2 v = __ldcg(reinterpret_cast<const uint2*>(shist) + lane);
+          h0 = v.x;
+          h1 = v.y;
+          pending = 1;
+        }
+      }
+      if (i < n_mine) {
+        // ---- stage tile (c, ty): rows [y0-1, y0+33) of the plane, contiguous; rows outside the image are zero ----
+        float* dst = ring + (size_t)st * kStTileFloats;
+        const int y0 = ty * kStRows;
+        const int ylo = max(y0 - 1, 0), yhi = min(y0 + kStRows + 1, H);
+        const int r_lo = ylo - (y0 - 1), r_hi = yhi - (y0 - 1);
+        if (r_lo > 0 || r_hi < kStRows + 2) {
+          for (int q = lane; q < r_lo * W; q += 32) dst[q] = 0.f;
+          for (int q = r_hi * W + lane; q < (kStRows + 2) * W; q += 32) dst[q] = 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          s.tile_c[st] = c;
+          s.tile_ty[st] = ty;
+          s.thr[st] = thr;
+          const unsigned bytes = (unsigned)((yhi - ylo) * W) * 4u;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(&s.full[st], bytes);
+          bulk_load_1d(dst + r_lo * W, sample + (long long)c * g.HW + (long long)ylo * W, bytes, &s.full[st]);
+        }
+        c += dc;
+        ty += dty;
+        if (ty >= g.tiles_y) { ty -= g.tiles_y; ++c; }
+      } else if (i == n_mine) {
+        if (lane == 0) {                                     // out of tiles: wake the consumers
+          s.tile_c[st] = -1;
+          mbar_arrive(&s.full[st]);
+        }
+      }
+    }
+    if (lane == 0) {
+      g.cta_cnt[(long long)b * g.G + j] = local_cnt;
+      if (overflow) g.state[b].overflow = 1u;
+    }
+    dbg_stamp(g.dbg, 2);
+    return;
+  }
+
+  // ================= consumers =================
+  const int lane_col = 4 * lane;
+  const unsigned colmask = W - lane_col >= 4 ? 15u : (W - lane_col <= 0 ? 0u : ((1u << (W - lane_col)) - 1u));
+  const bool last_lane = lane_col + 4 >= W;
+#pragma unroll 1
+  for (int i = 0;; ++i) {
+    const int st = i % kStStages;
+    mbar_wait(&s.full[st], (unsigned)((i / kStStages) & 1));    // acquires the tile's meta data
+    const int c = s.tile_c[st];
+    if (c < 0) break;
+    const int ty = s.tile_ty[st];
+    const unsigned thr = s.thr[st];
+    scan_rows_group<kStRows / kWarps>(s.cand[st], &s.cnt[st], (unsigned)kStCap, ring + (size_t)st * kStTileFloats, W,
+                                      colmask, last_lane, thr,
+                                      (unsigned)c * (unsigned)g.HW + (unsigned)(ty * kStRows) * (unsigned)W, warp);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.empty[st]);
+  }
+  if (tid == 0) dbg_stamp(g.dbg, 1);
+}
+
+// One CTA per sample: final threshold from the sample's two-level histogram, survivors from the G slices into
+// shared memory, selection + sort + filler + gather + boxes (select_sort_emit), and the sample's global state
+// left zeroed for the next launch.  Samples whose overflow flag is up are left to the cluster kernel.
+__global__ void __launch_bounds__(kThreads)
+decode_finish_kernel(const cnh_decode_args a, const DecGeo g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  MergeSmem& s = *reinterpret_cast<MergeSmem*>(smem_raw);
+  constexpr int kKeyCap = MergeSmem::kKeyCap;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b = (int)blockIdx.x, K = a.K;
+  unsigned* const shist = g.shist + (long long)b * kSuperBins;
+  unsigned* const fhist = g.fhist + (long long)b * kFineBins;
+  unsigned* const cta_cnt = g.cta_cnt + (long long)b * g.G;
+  const u64* const slices = g.slices + (long long)b * g.G * kSliceCap;
+  for (int q = 0; q < kFineBins / 2 / kThreads; ++q) s.hist[tid + q * kThreads] = 0u;
+  if (tid == 0) { s.cnt = 0; s.cnt2 = 0; s.sh_thr = 0u; }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");        // PDL: the stream kernel's writes are visible from here
+  dbg_stamp(g.dbg, 5);
+  const bool skip = __ldcg(&g.state[b].overflow) != 0u;    // the cluster kernel redoes this sample
+  __syncthreads();
+  if (!skip) {
+    // ---- the K-th key's fine bin (warp 0; same two-level walk as the stream kernel's producers) ----
+    if (tid < 32) {
+      const uint2 v = __ldcg(reinterpret_cast<const uint2*>(shist) + lane);
+      unsigned mine = v.x + v.y, incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += u;
+      }
+      unsigned above = incl - mine;
+      int sel = -1;
+      unsigned ab = 0;
+      if (above < (unsigned)K && incl >= (unsigned)K) {
+        if (above + v.y >= (unsigned)K) { sel = 2 * lane + 1; ab = above; }
+        else { sel = 2 * lane; ab = above + v.y; }
+      }
+      const unsigned who = __ballot_sync(0xffffffffu, sel >= 0);
+      if (who != 0u) {
+        const int src = __ffs(who) - 1;
+        const int sb = __shfl_sync(0xffffffffu, sel, src);
+        const unsigned above_sb = __shfl_sync(0xffffffffu, ab, src);
+        const uint2 f = __ldcg(reinterpret_cast<const uint2*>(fhist + sb * 64) + lane);
+        mine = f.x + f.y;
+        incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned u = __shfl_down_sync(0xffffffffu, incl, o);
+          if (lane + o < 32) incl += u;
+        }
+        above = above_sb + incl - mine;
+        if (above < (unsigned)K && above + mine >= (unsigned)K)
+          s.sh_thr = __float_as_uint((float)(sb * 64 + ((above + f.y >= (unsigned)K) ? 2 * lane + 1 : 2 * lane)) *
+                                     (1.0f / (float)kFineBins));
+      }
+    }
+    __syncthreads();
+    const unsigned thr_final = s.sh_thr;                     // 0: fewer than K peaks in the sample, keep everything
+    dbg_stamp(g.dbg, 6);
+    // ---- survivors of every slice -> shared memory keys + packed fine histogram ----
+    auto for_each_survivor = [&](auto f) {
+      for (int jj = 0; jj < g.G; ++jj) {
+        const unsigned nc = __ldcg(cta_cnt + jj);
+        const u64* cand = slices + (long long)jj * kSliceCap;
+        for (unsigned e0 = 0; e0 < nc; e0 += kThreads) {     // block-uniform trip count
+          const unsigned e = e0 + tid;
+          const u64 k = (e < nc) ? __ldcg(cand + e) : 0ull;
+          f(e < nc && (unsigned)(k >> 32) >= thr_final, k);
+        }
+      }
+    };
+    for_each_survivor([&](bool ok, u64 k) {
+      append_if(ok, k, s.keys, &s.cnt, (unsigned)kKeyCap);
+      if (ok) hist_add(s.hist, fine_bin((unsigned)(k >> 32)));
+    });
+    __syncthreads();
+    dbg_stamp(g.dbg, 7);
+    select_sort_emit(a, g, s, b, s.keys, (int)s.cnt, kKeyCap,
+                     [&](auto f) { for_each_survivor([&](bool ok, u64 k) { if (ok) f(k); }); });
+    dbg_stamp(g.dbg, 10);
+  }
+  // ---- leave the sample's global state zeroed for the next launch (the overflow flag: the cluster kernel) ----
+  __syncthreads();
+  for (int q = tid; q < kFineBins; q += kThreads) fhist[q] = 0u;
+  if (tid < kSuperBins) shist[tid] = 0u;
+  for (int q = tid; q < g.G; q += kThreads) cta_cnt[q] = 0u;
+}
+
 // ---- host ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1415,6 +1617,12 @@ static int validate(const cnh_decode_args* a) {
 
 static size_t up128(size_t v) { return (v + 127) / 128 * 128; }
 
+// keys of one sample's candidate list of the two-kernel path (16-row tiling has the most tiles)
+static size_t cand_keys_per_sample(const cnh_decode_args* a) {
+  const size_t tiles16 = (size_t)a->C * ((a->W + kCols - 1) / kCols) * ((a->H + 15) / 16);
+  return tiles16 * (size_t)(a->K + kSlack);
+}
+
 static DecGeo make_geo(const cnh_decode_args* a, void* ws, int rows) {
   DecGeo g;
   g.rows = rows;
@@ -1427,10 +1635,6 @@ static DecGeo make_geo(const cnh_decode_args* a, void* ws, int rows) {
   const int tw = a->W < kCols ? a->W : kCols;
   g.box_w = ((tw + 3) / 4) * 4 + 2 * kPadL;
   g.use_tma = 0;
-  static const int pf_env = getenv("CNH_DECODE_PF") ? atoi(getenv("CNH_DECODE_PF")) : 2;
-  static const unsigned cut_env = getenv("CNH_DECODE_CUTMASK") ? (unsigned)strtoul(getenv("CNH_DECODE_CUTMASK"), nullptr, 0) : 0x8bu;
-  g.pf_cycles = pf_env < 0 ? 0 : (pf_env > 8 ? 8 : pf_env);
-  g.cut_mask = cut_env;                    // default: after rounds 0, 1, 3, 7
   g.dbg = debug_buffer();
   g.slot = a->K + kSlack;
   char* p = static_cast<char*>(ws);
@@ -1439,22 +1643,54 @@ static DecGeo make_geo(const cnh_decode_args* a, void* ws, int rows) {
   g.ghist = reinterpret_cast<unsigned*>(p);
   p += up128((size_t)a->B * kCoarseBins * sizeof(unsigned));
   g.cand = reinterpret_cast<u64*>(p);
+  // streaming path: G CTAs per sample (two CTAs per SM over the batch, at most one per 32-row tile)
+  const int tiles32 = a->C * ((a->H + kStRows - 1) / kStRows);
+  int G = (2 * sm_count()) / a->B;
+  if (G > tiles32) G = tiles32;
+  if (G < 1) G = 1;
+  g.G = G;
+  g.only_overflow = 0;
+  p += up128((size_t)a->B * cand_keys_per_sample(a) * sizeof(u64));
+  g.shist = reinterpret_cast<unsigned*>(p);
+  p += up128((size_t)a->B * kSuperBins * sizeof(unsigned));
+  g.fhist = reinterpret_cast<unsigned*>(p);
+  p += up128((size_t)a->B * kFineBins * sizeof(unsigned));
+  g.cta_cnt = reinterpret_cast<unsigned*>(p);
+  p += up128((size_t)a->B * G * sizeof(unsigned));
+  g.slices = reinterpret_cast<u64*>(p);
   return g;
 }
 
 static size_t decode_ws_bytes(const cnh_decode_args* a) {
-  DecGeo g = make_geo(a, nullptr, 16);     // 16-row tiling has the most tiles: sizes the candidate lists
+  DecGeo g = make_geo(a, nullptr, 16);
   return up128((size_t)a->B * sizeof(SampleState)) + up128((size_t)a->B * kCoarseBins * sizeof(unsigned)) +
-         (size_t)a->B * g.tiles_per_sample * g.slot * sizeof(u64);
+         up128((size_t)a->B * cand_keys_per_sample(a) * sizeof(u64)) +
+         up128((size_t)a->B * kSuperBins * sizeof(unsigned)) + up128((size_t)a->B * kFineBins * sizeof(unsigned)) +
+         up128((size_t)a->B * g.G * sizeof(unsigned)) + (size_t)a->B * g.G * kSliceCap * sizeof(u64);
+}
+
+// environment switches of the tests / tools, read once per process... unless CNH_DECODE_ENV_RELOAD is set (the
+// parity tests flip the switches between cases inside one process)
+struct DecodeEnv { bool rows16, two_kernel, reload; int stream; };
+static const DecodeEnv& decode_env() {
+  static DecodeEnv e = {false, false, true, -1};
+  if (e.reload) {
+    const char* rows = getenv("CNH_DECODE_ROWS");
+    e.rows16 = rows != nullptr && atoi(rows) == 16;
+    e.two_kernel = getenv("CNH_DECODE_TWO_KERNEL") != nullptr;
+    const char* st = getenv("CNH_DECODE_STREAM");            // 1 / 0 force the streaming path on / off; unset: by size
+    e.stream = st != nullptr ? atoi(st) : -1;
+    e.reload = getenv("CNH_DECODE_ENV_RELOAD") != nullptr;
+  }
+  return e;
 }
 
 constexpr int kClusterUnavailable = -999;
 constexpr int kClMaxSmem = 227 * 1024;
 
 // co-resident clusters of cs CTAs at one CTA per SM on device `dev` (cached; -1 = unavailable)
-constexpr int kMaxClusterSize = 16;                // 8 is the portable limit; 9..16 need the non-portable attribute
 static int active_clusters(int dev, int cs) {
-  static int max_clusters[64][kMaxClusterSize + 1] = {};   // 0 = not queried
+  static int max_clusters[64][9] = {};            // 0 = not queried
   if (max_clusters[dev][cs] == 0) {
     cudaLaunchConfig_t q;
     memset(&q, 0, sizeof(q));
@@ -1478,30 +1714,25 @@ static int active_clusters(int dev, int cs) {
   return max_clusters[dev][cs];
 }
 
-// The cluster size whose B clusters are all co-resident (one CTA per SM) and cover the most SMs; ties go to the
-// smaller cluster (cheaper histogram merge).  Sizes 9..16 are non-portable: a GPC of the B200 holds two 9-CTA
-// clusters, so a batch of 16 can run as 16 x 9 = 144 CTAs where the portable sizes stop at 16 x 6 = 96.
-// CNH_DECODE_CS caps the size (experiments).  Nothing fits: 1 (samples then run in waves).
+// Largest cluster size <= 8 whose B clusters are co-resident, else 1 (samples then run in waves).
+// (On a B200 fifteen 8-CTA clusters fit at one CTA per SM, so a batch of 16 runs as 16 clusters of 7.)
 static int pick_cluster_size(int B, int tiles_per_sample, int dev) {
-  static const int cap_env = getenv("CNH_DECODE_CS") ? atoi(getenv("CNH_DECODE_CS")) : 0;
-  const int cap = cap_env >= 1 && cap_env <= kMaxClusterSize ? cap_env : kMaxClusterSize;
-  int best = 0;
-  for (int cs = 2; cs <= cap; ++cs) {
-    if (cs > tiles_per_sample) break;
-    if ((long long)B <= (long long)active_clusters(dev, cs) && cs > best) best = cs;
+  for (int cs = 8; cs > 1; --cs) {
+    if (cs > tiles_per_sample) continue;
+    if ((long long)B <= (long long)active_clusters(dev, cs)) return cs;
   }
-  if (best) return best;
   return active_clusters(dev, 1) < 1 ? -1 : 1;
 }
 
 template <int R>
-static int launch_cluster_rows(const cnh_decode_args* a, const DecGeo& g0, int cs, cudaStream_t st) {
+static int launch_cluster_rows(const cnh_decode_args* a, const DecGeo& g0, int cs, cudaStream_t st, int only_overflow = 0) {
   typedef ClCfg<R> Cfg;
   DecGeo g = g0;
   g.n_stages = Cfg::kStages;
   g.use_tma = 1;
+  g.only_overflow = only_overflow;
   const size_t smem = sizeof(ClSmemT<R>) + (size_t)Cfg::kStages * Cfg::kTileFloats * sizeof(float);
-  static_assert((size_t)Cfg::kStages * Cfg::kTileFloats * sizeof(float) >= (size_t)kMaxClusterSize * kMaxK * sizeof(u64), "the ring holds the inbox");
+  static_assert((size_t)Cfg::kStages * Cfg::kTileFloats * sizeof(float) >= (size_t)8 * kStageCap * sizeof(u64), "the ring holds the inbox");
   static_assert(sizeof(ClSmemT<R>) + (size_t)Cfg::kStages * Cfg::kTileFloats * sizeof(float) <= (size_t)kClMaxSmem, "shared memory");
   static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
   cudaLaunchConfig_t lc;
@@ -1535,10 +1766,6 @@ static bool cluster_attrs(int dev) {
       cudaGetLastError();
       return false;
     }
-    // clusters of 9..16 CTAs (non-portable); if the driver refuses, active_clusters() reports them unavailable
-    if (cudaFuncSetAttribute(decode_cluster_kernel<32>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_cluster_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
-      cudaGetLastError();
     attr_set[dev] = true;
   }
   return true;
@@ -1552,10 +1779,57 @@ static int launch_cluster(const cnh_decode_args* a, void* workspace, int dev, cu
   DecGeo g32 = make_geo(a, workspace, 32);
   const int cs = pick_cluster_size(a->B, g32.tiles_per_sample, dev);
   if (cs < 1) return kClusterUnavailable;
-  const char* force = getenv("CNH_DECODE_ROWS");            // tests: force one shape
-  const bool rows16 = force != nullptr && atoi(force) == 16;
+  const bool rows16 = decode_env().rows16;                  // tests: force one shape
   if (!rows16) return launch_cluster_rows<32>(a, g32, cs, st);
   return launch_cluster_rows<16>(a, make_geo(a, workspace, 16), cs, st);
+}
+
+// Streaming path: stream kernel (scan + candidate lists + thresholds) -> finish kernel (one CTA per sample) -> the
+// cluster kernel as the fallback for samples whose buffers ran over (it exits at once for all others).  All three
+// carry the programmatic-stream-serialisation attribute: each starts with griddepcontrol.wait.
+static int launch_stream(const cnh_decode_args* a, void* workspace, int dev, cudaStream_t st) {
+  if (!cluster_attrs(dev)) return kClusterUnavailable;
+  DecGeo g = make_geo(a, workspace, kStRows);
+  const int cs = pick_cluster_size(a->B, g.tiles_per_sample, dev);
+  if (cs < 1) return kClusterUnavailable;
+  static bool attr_set[64] = {false};
+  if (!attr_set[dev]) {
+    if (cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)) != cudaSuccess) {
+      cudaGetLastError();
+      return kClusterUnavailable;
+    }
+    attr_set[dev] = true;
+  }
+  static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.stream = st;
+  lc.attrs = attr;
+  lc.numAttrs = use_pdl ? 1 : 0;
+  lc.gridDim = dim3((unsigned)a->B * (unsigned)g.G);
+  lc.blockDim = dim3(kStThreads);
+  lc.dynamicSmemBytes = kStSmemBytes;
+  CNH_CUDA(cudaLaunchKernelEx(&lc, decode_stream_kernel, *a, g));
+  lc.gridDim = dim3((unsigned)a->B);
+  lc.blockDim = dim3(kThreads);
+  lc.dynamicSmemBytes = sizeof(MergeSmem);
+  CNH_CUDA(cudaLaunchKernelEx(&lc, decode_finish_kernel, *a, g));
+  const int rc = launch_cluster_rows<32>(a, g, cs, st, 1);
+  CNH_REQUIRE(rc != kClusterUnavailable, CNH_E_UNSUPPORTED, "decode: the cluster launch of the streaming path's fallback was refused");
+  return rc;
+}
+
+static bool want_stream(const cnh_decode_args* a) {
+  const int force = decode_env().stream;
+  if (a->apply_sigmoid || force == 0) return false;
+  if (force == 1) return true;
+  // long walks only: at least four 32-row tiles for each of the two CTAs per SM
+  const long long tiles = (long long)a->B * a->C * ((a->H + kStRows - 1) / kStRows);
+  return tiles >= 8ll * sm_count();
 }
 
 }  // namespace cnh
@@ -1570,13 +1844,6 @@ extern "C" int cnh_debug_decode_cluster(const cnh_decode_args* a) {
   DecGeo g = make_geo(a, nullptr, 32);
   const int cs = pick_cluster_size(a->B, g.tiles_per_sample, dev);
   return (cs < 0 ? 0 : cs) * 1000 + active_clusters(dev, 8);
-}
-
-// not part of the public ABI (tools/): co-resident clusters of `cs` CTAs of the decode kernel on the current device
-extern "C" int cnh_debug_active_clusters(int cs) {
-  int dev = 0;
-  if (cs < 1 || cs > kMaxClusterSize || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !cluster_attrs(dev)) return -1;
-  return active_clusters(dev, cs);
 }
 
 extern "C" size_t cnh_decode_workspace_bytes(const cnh_decode_args* a) {
@@ -1594,7 +1861,11 @@ extern "C" int cnh_decode(const cnh_decode_args* a, void* workspace, size_t work
   int dev = 0;
   CNH_CUDA(cudaGetDevice(&dev));
   // ---- cluster path (one launch, no global scratch) when a tile's rows are contiguous and 16-byte aligned ----
-  if (a->W <= kCols && a->W % 4 == 0 && aligned16(a->heat) && getenv("CNH_DECODE_TWO_KERNEL") == nullptr) {
+  if (a->W <= kCols && a->W % 4 == 0 && aligned16(a->heat) && !decode_env().two_kernel) {
+    if (want_stream(a)) {                                    // long walks: streaming kernel + finish kernel (+ fallback)
+      const int rc = launch_stream(a, workspace, dev, st);
+      if (rc != kClusterUnavailable) return rc;
+    }
     const int rc = launch_cluster(a, workspace, dev, st);
     if (rc != kClusterUnavailable) return rc;
   }

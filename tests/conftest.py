@@ -7,6 +7,8 @@ import numpy as np
 import pytest
 import torch
 
+os.environ.setdefault("CNH_DECODE_ENV_RELOAD", "1")   # the decode tests flip the library's launch-shape switches per case
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "centernet-uda_b200")
 GOLDEN = os.path.join(ROOT, "tests", "golden")

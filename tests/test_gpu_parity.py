@@ -202,15 +202,115 @@ def test_large_problem_precount_schedule():
 
 
 # ---------------------------------------------------------------------------------------------
+# element-wise accuracy against the float64 oracle (north_star: "within 1e-5 relative in fp32")
+# ---------------------------------------------------------------------------------------------
+def elementwise_violations(gpu, ref32, ref64, k=4.0, rel=1e-5, floor=0.0):
+    """elements with |gpu - f64| > max(k * |ref32 - f64|, rel * |f64|, floor): the GPU result may be no worse than
+    k times the fp32 reference's OWN error to the float64 truth, or within `rel` of the truth.  Returns
+    (violations, elements, worst ratio error/bound)."""
+    gpu, ref32, ref64 = (torch.as_tensor(t).double().flatten() for t in (gpu, ref32, ref64))
+    err = (gpu - ref64).abs()
+    bound = torch.maximum(torch.maximum(k * (ref32 - ref64).abs(), rel * ref64.abs()), torch.full_like(err, floor))
+    bad = err > bound
+    worst = float((err[bad] / bound[bad].clamp_min(1e-300)).max()) if bool(bad.any()) else 0.0
+    return int(bad.sum()), err.numel(), worst
+
+
+def _f64(d):
+    return {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("cfg_name,batch", [("cfg2", None), ("cfg3", None), ("cfg5", 16)])
+@pytest.mark.parametrize("accurate", [True, False])
+def test_gradients_elementwise_vs_float64_oracle(cfg_name, batch, accurate, monkeypatch):
+    """Loss gradients, element by element, against the float64 oracle at cfg2 / cfg3 and a full cfg5 shard
+    (16 x 80 x 128^2: the pre-count schedule with its reverse-order pass and sparse sub-block skipping).
+    CNH_ACCURATE_MATH (expf / logf / IEEE divide): every element within max(4 x the fp32 reference's own error,
+    1e-5 relative).  Default FAST math (ex2 / lg2 / rcp.approx): lg2.approx carries 2^-22 ABSOLUTE error, which
+    log(1 - p) for p -> 1e-4 amplifies exactly like the reference's own rounding of 1 - p, only ~8x larger; the
+    test bounds the violating fraction and the worst ratio and prints them."""
+    from cnhead import synthetic, functional as F
+    monkeypatch.setattr(F, "_ACCURATE", accurate)
+    cfg = synthetic.CONFIGS[cfg_name]
+    data = synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0)
+    kw = synthetic.loss_kwargs(cfg)
+    l32, s32, p32, g32 = oracle.detection_loss_with_grads(data["output"], data["batch"], **kw)
+    l64, s64, p64, g64 = oracle.detection_loss_with_grads(_f64(data["output"]), _f64(data["batch"]), **kw)
+    loss, stats, prob, grads = run_plugin_loss(data["output"], data["batch"], kw)
+    assert abs(float(loss) - float(l64)) <= max(4 * abs(float(l32) - float(l64)), 1e-5 * abs(float(l64)))
+    report = {}
+    for k in ("hm", "wh", "reg"):
+        report[k] = elementwise_violations(grads[k], g32[k], g64[k])
+    print(f"[elementwise {cfg_name} accurate={accurate}] (violations, elements, worst err/bound): {report}")
+    if accurate:
+        for k, (bad, n, worst) in report.items():
+            assert bad == 0, (k, bad, n, worst)
+    else:
+        for k, (bad, n, worst) in report.items():
+            assert bad <= 2e-3 * n and worst <= 64.0, (k, bad, n, worst)
+        assert report["wh"][0] == 0 and report["reg"][0] == 0
+
+
+@pytest.mark.parametrize("cfg_name", ["cfg2", "cfg3"])
+@pytest.mark.parametrize("accurate", [True, False])
+def test_chained_loss_then_decode_vs_oracle_chain(cfg_name, accurate, monkeypatch):
+    """uda/base.py:43,76-82 as a CHAIN on both sides: the oracle decodes ITS OWN probabilities (ATen sigmoid), the
+    GPU decodes the probabilities its loss kernel wrote.  Probabilities differ by <= 4 ulp, so near-ties may swap:
+    every detection the two sides disagree on must be such a near-tie (score within 8 ulp of a neighbour in the
+    other list), the top-K index SET may only differ at near-ties straddling the K-th score, and rotated boxes
+    agree element-wise with the float64 chain."""
+    from cnhead import synthetic, functional as F
+    from losses.centernet import DetectionLoss
+    monkeypatch.setattr(F, "_ACCURATE", accurate)
+    cfg = synthetic.CONFIGS[cfg_name]
+    data = synthetic.make_inputs(cfg, hm_sigma=2.0)
+    out = dev(data["output"])
+    with torch.no_grad():
+        DetectionLoss(**synthetic.loss_kwargs(cfg))(out, dev(data["batch"]))
+        dets, inds = F.decode(out["hm"], out["wh"], out["reg"], K=cfg.K, rotated=cfg.rotated, return_inds=True)
+    dets, inds = dets.cpu(), inds.cpu()
+    p32 = oracle.sigmoid_clamp(data["output"]["hm"])
+    ref, rinds = oracle.decode_stable(p32, data["output"]["wh"], data["output"]["reg"], K=cfg.K, rotated=cfg.rotated)
+    sc = 5 if cfg.rotated else 4
+    ulp = 2.0 ** -24
+    B, K = inds.shape
+    same_pos = (inds == rinds)
+    set_agree, disagreements = 0, 0
+    for b in range(B):
+        gs, rs = set(inds[b].tolist()), set(rinds[b].tolist())
+        set_agree += len(gs & rs)
+        kth = float(ref[b, -1, sc])
+        for i in rs - gs:                                    # the reference kept it, we did not: a tie at the cut
+            score = float(p32[b].flatten()[i])
+            assert abs(score - kth) <= 8 * ulp, (b, i, score, kth)
+        disagreements += len(rs - gs)
+    rate = set_agree / float(B * K)
+    print(f"[chain {cfg_name} accurate={accurate}] top-K index-set agreement {rate:.6f} ({disagreements} of {B * K} differ), "
+          f"same position {float(same_pos.float().mean()):.6f}")
+    assert rate >= 0.999
+    assert (dets[..., sc] - ref[..., sc]).abs().max().item() <= PROB_ATOL          # scores: the K sorted values
+    if same_pos.any():
+        d64, _ = oracle.decode_stable(oracle.sigmoid_clamp(data["output"]["hm"].double()), data["output"]["wh"].double(),
+                                      data["output"]["reg"].double(), K=cfg.K, rotated=cfg.rotated)
+        m = same_pos & (_ := torch.ones_like(same_pos))
+        cols = [c for c in range(dets.shape[-1]) if c != sc]
+        bad, n, worst = elementwise_violations(dets[m][:, cols], ref[m][:, cols], d64[m][:, cols], floor=360.0 * 2.0 ** -23)
+        assert bad == 0, (bad, n, worst)
+
+
+# ---------------------------------------------------------------------------------------------
 # decode
 # ---------------------------------------------------------------------------------------------
-@pytest.fixture(params=["cluster", "cluster_rows16", "cluster_rows32", "two_kernel"])
+@pytest.fixture(params=["cluster", "cluster_rows16", "cluster_rows32", "two_kernel", "stream"])
 def decode_path(request, monkeypatch):
     """csrc/decode.cu has a one-launch cluster path (contiguous, aligned tile rows; in two shapes: 32-row
-    tiles for short walks, 16-row tiles with a deeper ring for long ones) and the persistent tile kernel +
-    merge kernel path (everything else); environment switches force each of them everywhere."""
+    tiles for short walks, 16-row tiles with a deeper ring), the streaming path for long walks (persistent
+    producer/consumer CTAs + a finish kernel, with the cluster kernel as the fallback when a candidate buffer
+    runs over), and the persistent tile kernel + merge kernel path (everything else); environment switches
+    force each of them everywhere."""
     monkeypatch.delenv("CNH_DECODE_TWO_KERNEL", raising=False)
     monkeypatch.delenv("CNH_DECODE_ROWS", raising=False)
+    monkeypatch.setenv("CNH_DECODE_STREAM", "1" if request.param == "stream" else "0")
     if request.param == "two_kernel":
         monkeypatch.setenv("CNH_DECODE_TWO_KERNEL", "1")
     elif request.param.startswith("cluster_rows"):

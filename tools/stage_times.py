@@ -57,6 +57,14 @@ for rep in range(2):
     L.check(lib.cnh_decode(C.byref(d.dec_args[rep]), d.ws_dec.data_ptr(), d.ws_dec.numel(), L.stream_ptr()), "d")
     show(f"decode {name} rep{rep}", 16)
     t = dbg.cpu(); used = t[:, 0] != 0
+    if used.any():
+        u = t[used].float() / 1e3
+        print("  cluster loop, thread 0 per CTA (us) median [min..max]: " + " | ".join(
+            f"{nm} {u[:, c].median():.2f} [{u[:, c].min():.2f}..{u[:, c].max():.2f}]"
+            for nm, c in (("tile wait", 12), ("scan", 13), ("round barrier", 14), ("refill", 15), ("cluster cuts", 8))))
+        lc = t[used][:, 10]
+        print("  local cuts per CTA: median", int((lc >> 40).median()), "time (us) median", float(((lc & ((1 << 40) - 1)).float() / 1e3).median()))
+    continue
     mg = t[:batch]; print("  merge m/got:", mg[:, 12].tolist()[:8], mg[:, 13].tolist()[:8])
     used = used & (torch.arange(t.shape[0]) >= batch)
     print("  per-CTA: tiles", t[used, 15].float().mean().item(), "heavy tiles", t[used, 12].float().mean().item(), "max", t[used, 12].max().item(),
