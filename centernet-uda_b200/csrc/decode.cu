@@ -595,7 +595,7 @@ __device__ void merge_sample(const cnh_decode_args& a, const DecGeo& g, MergeSme
   __syncthreads();
   dbg_stamp(g.dbg, 7);
   select_sort_emit(a, g, s, b, s.keys, (int)s.cnt, kKeyCap,
-                   [&](auto f) { for_each_survivor([&](bool ok, u64 k) { if (ok) f(k); }); });
+                   [&](auto f) { for_each_survivor([&](bool ok, u64 k) { f(ok ? k : 0ull); }); });   // convergent: f may vote
   dbg_stamp(g.dbg, 10);
   // ---- leave the per-sample state zeroed for the next launch ---------------------------------
   __syncthreads();
@@ -1307,6 +1307,8 @@ struct __align__(128) StSmem {
   u64 empty[kStStages];
   unsigned cnt[kStStages];
   unsigned thr[kStStages];
+  unsigned thr_start;                                     // threshold after the first tile (start-up tiles were issued with 0)
+  unsigned go;                                            // set by the producer once thr_start is valid
   int tile_c[kStStages];                                  // class plane of the staged tile, -1 = no more tiles
   int tile_ty[kStStages];
 };
@@ -1336,6 +1338,8 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
       mbar_init(&s.empty[i], kWarps);
       s.cnt[i] = 0u;
     }
+    s.go = 0u;
+    s.thr_start = 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
@@ -1347,85 +1351,101 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
     u64* const slice = g.slices + ((long long)b * g.G + j) * kSliceCap;
     unsigned local_cnt = 0, thr = 0;
     bool overflow = false;
-    // threshold refresh, pipelined over the producer's iterations: 0 idle -> 1 super-bin counts in flight ->
-    // 2 the fine bins of the K-th key's super bin in flight -> 0
-    int pending = 0, sb_sel = 0;
+    // Threshold refresh from the sample's global histogram, pipelined over the producer's iterations so that no
+    // load is ever waited for: state 0 idle -> 1 super-bin counts in flight -> 2 the fine bins of the K-th key's
+    // super bin in flight -> 0; a load is consumed kAge iterations after it was issued.  (The first refresh, right
+    // after the first tile, is waited for: see below.)
+    constexpr int kAge = 3;
+    int pending = 0, sb_sel = 0, issued_at = 0;
     unsigned h0 = 0, h1 = 0, above_sb = 0;
+    auto super_step = [&]() -> bool {                        // h0/h1 = this lane's two super bins; true: fine loads issued
+      const unsigned mine = h0 + h1;
+      unsigned incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += v;
+      }
+      const unsigned above = incl - mine;                    // keys in the super bins above this lane's pair
+      int sel = -1;
+      unsigned ab = 0;
+      if (above < (unsigned)K && incl >= (unsigned)K) {
+        if (above + h1 >= (unsigned)K) { sel = 2 * lane + 1; ab = above; }
+        else { sel = 2 * lane; ab = above + h1; }
+      }
+      const unsigned who = __ballot_sync(0xffffffffu, sel >= 0);
+      if (who == 0u) return false;                           // fewer than K keys counted so far: no threshold yet
+      const int src = __ffs(who) - 1;
+      sb_sel = __shfl_sync(0xffffffffu, sel, src);
+      above_sb = __shfl_sync(0xffffffffu, ab, src);
+      const uint2 f = __ldcg(reinterpret_cast<const uint2*>(fhist + sb_sel * 64) + lane);
+      h0 = f.x;
+      h1 = f.y;
+      return true;
+    };
+    auto fine_step = [&]() {                                 // h0/h1 = this lane's two fine bins of super bin sb_sel
+      const unsigned mine = h0 + h1;
+      unsigned incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += v;
+      }
+      const unsigned above = above_sb + incl - mine;
+      int sel = -1;
+      if (above < (unsigned)K && above + mine >= (unsigned)K) sel = (above + h1 >= (unsigned)K) ? 2 * lane + 1 : 2 * lane;
+      const unsigned who = __ballot_sync(0xffffffffu, sel >= 0);
+      if (who != 0u) {
+        const int fb = sb_sel * 64 + __shfl_sync(0xffffffffu, sel, __ffs(who) - 1);
+        const unsigned t_new = __float_as_uint((float)fb * (1.0f / (float)kFineBins));
+        if (t_new > thr) thr = t_new;
+      }
+    };
+    auto load_super = [&]() {
+      const uint2 v = __ldcg(reinterpret_cast<const uint2*>(shist) + lane);
+      h0 = v.x;
+      h1 = v.y;
+    };
+    // forward the candidates of stage st to the slice, counting them into the sample's histogram
+    auto flush = [&](int st) {
+      unsigned n = *reinterpret_cast<volatile unsigned*>(&s.cnt[st]);
+      if (n > (unsigned)kStCap) { overflow = true; n = (unsigned)kStCap; }
+      if (local_cnt + n > (unsigned)kSliceCap) { overflow = true; n = (unsigned)kSliceCap - local_cnt; }
+      for (unsigned k = lane; k < n; k += 32) {
+        const u64 key = s.cand[st][k];
+        slice[local_cnt + k] = key;
+        const int bin = fine_bin((unsigned)(key >> 32));
+        red_add_u32(fhist + bin, 1u);
+        red_add_u32(shist + (bin >> 6), 1u);
+      }
+      local_cnt += n;
+      __syncwarp();
+      if (lane == 0) s.cnt[st] = 0u;
+    };
     int c = 0, ty = 0;                                       // cursor of the next tile to issue: t = j + i * G
     { const int t0 = j; c = t0 / g.tiles_y; ty = t0 - c * g.tiles_y; }
     const int dc = g.G / g.tiles_y, dty = g.G - dc * g.tiles_y;
+    // Start-up: the ring is filled with the first kStStages tiles at once, but only the first is scanned without a
+    // threshold.  The consumers then wait (s.go) until this warp has forwarded that tile's peaks and read back the
+    // sample's histogram -- by then it holds the first tile of most CTAs of the sample -- while the other copies
+    // keep landing.  Costs two L2 round trips once; saves every CTA thousands of useless candidates.
     for (int i = 0; i < n_mine + kStStages; ++i) {
       const int st = i % kStStages;
       if (i >= kStStages) {
         // ---- stage st is free once the eight consumer warps have arrived: forward its candidates ----
         mbar_wait(&s.empty[st], (unsigned)(((i / kStStages) - 1) & 1));
-        unsigned n = *reinterpret_cast<volatile unsigned*>(&s.cnt[st]);
-        if (n > (unsigned)kStCap) { overflow = true; n = (unsigned)kStCap; }
-        if (local_cnt + n > (unsigned)kSliceCap) { overflow = true; n = (unsigned)kSliceCap - local_cnt; }
-        for (unsigned k = lane; k < n; k += 32) {
-          const u64 key = s.cand[st][k];
-          slice[local_cnt + k] = key;
-          const int bin = fine_bin((unsigned)(key >> 32));
-          red_add_u32(fhist + bin, 1u);
-          red_add_u32(shist + (bin >> 6), 1u);
-        }
-        local_cnt += n;
-        __syncwarp();
-        if (lane == 0) s.cnt[st] = 0u;
-        // ---- threshold refresh ----
-        if (pending == 1) {
-          // lane owns super bins 2*lane, 2*lane+1; suffix sums from the top
-          const unsigned mine = h0 + h1;
-          unsigned incl = mine;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
-            if (lane + o < 32) incl += v;
-          }
-          const unsigned above = incl - mine;                // keys in super bins above this lane's pair
-          int sel = -1;
-          unsigned ab = 0;
-          if (above < (unsigned)K && incl >= (unsigned)K) {
-            if (above + h1 >= (unsigned)K) { sel = 2 * lane + 1; ab = above; }
-            else { sel = 2 * lane; ab = above + h1; }
-          }
-          const unsigned who = __ballot_sync(0xffffffffu, sel >= 0);
-          if (who != 0u) {
-            const int src = __ffs(who) - 1;
-            sb_sel = __shfl_sync(0xffffffffu, sel, src);
-            above_sb = __shfl_sync(0xffffffffu, ab, src);
-            const uint2 f = __ldcg(reinterpret_cast<const uint2*>(fhist + sb_sel * 64) + lane);
-            h0 = f.x;
-            h1 = f.y;
-            pending = 2;
-          } else {
-            pending = 0;                                     // fewer than K keys counted so far: no threshold yet
-          }
-        } else if (pending == 2) {
-          // lane owns fine bins sb_sel*64 + 2*lane, +1; the K-th key's bin: suffix sums from the top, offset above_sb
-          const unsigned mine = h0 + h1;
-          unsigned incl = mine;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
-            if (lane + o < 32) incl += v;
-          }
-          const unsigned above = above_sb + incl - mine;
-          int sel = -1;
-          if (above < (unsigned)K && above + mine >= (unsigned)K) sel = (above + h1 >= (unsigned)K) ? 2 * lane + 1 : 2 * lane;
-          const unsigned who = __ballot_sync(0xffffffffu, sel >= 0);
-          if (who != 0u) {
-            const int fb = sb_sel * 64 + __shfl_sync(0xffffffffu, sel, __ffs(who) - 1);
-            const unsigned t_new = __float_as_uint((float)fb * (1.0f / (float)kFineBins));
-            if (t_new > thr) thr = t_new;
-          }
+        flush(st);
+        if (pending == 1 && i - issued_at >= kAge) {
+          pending = super_step() ? 2 : 0;
+          issued_at = i;
+        } else if (pending == 2 && i - issued_at >= kAge) {
+          fine_step();
           pending = 0;
         }
         if (pending == 0 && i < n_mine) {
-          const uint2 v = __ldcg(reinterpret_cast<const uint2*>(shist) + lane);
-          h0 = v.x;
-          h1 = v.y;
+          load_super();
           pending = 1;
+          issued_at = i;
         }
       }
       if (i < n_mine) {
@@ -1457,6 +1477,20 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
           mbar_arrive(&s.full[st]);
         }
       }
+      if (n_mine > 0 && i == min(kStStages - 1, n_mine)) {
+        // ---- every start-up copy is on its way: the first threshold (n_mine >= 1: G <= tiles per sample) ----
+        mbar_wait(&s.empty[0], 0u);                          // tile 0 scanned
+        flush(0);
+        __threadfence();
+        load_super();
+        if (super_step()) fine_step();
+        if (lane == 0) {
+          s.thr_start = thr;
+          __threadfence_block();
+          *reinterpret_cast<volatile unsigned*>(&s.go) = 1u;
+        }
+        __syncwarp();
+      }
     }
     if (lane == 0) {
       g.cta_cnt[(long long)b * g.G + j] = local_cnt;
@@ -1476,8 +1510,13 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
     mbar_wait(&s.full[st], (unsigned)((i / kStStages) & 1));    // acquires the tile's meta data
     const int c = s.tile_c[st];
     if (c < 0) break;
+    if (i == 1) {                                            // start-up: wait for the threshold of the first tiles
+      while (*reinterpret_cast<volatile unsigned*>(&s.go) == 0u) __nanosleep(64);
+      __syncwarp();
+    }
     const int ty = s.tile_ty[st];
-    const unsigned thr = s.thr[st];
+    unsigned thr = s.thr[st];
+    if (i >= 1 && i < kStStages) thr = max(thr, *reinterpret_cast<volatile unsigned*>(&s.thr_start));
     scan_rows_group<kStRows / kWarps>(s.cand[st], &s.cnt[st], (unsigned)kStCap, ring + (size_t)st * kStTileFloats, W,
                                       colmask, last_lane, thr,
                                       (unsigned)c * (unsigned)g.HW + (unsigned)(ty * kStRows) * (unsigned)W, warp);
@@ -1548,14 +1587,26 @@ decode_finish_kernel(const cnh_decode_args a, const DecGeo g) {
     const unsigned thr_final = s.sh_thr;                     // 0: fewer than K peaks in the sample, keep everything
     dbg_stamp(g.dbg, 6);
     // ---- survivors of every slice -> shared memory keys + packed fine histogram ----
+    // (slices are 16-byte aligned; two keys per load, four loads in flight per thread; block-uniform trip counts)
     auto for_each_survivor = [&](auto f) {
       for (int jj = 0; jj < g.G; ++jj) {
         const unsigned nc = __ldcg(cta_cnt + jj);
-        const u64* cand = slices + (long long)jj * kSliceCap;
-        for (unsigned e0 = 0; e0 < nc; e0 += kThreads) {     // block-uniform trip count
-          const unsigned e = e0 + tid;
-          const u64 k = (e < nc) ? __ldcg(cand + e) : 0ull;
-          f(e < nc && (unsigned)(k >> 32) >= thr_final, k);
+        const ulonglong2* cand = reinterpret_cast<const ulonglong2*>(slices + (long long)jj * kSliceCap);
+        const unsigned np = (nc + 1u) >> 1;                  // pairs
+        for (unsigned e0 = 0; e0 < np; e0 += 4 * kThreads) {
+          ulonglong2 k[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const unsigned e = e0 + q * kThreads + tid;
+            k[q] = (e < np) ? __ldcg(cand + e) : make_ulonglong2(0ull, 0ull);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (e0 + q * kThreads >= np) break;              // block-uniform
+            const unsigned e = e0 + q * kThreads + tid;
+            f(2 * e < nc && (unsigned)(k[q].x >> 32) >= thr_final, k[q].x);
+            f(2 * e + 1 < nc && (unsigned)(k[q].y >> 32) >= thr_final, k[q].y);
+          }
         }
       }
     };
@@ -1566,7 +1617,7 @@ decode_finish_kernel(const cnh_decode_args a, const DecGeo g) {
     __syncthreads();
     dbg_stamp(g.dbg, 7);
     select_sort_emit(a, g, s, b, s.keys, (int)s.cnt, kKeyCap,
-                     [&](auto f) { for_each_survivor([&](bool ok, u64 k) { if (ok) f(k); }); });
+                     [&](auto f) { for_each_survivor([&](bool ok, u64 k) { f(ok ? k : 0ull); }); });   // convergent: f may vote
     dbg_stamp(g.dbg, 10);
   }
   // ---- leave the sample's global state zeroed for the next launch (the overflow flag: the cluster kernel) ----
@@ -1623,7 +1674,7 @@ static size_t cand_keys_per_sample(const cnh_decode_args* a) {
   return tiles16 * (size_t)(a->K + kSlack);
 }
 
-static DecGeo make_geo(const cnh_decode_args* a, void* ws, int rows) {
+static DecGeo make_geo(const cnh_decode_args* a, void* ws, int rows, int stream_ctas_per_sm = 2) {
   DecGeo g;
   g.rows = rows;
   g.HW = a->H * a->W;
@@ -1645,7 +1696,7 @@ static DecGeo make_geo(const cnh_decode_args* a, void* ws, int rows) {
   g.cand = reinterpret_cast<u64*>(p);
   // streaming path: G CTAs per sample (two CTAs per SM over the batch, at most one per 32-row tile)
   const int tiles32 = a->C * ((a->H + kStRows - 1) / kStRows);
-  int G = (2 * sm_count()) / a->B;
+  int G = (stream_ctas_per_sm * sm_count()) / a->B;        // (the workspace is sized for two CTAs per SM)
   if (G > tiles32) G = tiles32;
   if (G < 1) G = 1;
   g.G = G;
@@ -1789,18 +1840,22 @@ static int launch_cluster(const cnh_decode_args* a, void* workspace, int dev, cu
 // carry the programmatic-stream-serialisation attribute: each starts with griddepcontrol.wait.
 static int launch_stream(const cnh_decode_args* a, void* workspace, int dev, cudaStream_t st) {
   if (!cluster_attrs(dev)) return kClusterUnavailable;
-  DecGeo g = make_geo(a, workspace, kStRows);
-  const int cs = pick_cluster_size(a->B, g.tiles_per_sample, dev);
-  if (cs < 1) return kClusterUnavailable;
-  static bool attr_set[64] = {false};
-  if (!attr_set[dev]) {
+  static int occ[64] = {0};                                 // resident stream CTAs per SM (0 = not set up yet)
+  if (dev < 0 || dev >= 64) return kClusterUnavailable;
+  if (occ[dev] == 0) {
+    int n = 0;
     if (cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)) != cudaSuccess) {
+        cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_stream_kernel, kStThreads, kStSmemBytes) != cudaSuccess || n < 1) {
       cudaGetLastError();
       return kClusterUnavailable;
     }
-    attr_set[dev] = true;
+    occ[dev] = n > 2 ? 2 : n;
   }
+  DecGeo g = make_geo(a, workspace, kStRows, occ[dev]);
+  const int cs = pick_cluster_size(a->B, g.tiles_per_sample, dev);
+  if (cs < 1) return kClusterUnavailable;
   static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1844,6 +1899,13 @@ extern "C" int cnh_debug_decode_cluster(const cnh_decode_args* a) {
   DecGeo g = make_geo(a, nullptr, 32);
   const int cs = pick_cluster_size(a->B, g.tiles_per_sample, dev);
   return (cs < 0 ? 0 : cs) * 1000 + active_clusters(dev, 8);
+}
+
+// not part of the public ABI (tools/): co-resident clusters of `cs` CTAs of the decode kernel on the current device
+extern "C" int cnh_debug_active_clusters(int cs) {
+  int dev = 0;
+  if (cs < 1 || cs > 8 || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !cluster_attrs(dev)) return -1;
+  return active_clusters(dev, cs);
 }
 
 extern "C" size_t cnh_decode_workspace_bytes(const cnh_decode_args* a) {

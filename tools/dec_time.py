@@ -18,7 +18,7 @@ peak, _ = bench.hbm_peak()
 lib = L.lib()
 lib.cnh_debug_active_clusters.argtypes = [C.c_int]
 if os.environ.get("CNH_DECODE_CS") is None:
-    print("co-resident clusters per size:", {cs: lib.cnh_debug_active_clusters(cs) for cs in range(1, 17)})
+    print("co-resident clusters per size:", {cs: lib.cnh_debug_active_clusters(cs) for cs in range(1, 9)})
 out = {}
 for name in sys.argv[1:] or ["cfg2", "cfg5"]:
     cfg = synthetic.CONFIGS[name]
