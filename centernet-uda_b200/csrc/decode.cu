@@ -1201,7 +1201,9 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   dbg_stamp(g.dbg, 7);
   cluster.sync();                                           // release/acquire: the inbox is complete
   if (rank != 0) return;
-  if (g.only_overflow && tid == 0) g.state[b].overflow = 0u;
+  // redone here: the finish kernel, if it runs behind this launch (only_overflow == 1), must still skip the sample
+  // and clears the word itself
+  if (g.only_overflow && tid == 0) g.state[b].overflow = g.only_overflow == 1 ? 2u : 0u;
   dbg_stamp(g.dbg, 3);
 
   // ---- leader: final selection (all warps) + sort + gather (warps 0-7) -------------------------------------
@@ -1482,6 +1484,7 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
         mbar_wait(&s.empty[0], 0u);                          // tile 0 scanned
         flush(0);
         __threadfence();
+        __nanosleep(600);                                    // the other CTAs of the sample are at the same point: let their REDs land
         load_super();
         if (super_step()) fine_step();
         if (lane == 0) {
@@ -1491,6 +1494,23 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
         }
         __syncwarp();
       }
+    }
+    // ---- the slice once more against the latest threshold: most of what it holds is the first tile, scanned
+    // without one; what the finish kernel has to read shrinks from thousands of keys per CTA to a few dozen ----
+    if (!overflow && local_cnt > 0u) {
+      __threadfence();
+      load_super();
+      if (super_step()) fine_step();
+      unsigned kept = 0;
+      for (unsigned k0 = 0; k0 < local_cnt; k0 += 32) {      // in place: a chunk is read before anything at or below it is written
+        const unsigned k = k0 + lane;
+        const u64 key = k < local_cnt ? __ldcg(slice + k) : 0ull;
+        const bool keep = k < local_cnt && (unsigned)(key >> 32) >= thr;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) slice[kept + __popc(bal & ((1u << lane) - 1u))] = key;
+        kept += __popc(bal);
+      }
+      local_cnt = kept;
     }
     if (lane == 0) {
       g.cta_cnt[(long long)b * g.G + j] = local_cnt;
@@ -1545,7 +1565,10 @@ decode_finish_kernel(const cnh_decode_args a, const DecGeo g) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");        // PDL: the stream kernel's writes are visible from here
   dbg_stamp(g.dbg, 5);
-  const bool skip = __ldcg(&g.state[b].overflow) != 0u;    // the cluster kernel redoes this sample
+  const unsigned ovf = __ldcg(&g.state[b].overflow);       // 1: the cluster kernel will redo this sample, 2: it has
+  const bool skip = ovf != 0u;
+  unsigned* const n_slice = reinterpret_cast<unsigned*>(s.stage);           // [G] keys per slice (`stage` is free until the sort)
+  for (int q = tid; q < g.G; q += kThreads) n_slice[q] = __ldcg(cta_cnt + q);
   __syncthreads();
   if (!skip) {
     // ---- the K-th key's fine bin (warp 0; same two-level walk as the stream kernel's producers) ----
@@ -1587,23 +1610,24 @@ decode_finish_kernel(const cnh_decode_args a, const DecGeo g) {
     const unsigned thr_final = s.sh_thr;                     // 0: fewer than K peaks in the sample, keep everything
     dbg_stamp(g.dbg, 6);
     // ---- survivors of every slice -> shared memory keys + packed fine histogram ----
-    // (slices are 16-byte aligned; two keys per load, four loads in flight per thread; block-uniform trip counts)
+    // Slices are dealt to the warps (f may vote: warp-uniform trip counts); two keys per 16-byte load, four loads in
+    // flight per lane.  The slice sizes were read in one go (n_slice, shared memory).
     auto for_each_survivor = [&](auto f) {
-      for (int jj = 0; jj < g.G; ++jj) {
-        const unsigned nc = __ldcg(cta_cnt + jj);
+      for (int jj = tid >> 5; jj < g.G; jj += kWarps) {
+        const unsigned nc = n_slice[jj];
         const ulonglong2* cand = reinterpret_cast<const ulonglong2*>(slices + (long long)jj * kSliceCap);
         const unsigned np = (nc + 1u) >> 1;                  // pairs
-        for (unsigned e0 = 0; e0 < np; e0 += 4 * kThreads) {
+        for (unsigned e0 = 0; e0 < np; e0 += 4 * 32) {
           ulonglong2 k[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const unsigned e = e0 + q * kThreads + tid;
+            const unsigned e = e0 + q * 32 + lane;
             k[q] = (e < np) ? __ldcg(cand + e) : make_ulonglong2(0ull, 0ull);
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (e0 + q * kThreads >= np) break;              // block-uniform
-            const unsigned e = e0 + q * kThreads + tid;
+            if (e0 + q * 32 >= np) break;                    // warp-uniform
+            const unsigned e = e0 + q * 32 + lane;
             f(2 * e < nc && (unsigned)(k[q].x >> 32) >= thr_final, k[q].x);
             f(2 * e + 1 < nc && (unsigned)(k[q].y >> 32) >= thr_final, k[q].y);
           }
@@ -1620,8 +1644,9 @@ decode_finish_kernel(const cnh_decode_args a, const DecGeo g) {
                      [&](auto f) { for_each_survivor([&](bool ok, u64 k) { f(ok ? k : 0ull); }); });   // convergent: f may vote
     dbg_stamp(g.dbg, 10);
   }
-  // ---- leave the sample's global state zeroed for the next launch (the overflow flag: the cluster kernel) ----
+  // ---- leave the sample's global state zeroed for the next launch ----
   __syncthreads();
+  if (tid == 0 && ovf == 2u) g.state[b].overflow = 0u;
   for (int q = tid; q < kFineBins; q += kThreads) fhist[q] = 0u;
   if (tid < kSuperBins) shist[tid] = 0u;
   for (int q = tid; q < g.G; q += kThreads) cta_cnt[q] = 0u;
@@ -1869,13 +1894,24 @@ static int launch_stream(const cnh_decode_args* a, void* workspace, int dev, cud
   lc.blockDim = dim3(kStThreads);
   lc.dynamicSmemBytes = kStSmemBytes;
   CNH_CUDA(cudaLaunchKernelEx(&lc, decode_stream_kernel, *a, g));
+  // the fallback sits BETWEEN the two (it exits at once unless a flag is up, its launch hides under the stream
+  // kernel's tail): behind the finish kernel its launch and drain would end the step 4 us later (measured)
+  static const bool fallback_last = getenv("CNH_DECODE_FALLBACK_LAST") != nullptr;
+  if (!fallback_last) {
+    const int rc = launch_cluster_rows<32>(a, g, cs, st, 1);
+    CNH_REQUIRE(rc != kClusterUnavailable, CNH_E_UNSUPPORTED, "decode: the cluster launch of the streaming path's fallback was refused");
+    if (rc != CNH_OK) return rc;
+  }
   lc.gridDim = dim3((unsigned)a->B);
   lc.blockDim = dim3(kThreads);
   lc.dynamicSmemBytes = sizeof(MergeSmem);
   CNH_CUDA(cudaLaunchKernelEx(&lc, decode_finish_kernel, *a, g));
-  const int rc = launch_cluster_rows<32>(a, g, cs, st, 1);
-  CNH_REQUIRE(rc != kClusterUnavailable, CNH_E_UNSUPPORTED, "decode: the cluster launch of the streaming path's fallback was refused");
-  return rc;
+  if (fallback_last) {
+    const int rc = launch_cluster_rows<32>(a, g, cs, st, 2);
+    CNH_REQUIRE(rc != kClusterUnavailable, CNH_E_UNSUPPORTED, "decode: the cluster launch of the streaming path's fallback was refused");
+    return rc;
+  }
+  return CNH_OK;
 }
 
 static bool want_stream(const cnh_decode_args* a) {
