@@ -1497,18 +1497,35 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
     }
     // ---- the slice once more against the latest threshold: most of what it holds is the first tile, scanned
     // without one; what the finish kernel has to read shrinks from thousands of keys per CTA to a few dozen ----
+    // (in place, eight 32-key chunks per batch: a batch is in registers before anything at or below it is written.
+    // The survivors' reg / wh cache lines are started towards L2: the finish kernel's gather then hits L2.)
     if (!overflow && local_cnt > 0u) {
-      __threadfence();
-      load_super();
-      if (super_step()) fine_step();
+      if (pending == 2) fine_step();                         // a refresh that is still in flight
       unsigned kept = 0;
-      for (unsigned k0 = 0; k0 < local_cnt; k0 += 32) {      // in place: a chunk is read before anything at or below it is written
-        const unsigned k = k0 + lane;
-        const u64 key = k < local_cnt ? __ldcg(slice + k) : 0ull;
-        const bool keep = k < local_cnt && (unsigned)(key >> 32) >= thr;
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) slice[kept + __popc(bal & ((1u << lane) - 1u))] = key;
-        kept += __popc(bal);
+      constexpr int kBatch = 8;
+      for (unsigned k0 = 0; k0 < local_cnt; k0 += 32 * kBatch) {
+        u64 key[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+          const unsigned k = k0 + q * 32 + lane;
+          key[q] = k < local_cnt ? __ldcg(slice + k) : 0ull;
+        }
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+          const bool keep = (unsigned)(key[q] >> 32) >= thr && key[q] != 0ull;
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (keep) {
+            slice[kept + __popc(bal & ((1u << lane) - 1u))] = key[q];
+            const unsigned pix = (0xffffffffu - (unsigned)(key[q] & 0xffffffffu)) % (unsigned)g.HW;
+            if (a.reg) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.reg + ((long long)b * 2 + 0) * g.HW + pix));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.reg + ((long long)b * 2 + 1) * g.HW + pix));
+            }
+            for (int d = 0; d < (a.rotated ? 3 : 2); ++d)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.wh + ((long long)b * a.D + d) * g.HW + pix));
+          }
+          kept += __popc(bal);
+        }
       }
       local_cnt = kept;
     }
@@ -1571,43 +1588,9 @@ decode_finish_kernel(const cnh_decode_args a, const DecGeo g) {
   for (int q = tid; q < g.G; q += kThreads) n_slice[q] = __ldcg(cta_cnt + q);
   __syncthreads();
   if (!skip) {
-    // ---- the K-th key's fine bin (warp 0; same two-level walk as the stream kernel's producers) ----
-    if (tid < 32) {
-      const uint2 v = __ldcg(reinterpret_cast<const uint2*>(shist) + lane);
-      unsigned mine = v.x + v.y, incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned u = __shfl_down_sync(0xffffffffu, incl, o);
-        if (lane + o < 32) incl += u;
-      }
-      unsigned above = incl - mine;
-      int sel = -1;
-      unsigned ab = 0;
-      if (above < (unsigned)K && incl >= (unsigned)K) {
-        if (above + v.y >= (unsigned)K) { sel = 2 * lane + 1; ab = above; }
-        else { sel = 2 * lane; ab = above + v.y; }
-      }
-      const unsigned who = __ballot_sync(0xffffffffu, sel >= 0);
-      if (who != 0u) {
-        const int src = __ffs(who) - 1;
-        const int sb = __shfl_sync(0xffffffffu, sel, src);
-        const unsigned above_sb = __shfl_sync(0xffffffffu, ab, src);
-        const uint2 f = __ldcg(reinterpret_cast<const uint2*>(fhist + sb * 64) + lane);
-        mine = f.x + f.y;
-        incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const unsigned u = __shfl_down_sync(0xffffffffu, incl, o);
-          if (lane + o < 32) incl += u;
-        }
-        above = above_sb + incl - mine;
-        if (above < (unsigned)K && above + mine >= (unsigned)K)
-          s.sh_thr = __float_as_uint((float)(sb * 64 + ((above + f.y >= (unsigned)K) ? 2 * lane + 1 : 2 * lane)) *
-                                     (1.0f / (float)kFineBins));
-      }
-    }
-    __syncthreads();
-    const unsigned thr_final = s.sh_thr;                     // 0: fewer than K peaks in the sample, keep everything
+    // (no threshold walk here: the producers re-pruned their slices against the latest threshold on their way out;
+    // what is left -- the top K plus a few hundred keys -- is cut by select_sort_emit's local histogram)
+    const unsigned thr_final = 0u;
     dbg_stamp(g.dbg, 6);
     // ---- survivors of every slice -> shared memory keys + packed fine histogram ----
     // Slices are dealt to the warps (f may vote: warp-uniform trip counts); two keys per 16-byte load, four loads in
