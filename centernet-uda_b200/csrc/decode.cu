@@ -32,6 +32,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "cand.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -49,7 +50,6 @@ constexpr int kBoxWMax = kCols + 2 * kPadL;
 __host__ __device__ constexpr int tile_floats(int rows) { return ((rows + 2) * kBoxWMax + 31) / 32 * 32; }   // 128-byte multiples
 constexpr int kMergeKeyCap = 4096;        // survivors the merge kernel can hold in shared memory
 constexpr int kMaxK = 1024;
-constexpr int kFineBins = 4096;           // local histogram: bin = min(4095, int(score * 4096))
 constexpr int kCoarseBins = 1024;         // per-sample global histogram: fine bin >> 2
 constexpr int kSlack = 64;                // a tile forwards at most K + kSlack keys
 constexpr int kStageCap = kMaxK + kSlack; // staging buffer (keys) per CTA
@@ -57,8 +57,7 @@ constexpr int kStageCap = kMaxK + kSlack; // staging buffer (keys) per CTA
 struct SampleState {                      // zero between launches
   unsigned cand_cnt;
   unsigned thr_bits;
-  unsigned overflow;                      // streaming path: a candidate buffer ran over -> the cluster kernel redoes the sample
-  unsigned pad;
+  unsigned pad[2];
 };
 
 struct DecGeo {
@@ -68,16 +67,13 @@ struct DecGeo {
   unsigned* ghist;                        // [B][kCoarseBins]           zero between launches
   u64* cand;                              // [B][tiles_per_sample * slot]  dense per-sample lists
   long long* dbg;
-  // streaming path (decode_stream_kernel + decode_finish_kernel)
-  int G;                                  // CTAs per sample
+  // candidate lists (cand.cuh): filled by decode_stream_kernel or by the detection-loss kernels, consumed by
+  // decode_finish_kernel
+  CandGeo cl;
   int only_overflow;                      // cluster kernel launched as the fallback: samples without the flag exit at once
-  unsigned* shist;                        // [B][kSuperBins]  keys per 64 fine bins       zero between launches
-  unsigned* fhist;                        // [B][kFineBins]   keys per fine bin           zero between launches
-  unsigned* cta_cnt;                      // [B][G]           keys in every CTA's slice   zero between launches
-  u64* slices;                            // [B][G][kSliceCap] candidate keys, one private slice per CTA
+  int verify_rows;                        // finish: candidates of the first / last row of every `verify_rows`-row tile were
+                                          // tested without the row beyond the tile (0: every candidate is a verified peak)
 };
-constexpr int kSuperBins = 64;            // kFineBins / 64
-constexpr int kSliceCap = 4096;           // keys a CTA of the streaming path may forward
 
 constexpr int kMaxStages = 8;
 template <int KEYS>
@@ -124,10 +120,6 @@ __device__ __forceinline__ unsigned block_suffix_excl(unsigned v, unsigned* warp
   return higher + (incl - v);
 }
 
-__device__ __forceinline__ int fine_bin(unsigned score_bits) {
-  const int b = (int)(__uint_as_float(score_bits) * (float)kFineBins);   // exact: power-of-two scale
-  return b < kFineBins - 1 ? b : kFineBins - 1;
-}
 __device__ __forceinline__ void hist_add(unsigned* hist, int bin) {
   atomicAdd(&hist[bin >> 1], (bin & 1) ? 0x10000u : 1u);
 }
@@ -1027,7 +1019,7 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   asm volatile("griddepcontrol.wait;" ::: "memory");        // PDL: the producer of `heat` has completed
   // launched behind the streaming path as its fallback: only samples whose overflow flag is up are redone (every CTA
   // of the cluster reads the same word, before anyone can have cleared it: the leader does so after the last barrier)
-  if (g.only_overflow && __ldcg(&g.state[b].overflow) == 0u) return;
+  if (g.only_overflow && __ldcg(&g.cl.state[b].overflow) == 0u) return;
   if (tid == 0) {
     s.cnt = 0;
     s.cnt2 = 0;
@@ -1203,7 +1195,7 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   if (rank != 0) return;
   // redone here: the finish kernel, if it runs behind this launch (only_overflow == 1), must still skip the sample
   // and clears the word itself
-  if (g.only_overflow && tid == 0) g.state[b].overflow = g.only_overflow == 1 ? 2u : 0u;
+  if (g.only_overflow && tid == 0) g.cl.state[b].overflow = g.only_overflow == 1 ? 2u : 0u;
   dbg_stamp(g.dbg, 3);
 
   // ---- leader: final selection (all warps) + sort + gather (warps 0-7) -------------------------------------
@@ -1316,19 +1308,16 @@ struct __align__(128) StSmem {
 };
 constexpr size_t kStSmemBytes = sizeof(StSmem) + (size_t)kStStages * kStTileFloats * sizeof(float);
 
-__device__ __forceinline__ void red_add_u32(unsigned* p, unsigned v) {
-  asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 __global__ void __launch_bounds__(kStThreads, 2)
 decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_constant__ DecGeo g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StSmem& s = *reinterpret_cast<StSmem*>(smem_raw);
   float* const ring = reinterpret_cast<float*>(smem_raw + sizeof(StSmem));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = (int)blockIdx.x / g.G, j = (int)blockIdx.x - b * g.G;
+  const int G = g.cl.G;
+  const int b = (int)blockIdx.x / G, j = (int)blockIdx.x - b * G;
   const int W = a.W, H = a.H, K = a.K;
-  const int n_mine = j < g.tiles_per_sample ? (g.tiles_per_sample - j + g.G - 1) / g.G : 0;
+  const int n_mine = j < g.tiles_per_sample ? (g.tiles_per_sample - j + G - 1) / G : 0;
   const float* const sample = a.heat + (long long)b * a.C * g.HW;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -1348,85 +1337,16 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
 
   if (warp == kWarps) {
     // ================= producer =================
-    unsigned* const shist = g.shist + (long long)b * kSuperBins;
-    unsigned* const fhist = g.fhist + (long long)b * kFineBins;
-    u64* const slice = g.slices + ((long long)b * g.G + j) * kSliceCap;
-    unsigned local_cnt = 0, thr = 0;
-    bool overflow = false;
-    // Threshold refresh from the sample's global histogram, pipelined over the producer's iterations so that no
-    // load is ever waited for: state 0 idle -> 1 super-bin counts in flight -> 2 the fine bins of the K-th key's
-    // super bin in flight -> 0; a load is consumed kAge iterations after it was issued.  (The first refresh, right
-    // after the first tile, is waited for: see below.)
-    constexpr int kAge = 3;
-    int pending = 0, sb_sel = 0, issued_at = 0;
-    unsigned h0 = 0, h1 = 0, above_sb = 0;
-    auto super_step = [&]() -> bool {                        // h0/h1 = this lane's two super bins; true: fine loads issued
-      const unsigned mine = h0 + h1;
-      unsigned incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
-        if (lane + o < 32) incl += v;
-      }
-      const unsigned above = incl - mine;                    // keys in the super bins above this lane's pair
-      int sel = -1;
-      unsigned ab = 0;
-      if (above < (unsigned)K && incl >= (unsigned)K) {
-        if (above + h1 >= (unsigned)K) { sel = 2 * lane + 1; ab = above; }
-        else { sel = 2 * lane; ab = above + h1; }
-      }
-      const unsigned who = __ballot_sync(0xffffffffu, sel >= 0);
-      if (who == 0u) return false;                           // fewer than K keys counted so far: no threshold yet
-      const int src = __ffs(who) - 1;
-      sb_sel = __shfl_sync(0xffffffffu, sel, src);
-      above_sb = __shfl_sync(0xffffffffu, ab, src);
-      const uint2 f = __ldcg(reinterpret_cast<const uint2*>(fhist + sb_sel * 64) + lane);
-      h0 = f.x;
-      h1 = f.y;
-      return true;
-    };
-    auto fine_step = [&]() {                                 // h0/h1 = this lane's two fine bins of super bin sb_sel
-      const unsigned mine = h0 + h1;
-      unsigned incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
-        if (lane + o < 32) incl += v;
-      }
-      const unsigned above = above_sb + incl - mine;
-      int sel = -1;
-      if (above < (unsigned)K && above + mine >= (unsigned)K) sel = (above + h1 >= (unsigned)K) ? 2 * lane + 1 : 2 * lane;
-      const unsigned who = __ballot_sync(0xffffffffu, sel >= 0);
-      if (who != 0u) {
-        const int fb = sb_sel * 64 + __shfl_sync(0xffffffffu, sel, __ffs(who) - 1);
-        const unsigned t_new = __float_as_uint((float)fb * (1.0f / (float)kFineBins));
-        if (t_new > thr) thr = t_new;
-      }
-    };
-    auto load_super = [&]() {
-      const uint2 v = __ldcg(reinterpret_cast<const uint2*>(shist) + lane);
-      h0 = v.x;
-      h1 = v.y;
-    };
-    // forward the candidates of stage st to the slice, counting them into the sample's histogram
+    CandEmitter em;
+    em.init(g.cl, b, j, K);
+    auto every_key = [](u64) { return true; };               // every candidate of this kernel passed the full 3x3 test
     auto flush = [&](int st) {
-      unsigned n = *reinterpret_cast<volatile unsigned*>(&s.cnt[st]);
-      if (n > (unsigned)kStCap) { overflow = true; n = (unsigned)kStCap; }
-      if (local_cnt + n > (unsigned)kSliceCap) { overflow = true; n = (unsigned)kSliceCap - local_cnt; }
-      for (unsigned k = lane; k < n; k += 32) {
-        const u64 key = s.cand[st][k];
-        slice[local_cnt + k] = key;
-        const int bin = fine_bin((unsigned)(key >> 32));
-        red_add_u32(fhist + bin, 1u);
-        red_add_u32(shist + (bin >> 6), 1u);
-      }
-      local_cnt += n;
-      __syncwarp();
+      em.forward(s.cand[st], *reinterpret_cast<volatile unsigned*>(&s.cnt[st]), (unsigned)kStCap, every_key);
       if (lane == 0) s.cnt[st] = 0u;
     };
     int c = 0, ty = 0;                                       // cursor of the next tile to issue: t = j + i * G
     { const int t0 = j; c = t0 / g.tiles_y; ty = t0 - c * g.tiles_y; }
-    const int dc = g.G / g.tiles_y, dty = g.G - dc * g.tiles_y;
+    const int dc = G / g.tiles_y, dty = G - dc * g.tiles_y;
     // Start-up: the ring is filled with the first kStStages tiles at once, but only the first is scanned without a
     // threshold.  The consumers then wait (s.go) until this warp has forwarded that tile's peaks and read back the
     // sample's histogram -- by then it holds the first tile of most CTAs of the sample -- while the other copies
@@ -1437,18 +1357,7 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
         // ---- stage st is free once the eight consumer warps have arrived: forward its candidates ----
         mbar_wait(&s.empty[st], (unsigned)(((i / kStStages) - 1) & 1));
         flush(st);
-        if (pending == 1 && i - issued_at >= kAge) {
-          pending = super_step() ? 2 : 0;
-          issued_at = i;
-        } else if (pending == 2 && i - issued_at >= kAge) {
-          fine_step();
-          pending = 0;
-        }
-        if (pending == 0 && i < n_mine) {
-          load_super();
-          pending = 1;
-          issued_at = i;
-        }
+        em.refresh_step(i, i < n_mine);
       }
       if (i < n_mine) {
         // ---- stage tile (c, ty): rows [y0-1, y0+33) of the plane, contiguous; rows outside the image are zero ----
@@ -1464,7 +1373,7 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
         if (lane == 0) {
           s.tile_c[st] = c;
           s.tile_ty[st] = ty;
-          s.thr[st] = thr;
+          s.thr[st] = em.thr;
           const unsigned bytes = (unsigned)((yhi - ylo) * W) * 4u;
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_expect_tx(&s.full[st], bytes);
@@ -1485,10 +1394,9 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
         flush(0);
         __threadfence();
         __nanosleep(600);                                    // the other CTAs of the sample are at the same point: let their REDs land
-        load_super();
-        if (super_step()) fine_step();
+        em.refresh_blocking();
         if (lane == 0) {
-          s.thr_start = thr;
+          s.thr_start = em.thr;
           __threadfence_block();
           *reinterpret_cast<volatile unsigned*>(&s.go) = 1u;
         }
@@ -1497,41 +1405,19 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
     }
     // ---- the slice once more against the latest threshold: most of what it holds is the first tile, scanned
     // without one; what the finish kernel has to read shrinks from thousands of keys per CTA to a few dozen ----
-    // (in place, eight 32-key chunks per batch: a batch is in registers before anything at or below it is written.
-    // The survivors' reg / wh cache lines are started towards L2: the finish kernel's gather then hits L2.)
-    if (!overflow && local_cnt > 0u) {
-      if (pending == 2) fine_step();                         // a refresh that is still in flight
-      unsigned kept = 0;
-      constexpr int kBatch = 8;
-      for (unsigned k0 = 0; k0 < local_cnt; k0 += 32 * kBatch) {
-        u64 key[kBatch];
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-          const unsigned k = k0 + q * 32 + lane;
-          key[q] = k < local_cnt ? __ldcg(slice + k) : 0ull;
-        }
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-          const bool keep = (unsigned)(key[q] >> 32) >= thr && key[q] != 0ull;
-          const unsigned bal = __ballot_sync(0xffffffffu, keep);
-          if (keep) {
-            slice[kept + __popc(bal & ((1u << lane) - 1u))] = key[q];
-            const unsigned pix = (0xffffffffu - (unsigned)(key[q] & 0xffffffffu)) % (unsigned)g.HW;
-            if (a.reg) {
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.reg + ((long long)b * 2 + 0) * g.HW + pix));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.reg + ((long long)b * 2 + 1) * g.HW + pix));
-            }
-            for (int d = 0; d < (a.rotated ? 3 : 2); ++d)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.wh + ((long long)b * a.D + d) * g.HW + pix));
-          }
-          kept += __popc(bal);
-        }
+    // (the survivors' reg / wh cache lines are started towards L2: the finish kernel's gather then hits L2)
+    em.reprune([&](u64 key) {
+      const unsigned pix = (0xffffffffu - (unsigned)(key & 0xffffffffu)) % (unsigned)g.HW;
+      if (a.reg) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.reg + ((long long)b * 2 + 0) * g.HW + pix));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.reg + ((long long)b * 2 + 1) * g.HW + pix));
       }
-      local_cnt = kept;
-    }
+      for (int d = 0; d < (a.rotated ? 3 : 2); ++d)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.wh + ((long long)b * a.D + d) * g.HW + pix));
+    });
     if (lane == 0) {
-      g.cta_cnt[(long long)b * g.G + j] = local_cnt;
-      if (overflow) g.state[b].overflow = 1u;
+      g.cl.cta_cnt[(long long)b * G + j] = em.local_cnt;
+      if (em.overflow) g.cl.state[b].overflow = 1u;
     }
     dbg_stamp(g.dbg, 2);
     return;
@@ -1573,19 +1459,20 @@ decode_finish_kernel(const cnh_decode_args a, const DecGeo g) {
   constexpr int kKeyCap = MergeSmem::kKeyCap;
   const int tid = threadIdx.x, lane = tid & 31;
   const int b = (int)blockIdx.x, K = a.K;
-  unsigned* const shist = g.shist + (long long)b * kSuperBins;
-  unsigned* const fhist = g.fhist + (long long)b * kFineBins;
-  unsigned* const cta_cnt = g.cta_cnt + (long long)b * g.G;
-  const u64* const slices = g.slices + (long long)b * g.G * kSliceCap;
+  const int G = g.cl.G;
+  unsigned* const shist = g.cl.shist + (long long)b * kSuperBins;
+  unsigned* const fhist = g.cl.fhist + (long long)b * kFineBins;
+  unsigned* const cta_cnt = g.cl.cta_cnt + (long long)b * G;
+  const u64* const slices = g.cl.slices + (long long)b * G * kSliceCap;
   for (int q = 0; q < kFineBins / 2 / kThreads; ++q) s.hist[tid + q * kThreads] = 0u;
   if (tid == 0) { s.cnt = 0; s.cnt2 = 0; s.sh_thr = 0u; }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");        // PDL: the stream kernel's writes are visible from here
   dbg_stamp(g.dbg, 5);
-  const unsigned ovf = __ldcg(&g.state[b].overflow);       // 1: the cluster kernel will redo this sample, 2: it has
+  const unsigned ovf = __ldcg(&g.cl.state[b].overflow);  // 1: the cluster kernel will redo this sample, 2: it has
   const bool skip = ovf != 0u;
   unsigned* const n_slice = reinterpret_cast<unsigned*>(s.stage);           // [G] keys per slice (`stage` is free until the sort)
-  for (int q = tid; q < g.G; q += kThreads) n_slice[q] = __ldcg(cta_cnt + q);
+  for (int q = tid; q < G; q += kThreads) n_slice[q] = __ldcg(cta_cnt + q);
   __syncthreads();
   if (!skip) {
     // (no threshold walk here: the producers re-pruned their slices against the latest threshold on their way out;
@@ -1593,10 +1480,30 @@ decode_finish_kernel(const cnh_decode_args a, const DecGeo g) {
     const unsigned thr_final = 0u;
     dbg_stamp(g.dbg, 6);
     // ---- survivors of every slice -> shared memory keys + packed fine histogram ----
+    // Candidates that came out of a tile scanned WITHOUT its halo rows (the detection-loss kernels emit them from their
+    // own 32-row chunks) were tested against the neighbours inside the tile only: those of a tile's first / last row
+    // are checked here against the three pixels of the row beyond it (read from the heat map: a few dozen keys).
+    auto verified = [&](u64 key) -> bool {
+      if (g.verify_rows == 0 || key == 0ull) return true;
+      const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+      const unsigned cls = flat / (unsigned)g.HW, pix = flat - cls * (unsigned)g.HW;
+      const int y = (int)(pix / (unsigned)a.W), x = (int)(pix - (unsigned)y * (unsigned)a.W);
+      const int r = y % g.verify_rows;
+      int yy = -1;
+      if (r == 0 && y > 0) yy = y - 1;
+      else if (r == g.verify_rows - 1 && y < a.H - 1) yy = y + 1;
+      if (yy < 0) return true;
+      const float score = __uint_as_float((unsigned)(key >> 32));
+      const float* row = a.heat + ((long long)b * a.C + cls) * g.HW + (long long)yy * a.W;
+      float m = __ldcg(row + x);
+      if (x > 0) m = fmaxf(m, __ldcg(row + x - 1));
+      if (x < a.W - 1) m = fmaxf(m, __ldcg(row + x + 1));
+      return m <= score;
+    };
     // Slices are dealt to the warps (f may vote: warp-uniform trip counts); two keys per 16-byte load, four loads in
     // flight per lane.  The slice sizes were read in one go (n_slice, shared memory).
     auto for_each_survivor = [&](auto f) {
-      for (int jj = tid >> 5; jj < g.G; jj += kWarps) {
+      for (int jj = tid >> 5; jj < G; jj += kWarps) {
         const unsigned nc = n_slice[jj];
         const ulonglong2* cand = reinterpret_cast<const ulonglong2*>(slices + (long long)jj * kSliceCap);
         const unsigned np = (nc + 1u) >> 1;                  // pairs
@@ -1611,8 +1518,8 @@ decode_finish_kernel(const cnh_decode_args a, const DecGeo g) {
           for (int q = 0; q < 4; ++q) {
             if (e0 + q * 32 >= np) break;                    // warp-uniform
             const unsigned e = e0 + q * 32 + lane;
-            f(2 * e < nc && (unsigned)(k[q].x >> 32) >= thr_final, k[q].x);
-            f(2 * e + 1 < nc && (unsigned)(k[q].y >> 32) >= thr_final, k[q].y);
+            f(2 * e < nc && (unsigned)(k[q].x >> 32) >= thr_final && verified(k[q].x), k[q].x);
+            f(2 * e + 1 < nc && (unsigned)(k[q].y >> 32) >= thr_final && verified(k[q].y), k[q].y);
           }
         }
       }
@@ -1629,10 +1536,10 @@ decode_finish_kernel(const cnh_decode_args a, const DecGeo g) {
   }
   // ---- leave the sample's global state zeroed for the next launch ----
   __syncthreads();
-  if (tid == 0 && ovf == 2u) g.state[b].overflow = 0u;
+  if (tid == 0 && ovf == 2u) g.cl.state[b].overflow = 0u;
   for (int q = tid; q < kFineBins; q += kThreads) fhist[q] = 0u;
   if (tid < kSuperBins) shist[tid] = 0u;
-  for (int q = tid; q < g.G; q += kThreads) cta_cnt[q] = 0u;
+  for (int q = tid; q < G; q += kThreads) cta_cnt[q] = 0u;
 }
 
 // ---- host ---------------------------------------------------------------------------------------
@@ -1707,25 +1614,17 @@ static DecGeo make_geo(const cnh_decode_args* a, void* ws, int rows, int stream_
   int G = (stream_ctas_per_sm * sm_count()) / a->B;        // (the workspace is sized for two CTAs per SM)
   if (G > tiles32) G = tiles32;
   if (G < 1) G = 1;
-  g.G = G;
   g.only_overflow = 0;
+  g.verify_rows = 0;
   p += up128((size_t)a->B * cand_keys_per_sample(a) * sizeof(u64));
-  g.shist = reinterpret_cast<unsigned*>(p);
-  p += up128((size_t)a->B * kSuperBins * sizeof(unsigned));
-  g.fhist = reinterpret_cast<unsigned*>(p);
-  p += up128((size_t)a->B * kFineBins * sizeof(unsigned));
-  g.cta_cnt = reinterpret_cast<unsigned*>(p);
-  p += up128((size_t)a->B * G * sizeof(unsigned));
-  g.slices = reinterpret_cast<u64*>(p);
+  g.cl = cand_geo(p, a->B, G);
   return g;
 }
 
 static size_t decode_ws_bytes(const cnh_decode_args* a) {
   DecGeo g = make_geo(a, nullptr, 16);
   return up128((size_t)a->B * sizeof(SampleState)) + up128((size_t)a->B * kCoarseBins * sizeof(unsigned)) +
-         up128((size_t)a->B * cand_keys_per_sample(a) * sizeof(u64)) +
-         up128((size_t)a->B * kSuperBins * sizeof(unsigned)) + up128((size_t)a->B * kFineBins * sizeof(unsigned)) +
-         up128((size_t)a->B * g.G * sizeof(unsigned)) + (size_t)a->B * g.G * kSliceCap * sizeof(u64);
+         up128((size_t)a->B * cand_keys_per_sample(a) * sizeof(u64)) + cand_ws_bytes(a->B, g.cl.G);
 }
 
 // environment switches of the tests / tools, read once per process... unless CNH_DECODE_ENV_RELOAD is set (the
@@ -1873,7 +1772,7 @@ static int launch_stream(const cnh_decode_args* a, void* workspace, int dev, cud
   lc.stream = st;
   lc.attrs = attr;
   lc.numAttrs = use_pdl ? 1 : 0;
-  lc.gridDim = dim3((unsigned)a->B * (unsigned)g.G);
+  lc.gridDim = dim3((unsigned)a->B * (unsigned)g.cl.G);
   lc.blockDim = dim3(kStThreads);
   lc.dynamicSmemBytes = kStSmemBytes;
   CNH_CUDA(cudaLaunchKernelEx(&lc, decode_stream_kernel, *a, g));
