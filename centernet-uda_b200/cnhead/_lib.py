@@ -30,13 +30,19 @@ class Head(C.Structure):
                 ("weight", C.c_float), ("angle_weight", C.c_float), ("n_pairs", C.c_int32), ("pairs", C.c_void_p)]
 
 
+class Cand(C.Structure):
+    _fields_ = [("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("K", C.c_int32), ("G", C.c_int32),
+                ("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
 class DetLossArgs(C.Structure):
     _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("M", C.c_int32),
                 ("n_heads", C.c_int32), ("flags", C.c_int32), ("B_global", C.c_int32),
                 ("hm_logits", C.c_void_p), ("hm_gt", C.c_void_p), ("prob", C.c_void_p), ("grad_hm", C.c_void_p),
                 ("ind", C.c_void_p), ("hm_weight", C.c_float), ("_pad", C.c_int32),
                 ("heads", Head * MAX_HEADS),
-                ("scalars", C.c_void_p), ("totals", C.c_void_p), ("norm", C.c_void_p), ("norm_out", C.c_void_p)]
+                ("scalars", C.c_void_p), ("totals", C.c_void_p), ("norm", C.c_void_p), ("norm_out", C.c_void_p),
+                ("cand", C.POINTER(Cand))]
 
 
 MAX_PEERS = 8
@@ -121,6 +127,12 @@ def lib() -> C.CDLL:
         L.cnh_decode_workspace_bytes.argtypes = [C.POINTER(DecodeArgs)]
         L.cnh_decode.restype = C.c_int
         L.cnh_decode.argtypes = [C.POINTER(DecodeArgs), vp, sz, st]
+        L.cnh_cand_workspace_bytes.restype = sz
+        L.cnh_cand_workspace_bytes.argtypes = [i32]
+        L.cnh_cand_state_bytes.restype = sz
+        L.cnh_cand_state_bytes.argtypes = [C.POINTER(Cand)]
+        L.cnh_decode_candidates.restype = C.c_int
+        L.cnh_decode_candidates.argtypes = [C.POINTER(DecodeArgs), C.POINTER(Cand), st]
         L.cnh_raster_targets.restype = C.c_int
         L.cnh_raster_targets.argtypes = [C.POINTER(RasterArgs), st]
         _lib = L

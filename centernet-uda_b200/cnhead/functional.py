@@ -91,12 +91,55 @@ def _check_heads(hm, gt, ind, heads):
             raise RuntimeError(f"cnhead: head mask {tuple(h.mask.shape)} != {want}")
 
 
+class Candidates:
+    """Peak candidates a detection-loss launch emitted for its own probability map (include/cnhead.h: cnh_cand).
+    ``decode`` (below) uses them when it is handed that very map: the heat map is then not read again."""
+
+    _dirty = {}                                         # workspace key -> Candidates whose lists were never decoded
+
+    def __init__(self, K: int, device):
+        self.c = L.Cand()
+        self.K = int(K)
+        nbytes = 0
+        self.ws = None
+        self.key = None
+        self.prob_ptr, self.prob_version, self.stream = None, None, None
+        self.device = device
+
+    def prepare(self, B: int):
+        """workspace of this (device, stream, batch): zeroed once; cleaned again here if its last lists were dropped"""
+        nbytes = L.lib().cnh_cand_workspace_bytes(B)
+        kind = f"cand:{B}"
+        self.ws = L.workspace(kind, nbytes, self.device)
+        self.key = (self.ws.data_ptr(), kind)
+        stale = Candidates._dirty.pop(self.key, None)
+        if stale is not None and stale.c.G > 0:
+            n = L.lib().cnh_cand_state_bytes(C.byref(stale.c))
+            self.ws[:n].zero_()
+        self.c.workspace, self.c.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
+        self.c.K, self.c.G = self.K, 0
+
+    def emitted(self, prob: torch.Tensor):
+        if self.c.G > 0:
+            self.prob_ptr, self.prob_version, self.stream = prob.data_ptr(), prob._version, L.stream_ptr()
+            Candidates._dirty[self.key] = self
+
+    def usable_for(self, heat: torch.Tensor, K: int) -> bool:
+        return (self.c.G > 0 and self.prob_ptr == heat.data_ptr() and self.prob_version == heat._version and
+                K <= self.K and tuple(heat.shape) == (self.c.B, self.c.C, self.c.H, self.c.W) and
+                self.stream == L.stream_ptr() and Candidates._dirty.get(self.key) is self)
+
+    def consumed(self):
+        Candidates._dirty.pop(self.key, None)
+        self.c.G = 0
+
+
 class _DetectionLossFn(torch.autograd.Function):
     """inputs: hm logits, then one map per head.  Outputs: scalars[8], clamped prob, totals[24]."""
 
     @staticmethod
     def forward(ctx, meta, hm, *maps):
-        gt, ind, specs, hm_weight = meta
+        gt, ind, specs, hm_weight, cand = meta
         heads = [HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode, s.elementwise_mask, s.pairs)
                  for m, s in zip(maps, specs)]
         need_grad = any(ctx.needs_input_grad[1:])
@@ -105,9 +148,14 @@ class _DetectionLossFn(torch.autograd.Function):
         scalars = torch.empty(L.SCALARS, dtype=torch.float32, device=hm.device)
         totals = torch.empty(L.TOTALS, dtype=torch.int64, device=hm.device)
         a = fill_detloss_args(hm, gt, ind, heads, hm_weight, prob, grads, scalars, totals)
+        if cand is not None:
+            cand.prepare(hm.shape[0])
+            a.cand = C.pointer(cand.c)
         nbytes = L.lib().cnh_detloss_workspace_bytes(C.byref(a))
         ws = L.workspace("detloss", nbytes, hm.device)
         L.check(L.lib().cnh_detloss_fused(C.byref(a), ws.data_ptr(), ws.numel(), L.stream_ptr()), "detloss_fused")
+        if cand is not None:
+            cand.emitted(prob)
         ctx.grads = grads
         ctx.used = False
         ctx.mark_non_differentiable(prob, totals)
@@ -159,8 +207,10 @@ def _spec_of(h: "HeadSpec") -> "_Spec":
 
 
 def detection_loss(hm: torch.Tensor, gt: torch.Tensor, ind: torch.Tensor, heads: Sequence[HeadSpec],
-                   hm_weight: float = 1.0):
-    """Fused DetectionLoss core.  Returns (scalars[8], prob, totals[24] int64); see include/cnhead.h."""
+                   hm_weight: float = 1.0, decode_K: Optional[int] = None):
+    """Fused DetectionLoss core.  Returns (scalars[8], prob, totals[24] int64); see include/cnhead.h.
+    ``decode_K``: also emit the peak candidates of the probability map for a later ``decode(prob, ..., K <= decode_K)``
+    (large heat maps only; the returned map then carries them as ``prob._cnh_cand``)."""
     hm = L.require(hm, "output['hm']")
     gt = L.require(gt, "batch['hm']")
     ind = L.require(ind, "batch['ind']", torch.int64)
@@ -170,7 +220,11 @@ def detection_loss(hm: torch.Tensor, gt: torch.Tensor, ind: torch.Tensor, heads:
         maps.append(L.require(h.fmap, "head map"))
     _check_heads(hm, gt, ind, [HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode,
                                         s.elementwise_mask, s.pairs) for m, s in zip(maps, specs)])
-    return _DetectionLossFn.apply((gt, ind, specs, float(hm_weight)), hm, *maps)
+    cand = Candidates(decode_K, hm.device) if decode_K else None
+    scalars, prob, totals = _DetectionLossFn.apply((gt, ind, specs, float(hm_weight), cand), hm, *maps)
+    if cand is not None and cand.c.G > 0:
+        prob._cnh_cand = cand
+    return scalars, prob, totals
 
 
 # ----------------------------------------------------------------------------------------------
@@ -271,6 +325,7 @@ def decode(heat, wh, reg=None, kps=None, K=100, rotated=False, apply_sigmoid=Fal
     ``return_inds`` (flat peak indices) and ``score_threshold`` -> an extra int32 ``[B]`` tensor with the number
     of rows per sample whose score reaches it (rows are sorted, so they are the first ones;
     evaluation/coco.py:266-267).  Returns dets[, kps][, inds][, counts]."""
+    heat_in = heat
     heat = L.require(heat.detach(), "heat")
     wh = L.require(wh.detach(), "wh")
     reg = L.require(reg.detach(), "reg") if reg is not None else None
@@ -298,11 +353,17 @@ def decode(heat, wh, reg=None, kps=None, K=100, rotated=False, apply_sigmoid=Fal
     if score_threshold is not None:
         counts = torch.empty(B, dtype=torch.int32, device=heat.device)
         a.counts_out, a.score_threshold = counts.data_ptr(), float(score_threshold)
-    nbytes = L.lib().cnh_decode_workspace_bytes(C.byref(a))
-    if nbytes == 0:
-        L.check(-2, "decode")
-    ws = L.workspace(f"decode:{B}x{Cc}x{H}x{W}:{K}", nbytes, heat.device)   # layout depends on the dims
-    L.check(L.lib().cnh_decode(C.byref(a), ws.data_ptr(), ws.numel(), L.stream_ptr()), "decode")
+    cand = getattr(heat_in, "_cnh_cand", None)
+    if cand is not None and not apply_sigmoid and cand.usable_for(heat, K):
+        # the loss launch that wrote this very map left its peak candidates: the heat map is not read again
+        L.check(L.lib().cnh_decode_candidates(C.byref(a), C.byref(cand.c), L.stream_ptr()), "decode_candidates")
+        cand.consumed()
+    else:
+        nbytes = L.lib().cnh_decode_workspace_bytes(C.byref(a))
+        if nbytes == 0:
+            L.check(-2, "decode")
+        ws = L.workspace(f"decode:{B}x{Cc}x{H}x{W}:{K}", nbytes, heat.device)   # layout depends on the dims
+        L.check(L.lib().cnh_decode(C.byref(a), ws.data_ptr(), ws.numel(), L.stream_ptr()), "decode")
     res = (dets,)
     if kps is not None:
         res += (kout,)

@@ -57,6 +57,75 @@ __device__ __forceinline__ void red_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Scan of a HALO-LESS candidate tile: 32 rows x 128 columns of clamped probabilities in shared memory (what a
+// detection-loss chunk leaves of one class plane), four rows per warp (warp w of 8: rows 4w..4w+3), lane owns
+// columns [4*lane, 4*lane+4).  The rows above row 0 and below row 31 belong to other chunks and are taken as 0: a
+// pixel of those two rows is tested against its five neighbours inside the tile only (the finish kernel checks the
+// other three, see `verify_rows`).  Peaks >= thr are appended to keys[*key_cnt ...] (bounded by cap; the counter may
+// run past it).  Key = (score bits << 32) | ~(flat index): descending key order = score descending, ties to the lower
+// index.
+__device__ __forceinline__ void scan_chunk_rows(u64* keys, unsigned* key_cnt, unsigned cap, const float* tile, unsigned thr,
+                                                unsigned flat_tile0, int warp) {
+  constexpr int W = 128, RW = 4;
+  const int lane = threadIdx.x & 31;
+  const int r0 = RW * warp;
+  const float* base_row = tile + r0 * W + 4 * lane;                               // the warp's first row
+  const float thr_eff = fmaxf(__uint_as_float(thr), __uint_as_float(1u));      // >= thr and > 0
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 up = r0 > 0 ? *reinterpret_cast<const float4*>(base_row - W) : zero;
+  float4 mid = *reinterpret_cast<const float4*>(base_row);
+  unsigned flags = 0;                                                             // bit 4*rr + e
+#pragma unroll
+  for (int rr = 0; rr < RW; ++rr) {
+    const float4 dn = (r0 + rr + 1 < kCandRows) ? *reinterpret_cast<const float4*>(base_row + (rr + 1) * W) : zero;
+    const bool any = fmaxf(fmaxf(mid.x, mid.y), fmaxf(mid.z, mid.w)) >= thr_eff;
+    if (__ballot_sync(0xffffffffu, any) != 0u) {
+      const unsigned pass = (mid.x >= thr_eff ? 1u : 0u) | (mid.y >= thr_eff ? 2u : 0u) | (mid.z >= thr_eff ? 4u : 0u) |
+                            (mid.w >= thr_eff ? 8u : 0u);
+      const float v0 = fmaxf(fmaxf(up.x, mid.x), dn.x), v1 = fmaxf(fmaxf(up.y, mid.y), dn.y);
+      const float v2 = fmaxf(fmaxf(up.z, mid.z), dn.z), v3 = fmaxf(fmaxf(up.w, mid.w), dn.w);
+      float left = __shfl_up_sync(0xffffffffu, v3, 1), right = __shfl_down_sync(0xffffffffu, v0, 1);
+      if (lane == 0) left = 0.f;
+      if (lane == 31) right = 0.f;
+      const float h0 = fmaxf(fmaxf(left, v0), v1), h1 = fmaxf(fmaxf(v0, v1), v2);
+      const float h2 = fmaxf(fmaxf(v1, v2), v3), h3 = fmaxf(fmaxf(v2, v3), right);
+      const unsigned f = pass & ((mid.x == h0 ? 1u : 0u) | (mid.y == h1 ? 2u : 0u) | (mid.z == h2 ? 4u : 0u) |
+                                 (mid.w == h3 ? 8u : 0u));
+      flags |= f << (4 * rr);
+    }
+    up = mid;
+    mid = dn;
+  }
+  if (__ballot_sync(0xffffffffu, flags != 0u) == 0u) return;
+  const int mine = __popc(flags);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    incl += (lane >= o) ? v : 0;
+  }
+  unsigned base = 0;
+  if (lane == 31) base = atomicAdd(key_cnt, (unsigned)incl);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  unsigned pos = base + (unsigned)(incl - mine);
+  const unsigned flat_lane0 = flat_tile0 + (unsigned)r0 * (unsigned)W + 4u * (unsigned)lane;
+  while (flags) {
+    const int bit = __ffs(flags) - 1;
+    flags &= flags - 1u;
+    const int rr = bit >> 2, e = bit & 3;
+    const float v = base_row[rr * W + e];
+    if (pos < cap) keys[pos] = ((u64)__float_as_uint(v) << 32) | (u64)(0xffffffffu - (flat_lane0 + (unsigned)(rr * W + e)));
+    ++pos;
+  }
+}
+// may a key of such a tile enter the threshold histogram?  Only if its 3x3 test was complete.
+__device__ __forceinline__ bool chunk_key_verified(u64 key, int HW, int H) {
+  const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+  const int y = (int)((flat % (unsigned)HW) >> 7);           // W == 128
+  const int r = y & (kCandRows - 1);
+  return !((r == 0 && y > 0) || (r == kCandRows - 1 && y < H - 1));
+}
+
 // One warp forwards candidate keys to its CTA's slice of a sample's list, counts them into the sample's two-level
 // histogram (fire-and-forget REDs) and derives the pruning threshold from that histogram: the lower edge of the fine
 // bin of the K-th counted key.  Only keys already forwarded are counted, so every threshold is valid (at least K real

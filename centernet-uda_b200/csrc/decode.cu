@@ -1742,6 +1742,8 @@ static int launch_cluster(const cnh_decode_args* a, void* workspace, int dev, cu
   return launch_cluster_rows<16>(a, make_geo(a, workspace, 16), cs, st);
 }
 
+static int launch_finish(const cnh_decode_args* a, const DecGeo& g, int cs, cudaStream_t st);
+
 // Streaming path: stream kernel (scan + candidate lists + thresholds) -> finish kernel (one CTA per sample) -> the
 // cluster kernel as the fallback for samples whose buffers ran over (it exits at once for all others).  All three
 // carry the programmatic-stream-serialisation attribute: each starts with griddepcontrol.wait.
@@ -1776,24 +1778,52 @@ static int launch_stream(const cnh_decode_args* a, void* workspace, int dev, cud
   lc.blockDim = dim3(kStThreads);
   lc.dynamicSmemBytes = kStSmemBytes;
   CNH_CUDA(cudaLaunchKernelEx(&lc, decode_stream_kernel, *a, g));
-  // the fallback sits BETWEEN the two (it exits at once unless a flag is up, its launch hides under the stream
-  // kernel's tail): behind the finish kernel its launch and drain would end the step 4 us later (measured)
+  // the fallback sits BETWEEN the stream and the finish kernel (it exits at once unless a flag is up, its launch hides
+  // under the stream kernel's tail): behind the finish kernel its launch and drain end the step 4 us later (measured)
+  return launch_finish(a, g, cs, st);
+}
+
+// fallback cluster launch (exits at once unless a sample's overflow flag is up) + finish kernel over the candidate
+// lists in g.cl; CNH_DECODE_FALLBACK_LAST: the fallback behind the finish kernel (experiments)
+static int launch_finish(const cnh_decode_args* a, const DecGeo& g, int cs, cudaStream_t st) {
+  static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
   static const bool fallback_last = getenv("CNH_DECODE_FALLBACK_LAST") != nullptr;
-  if (!fallback_last) {
-    const int rc = launch_cluster_rows<32>(a, g, cs, st, 1);
-    CNH_REQUIRE(rc != kClusterUnavailable, CNH_E_UNSUPPORTED, "decode: the cluster launch of the streaming path's fallback was refused");
-    if (rc != CNH_OK) return rc;
-  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.stream = st;
+  lc.attrs = attr;
+  lc.numAttrs = use_pdl ? 1 : 0;
   lc.gridDim = dim3((unsigned)a->B);
   lc.blockDim = dim3(kThreads);
   lc.dynamicSmemBytes = sizeof(MergeSmem);
+  if (!fallback_last) {
+    const int rc = launch_cluster_rows<32>(a, g, cs, st, 1);
+    CNH_REQUIRE(rc != kClusterUnavailable, CNH_E_UNSUPPORTED, "decode: the cluster launch of the candidate path's fallback was refused");
+    if (rc != CNH_OK) return rc;
+  }
   CNH_CUDA(cudaLaunchKernelEx(&lc, decode_finish_kernel, *a, g));
   if (fallback_last) {
     const int rc = launch_cluster_rows<32>(a, g, cs, st, 2);
-    CNH_REQUIRE(rc != kClusterUnavailable, CNH_E_UNSUPPORTED, "decode: the cluster launch of the streaming path's fallback was refused");
+    CNH_REQUIRE(rc != kClusterUnavailable, CNH_E_UNSUPPORTED, "decode: the cluster launch of the candidate path's fallback was refused");
     return rc;
   }
   return CNH_OK;
+}
+
+static bool finish_attr(int dev) {
+  static bool set[64] = {false};
+  if (dev < 0 || dev >= 64) return false;
+  if (!set[dev]) {
+    if (cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    set[dev] = true;
+  }
+  return true;
 }
 
 static bool want_stream(const cnh_decode_args* a) {
@@ -1824,6 +1854,34 @@ extern "C" int cnh_debug_active_clusters(int cs) {
   int dev = 0;
   if (cs < 1 || cs > 8 || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !cluster_attrs(dev)) return -1;
   return active_clusters(dev, cs);
+}
+
+extern "C" int cnh_decode_candidates(const cnh_decode_args* a, const cnh_cand* cand, cnh_stream_t stream) {
+  if (int rc = validate(a)) return rc;
+  CNH_REQUIRE(cand != nullptr && cand->workspace != nullptr, CNH_E_NULL, "decode_candidates: cand / its workspace is NULL");
+  CNH_REQUIRE(cand->G >= 1, CNH_E_UNSUPPORTED, "decode_candidates: the loss launch emitted no candidates (G = 0): use cnh_decode");
+  CNH_REQUIRE(cand->B == a->B && cand->C == a->C && cand->H == a->H && cand->W == a->W, CNH_E_SHAPE,
+              "decode_candidates: candidates of a %dx%dx%dx%d heat map, decode of %dx%dx%dx%d", cand->B, cand->C, cand->H,
+              cand->W, a->B, a->C, a->H, a->W);
+  CNH_REQUIRE(a->K <= cand->K, CNH_E_SHAPE, "decode_candidates: K=%d but the candidates were pruned for K=%d", a->K, cand->K);
+  CNH_REQUIRE(!a->apply_sigmoid, CNH_E_UNSUPPORTED, "decode_candidates: heat must be the probability map the loss launch wrote");
+  CNH_REQUIRE(a->W <= kCols && a->W % 4 == 0 && aligned16(a->heat), CNH_E_UNSUPPORTED, "decode_candidates: unsupported heat map layout");
+  CNH_REQUIRE(cand_ws_bytes(cand->B, cand->G) <= cand->workspace_bytes, CNH_E_WORKSPACE, "decode_candidates: candidate workspace too small");
+  int dev = 0;
+  CNH_CUDA(cudaGetDevice(&dev));
+  CNH_REQUIRE(cluster_attrs(dev) && finish_attr(dev), CNH_E_UNSUPPORTED, "decode_candidates: kernel attributes refused");
+  DecGeo g = make_geo(a, nullptr, kStRows);
+  const int cs = pick_cluster_size(a->B, g.tiles_per_sample, dev);
+  CNH_REQUIRE(cs >= 1, CNH_E_UNSUPPORTED, "decode_candidates: no cluster launch possible on this device");
+  g.cl = cand_geo(cand->workspace, cand->B, cand->G);
+  g.verify_rows = kCandRows;
+  return launch_finish(a, g, cs, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t cnh_cand_state_bytes(const cnh_cand* cand) {
+  if (cand == nullptr || cand->B < 1 || cand->G < 1) return 0;
+  const CandGeo c = cand_geo(nullptr, cand->B, cand->G);
+  return (size_t)(reinterpret_cast<const char*>(c.slices) - static_cast<const char*>(nullptr));
 }
 
 extern "C" size_t cnh_decode_workspace_bytes(const cnh_decode_args* a) {

@@ -40,6 +40,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "cand.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -165,6 +166,9 @@ struct Geo {
   long long timeout_ns;    // peers: bound of every wait on another rank
   WsHeader* hdr;
   unsigned* sparse;        // [n_chunks] bit v: sub-block v of the chunk's target is not all zero
+  unsigned* next_b;        // [B] candidate emission: per-sample chunk tickets (zero between launches)
+  CandGeo cand;            // candidate emission (cand.cuh): where the peaks of the probability tiles go
+  int cand_K;              // top-K the candidates are pruned for (0: no emission)
   long long* dbg;
 };
 
@@ -219,6 +223,19 @@ __device__ __host__ __forceinline__ double fixed_to_double(long long hi, long lo
 //        -(1-gt)^4 (s^3 - 2 s^2 (1-s) log(1-s))    for gt <  1
 // so one log and no second reciprocal per element.
 // FAST accumulates `term` in log2 units (the caller multiplies the per-thread sum by ln2 once).
+// log of an argument whose distance from 1, t = 1 - arg, is known exactly.  FAST: lg2.approx carries 2^-22 ABSOLUTE
+// error, which for arg -> 1 (log(1 - p) of the many background pixels with small p) is a large RELATIVE error of a
+// value that is itself ~ -t.  For t < 2^-5 the series log(1 - t) = -t (1 + t/2 + t^2/3 + t^3/4) (truncation < 2e-7
+// relative) is used instead, in the unit the fast path accumulates in (log2): four fused multiply-adds.
+constexpr float kNear1 = 0.03125f;
+constexpr float kL1 = -1.4426950408889634f, kL2 = kL1 / 2.0f, kL3 = kL1 / 3.0f, kL4 = kL1 / 4.0f;
+template <bool FAST>
+__device__ __forceinline__ float log_unit_near1(float arg, float t) {
+  if (!FAST) return logf(arg);
+  const float series = __fmul_rn(t, __fmaf_rn(t, __fmaf_rn(t, __fmaf_rn(t, kL4, kL3), kL2), kL1));
+  return t < kNear1 ? series : lg2_ftz(arg);
+}
+
 template <bool FAST>
 __device__ __forceinline__ void focal_elem(float x, float gt, float& p, float& term, float& graw,
                                            int& npos) {
@@ -230,8 +247,8 @@ __device__ __forceinline__ void focal_elem(float x, float gt, float& p, float& t
   // produces bit-identical terms and gradients
   const float q = __fsub_rn(1.0f, p);
   const float arg = pos ? p : q;              // argument of the log
-  const float a = pos ? q : p;                // the squared factor
-  const float L = log_unit<FAST>(arg);
+  const float a = pos ? q : p;                // the squared factor (= 1 - arg)
+  const float L = log_unit_near1<FAST>(arg, a);
   const float omg = __fsub_rn(1.0f, gt);
   float w4 = __fmul_rn(omg, omg);
   w4 = __fmul_rn(w4, w4);
@@ -251,7 +268,7 @@ __device__ __forceinline__ void focal_elem_neg(float x, float gt, float& p, floa
   const float s = sigmoidf_<FAST>(x);
   p = clamp_prob(s);
   const float q = __fsub_rn(1.0f, p);
-  const float L = log_unit<FAST>(q);
+  const float L = log_unit_near1<FAST>(q, p);
   const float omg = __fsub_rn(1.0f, gt);
   float w4 = __fmul_rn(omg, omg);
   w4 = __fmul_rn(w4, w4);
@@ -314,8 +331,16 @@ __device__ __forceinline__ void focal_pair_neg(float x0, float x1, float g0, flo
   const u64 q = add2(pk(1.0f, 1.0f), pk(-p0, -p1));          // 1 - p   (x + (-y) == x - y, exactly)
   float q0, q1;
   upk(q, q0, q1);
-  L0 = log_unit<FAST>(q0);
-  L1 = log_unit<FAST>(q1);
+  if (FAST) {                                                // log_unit_near1 on the pair (same operations, same bits)
+    const u64 ser = mul2(p, fma2(p, fma2(p, fma2(p, pk(kL4, kL4), pk(kL3, kL3)), pk(kL2, kL2)), pk(kL1, kL1)));
+    float s0, s1;
+    upk(ser, s0, s1);
+    L0 = p0 < kNear1 ? s0 : lg2_ftz(q0);
+    L1 = p1 < kNear1 ? s1 : lg2_ftz(q1);
+  } else {
+    L0 = logf(q0);
+    L1 = logf(q1);
+  }
   const u64 L = pk(L0, L1);
   const u64 omg = add2(pk(1.0f, 1.0f), pk(-g0, -g1));
   u64 w4 = mul2(omg, omg);
@@ -413,7 +438,8 @@ __device__ __forceinline__ void loss_acc_add(LossAcc& la, float v) {
 // known (NEED_GRAD && !KEEP), or (KEEP, single wave) it replaces the logits in the stage, unscaled.
 // Loss terms and num_pos go to the thread-local accumulators.  No barrier inside: a thread only
 // touches its own slots of the stage (WAIT: the stage is filled by bulk copies, wait for each sub-block).
-template <bool NEED_GRAD, bool FAST, bool WAIT, bool KEEP>
+// PTILE (candidate emission): the probabilities also replace the logits in the stage -- the tile the peak scan reads.
+template <bool NEED_GRAD, bool FAST, bool WAIT, bool KEEP, bool PTILE = false>
 __device__ __forceinline__ void process_chunk(const cnh_detloss_args& a, const ChunkRef& r, Stage& st, u64* bar,
                                               unsigned parity, unsigned gmask, float scale, LossAcc& la) {
   constexpr bool VEC = WAIT;                  // bulk-copied stages imply 16-byte aligned tensors and n % 4 == 0
@@ -477,6 +503,7 @@ __device__ __forceinline__ void process_chunk(const cnh_detloss_args& a, const C
         }
     }
     if (NEED_GRAD && KEEP) *reinterpret_cast<float4*>(st.x + off) = make_float4(gr[0], gr[1], gr[2], gr[3]);
+    if (PTILE) *reinterpret_cast<float4*>(st.x + off) = make_float4(ps[0], ps[1], ps[2], ps[3]);
   }
   if (FAST) sum = __fmul_rn(sum, kLn2F);      // log2 -> natural log, once per thread and chunk
   loss_acc_add(la, sum);
@@ -1341,8 +1368,18 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
 //           loss terms into thread-local exact accumulators; one arrival per warp frees the stage.
 //           No block barrier and no atomic per chunk.
 // ================================================================================================
-template <int MODE, bool FAST, bool VEC>
-__global__ void __launch_bounds__(kStashThreads, 2)
+// EMIT (candidate emission; needs W == 128, H*W % 4096 == 0: a chunk is 32 full rows of one class plane): a tenth warp.
+//   consumers: the probabilities of the chunk also go into the stage (over the logits); after a barrier of the eight
+//           warps each scans four rows of that tile for 3x3 peaks above the sample's pruning threshold and appends them
+//           to the stage's candidate buffer (the target's half of the stage, free by then); arrival on `scanned`.
+//   warp 9 (emitter): forwards the buffer to this CTA's slice of the sample's candidate list, counts the keys into the
+//           sample's histogram, keeps the threshold current (cand.cuh: CandEmitter), frees the stage for the producer.
+//   Every CTA serves ONE sample (CTA i: sample i % B, chunk tickets per sample), so a slice holds one sample's keys.
+// The decode (cnh_decode_candidates) then never reads the heat map: 4*C*H*W bytes per sample and a launch less.
+constexpr int kEmitThreads = kStashThreads + 32;
+constexpr int kEmitCap = kChunk * 4 / 8;                    // keys the target half of a stage holds
+template <int MODE, bool FAST, bool VEC, bool EMIT = false>
+__global__ void __launch_bounds__(EMIT ? kEmitThreads : kStashThreads, 2)
 detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Stage* const stages = reinterpret_cast<Stage*>(smem_raw);
@@ -1356,11 +1393,17 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   __shared__ unsigned long long sh_tag;
   __shared__ unsigned sh_mask[kMaxStages];
   __shared__ int sh_chunk[kMaxStages];
+  __shared__ u64 scanned[kMaxStages];          // EMIT: the eight consumer warps are done with the stage's tile
+  __shared__ unsigned sh_cnt[kMaxStages];      // EMIT: keys in the stage's candidate buffer
+  __shared__ unsigned sh_thr, sh_go;           // EMIT: pruning threshold of this CTA's sample; set once the first is valid
   const int bid = blockIdx.x, grid = gridDim.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool consumer = warp < kWarps;
   constexpr bool kGrad = (MODE == M_PRECOUNT || MODE == M_MAIN);
   const int S = g.n_stages;
+  // EMIT: this CTA's sample and slice (CTAs beyond B * G draw no chunks)
+  const int my_b = EMIT ? bid % a.B : 0, my_j = EMIT ? bid / a.B : 0;
+  const bool has_sample = !EMIT || my_j < g.cand.G;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: see detloss_stash_kernel
   asm volatile("griddepcontrol.wait;" ::: "memory");                // (cooperative launches carry the PDL attribute)
@@ -1368,7 +1411,12 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   if (tid == 0) {
     if (MODE != M_COUNT && VEC) {
       for (int i = 0; i < S * kSubs; ++i) mbar_init(&full[i], 1);
-      for (int i = 0; i < S; ++i) mbar_init(&empty[i], kWarps);
+      for (int i = 0; i < S; ++i) mbar_init(&empty[i], EMIT ? 1 : kWarps);
+      if (EMIT) {
+        for (int i = 0; i < S; ++i) { mbar_init(&scanned[i], kWarps); sh_cnt[i] = 0u; }
+        sh_thr = 0u;
+        sh_go = 0u;
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     sh_parity = __ldcg(&g.hdr->parity) & 1u;   // ticket modes leave their set zeroed: parity stays what it is
@@ -1458,7 +1506,13 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   if (MODE != M_COUNT) {
     // ---- the streaming pass -----------------------------------------------------------------------
     // ticket t -> chunk: reverse order after a pre-count (the tail of the target is still in L2)
-    auto chunk_of = [&](int t) { return (MODE == M_PRECOUNT) ? g.n_chunks - 1 - t : t; };
+    // (EMIT: tickets are per sample, t counts this sample's chunks)
+    const int n_tickets = EMIT ? (has_sample ? g.cps : 0) : g.n_chunks;
+    unsigned* const ticket_ctr = EMIT ? g.next_b + my_b : &g.hdr->next;
+    auto chunk_of = [&](int t) {
+      if (EMIT) return my_b * g.cps + ((MODE == M_PRECOUNT) ? g.cps - 1 - t : t);
+      return (MODE == M_PRECOUNT) ? g.n_chunks - 1 - t : t;
+    };
     LossAcc la = {0ll, 0ll, 0};
     // regression units first (the last CTAs get them): the chunk tickets are dynamic, a CTA that is busy
     // here simply draws fewer chunks -- nothing is left to do after the streaming loop
@@ -1486,7 +1540,7 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
           fill_stage_sync(a, cr, stages[0]);
           process_chunk<kGrad, FAST, false, false>(a, cr, stages[0], full, 0u, 0xfu, scale, la);
         }
-    } else if (!consumer) {
+    } else if (warp == kWarps) {
       // ---- producer ----
       if (lane == 0) {
         // sparsity words: PRECOUNT wrote them in phase 0; MAIN may use the ones a preceding COUNT left
@@ -1499,18 +1553,18 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
         // while issue j is prepared -- no round trip of the (loaded) memory system is ever waited for
         auto load_mask = [&](unsigned t) -> unsigned {
           unsigned m = 0xfu;
-          if (sparse_ok && t < (unsigned)g.n_chunks)
+          if (sparse_ok && t < (unsigned)n_tickets)
             asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(m) : "l"(g.sparse + chunk_of((int)t)));
           return m;
         };
-        unsigned t_a = atomicAdd(&g.hdr->next, 1u);
-        unsigned t_b = atomicAdd(&g.hdr->next, 1u);
+        unsigned t_a = atomicAdd(ticket_ctr, 1u);
+        unsigned t_b = atomicAdd(ticket_ctr, 1u);
         unsigned m_a = load_mask(t_a);
         for (int j = 0;; ++j) {
           const int s = j % S;
-          const unsigned t_c = atomicAdd(&g.hdr->next, 1u);
+          const unsigned t_c = atomicAdd(ticket_ctr, 1u);
           const unsigned m_b = load_mask(t_b);
-          if (t_b < (unsigned)g.n_chunks) {                                  // next issue's chunk: start it towards L2 now
+          if (t_b < (unsigned)n_tickets) {                                   // next issue's chunk: start it towards L2 now
             const ChunkRef nr = chunk_ref(g, chunk_of((int)t_b));
             const unsigned bytes = (unsigned)nr.n * 4u;
             l2_prefetch_bulk(a.hm_logits + nr.base, bytes);
@@ -1520,7 +1574,7 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
           if (g.dbg != nullptr) tw0 = clock_ns();
           if (j >= S) mbar_wait(&empty[s], (unsigned)(((j / S) - 1) & 1));   // every consumer warp is done with the stage
           if (g.dbg != nullptr) g.dbg[(long long)bid * 16 + 10] += clock_ns() - tw0;
-          if (t_a >= (unsigned)g.n_chunks) {                                 // out of work: wake the consumers
+          if (t_a >= (unsigned)n_tickets) {                                  // out of work: wake the consumers
             sh_chunk[s] = -1;
             mbar_arrive(&full[s * kSubs]);
             break;
@@ -1535,7 +1589,51 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
           m_a = m_b;
         }
       }
-    } else {
+    } else if (EMIT && warp == kWarps + 1) {
+      // ---- emitter ----
+      CandEmitter em;
+      em.init(g.cand, my_b, has_sample ? my_j : 0, g.cand_K);
+      const int HW = g.HW, H = a.H;
+      auto counted = [&](u64 key) { return chunk_key_verified(key, HW, H); };
+#pragma unroll 1
+      for (int i = 0;; ++i) {
+        const int s = i % S;
+        const unsigned ph = (unsigned)((i / S) & 1);
+        mbar_wait(&full[s * kSubs], ph);                     // (the chunk's meta data)
+        if (sh_chunk[s] < 0) break;
+        mbar_wait(&scanned[s], ph);                          // the consumers' candidates of this tile are complete
+        em.forward(reinterpret_cast<const u64*>(stages[s].g), *reinterpret_cast<volatile unsigned*>(&sh_cnt[s]),
+                   (unsigned)kEmitCap, counted);
+        if (lane == 0) {
+          sh_cnt[s] = 0u;
+          mbar_arrive(&empty[s]);                            // the producer may refill the stage
+        }
+        if (i == 0) {
+          // first threshold: waited for (two L2 round trips), while the consumers work on the next chunk's loss terms;
+          // they wait for it before they SCAN that chunk (sh_go)
+          __threadfence();
+          __nanosleep(600);                                  // the sample's other CTAs are at the same point: let their REDs land
+          em.refresh_blocking();
+        } else {
+          em.refresh_step(i, true);
+        }
+        if (lane == 0) {
+          *reinterpret_cast<volatile unsigned*>(&sh_thr) = em.thr;
+          if (i == 0) {
+            __threadfence_block();
+            *reinterpret_cast<volatile unsigned*>(&sh_go) = 1u;
+          }
+        }
+        __syncwarp();
+      }
+      if (has_sample) {
+        em.reprune([](u64) {});
+        if (lane == 0) {
+          g.cand.cta_cnt[(long long)my_b * g.cand.G + my_j] = em.local_cnt;
+          if (em.overflow) g.cand.state[my_b].overflow = 1u;
+        }
+      }
+    } else if (consumer) {
       // ---- consumers ----
 #pragma unroll 1
       for (int i = 0;; ++i) {
@@ -1548,9 +1646,23 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
         const int chunk = sh_chunk[s];
         if (chunk < 0) break;
         const unsigned m = sh_mask[s];
-        process_chunk<kGrad, FAST, true, false>(a, chunk_ref(g, chunk), stages[s], &full[s * kSubs], ph, m, scale, la);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        process_chunk<kGrad, FAST, true, false, EMIT>(a, chunk_ref(g, chunk), stages[s], &full[s * kSubs], ph, m, scale, la);
+        if (EMIT) {
+          sync_compute();                                    // the probability tile is complete, the target half is free
+          if (i == 1) {                                      // start-up: the first threshold (see the emitter)
+            while (*reinterpret_cast<volatile unsigned*>(&sh_go) == 0u) __nanosleep(64);
+          }
+          const unsigned thr = *reinterpret_cast<volatile unsigned*>(&sh_thr);
+          // chunk -> (class plane c, first row): the chunk is rows [32*ty, 32*ty+32) of plane c of sample my_b
+          const int jc = chunk - my_b * g.cps;               // chunk index inside the sample = c * (H/32) + ty
+          scan_chunk_rows(reinterpret_cast<u64*>(stages[s].g), &sh_cnt[s], (unsigned)kEmitCap, stages[s].x, thr,
+                          (unsigned)jc * (unsigned)kChunk, warp);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&scanned[s]);
+        } else {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+        }
       }
     }
     dbg_stamp(g.dbg, 3);
@@ -1592,6 +1704,8 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
     g.hdr->next = 0;
     g.hdr->next0 = 0;
   }
+  if (EMIT)
+    for (int i = tid; i < a.B; i += blockDim.x) g.next_b[i] = 0u;
   dbg_stamp(g.dbg, 4);
 }
 
@@ -1718,6 +1832,8 @@ static long long n_chunks_of(const cnh_detloss_args* a) {
   return (long long)a->B * ((CHW + kChunk - 1) / kChunk);
 }
 
+static size_t sparse_bytes(const cnh_detloss_args* a) { return ((size_t)n_chunks_of(a) * sizeof(unsigned) + 255) / 256 * 256; }
+
 static Geo make_geo(const cnh_detloss_args* a, void* ws) {
   Geo g;
   g.HW = a->H * a->W;
@@ -1755,12 +1871,15 @@ static Geo make_geo(const cnh_detloss_args* a, void* ws) {
   for (int i = 0; i < CNH_MAX_PEERS; ++i) g.mailbox[i] = nullptr;
   g.hdr = static_cast<WsHeader*>(ws);
   g.sparse = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + kHeaderBytes);
+  g.next_b = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + kHeaderBytes + sparse_bytes(a));
+  g.cand_K = 0;
+  g.cand = cand_geo(nullptr, a->B, 0);
   g.dbg = debug_buffer();
   return g;
 }
 
 static size_t ws_bytes(const cnh_detloss_args* a) {
-  return kHeaderBytes + ((size_t)n_chunks_of(a) * sizeof(unsigned) + 255) / 256 * 256;
+  return kHeaderBytes + sparse_bytes(a) + ((size_t)a->B * sizeof(unsigned) + 255) / 256 * 256;   // + per-sample tickets
 }
 
 static bool use_vec(const cnh_detloss_args* a, const Geo& g) {
@@ -1771,6 +1890,10 @@ static bool use_vec(const cnh_detloss_args* a, const Geo& g) {
 static const void* pick_stash(bool fast, bool vec) {
   if (fast) return vec ? (const void*)detloss_stash_kernel<true, true> : (const void*)detloss_stash_kernel<true, false>;
   return vec ? (const void*)detloss_stash_kernel<false, true> : (const void*)detloss_stash_kernel<false, false>;
+}
+template <int MODE>
+static const void* pick_stream_emit(bool fast) {          // candidate emission: bulk-staged (VEC) shapes only
+  return fast ? (const void*)detloss_stream_kernel<MODE, true, true, true> : (const void*)detloss_stream_kernel<MODE, false, true, true>;
 }
 template <int MODE>
 static const void* pick_stream(bool fast, bool vec) {
@@ -1846,12 +1969,49 @@ static bool plan_stash(const void* kernel, Geo& g) {
   return false;
 }
 
-static int stream_grid(const void* kernel, const Geo& g, long long warp_units, int stages = kStreamStages) {
+static size_t cand_ws_upper(int B) {
+  int G = (3 * sm_count()) / (B > 0 ? B : 1);
+  if (G < 1) G = 1;
+  return cand_ws_bytes(B, G);
+}
+
+// Candidate emission for a streaming launch of `grid` CTAs: possible when a chunk is 32 full rows of one class plane
+// (W == 128, H*W % 4096 == 0), the tensors are bulk-staged, every sample gets at least one CTA and the caller's
+// workspace is large enough.  Fills a->cand (host) and g.cand / g.cand_K; false: the launch emits nothing (cand->G = 0).
+static bool setup_emission(const cnh_detloss_args* a, Geo& g, bool vec, int grid) {
+  cnh_cand* c = a->cand;
+  if (c == nullptr) return false;
+  c->G = 0;
+  c->B = a->B; c->C = a->C; c->H = a->H; c->W = a->W;
+  if (!vec || a->W != 128 || g.HW % kChunk != 0 || c->workspace == nullptr || c->K < 1 || c->K > 1024) return false;
+  const int G = grid / a->B;
+  if (G < 1 || cand_ws_bytes(a->B, G) > c->workspace_bytes) return false;
+  g.cand = cand_geo(c->workspace, a->B, G);
+  g.cand_K = c->K;
+  c->G = G;
+  return true;
+}
+
+static int stream_grid(const void* kernel, const Geo& g, long long warp_units, int stages = kStreamStages,
+                       int threads = kStashThreads) {
   long long want = g.n_chunks + (warp_units + kWarps - 1) / kWarps;
   if (want < 1) want = 1;
-  int cap = resident_ctas(kernel, stages, kStashThreads);
+  int cap = resident_ctas(kernel, stages, threads);
   if (cap < 1) cap = 1;
   return (int)(want < cap ? want : cap);
+}
+
+// one streaming launch (PRECOUNT / MAIN / FWD), with candidate emission when the caller asked for it and it is possible
+template <int MODE>
+static int launch_stream(const cnh_detloss_args* a, Geo& g, bool fast, bool vec, bool cooperative, cudaStream_t st) {
+  const long long units = g.n_items + g.n_count;
+  if (a->cand != nullptr) {
+    const void* ke = pick_stream_emit<MODE>(fast);
+    const int grid = stream_grid(ke, g, units, kStreamStages, kEmitThreads);
+    if (setup_emission(a, g, vec, grid)) return launch(ke, cooperative, grid, kStreamStages, a, g, st, kEmitThreads);
+  }
+  const void* k = pick_stream<MODE>(fast, vec);
+  return launch(k, cooperative, stream_grid(k, g, units), kStreamStages, a, g, st, kStashThreads);
 }
 
 }  // namespace cnh
@@ -1862,6 +2022,8 @@ extern "C" size_t cnh_detloss_workspace_bytes(const cnh_detloss_args* a) {
   if (validate(a, false) != CNH_OK) return 0;
   return ws_bytes(a);
 }
+
+extern "C" size_t cnh_cand_workspace_bytes(int32_t B) { return B > 0 ? cand_ws_upper(B) : 0; }
 
 extern "C" int cnh_detloss_single_wave(const cnh_detloss_args* a) {
   if (validate(a, false) != CNH_OK) return 0;
@@ -1909,6 +2071,7 @@ static int detloss_fused_impl(const cnh_detloss_args* a, const cnh_peers* peers,
   const bool fast = !(a->flags & CNH_FLAG_ACCURATE_MATH), vec = use_vec(a, g);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const void* ks = pick_stash(fast, vec);
+  if (a->cand != nullptr) a->cand->G = 0;                    // (the single-wave schedule emits no candidates)
   if (a->grad_hm == nullptr) {
     // forward only (torch.no_grad() validation): the single wave when it fits (its CTAs simply stop after the
     // loss terms; measured 17.6 -> see DESIGN at cfg2), else the streaming kernel
@@ -1916,25 +2079,24 @@ static int detloss_fused_impl(const cnh_detloss_args* a, const cnh_peers* peers,
       static const bool no_coop_f = (getenv("CNH_NO_COOP") != nullptr);
       return launch(ks, !no_coop_f, g.chunk_ctas + 1, g.n_stages, a, g, st, kStashThreads);
     }
-    const void* k = pick_stream<M_FWD>(fast, vec);
-    return launch(k, false, stream_grid(k, g, g.n_items + g.n_count), kStreamStages, a, g, st, kStashThreads);
+    g.n_stages = kStreamStages;
+    return launch_stream<M_FWD>(a, g, fast, vec, false, st);
   }
   if (!(a->flags & CNH_FLAG_NO_STASH) && plan_stash(ks, g)) {
     static const bool no_coop = (getenv("CNH_NO_COOP") != nullptr);      // experiment: plain launch of the single wave
     return launch(ks, !no_coop, g.chunk_ctas + 1, g.n_stages, a, g, st, kStashThreads);
   }
   g.n_stages = kStreamStages;
-  const void* kp = pick_stream<M_PRECOUNT>(fast, vec);
   if (g.world > 1) {
     // sharded pre-count launch: the normalisers are traded after the count phase's grid barrier; the totals always
     // by the one-warp finalize launch (here, unless the caller defers it to overlap it with other work)
     CNH_REQUIRE(a->totals != nullptr, CNH_E_NULL, "detloss_fused_peers: a->totals is NULL");
     const int want_finalize = !g.defer_totals;
     g.defer_totals = 1;
-    if (int rc = launch(kp, true, stream_grid(kp, g, g.n_items + g.n_count), kStreamStages, a, g, st, kStashThreads)) return rc;
+    if (int rc = launch_stream<M_PRECOUNT>(a, g, fast, vec, true, st)) return rc;
     return want_finalize ? launch_peers_finalize(a, g, st) : CNH_OK;
   }
-  return launch(kp, true, stream_grid(kp, g, g.n_items + g.n_count), kStreamStages, a, g, st, kStashThreads);
+  return launch_stream<M_PRECOUNT>(a, g, fast, vec, true, st);
 }
 
 static int launch_peers_finalize(const cnh_detloss_args* a, const Geo& g, cudaStream_t stream) {
@@ -2004,10 +2166,9 @@ extern "C" int cnh_detloss_main(const cnh_detloss_args* a, void* workspace, size
   CNH_REQUIRE(a->totals != nullptr, CNH_E_NULL, "detloss_main: totals is NULL");
   CNH_REQUIRE(workspace != nullptr && workspace_bytes >= ws_bytes(a), CNH_E_WORKSPACE,
               "detloss_main: workspace %zu < %zu bytes", workspace_bytes, ws_bytes(a));
-  const Geo g = make_geo(a, workspace);
-  const void* k = pick_stream<M_MAIN>(!(a->flags & CNH_FLAG_ACCURATE_MATH), use_vec(a, g));
-  return launch(k, false, stream_grid(k, g, g.n_items + g.n_count), kStreamStages, a, g,
-                static_cast<cudaStream_t>(stream), kStashThreads);
+  Geo g = make_geo(a, workspace);
+  if (a->cand != nullptr) a->cand->G = 0;
+  return launch_stream<M_MAIN>(a, g, !(a->flags & CNH_FLAG_ACCURATE_MATH), use_vec(a, g), false, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cnh_detloss_finalize(const cnh_detloss_args* a, const int64_t* totals, cnh_stream_t stream) {

@@ -12,6 +12,8 @@ Deliberate differences (no caller depends on them):
   * a graph can be backpropagated once (gradients are produced by the forward launch).
 CUDA fp32 tensors only: CPU tensors raise ``RuntimeError`` (there is no fallback path).
 """
+import os as _os
+
 import torch
 
 from cnhead import _lib as _L
@@ -21,8 +23,15 @@ from cnhead._dropin import reexport as _reexport
 
 class DetectionLoss(torch.nn.Module):
     def __init__(self, hm_weight, wh_weight, off_weight, kp_weight=None, angle_weight=1.0, periodic=False,
-                 kp_indices=None, kp_distance_weight=0.1, kp_distance_weight_l1=False):
+                 kp_indices=None, kp_distance_weight=0.1, kp_distance_weight_l1=False, max_detections=None):
+        """Same kwargs as the reference (configs/defaults.yaml:21-26) plus ``max_detections`` (default: the
+        environment variable CNH_FUSE_DECODE_K, else off): the loss launch also emits the peak candidates of its
+        probability map for a later ``decode_detection(output['hm'], ..., K <= max_detections)``, which then does not
+        read the heat map again (large maps only: the streaming schedule; small ones decode as usual)."""
         super().__init__()
+        if max_detections is None and _os.environ.get("CNH_FUSE_DECODE_K"):
+            max_detections = int(_os.environ["CNH_FUSE_DECODE_K"])
+        self.max_detections = int(max_detections) if max_detections else None
         self.hm_weight, self.wh_weight, self.off_weight = hm_weight, wh_weight, off_weight
         self.angle_weight, self.periodic = angle_weight, periodic
         self.with_keypoints = kp_weight is not None or kp_indices is not None
@@ -61,7 +70,7 @@ class DetectionLoss(torch.nn.Module):
     def forward(self, output, batch):
         heads = self._heads(output, batch)
         scalars, prob, totals = _F.detection_loss(output['hm'], batch['hm'], batch['ind'], heads,
-                                                    self.hm_weight)
+                                                    self.hm_weight, decode_K=self.max_detections)
         output['hm'] = prob                        # losses/centernet.py:34
         loss, hm_loss, wh_loss, off_loss = scalars[0], scalars[1], scalars[2], scalars[3]
         stats = {'centernet_loss': loss, 'hm_loss': hm_loss, 'wh_loss': wh_loss, 'off_loss': off_loss}

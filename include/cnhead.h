@@ -80,6 +80,22 @@ typedef struct cnh_head {
   const int32_t* pairs;  /* CNH_LIMB_*: [n_pairs,2] keypoint indices (device), the reference's kps_weight_indices */
 } cnh_head;
 
+/* Peak candidates for the decode, emitted by the detection-loss launch itself (nullable member of
+ * cnh_detloss_args).  The loss kernels have every clamped probability in shared memory anyway: with `cand` set they
+ * also run the 3x3 peak test there and keep, per sample, a superset of the top-K peaks in `workspace`
+ * (thresholds from a running histogram; cnh_cand_workspace_bytes(B); zero-filled ONCE by the caller, left clean by
+ * cnh_decode_candidates).  cnh_decode_candidates(decode args, cand) then produces the detections of
+ * backends/decode.py:35-76 without reading the heat map again: 4*C*H*W bytes per sample and most of a launch less.
+ * The loss launch fills G (0: it could not emit -- shape other than W == 128 with H*W % 4096 == 0, misaligned
+ * tensors, or the single-wave schedule -- and the caller uses cnh_decode) and the heat map's dimensions. */
+typedef struct cnh_cand {
+  void* workspace;
+  size_t workspace_bytes;
+  int32_t K;             /* in: largest K a later cnh_decode_candidates may ask for (1..1024)          */
+  int32_t G;             /* out: candidate slices per sample written by the loss launch (0 = none)    */
+  int32_t B, C, H, W;    /* out: heat map the candidates belong to                                     */
+} cnh_cand;
+
 #define CNH_MAX_HEADS 3
 #define CNH_TOTALS 24  /* int64 words, see below */
 #define CNH_SCALARS 8  /* floats, see below      */
@@ -109,6 +125,7 @@ typedef struct cnh_detloss_args {
   int64_t* totals;         /* [CNH_TOTALS] out: this launch's exact sums (nullable for fused)    */
   const double* norm;      /* [4] in (cnh_detloss_main): global num_pos, mask counts per head    */
   double* norm_out;        /* [4] out (cnh_detloss_count): this shard's num_pos, mask counts     */
+  cnh_cand* cand;          /* nullable: emit peak candidates for cnh_decode_candidates (see above) */
 } cnh_detloss_args;
 
 int cnh_version(void);
@@ -236,6 +253,16 @@ typedef struct cnh_decode_args {
 size_t cnh_decode_workspace_bytes(const cnh_decode_args* a);
 int cnh_decode(const cnh_decode_args* a, void* workspace, size_t workspace_bytes,
                cnh_stream_t stream);
+/* Decode from the candidates a detection-loss launch left (cnh_cand): a->heat must be the probability map that
+ * launch wrote (a few dozen candidates are re-checked against it; samples whose candidate buffers ran over --
+ * plateaus of thousands of equal scores -- are redone from it exactly), a->B/C/H/W must match cand, a->K <= cand->K,
+ * apply_sigmoid must be 0.  Same outputs, bit for bit, as cnh_decode.  cand->G == 0: CNH_E_UNSUPPORTED. */
+size_t cnh_cand_workspace_bytes(int32_t B);
+int cnh_decode_candidates(const cnh_decode_args* a, const cnh_cand* cand, cnh_stream_t stream);
+/* cnh_decode_candidates leaves the workspace clean for the next emitting loss launch.  If the candidates of a loss
+ * launch are NOT decoded, the caller must zero the first cnh_cand_state_bytes(cand) bytes of the workspace (counters
+ * and histograms; the key slices behind them need no clearing) before the next emitting launch. */
+size_t cnh_cand_state_bytes(const cnh_cand* cand);
 
 /* ---- target rasteriser (datasets/coco.py:168-215, utils/image.py:8-57) -----------
  * Builds the dense targets of DetectionLoss on the device from per-sample object lists.
