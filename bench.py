@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg5 / shapes blocks and the sharded parity check")
+    ap.add_argument("--no-fuse", action="store_true",
+                    help="do not let the loss launch emit the decode's peak candidates (decode re-reads the heat map)")
     return ap.parse_args()
 
 
@@ -224,6 +226,8 @@ class DeviceStep:
     NVLink-mapped mailboxes; the totals by a one-warp launch forked next to decode) or 'nccl' (sharded:
     count -> all-reduce -> main -> all-reduce (forked next to decode) -> finalize)."""
 
+    FUSE = True          # the loss launch emits the decode's peak candidates when the shape allows it (--no-fuse: off)
+
     def __init__(self, sets, cfg, world, group, schedule="auto"):
         import ctypes as C
         from cnhead import _lib as L, functional as F, sharded
@@ -232,9 +236,17 @@ class DeviceStep:
         self.lib = L.lib()
         dev = sets[0].hm.device
         self.loss_args, self.scale_args, self.dec_args = [], [], []
+        # candidate emission (include/cnhead.h: cnh_cand): one workspace, used by the steps in stream order
+        self.cand = L.Cand()
+        self.ws_cand = torch.zeros(self.lib.cnh_cand_workspace_bytes(sets[0].hm.shape[0]) + 256, dtype=torch.uint8, device=dev)
+        self.cand.workspace, self.cand.workspace_bytes = self.ws_cand.data_ptr(), self.ws_cand.numel()
+        self.cand.K, self.cand.G = cfg.K, 0
+        self.no_cand = C.POINTER(L.Cand)()
         for s in sets:
             a = F.fill_detloss_args(s.hm, s.gt, s.ind, s.heads, 1.0, s.prob, s.grads, s.scalars, s.totals,
                                     norm=s.norm, norm_out=s.norm, b_global=s.hm.shape[0] * world)
+            if DeviceStep.FUSE:
+                a.cand = C.pointer(self.cand)
             sc = L.ScaleArgs()
             sc.n_tensors = 3
             for i, t in enumerate(s.grads):
@@ -288,7 +300,15 @@ class DeviceStep:
                 self.schedule, self.box = "nccl", None
         self.launches_per_step = {"single": 3, "peers": 4, "nccl": 5}[self.schedule] + (3 if cfg.target_domain else 0)
 
+    def fused_decode(self):
+        return self.cand.G > 0
+
     def describe(self):
+        tail = (" [the loss launch emits the decode's peak candidates; cnh_decode_candidates does not read the heat map]"
+                if self.fused_decode() else "")
+        return self._describe() + tail
+
+    def _describe(self):
         if self.schedule == "single":
             return "single GPU: fused loss launch + backward scale + decode"
         if self.schedule == "peers":
@@ -301,10 +321,30 @@ class DeviceStep:
 
     # ---- pieces (also timed alone) -------------------------------------------------------------------------
     def loss_only(self, i):
+        """the fused loss launch alone, WITHOUT candidate emission (nothing would consume the candidates)"""
+        C, L = self.C, self.L
+        a = self.loss_args[i]
+        keep, a.cand = a.cand, self.no_cand
+        L.check(self.lib.cnh_detloss_fused(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), L.stream_ptr()),
+                "detloss_fused")
+        a.cand = keep
+
+    def loss_decode_pair(self, i):
+        """single GPU: the loss launch (emitting candidates when it can) + the decode that consumes them"""
         C, L = self.C, self.L
         a = self.loss_args[i]
         L.check(self.lib.cnh_detloss_fused(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), L.stream_ptr()),
                 "detloss_fused")
+        self.decode_step(i)
+
+    def decode_step(self, i):
+        """the decode of a step: from the loss launch's candidates when it emitted any, else the regular decode"""
+        L = self.L
+        if self.cand.G > 0:
+            L.check(self.lib.cnh_decode_candidates(self.C.byref(self.dec_args[i]), self.C.byref(self.cand), L.stream_ptr()),
+                    "decode_candidates")
+        else:
+            self.decode_only(i)
 
     def count_only(self, i):
         C, L = self.C, self.L
@@ -315,8 +355,9 @@ class DeviceStep:
         C, L = self.C, self.L
         a = self.loss_args[i]
         keep, a.scalars = a.scalars, None
+        keep_c, a.cand = a.cand, self.no_cand
         L.check(self.lib.cnh_detloss_main(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), L.stream_ptr()), "main")
-        a.scalars = keep
+        a.scalars, a.cand = keep, keep_c
 
     def allreduce_only(self, i):
         s = self.sets[i]
@@ -364,8 +405,7 @@ class DeviceStep:
                     L.check(self.lib.cnh_detloss_finalize(C.byref(a), s.totals.data_ptr(), L.stream_ptr()), "finalize")
                 self.ev_join.record(self.side)
         L.check(self.lib.cnh_scale_inplace(C.byref(self.scale_args[i]), st), "scale")            # backward
-        L.check(self.lib.cnh_decode(C.byref(self.dec_args[i]), self.ws_dec.data_ptr(), self.ws_dec.numel(), st),
-                "decode")
+        self.decode_step(i)
         if self.schedule != "single":
             torch.cuda.current_stream().wait_event(self.ev_join)
         if self.ws_soft is not None:               # cfg4: EntropyLoss and MaxSquareLoss fwd+bwd on the target batch
@@ -531,6 +571,8 @@ def kernel_block(w, steps, warmup, peak):
     sched = w.dstep.schedule
     if sched == "single":
         put("loss_fused", "loss_only", w.loss_bytes)
+        if w.dstep.fused_decode():
+            put("loss_emitting_candidates_plus_decode_from_them", "loss_decode_pair", w.loss_bytes + w.dec_bytes)
     if sched == "nccl":
         hw = w.cfg.height * w.cfg.width
         put("loss_count", "count_only", w.batch * 4 * w.cfg.classes * hw)
@@ -613,6 +655,7 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device for --impl ours"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    DeviceStep.FUSE = not args.no_fuse
     steps, warmup = args.steps, max(3, args.warmup)
     use_graph = not args.no_graph
     peak, peak_src = hbm_peak()

@@ -22,8 +22,11 @@ def test_plugin_names_and_signatures():
     from utils.image import entropy_map
     from utils.tensor import _sigmoid, _gather_feat, _transpose_and_gather_feat   # noqa: F401
     sig = inspect.signature(DetectionLoss.__init__)
+    # the reference's kwargs, in its order (losses/centernet.py:8-11), then this package's one extension
     assert list(sig.parameters)[1:] == ["hm_weight", "wh_weight", "off_weight", "kp_weight", "angle_weight",
-                                        "periodic", "kp_indices", "kp_distance_weight", "kp_distance_weight_l1"]
+                                        "periodic", "kp_indices", "kp_distance_weight", "kp_distance_weight_l1",
+                                        "max_detections"]
+    assert sig.parameters["max_detections"].default is None
     assert sig.parameters["angle_weight"].default == 1.0 and sig.parameters["periodic"].default is False
     assert list(inspect.signature(decode_detection).parameters) == ["heat", "wh", "reg", "kps", "K", "rotated",
                                                                     "nms_size"]
