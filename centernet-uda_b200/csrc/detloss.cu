@@ -1369,11 +1369,13 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
 //           No block barrier and no atomic per chunk.
 // ================================================================================================
 // EMIT (candidate emission; needs W == 128, H*W % 4096 == 0: a chunk is 32 full rows of one class plane): a tenth warp.
-//   consumers: the probabilities of the chunk also go into the stage (over the logits); after a barrier of the eight
-//           warps each scans four rows of that tile for 3x3 peaks above the sample's pruning threshold and appends them
-//           to the stage's candidate buffer (the target's half of the stage, free by then); arrival on `scanned`.
-//   warp 9 (emitter): forwards the buffer to this CTA's slice of the sample's candidate list, counts the keys into the
-//           sample's histogram, keeps the threshold current (cand.cuh: CandEmitter), frees the stage for the producer.
+//   consumers: the probabilities of the chunk also go into the stage (over the logits); one arrival per warp on
+//           `scanned` -- they never wait for the scan.
+//   warp 9 (emitter): once the eight warps have arrived, scans that 32 x 128 tile for 3x3 peaks above the sample's
+//           pruning threshold (a CTA finishes a chunk every ~4 us: one warp has time to spare), collects them in the
+//           target's half of the stage (free by then), forwards them to this CTA's slice of the sample's candidate
+//           list, counts them into the sample's histogram, keeps the threshold current (cand.cuh: CandEmitter), and
+//           frees the stage for the producer.
 //   Every CTA serves ONE sample (CTA i: sample i % B, chunk tickets per sample), so a slice holds one sample's keys.
 // The decode (cnh_decode_candidates) then never reads the heat map: 4*C*H*W bytes per sample and a launch less.
 constexpr int kEmitThreads = kStashThreads + 32;
@@ -1395,7 +1397,6 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   __shared__ int sh_chunk[kMaxStages];
   __shared__ u64 scanned[kMaxStages];          // EMIT: the eight consumer warps are done with the stage's tile
   __shared__ unsigned sh_cnt[kMaxStages];      // EMIT: keys in the stage's candidate buffer
-  __shared__ unsigned sh_thr, sh_go;           // EMIT: pruning threshold of this CTA's sample; set once the first is valid
   const int bid = blockIdx.x, grid = gridDim.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool consumer = warp < kWarps;
@@ -1414,8 +1415,6 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
       for (int i = 0; i < S; ++i) mbar_init(&empty[i], EMIT ? 1 : kWarps);
       if (EMIT) {
         for (int i = 0; i < S; ++i) { mbar_init(&scanned[i], kWarps); sh_cnt[i] = 0u; }
-        sh_thr = 0u;
-        sh_go = 0u;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -1601,28 +1600,26 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
         const unsigned ph = (unsigned)((i / S) & 1);
         mbar_wait(&full[s * kSubs], ph);                     // (the chunk's meta data)
         if (sh_chunk[s] < 0) break;
-        mbar_wait(&scanned[s], ph);                          // the consumers' candidates of this tile are complete
-        em.forward(reinterpret_cast<const u64*>(stages[s].g), *reinterpret_cast<volatile unsigned*>(&sh_cnt[s]),
-                   (unsigned)kEmitCap, counted);
+        mbar_wait(&scanned[s], ph);                          // the eight consumer warps have left the probability tile
+        // chunk -> rows [32*ty, 32*ty+32) of class plane c of sample my_b; jc = c * (H/32) + ty
+        const int jc = sh_chunk[s] - my_b * g.cps;
+        u64* const keys = reinterpret_cast<u64*>(stages[s].g);
+#pragma unroll 1
+        for (int q = 0; q < kWarps; ++q)                     // four rows per pass, as a consumer warp would
+          scan_chunk_rows(keys, &sh_cnt[s], (unsigned)kEmitCap, stages[s].x, em.thr, (unsigned)jc * (unsigned)kChunk, q);
+        __syncwarp();
+        em.forward(keys, *reinterpret_cast<volatile unsigned*>(&sh_cnt[s]), (unsigned)kEmitCap, counted);
         if (lane == 0) {
           sh_cnt[s] = 0u;
           mbar_arrive(&empty[s]);                            // the producer may refill the stage
         }
         if (i == 0) {
-          // first threshold: waited for (two L2 round trips), while the consumers work on the next chunk's loss terms;
-          // they wait for it before they SCAN that chunk (sh_go)
+          // first threshold: waited for (two L2 round trips, once) -- the first chunk was scanned without one
           __threadfence();
           __nanosleep(600);                                  // the sample's other CTAs are at the same point: let their REDs land
           em.refresh_blocking();
         } else {
           em.refresh_step(i, true);
-        }
-        if (lane == 0) {
-          *reinterpret_cast<volatile unsigned*>(&sh_thr) = em.thr;
-          if (i == 0) {
-            __threadfence_block();
-            *reinterpret_cast<volatile unsigned*>(&sh_go) = 1u;
-          }
         }
         __syncwarp();
       }
@@ -1648,17 +1645,8 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
         const unsigned m = sh_mask[s];
         process_chunk<kGrad, FAST, true, false, EMIT>(a, chunk_ref(g, chunk), stages[s], &full[s * kSubs], ph, m, scale, la);
         if (EMIT) {
-          sync_compute();                                    // the probability tile is complete, the target half is free
-          if (i == 1) {                                      // start-up: the first threshold (see the emitter)
-            while (*reinterpret_cast<volatile unsigned*>(&sh_go) == 0u) __nanosleep(64);
-          }
-          const unsigned thr = *reinterpret_cast<volatile unsigned*>(&sh_thr);
-          // chunk -> (class plane c, first row): the chunk is rows [32*ty, 32*ty+32) of plane c of sample my_b
-          const int jc = chunk - my_b * g.cps;               // chunk index inside the sample = c * (H/32) + ty
-          scan_chunk_rows(reinterpret_cast<u64*>(stages[s].g), &sh_cnt[s], (unsigned)kEmitCap, stages[s].x, thr,
-                          (unsigned)jc * (unsigned)kChunk, warp);
           __syncwarp();
-          if (lane == 0) mbar_arrive(&scanned[s]);
+          if (lane == 0) mbar_arrive(&scanned[s]);           // this warp's rows of the probability tile are in the stage
         } else {
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[s]);
