@@ -61,8 +61,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg5 / shapes blocks and the sharded parity check")
-    ap.add_argument("--no-fuse", action="store_true",
-                    help="do not let the loss launch emit the decode's peak candidates (decode re-reads the heat map)")
+    ap.add_argument("--fuse", action="store_true",
+                    help="let the loss launch emit the decode's peak candidates (cnh_cand; large shapes only). Built and "
+                         "bit-exact, but measured slower than loss + streaming decode so far (DESIGN 4.4): off by default")
     return ap.parse_args()
 
 
@@ -226,7 +227,7 @@ class DeviceStep:
     NVLink-mapped mailboxes; the totals by a one-warp launch forked next to decode) or 'nccl' (sharded:
     count -> all-reduce -> main -> all-reduce (forked next to decode) -> finalize)."""
 
-    FUSE = True          # the loss launch emits the decode's peak candidates when the shape allows it (--no-fuse: off)
+    FUSE = False         # --fuse: the loss launch emits the decode's peak candidates when the shape allows it
 
     def __init__(self, sets, cfg, world, group, schedule="auto"):
         import ctypes as C
@@ -241,10 +242,12 @@ class DeviceStep:
         self.ws_cand = torch.zeros(self.lib.cnh_cand_workspace_bytes(sets[0].hm.shape[0]) + 256, dtype=torch.uint8, device=dev)
         self.cand.workspace, self.cand.workspace_bytes = self.ws_cand.data_ptr(), self.ws_cand.numel()
         self.cand.K, self.cand.G = cfg.K, 0
-        self.no_cand = C.POINTER(L.Cand)()
+        self.plain_args = []                      # the same launches without candidate emission (timed alone)
         for s in sets:
             a = F.fill_detloss_args(s.hm, s.gt, s.ind, s.heads, 1.0, s.prob, s.grads, s.scalars, s.totals,
                                     norm=s.norm, norm_out=s.norm, b_global=s.hm.shape[0] * world)
+            self.plain_args.append(F.fill_detloss_args(s.hm, s.gt, s.ind, s.heads, 1.0, s.prob, s.grads, s.scalars, s.totals,
+                                                       norm=s.norm, norm_out=s.norm, b_global=s.hm.shape[0] * world))
             if DeviceStep.FUSE:
                 a.cand = C.pointer(self.cand)
             sc = L.ScaleArgs()
@@ -323,11 +326,9 @@ class DeviceStep:
     def loss_only(self, i):
         """the fused loss launch alone, WITHOUT candidate emission (nothing would consume the candidates)"""
         C, L = self.C, self.L
-        a = self.loss_args[i]
-        keep, a.cand = a.cand, self.no_cand
+        a = self.plain_args[i]
         L.check(self.lib.cnh_detloss_fused(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), L.stream_ptr()),
                 "detloss_fused")
-        a.cand = keep
 
     def loss_decode_pair(self, i):
         """single GPU: the loss launch (emitting candidates when it can) + the decode that consumes them"""
@@ -353,11 +354,9 @@ class DeviceStep:
 
     def main_only(self, i):
         C, L = self.C, self.L
-        a = self.loss_args[i]
-        keep, a.scalars = a.scalars, None
-        keep_c, a.cand = a.cand, self.no_cand
+        a = self.plain_args[i]
+        a.scalars = None
         L.check(self.lib.cnh_detloss_main(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), L.stream_ptr()), "main")
-        a.scalars, a.cand = keep, keep_c
 
     def allreduce_only(self, i):
         s = self.sets[i]
@@ -655,7 +654,7 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device for --impl ours"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    DeviceStep.FUSE = not args.no_fuse
+    DeviceStep.FUSE = bool(args.fuse)
     steps, warmup = args.steps, max(3, args.warmup)
     use_graph = not args.no_graph
     peak, peak_src = hbm_peak()

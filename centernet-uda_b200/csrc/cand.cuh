@@ -118,6 +118,116 @@ __device__ __forceinline__ void scan_chunk_rows(u64* keys, unsigned* key_cnt, un
     ++pos;
   }
 }
+// The same scan by ONE warp over rows [r_begin, r_end) of the tile, built for a warp that has nobody to hide its
+// latencies behind.  Pass 1: every lane marks, in four 32-bit row masks (one per column it owns), its pixels >= thr --
+// 32 independent LDS.128, no votes.  Pass 2: as long as any lane has a marked pixel, every such lane takes one and
+// tests it against its eight neighbours with scalar loads (0 beyond the tile: see scan_chunk_rows), all lanes at once:
+// the trip count is the largest number of marked pixels of any lane (one or two once the threshold has tightened),
+// not the number of rows that hold one.  Keys are appended to keys[n ...]; the new count is returned (it may run
+// past cap, the excess is not stored).
+__device__ __forceinline__ unsigned scan_chunk_warp(u64* keys, unsigned n, unsigned cap, const float* tile, unsigned thr,
+                                                    unsigned flat_tile0, int r_begin, int r_end) {
+  constexpr int W = 128;
+  const int lane = threadIdx.x & 31;
+  const float* col = tile + 4 * lane;
+  const float thr_eff = fmaxf(__uint_as_float(thr), __uint_as_float(1u));      // >= thr and > 0
+  unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+#pragma unroll
+  for (int r = 0; r < kCandRows; ++r) {
+    if (r >= r_begin && r < r_end) {
+      const float4 v = *reinterpret_cast<const float4*>(col + r * W);
+      m0 |= (v.x >= thr_eff ? 1u : 0u) << r;
+      m1 |= (v.y >= thr_eff ? 1u : 0u) << r;
+      m2 |= (v.z >= thr_eff ? 1u : 0u) << r;
+      m3 |= (v.w >= thr_eff ? 1u : 0u) << r;
+    }
+  }
+  while (__any_sync(0xffffffffu, (m0 | m1 | m2 | m3) != 0u)) {
+    int e = -1, r = 0;
+    if (m0) { e = 0; r = __ffs(m0) - 1; m0 &= m0 - 1u; }
+    else if (m1) { e = 1; r = __ffs(m1) - 1; m1 &= m1 - 1u; }
+    else if (m2) { e = 2; r = __ffs(m2) - 1; m2 &= m2 - 1u; }
+    else if (m3) { e = 3; r = __ffs(m3) - 1; m3 &= m3 - 1u; }
+    bool peak = false;
+    float v = 0.f;
+    int x = 0;
+    if (e >= 0) {
+      x = 4 * lane + e;
+      const float* p = tile + r * W + x;
+      v = p[0];
+      const bool l = x > 0, rt = x < W - 1, u = r > 0, d = r < kCandRows - 1;
+      float mx = v;
+      if (l) mx = fmaxf(mx, p[-1]);
+      if (rt) mx = fmaxf(mx, p[1]);
+      if (u) {
+        mx = fmaxf(mx, p[-W]);
+        if (l) mx = fmaxf(mx, p[-W - 1]);
+        if (rt) mx = fmaxf(mx, p[-W + 1]);
+      }
+      if (d) {
+        mx = fmaxf(mx, p[W]);
+        if (l) mx = fmaxf(mx, p[W - 1]);
+        if (rt) mx = fmaxf(mx, p[W + 1]);
+      }
+      peak = (v == mx);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, peak);
+    if (peak) {
+      const unsigned pos = n + (unsigned)__popc(bal & ((1u << lane) - 1u));
+      if (pos < cap) keys[pos] = ((u64)__float_as_uint(v) << 32) | (u64)(0xffffffffu - (flat_tile0 + (unsigned)(r * W + x)));
+    }
+    n += (unsigned)__popc(bal);
+  }
+  return n;
+}
+
+// The 3x3 test of a LIST of pixels of the tile (offsets inside the 32 x 128 tile, noted by the loss warps as they
+// produced the probabilities): lane k takes entry k, k + 32, ...  Pixels below thr (the threshold may have risen
+// since they were noted) are dropped.  Same key / append conventions as scan_chunk_warp.
+__device__ __forceinline__ unsigned test_pending_warp(u64* keys, unsigned n, unsigned cap, const float* tile,
+                                                      const unsigned short* pend, unsigned n_pend, unsigned thr,
+                                                      unsigned flat_tile0) {
+  constexpr int W = 128;
+  const int lane = threadIdx.x & 31;
+  const float thr_eff = fmaxf(__uint_as_float(thr), __uint_as_float(1u));
+  for (unsigned k0 = 0; k0 < n_pend; k0 += 32) {
+    const unsigned k = k0 + (unsigned)lane;
+    bool peak = false;
+    float v = 0.f;
+    int off = 0;
+    if (k < n_pend) {
+      off = (int)pend[k];
+      const int r = off >> 7, x = off & (W - 1);
+      const float* p = tile + off;
+      v = p[0];
+      if (v >= thr_eff) {
+        const bool l = x > 0, rt = x < W - 1, u = r > 0, d = r < kCandRows - 1;
+        float mx = v;
+        if (l) mx = fmaxf(mx, p[-1]);
+        if (rt) mx = fmaxf(mx, p[1]);
+        if (u) {
+          mx = fmaxf(mx, p[-W]);
+          if (l) mx = fmaxf(mx, p[-W - 1]);
+          if (rt) mx = fmaxf(mx, p[-W + 1]);
+        }
+        if (d) {
+          mx = fmaxf(mx, p[W]);
+          if (l) mx = fmaxf(mx, p[W - 1]);
+          if (rt) mx = fmaxf(mx, p[W + 1]);
+        }
+        peak = (v == mx);
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, peak);
+    if (peak) {
+      const unsigned pos = n + (unsigned)__popc(bal & ((1u << lane) - 1u));
+      if (pos < cap) keys[pos] = ((u64)__float_as_uint(v) << 32) | (u64)(0xffffffffu - (flat_tile0 + (unsigned)off));
+    }
+    n += (unsigned)__popc(bal);
+  }
+  return n;
+}
+
 // may a key of such a tile enter the threshold histogram?  Only if its 3x3 test was complete.
 __device__ __forceinline__ bool chunk_key_verified(u64 key, int HW, int H) {
   const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffu);
@@ -160,17 +270,75 @@ struct CandEmitter {
   __device__ __forceinline__ void forward(const u64* keys, unsigned n, unsigned cap, Counted counted) {
     if (n > cap) { overflow = true; n = cap; }
     if (local_cnt + n > (unsigned)kSliceCap) { overflow = true; n = (unsigned)kSliceCap - local_cnt; }
-    for (unsigned k = lane; k < n; k += 32) {
-      const u64 key = keys[k];
-      slice[local_cnt + k] = key;
-      if (counted(key)) {
-        const int bin = fine_bin((unsigned)(key >> 32));
-        red_add_u32(fhist + bin, 1u);
-        red_add_u32(shist + (bin >> 6), 1u);
+    // Keys of one 32-lane step that fall into the same bin are counted with ONE RED (match.any): the top bins of a
+    // sample are hit by every CTA that serves it, and same-address atomics serialise in the L2 slice.
+    for (unsigned k0 = 0; k0 < n; k0 += 32) {
+      const unsigned k = k0 + (unsigned)lane;
+      int bin = -1;
+      if (k < n) {
+        const u64 key = keys[k];
+        slice[local_cnt + k] = key;
+        if (counted(key)) bin = fine_bin((unsigned)(key >> 32));
+      }
+      const unsigned same_f = __match_any_sync(0xffffffffu, bin);
+      const unsigned same_s = __match_any_sync(0xffffffffu, bin >> 6);      // (-1 >> 6 == -1: the idle lanes pair up)
+      if (bin >= 0) {
+        if ((int)(__ffs(same_f) - 1) == lane) red_add_u32(fhist + bin, (unsigned)__popc(same_f));
+        if ((int)(__ffs(same_s) - 1) == lane) red_add_u32(shist + (bin >> 6), (unsigned)__popc(same_s));
       }
     }
     local_cnt += n;
     __syncwarp();
+  }
+  // one key per lane (or none) straight from registers; `count`: may it enter the histogram (complete 3x3 test)?
+  __device__ __forceinline__ void push(bool has, u64 key, bool count) {
+    const unsigned bal = __ballot_sync(0xffffffffu, has);
+    if (bal == 0u) return;
+    const unsigned n = (unsigned)__popc(bal);
+    if (local_cnt + n > (unsigned)kSliceCap) {
+      overflow = true;
+      return;
+    }
+    int bin = -1;
+    if (has) {
+      slice[local_cnt + (unsigned)__popc(bal & ((1u << lane) - 1u))] = key;
+      if (count) bin = fine_bin((unsigned)(key >> 32));
+    }
+    const unsigned same_f = __match_any_sync(0xffffffffu, bin);
+    const unsigned same_s = __match_any_sync(0xffffffffu, bin >> 6);
+    if (bin >= 0) {
+      if ((int)(__ffs(same_f) - 1) == lane) red_add_u32(fhist + bin, (unsigned)__popc(same_f));
+      if ((int)(__ffs(same_s) - 1) == lane) red_add_u32(shist + (bin >> 6), (unsigned)__popc(same_s));
+    }
+    local_cnt += n;
+  }
+  // up to four keys per lane (bit e of `flags` = key[e] is valid): one prefix sum for the warp, plain REDs
+  __device__ __forceinline__ void push4(unsigned flags, const u64 (&key)[4], bool count) {
+    if (__ballot_sync(0xffffffffu, flags != 0u) == 0u) return;
+    const int mine = __popc(flags);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      incl += (lane >= o) ? v : 0;
+    }
+    const unsigned n = (unsigned)__shfl_sync(0xffffffffu, incl, 31);
+    if (local_cnt + n > (unsigned)kSliceCap) {
+      overflow = true;
+      return;
+    }
+    unsigned pos = local_cnt + (unsigned)(incl - mine);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (flags & (1u << e)) {
+        slice[pos++] = key[e];
+        if (count) {
+          const int bin = fine_bin((unsigned)(key[e] >> 32));
+          red_add_u32(fhist + bin, 1u);
+          red_add_u32(shist + (bin >> 6), 1u);
+        }
+      }
+    local_cnt += n;
   }
   __device__ __forceinline__ void load_super() {
     const uint2 v = __ldcg(reinterpret_cast<const uint2*>(shist) + lane);
@@ -229,8 +397,8 @@ struct CandEmitter {
     pending = 0;
   }
   // one step of the pipelined refresh at iteration i: no load is consumed before it is kAge iterations old
+  template <int kAge = 3>
   __device__ __forceinline__ void refresh_step(int i, bool more) {
-    constexpr int kAge = 3;
     if (pending == 1 && i - issued_at >= kAge) {
       pending = super_step() ? 2 : 0;
       issued_at = i;
@@ -274,5 +442,114 @@ struct CandEmitter {
     local_cnt = kept;
   }
 };
+
+
+// ---- the emitter warp of the detection-loss kernels: peak tests on a 32 x 128 probability tile that lies in GLOBAL
+// memory (the chunk the CTA's other warps have just written; read through L2, so no shared-memory stage is held).
+// Rows beyond the tile are taken as 0 (see scan_chunk_rows / `verify_rows`).
+struct GTile {
+  const float* p;                          // tile origin (row 0, column 0), 128 floats per row
+  unsigned flat0;                          // flat index (inside the sample) of its first pixel
+  int y0, H, HW;                           // first image row, image height (which keys are complete tests)
+  __device__ __forceinline__ float at(int r, int x) const {
+    return (r >= 0 && r < kCandRows && x >= 0 && x < 128) ? __ldcg(p + r * 128 + x) : 0.f;
+  }
+  __device__ __forceinline__ bool complete(int r) const {          // was row r tested against real rows on both sides?
+    const int y = y0 + r;
+    return !((r == 0 && y > 0) || (r == kCandRows - 1 && y < H - 1));
+  }
+  __device__ __forceinline__ u64 key(float v, int r, int x) const {
+    return ((u64)__float_as_uint(v) << 32) | (u64)(0xffffffffu - (flat0 + (unsigned)(r * 128 + x)));
+  }
+};
+
+// (A) rows [r0, r0 + 4) with NO threshold, row-wise in registers (six 16-byte loads per lane, one round trip)
+__device__ __forceinline__ void gtile_rows_unpruned(CandEmitter& em, const GTile& t, int r0) {
+  const int lane = threadIdx.x & 31;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 row[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const int r = r0 - 1 + q;
+    row[q] = (r >= 0 && r < kCandRows) ? __ldcg(reinterpret_cast<const float4*>(t.p + r * 128) + lane) : zero;
+  }
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const float4 up = row[rr], mid = row[rr + 1], dn = row[rr + 2];
+    const float v0 = fmaxf(fmaxf(up.x, mid.x), dn.x), v1 = fmaxf(fmaxf(up.y, mid.y), dn.y);
+    const float v2 = fmaxf(fmaxf(up.z, mid.z), dn.z), v3 = fmaxf(fmaxf(up.w, mid.w), dn.w);
+    float left = __shfl_up_sync(0xffffffffu, v3, 1), right = __shfl_down_sync(0xffffffffu, v0, 1);
+    if (lane == 0) left = 0.f;
+    if (lane == 31) right = 0.f;
+    const float h[4] = {fmaxf(fmaxf(left, v0), v1), fmaxf(fmaxf(v0, v1), v2), fmaxf(fmaxf(v1, v2), v3), fmaxf(fmaxf(v2, v3), right)};
+    const float m[4] = {mid.x, mid.y, mid.z, mid.w};
+    unsigned flags = 0;
+    u64 key[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      flags |= (m[e] > 0.f && m[e] == h[e]) ? (1u << e) : 0u;
+      key[e] = t.key(m[e], r0 + rr, 4 * lane + e);
+    }
+    em.push4(flags, key, t.complete(r0 + rr));
+  }
+}
+
+// one pixel per lane (or none): the 3x3 test with scalar loads, then push
+__device__ __forceinline__ void gtile_test_push(CandEmitter& em, const GTile& t, bool has, int off, float thr_eff) {
+  bool peak = false;
+  float v = 0.f;
+  const int r = off >> 7, x = off & 127;
+  if (has) {
+    float nb[8];                                                       // the pixel and its neighbours: nine independent
+    int q = 0;                                                         // loads, ONE round trip through L2
+    v = __ldcg(t.p + off);
+#pragma unroll
+    for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx)
+        if (dr != 0 || dx != 0) nb[q++] = t.at(r + dr, x + dx);
+    float mx = v;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx = fmaxf(mx, nb[k]);
+    peak = (v >= thr_eff && v == mx);
+  }
+  em.push(peak, t.key(v, r, x), t.complete(r));
+}
+
+// (B) the pixels the loss warps noted (offsets inside the tile): lane k takes entry k, k + 32, ...
+__device__ __forceinline__ void gtile_pending(CandEmitter& em, const GTile& t, const unsigned short* pend, unsigned n_pend) {
+  const int lane = threadIdx.x & 31;
+  const float thr_eff = fmaxf(__uint_as_float(em.thr), __uint_as_float(1u));
+  for (unsigned k0 = 0; k0 < n_pend; k0 += 32) {
+    const unsigned k = k0 + (unsigned)lane;
+    gtile_test_push(em, t, k < n_pend, k < n_pend ? (int)pend[k] : 0, thr_eff);
+  }
+}
+
+// (C) rows [r_begin, 32) against em.thr without a list: pass 1 marks this lane's pixels >= thr (one 16-byte load per
+// row, all in flight), pass 2 tests them, every lane one pixel per trip
+__device__ __forceinline__ void gtile_scan(CandEmitter& em, const GTile& t, int r_begin) {
+  const int lane = threadIdx.x & 31;
+  const float thr_eff = fmaxf(__uint_as_float(em.thr), __uint_as_float(1u));
+  unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+#pragma unroll
+  for (int r = 0; r < kCandRows; ++r) {
+    if (r >= r_begin) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(t.p + r * 128) + lane);
+      m0 |= (v.x >= thr_eff ? 1u : 0u) << r;
+      m1 |= (v.y >= thr_eff ? 1u : 0u) << r;
+      m2 |= (v.z >= thr_eff ? 1u : 0u) << r;
+      m3 |= (v.w >= thr_eff ? 1u : 0u) << r;
+    }
+  }
+  while (__any_sync(0xffffffffu, (m0 | m1 | m2 | m3) != 0u)) {
+    int e = -1, r = 0;
+    if (m0) { e = 0; r = __ffs(m0) - 1; m0 &= m0 - 1u; }
+    else if (m1) { e = 1; r = __ffs(m1) - 1; m1 &= m1 - 1u; }
+    else if (m2) { e = 2; r = __ffs(m2) - 1; m2 &= m2 - 1u; }
+    else if (m3) { e = 3; r = __ffs(m3) - 1; m3 &= m3 - 1u; }
+    gtile_test_push(em, t, e >= 0, r * 128 + 4 * lane + (e >= 0 ? e : 0), thr_eff);
+  }
+}
 
 }  // namespace cnh

@@ -169,6 +169,7 @@ struct Geo {
   unsigned* next_b;        // [B] candidate emission: per-sample chunk tickets (zero between launches)
   CandGeo cand;            // candidate emission (cand.cuh): where the peaks of the probability tiles go
   int cand_K;              // top-K the candidates are pruned for (0: no emission)
+  int cand_dbg;            // tools/: 1 = the emitter relays the stage without scanning (cost of the schedule alone)
   long long* dbg;
 };
 
@@ -438,10 +439,21 @@ __device__ __forceinline__ void loss_acc_add(LossAcc& la, float v) {
 // known (NEED_GRAD && !KEEP), or (KEEP, single wave) it replaces the logits in the stage, unscaled.
 // Loss terms and num_pos go to the thread-local accumulators.  No barrier inside: a thread only
 // touches its own slots of the stage (WAIT: the stage is filled by bulk copies, wait for each sub-block).
-// PTILE (candidate emission): the probabilities also replace the logits in the stage -- the tile the peak scan reads.
+// PTILE (candidate emission): every pixel whose probability reaches the pruning threshold `pend.thr` is noted in the
+// stage's pending list (its offset in the chunk, 16 bits; one warp-aggregated shared-memory atomic per warp and
+// sub-block THAT HAS ONE -- rare once the threshold has tightened; six instructions otherwise).  thr == 0: nothing is
+// noted (the emitter scans the whole tile).
+constexpr int kPendCap = 256;                 // pending pixels per list; more: the emitter scans the whole tile
+constexpr int kPendSlots = 8;                 // lists in flight between the consumers and the emitter (a ring of its own)
+struct Pending {
+  unsigned short* list;                       // [kPendCap]
+  unsigned* count;
+  float thr;                                  // 0: do not note
+};
 template <bool NEED_GRAD, bool FAST, bool WAIT, bool KEEP, bool PTILE = false>
 __device__ __forceinline__ void process_chunk(const cnh_detloss_args& a, const ChunkRef& r, Stage& st, u64* bar,
-                                              unsigned parity, unsigned gmask, float scale, LossAcc& la) {
+                                              unsigned parity, unsigned gmask, float scale, LossAcc& la,
+                                              const Pending pend = Pending{nullptr, nullptr, 0.f}) {
   constexpr bool VEC = WAIT;                  // bulk-copied stages imply 16-byte aligned tensors and n % 4 == 0
   float* __restrict__ pp = a.prob + r.base;
   float* __restrict__ gq = NEED_GRAD ? a.grad_hm + r.base : nullptr;
@@ -503,7 +515,33 @@ __device__ __forceinline__ void process_chunk(const cnh_detloss_args& a, const C
         }
     }
     if (NEED_GRAD && KEEP) *reinterpret_cast<float4*>(st.x + off) = make_float4(gr[0], gr[1], gr[2], gr[3]);
-    if (PTILE) *reinterpret_cast<float4*>(st.x + off) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+    if (PTILE) {
+      if (pend.thr > 0.f) {
+        const bool any = fmaxf(fmaxf(ps[0], ps[1]), fmaxf(ps[2], ps[3])) >= pend.thr;
+        const unsigned who = __ballot_sync(0xffffffffu, any);
+        if (who != 0u) {                                       // (warp-uniform)
+          const unsigned bits = (ps[0] >= pend.thr ? 1u : 0u) | (ps[1] >= pend.thr ? 2u : 0u) | (ps[2] >= pend.thr ? 4u : 0u) |
+                                (ps[3] >= pend.thr ? 8u : 0u);
+          const int mine = __popc(bits), lane = threadIdx.x & 31;
+          int incl = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            incl += (lane >= o) ? t : 0;
+          }
+          unsigned base = 0;
+          if (lane == 31) base = atomicAdd(pend.count, (unsigned)incl);
+          base = __shfl_sync(0xffffffffu, base, 31);
+          unsigned pos = base + (unsigned)(incl - mine);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (bits & (1u << e)) {
+              if (pos < (unsigned)kPendCap) pend.list[pos] = (unsigned short)(off + e);
+              ++pos;
+            }
+        }
+      }
+    }
   }
   if (FAST) sum = __fmul_rn(sum, kLn2F);      // log2 -> natural log, once per thread and chunk
   loss_acc_add(la, sum);
@@ -1369,13 +1407,13 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
 //           No block barrier and no atomic per chunk.
 // ================================================================================================
 // EMIT (candidate emission; needs W == 128, H*W % 4096 == 0: a chunk is 32 full rows of one class plane): a tenth warp.
-//   consumers: the probabilities of the chunk also go into the stage (over the logits); one arrival per warp on
-//           `scanned` -- they never wait for the scan.
-//   warp 9 (emitter): once the eight warps have arrived, scans that 32 x 128 tile for 3x3 peaks above the sample's
-//           pruning threshold (a CTA finishes a chunk every ~4 us: one warp has time to spare), collects them in the
-//           target's half of the stage (free by then), forwards them to this CTA's slice of the sample's candidate
-//           list, counts them into the sample's histogram, keeps the threshold current (cand.cuh: CandEmitter), and
-//           frees the stage for the producer.
+//   consumers: note, per chunk, the pixels whose probability reaches the sample's pruning threshold (a handful once it
+//           has tightened) in a small shared-memory list; they free the stage themselves, as without emission.
+//   warp 9 (emitter): runs the 3x3 peak test on the noted pixels, reading the probabilities the consumers have just
+//           written to global memory back through L2 (no shared-memory stage is held: the kernel is issue-bound and a
+//           lone warp gets a fraction of an SM sub-partition's issue slots -- whatever it does must not sit between a
+//           stage and its refill); forwards the peaks to this CTA's slice of the sample's candidate list, counts them
+//           into the sample's histogram, keeps the threshold current (cand.cuh: CandEmitter).
 //   Every CTA serves ONE sample (CTA i: sample i % B, chunk tickets per sample), so a slice holds one sample's keys.
 // The decode (cnh_decode_candidates) then never reads the heat map: 4*C*H*W bytes per sample and a launch less.
 constexpr int kEmitThreads = kStashThreads + 32;
@@ -1395,8 +1433,14 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   __shared__ unsigned long long sh_tag;
   __shared__ unsigned sh_mask[kMaxStages];
   __shared__ int sh_chunk[kMaxStages];
-  __shared__ u64 scanned[kMaxStages];          // EMIT: the eight consumer warps are done with the stage's tile
-  __shared__ unsigned sh_cnt[kMaxStages];      // EMIT: keys in the stage's candidate buffer
+  // EMIT: a ring of kPendSlots pending lists between the consumers and the emitter (slot = chunk count % kPendSlots)
+  __shared__ u64 scanned[kPendSlots];          // the eight consumer warps are done with the slot's chunk
+  __shared__ u64 pend_free[kPendSlots];        // the emitter has taken the slot's list
+  __shared__ int sh_pchunk[kPendSlots];        // the chunk the list belongs to (-1: no more)
+  __shared__ unsigned sh_npend[kPendSlots];    // pending pixels of the chunk (may run past kPendCap)
+  __shared__ unsigned sh_fullscan[kPendSlots]; // some warp had no threshold yet: the emitter scans the whole tile
+  __shared__ unsigned short sh_pend[EMIT ? kPendSlots : 1][EMIT ? kPendCap : 1];
+  __shared__ float sh_thr;                     // EMIT: the emitter's current threshold, read by the consumers per chunk
   const int bid = blockIdx.x, grid = gridDim.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool consumer = warp < kWarps;
@@ -1412,9 +1456,15 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   if (tid == 0) {
     if (MODE != M_COUNT && VEC) {
       for (int i = 0; i < S * kSubs; ++i) mbar_init(&full[i], 1);
-      for (int i = 0; i < S; ++i) mbar_init(&empty[i], EMIT ? 1 : kWarps);
+      for (int i = 0; i < S; ++i) mbar_init(&empty[i], kWarps);
       if (EMIT) {
-        for (int i = 0; i < S; ++i) { mbar_init(&scanned[i], kWarps); sh_cnt[i] = 0u; }
+        for (int i = 0; i < kPendSlots; ++i) {
+          mbar_init(&scanned[i], kWarps);
+          mbar_init(&pend_free[i], 1);
+          sh_npend[i] = 0u;
+          sh_fullscan[i] = 0u;
+        }
+        sh_thr = 0.f;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -1592,35 +1642,62 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
       // ---- emitter ----
       CandEmitter em;
       em.init(g.cand, my_b, has_sample ? my_j : 0, g.cand_K);
-      const int HW = g.HW, H = a.H;
-      auto counted = [&](u64 key) { return chunk_key_verified(key, HW, H); };
 #pragma unroll 1
       for (int i = 0;; ++i) {
-        const int s = i % S;
-        const unsigned ph = (unsigned)((i / S) & 1);
-        mbar_wait(&full[s * kSubs], ph);                     // (the chunk's meta data)
-        if (sh_chunk[s] < 0) break;
-        mbar_wait(&scanned[s], ph);                          // the eight consumer warps have left the probability tile
+        const int s = i % kPendSlots;
+        const unsigned ph = (unsigned)((i / kPendSlots) & 1);
+        // (only `scanned` is waited on: the producer may refill the stage -- and complete its `full` barrier a second time
+        // -- before this warp gets here; the consumers cannot run more than S chunks ahead, see pend_free)
+        long long te0 = 0;
+        if (g.dbg != nullptr && lane == 0) te0 = clock64();
+        mbar_wait(&scanned[s], ph);                          // the chunk's probabilities are in global memory, its list complete
+        const int chunk = sh_pchunk[s];
+        if (chunk < 0) break;
+        if (g.dbg != nullptr && lane == 0) { const long long t = clock64(); g.dbg[(long long)bid * 16 + 12] += t - te0; te0 = t; }
         // chunk -> rows [32*ty, 32*ty+32) of class plane c of sample my_b; jc = c * (H/32) + ty
-        const int jc = sh_chunk[s] - my_b * g.cps;
-        u64* const keys = reinterpret_cast<u64*>(stages[s].g);
-#pragma unroll 1
-        for (int q = 0; q < kWarps; ++q)                     // four rows per pass, as a consumer warp would
-          scan_chunk_rows(keys, &sh_cnt[s], (unsigned)kEmitCap, stages[s].x, em.thr, (unsigned)jc * (unsigned)kChunk, q);
+        const int jc = chunk - my_b * g.cps;
+        GTile t;
+        t.p = a.prob + (long long)chunk * kChunk;
+        t.flat0 = (unsigned)jc * (unsigned)kChunk;
+        t.y0 = (jc % (a.H / kCandRows)) * kCandRows;
+        t.H = a.H;
+        t.HW = g.HW;
+        const unsigned n_pend = *reinterpret_cast<volatile unsigned*>(&sh_npend[s]);
+        const bool fullscan = i == 0 || *reinterpret_cast<volatile unsigned*>(&sh_fullscan[s]) != 0u || n_pend > (unsigned)kPendCap;
+        // the list is taken (into a register when it has at most one entry per lane), the stage's list is free again
+        int my_off = -1;
+        const bool small = !fullscan && n_pend <= 32u;
+        if (small && (unsigned)lane < n_pend) my_off = (int)sh_pend[s][lane];
         __syncwarp();
-        em.forward(keys, *reinterpret_cast<volatile unsigned*>(&sh_cnt[s]), (unsigned)kEmitCap, counted);
-        if (lane == 0) {
-          sh_cnt[s] = 0u;
-          mbar_arrive(&empty[s]);                            // the producer may refill the stage
+        if (small || fullscan) {
+          if (lane == 0) { sh_npend[s] = 0u; sh_fullscan[s] = 0u; mbar_arrive(&pend_free[s]); }
         }
-        if (i == 0) {
-          // first threshold: waited for (two L2 round trips, once) -- the first chunk was scanned without one
+        if (g.cand_dbg & 1) {
+        } else if (i == 0) {
+          // The first chunk, with no threshold yet: its first eight rows are tested unpruned; their peaks are forwarded
+          // and the first threshold is waited for (two L2 round trips, once -- by then the histogram holds the first
+          // rows of most CTAs of the sample); the other 24 rows follow with it.
+          gtile_rows_unpruned(em, t, 0);
+          gtile_rows_unpruned(em, t, 4);
           __threadfence();
           __nanosleep(600);                                  // the sample's other CTAs are at the same point: let their REDs land
           em.refresh_blocking();
+          gtile_scan(em, t, 8);
+        } else if (fullscan) {
+          gtile_scan(em, t, 0);
+        } else if (small) {
+          const float thr_eff = fmaxf(__uint_as_float(em.thr), __uint_as_float(1u));
+          gtile_test_push(em, t, my_off >= 0, my_off >= 0 ? my_off : 0, thr_eff);
         } else {
-          em.refresh_step(i, true);
+          gtile_pending(em, t, sh_pend[s], n_pend);
+          if (lane == 0) { sh_npend[s] = 0u; sh_fullscan[s] = 0u; mbar_arrive(&pend_free[s]); }
         }
+        if (g.dbg != nullptr && lane == 0) { const long long tt = clock64(); g.dbg[(long long)bid * 16 + 11] += tt - te0; te0 = tt; }
+        // the threshold: one step of the pipelined refresh per chunk (loads issued at the previous chunk have landed
+        // by now: nothing is waited for)
+        if (!(g.cand_dbg & 4)) em.refresh_step<1>(i, true);
+        if (lane == 0) *reinterpret_cast<volatile float*>(&sh_thr) = __uint_as_float(em.thr);
+        if (g.dbg != nullptr && lane == 0) { g.dbg[(long long)bid * 16 + 13] += clock64() - te0; g.dbg[(long long)bid * 16 + 14] = (long long)em.local_cnt; }
         __syncwarp();
       }
       if (has_sample) {
@@ -1637,19 +1714,38 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
         const int s = i % S;
         const unsigned ph = (unsigned)((i / S) & 1);
         long long tw0 = 0;
-        if (g.dbg != nullptr && tid == 0) tw0 = clock_ns();
+        if (g.dbg != nullptr && tid == 0) tw0 = clock64();
         mbar_wait(&full[s * kSubs], ph);                     // acquires sh_chunk / sh_mask of this fill
-        if (g.dbg != nullptr && tid == 0) { g.dbg[(long long)bid * 16 + 8] += clock_ns() - tw0; g.dbg[(long long)bid * 16 + 9] += 1; }
+        if (g.dbg != nullptr && tid == 0) { g.dbg[(long long)bid * 16 + 8] += clock64() - tw0; g.dbg[(long long)bid * 16 + 9] += 1; }
         const int chunk = sh_chunk[s];
+        const int ps = i % kPendSlots;                       // EMIT: this chunk's slot in the ring of pending lists
+        if (EMIT) {
+          // the emitter has taken the list this slot held kPendSlots chunks ago (it lags that far only rarely); then the
+          // chunk is handed to it by name -- sh_chunk[s] may be overwritten by the next refill before it looks
+          if (i >= kPendSlots) mbar_wait(&pend_free[ps], (unsigned)(((i / kPendSlots) - 1) & 1));
+          if (tid == 0) sh_pchunk[ps] = chunk;
+          if (chunk < 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&scanned[ps]);        // wake the emitter: no more chunks
+          }
+        }
         if (chunk < 0) break;
         const unsigned m = sh_mask[s];
-        process_chunk<kGrad, FAST, true, false, EMIT>(a, chunk_ref(g, chunk), stages[s], &full[s * kSubs], ph, m, scale, la);
+        Pending pend = {nullptr, nullptr, 0.f};
         if (EMIT) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&scanned[s]);           // this warp's rows of the probability tile are in the stage
-        } else {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[s]);
+          // Every warp takes the emitter's threshold as it stands (no agreement needed: it only rises, so whatever the
+          // emitter still wants when it gets to this tile has been noted by every warp).  A warp that finds none yet
+          // notes nothing and tells the emitter to scan the whole tile.
+          pend.list = sh_pend[ps];
+          pend.count = &sh_npend[ps];
+          pend.thr = *reinterpret_cast<volatile float*>(&sh_thr);
+          if (pend.thr == 0.f && lane == 0) sh_fullscan[ps] = 1u;
+        }
+        process_chunk<kGrad, FAST, true, false, EMIT>(a, chunk_ref(g, chunk), stages[s], &full[s * kSubs], ph, m, scale, la, pend);
+        __syncwarp();
+        if (lane == 0) {
+          if (EMIT) mbar_arrive(&scanned[ps]);               // this warp's probabilities and pending pixels of the chunk are out
+          mbar_arrive(&empty[s]);
         }
       }
     }
@@ -1861,6 +1957,8 @@ static Geo make_geo(const cnh_detloss_args* a, void* ws) {
   g.sparse = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + kHeaderBytes);
   g.next_b = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + kHeaderBytes + sparse_bytes(a));
   g.cand_K = 0;
+  static const int cand_dbg = getenv("CNH_EMIT_DEBUG") ? atoi(getenv("CNH_EMIT_DEBUG")) : 0;
+  g.cand_dbg = cand_dbg;
   g.cand = cand_geo(nullptr, a->B, 0);
   g.dbg = debug_buffer();
   return g;
@@ -1900,7 +1998,13 @@ static int resident_ctas(const void* kernel, int stages, int threads = kThreads)
     if (cache[i].k == kernel && cache[i].dev == dev && cache[i].stages == stages) return cache[i].ctas;
   const size_t smem = (size_t)stages * sizeof(Stage);
   int per_sm = 0;
-  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxStages * sizeof(Stage))) != cudaSuccess ||
+  // opt in to as much dynamic shared memory as the kernel's static part leaves of the 227 KB a CTA may own
+  cudaFuncAttributes fa;
+  size_t dyn_max = kMaxStages * sizeof(Stage);
+  if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess && fa.sharedSizeBytes + dyn_max > (size_t)227 * 1024)
+    dyn_max = (size_t)227 * 1024 - fa.sharedSizeBytes;
+  if (smem > dyn_max ||
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     per_sm = 0;

@@ -3,8 +3,9 @@ import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "centernet-uda_b200"), ROOT]
 import torch, bench
+bench.DeviceStep.FUSE = "--emit" in sys.argv
 from cnhead import _lib as L, synthetic
-name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+name = next((x for x in sys.argv[1:] if not x.startswith("-")), "cfg2")
 cfg = synthetic.CONFIGS[name]
 batch = cfg.batch if name != "cfg5" else 16
 dev = torch.device("cuda", 0)
@@ -39,6 +40,17 @@ for rep in range(2):
     d.loss_only(rep)
     show(f"detloss {name} rep{rep}", 8)
     t = dbg.cpu(); used = (t[:, 0] != 0) & (t[:, 1] != 0)
+    if name == "cfg5" and "--emit" in sys.argv:
+        dbg.zero_(); torch.cuda.synchronize()
+        L.check(lib.cnh_detloss_fused(C.byref(d.loss_args[rep]), d.ws_loss.data_ptr(), d.ws_loss.numel(), L.stream_ptr()), "f")
+        show(f"detloss+emit {name} rep{rep}", 5)
+        d.decode_step(rep); torch.cuda.synchronize()
+        t = dbg.cpu(); u2 = t[:, 9] > 0
+        f = lambda c: (t[u2, c].float() / 1965.0)        # SM cycles -> us at 1965 MHz
+        print("  EMIT (clock64, us at 1965 MHz): consumer blocked on full median/max:", round(f(8).median().item(), 2), round(f(8).max().item(), 2),
+              "| emitter: wait scanned", round(f(12).median().item(), 2), "scan+forward", round(f(11).median().item(), 2), "refresh", round(f(13).median().item(), 2),
+              "| keys forwarded per CTA median/max", t[u2, 14].median().item(), t[u2, 14].max().item())
+        t = dbg.cpu()
     if name == "cfg5":
         u2 = t[:, 9] > 0
         print("  consumer blocked on full (us) median/max:", (t[u2, 8].float() / 1e3).median().item(), (t[u2, 8].float() / 1e3).max().item(),

@@ -1,5 +1,5 @@
 """Where a step's time goes: CUDA events after every launch of a cfg5 (or given) step, eager launches,
-averaged.  Usage: python tools/step_events.py [cfg5] [--no-fuse]"""
+averaged.  Usage: python tools/step_events.py [cfg5] [--fuse]"""
 import ctypes as C
 import os
 import sys
@@ -11,7 +11,7 @@ import bench
 from cnhead import _lib as L, synthetic
 
 name = next((a for a in sys.argv[1:] if not a.startswith("-")), "cfg5")
-bench.DeviceStep.FUSE = "--no-fuse" not in sys.argv
+bench.DeviceStep.FUSE = "--fuse" in sys.argv
 cfg = synthetic.CONFIGS[name]
 batch = cfg.batch if name != "cfg5" else 16
 dev = torch.device("cuda", 0)
