@@ -69,6 +69,12 @@ def parse():
 
 def workload_name(cfg, batch):
     extra = " + rotated/periodic angle head" if cfg.angle else ""
+    if getattr(cfg, "advent", False):
+        return (f"{cfg.name}: batch {batch} per GPU, {cfg.classes} classes, {cfg.height}x{cfg.width} heat maps, the head-path "
+                f"kernels of one ADVENT step (uda/adversarial_entropy_minimization.py:77-152): source DetectionLoss fwd+bwd, "
+                f"entropy_map of the target logits forward + backward (dense upstream gradient), entropy_map of the sigmoided "
+                f"source map and of the target logits for the two discriminator passes, three AdventLoss fwd+bwd on "
+                f"[{batch},1,4,4] discriminator logits (the discriminator network itself is torch/cuDNN: not on the path)")
     if cfg.target_domain:
         extra += " + EntropyLoss and MaxSquareLoss fwd+bwd on a target-domain batch"
     return (f"{cfg.name}: batch {batch} per GPU, {cfg.classes} classes, {cfg.height}x{cfg.width} heat maps, "
@@ -212,11 +218,21 @@ class BufferSet:
             self.tdom = data["target"]["hm"].to(dev)
             self.tgrads = [torch.empty_like(self.tdom), torch.empty_like(self.tdom)]
             self.tloss = torch.zeros(2, device=dev)
+        if getattr(cfg, "advent", False):          # ADVENT: maps, a dense upstream gradient, discriminator logits
+            g = torch.Generator().manual_seed(99)
+            B = self.hm.shape[0]
+            self.maps = [torch.empty_like(self.tdom) for _ in range(3)]
+            self.upstream = (torch.randn(self.tdom.shape, generator=g) * 1e-3).to(dev)
+            self.disc_y = [torch.randn(B, 1, 4, 4, generator=g).to(dev) for _ in range(3)]
+            self.disc_g = [torch.empty_like(y) for y in self.disc_y]
+            self.adv_loss = torch.zeros(3, device=dev)
 
     def nbytes(self):
         ts = [self.hm, self.wh, self.reg, self.gt, self.prob] + self.grads
         if self.tdom is not None:
             ts += [self.tdom] + self.tgrads
+        if hasattr(self, "maps"):
+            ts += self.maps + [self.upstream]
         return sum(t.numel() * t.element_size() for t in ts)
 
 
@@ -270,7 +286,8 @@ class DeviceStep:
         self.ws_dec = torch.zeros(self.lib.cnh_decode_workspace_bytes(C.byref(self.dec_args[0])) + 256,
                                   dtype=torch.uint8, device=dev)
         self.uda_scale, self.ws_soft = [], None
-        if cfg.target_domain:
+        self.advent = bool(getattr(cfg, "advent", False))
+        if cfg.target_domain and not self.advent:
             s0 = sets[0]
             N, Cc, H, W = s0.tdom.shape
             self.uda_dims = (N, Cc, H, W, N * world)
@@ -301,7 +318,9 @@ class DeviceStep:
             torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
             if int(flag.item()) == 0:
                 self.schedule, self.box = "nccl", None
-        self.launches_per_step = {"single": 3, "peers": 4, "nccl": 5}[self.schedule] + (3 if cfg.target_domain else 0)
+        self.launches_per_step = {"single": 3, "peers": 4, "nccl": 5}[self.schedule] + (3 if self.ws_soft is not None else 0)
+        if self.advent:
+            self.launches_per_step += 7 - 1           # three maps forward, one backward, three BCE; no decode
 
     def fused_decode(self):
         return self.cand.G > 0
@@ -371,6 +390,22 @@ class DeviceStep:
         L.check(self.lib.cnh_decode(self.C.byref(self.dec_args[i]), self.ws_dec.data_ptr(), self.ws_dec.numel(),
                                     L.stream_ptr()), "decode")
 
+    def advent_tail(self, i, st):
+        """uda/adversarial_entropy_minimization.py:91-133 after the source loss: generator pass (map forward, BCE against
+        the source label, backward through the map with the discriminator's input gradient), then the two detached
+        discriminator passes -- the source map taken over the ALREADY SIGMOIDED tensor (:116)."""
+        L, lib, s = self.L, self.lib, self.sets[i]
+        N, Cc, H, W = s.tdom.shape
+        n = s.disc_y[0].numel()
+        L.check(lib.cnh_entropy_map_fwd(s.tdom.data_ptr(), s.maps[0].data_ptr(), N, Cc, H, W, st), "entropy_map_fwd")
+        L.check(lib.cnh_bce_const(s.disc_y[0].data_ptr(), s.disc_g[0].data_ptr(), s.adv_loss[0:].data_ptr(), n, 0.0, st), "bce")
+        L.check(lib.cnh_entropy_map_bwd(s.tdom.data_ptr(), s.upstream.data_ptr(), s.tgrads[0].data_ptr(), N, Cc, H, W, st),
+                "entropy_map_bwd")
+        L.check(lib.cnh_entropy_map_fwd(s.prob.data_ptr(), s.maps[1].data_ptr(), N, Cc, H, W, st), "entropy_map_fwd")
+        L.check(lib.cnh_bce_const(s.disc_y[1].data_ptr(), s.disc_g[1].data_ptr(), s.adv_loss[1:].data_ptr(), n, 0.0, st), "bce")
+        L.check(lib.cnh_entropy_map_fwd(s.tdom.data_ptr(), s.maps[2].data_ptr(), N, Cc, H, W, st), "entropy_map_fwd")
+        L.check(lib.cnh_bce_const(s.disc_y[2].data_ptr(), s.disc_g[2].data_ptr(), s.adv_loss[2:].data_ptr(), n, 1.0, st), "bce")
+
     # ---- the step -------------------------------------------------------------------------------------------
     def step(self, i):
         C, L = self.C, self.L
@@ -404,7 +439,10 @@ class DeviceStep:
                     L.check(self.lib.cnh_detloss_finalize(C.byref(a), s.totals.data_ptr(), L.stream_ptr()), "finalize")
                 self.ev_join.record(self.side)
         L.check(self.lib.cnh_scale_inplace(C.byref(self.scale_args[i]), st), "scale")            # backward
-        self.decode_step(i)
+        if self.advent:
+            self.advent_tail(i, st)
+        else:
+            self.decode_step(i)
         if self.schedule != "single":
             torch.cuda.current_stream().wait_event(self.ev_join)
         if self.ws_soft is not None:               # cfg4: EntropyLoss and MaxSquareLoss fwd+bwd on the target batch
@@ -674,7 +712,7 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     launch_mode, schedule, n_sets, set_bytes = w.launch_mode(), w.dstep.describe(), w.n_sets, w.set_bytes
     launches_per_step, loss_bytes, step_bytes = w.dstep.launches_per_step, w.loss_bytes, w.step_bytes
     parity = {}
-    if world > 1 and not args.no_extra:
+    if world > 1 and not args.no_extra and not getattr(cfg, "advent", False):
         parity[cfg.name] = sharded_parity(w, rank, world, dev)
     w.close()
 
@@ -709,7 +747,7 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
                                                            "kernels", "gpu_launches_per_step")}
             extra["cfg5"] = blk
         shapes = {}
-        for name in ("cfg1", "cfg3", "cfg4"):
+        for name in ("cfg1", "cfg3", "cfg4", "advent"):
             if name == cfg.name:
                 continue
             c = synthetic.CONFIGS[name]
@@ -860,6 +898,11 @@ def main():
     from cnhead import synthetic
     cfg = synthetic.CONFIGS[args.config]
     batch = args.batch or (cfg.batch if cfg.name != "cfg5" else 16)
+    if getattr(cfg, "advent", False):              # kernels of the ADVENT step: no decode, no plugin-level e2e / CPU leg
+        args.no_e2e, args.no_cpu_baseline = True, True
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "--config advent times the CUDA kernels of the ADVENT step only"}))
+            return
     if args.impl == "reference":
         run_reference(args, cfg, batch, rank, world)
         return

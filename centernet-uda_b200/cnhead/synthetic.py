@@ -33,6 +33,7 @@ class HeadConfig:
     rotated: bool = False
     target_domain: bool = False
     objects_hi: int = 20
+    advent: bool = False       # the ADVENT step (uda/adversarial_entropy_minimization.py:77-152) instead of decode
 
     @property
     def wh_channels(self) -> int:
@@ -42,6 +43,11 @@ class HeadConfig:
         """Algorithmic bytes per sample: focal 16*C*HW (12 without grad),
         dense wh/reg gradient maps 4*(D+2)*HW, decode 4*C*HW, each UDA loss 8*C*HW."""
         hw = self.height * self.width
+        if self.advent:
+            # source DetectionLoss fwd+bwd, three self-information maps forward (logits in, map out: 8*C*HW each), one
+            # backward through the map with a dense upstream gradient (logits + upstream in, gradient out: 12*C*HW);
+            # the discriminator's [N,1,h/32,w/32] logits and their BCE are negligible
+            return 16 * self.classes * hw + 4 * (self.wh_channels + 2) * hw + (3 * 8 + 12) * self.classes * hw
         n = (16 if grad else 12) * self.classes * hw
         if grad:
             n += 4 * (self.wh_channels + 2) * hw
@@ -58,6 +64,8 @@ CONFIGS: Dict[str, HeadConfig] = {
     "cfg3": HeadConfig("cfg3", 2, batch=16, classes=6, angle=True, periodic=True, rotated=True),
     "cfg4": HeadConfig("cfg4", 3, batch=16, classes=6, target_domain=True),
     "cfg5": HeadConfig("cfg5", 4, batch=128, classes=80, objects_hi=60),
+    # not a BASELINE config: the kernels of one ADVENT step around the (out-of-scope) discriminator network
+    "advent": HeadConfig("advent", 5, batch=16, classes=6, target_domain=True, advent=True),
 }
 
 
