@@ -907,6 +907,14 @@ def main():
         run_reference(args, cfg, batch, rank, world)
         return
     if world > 1:
+        # one process per GPU, each on its own slice of the host's cores: eight host threads that all launch kernels and
+        # stage pinned buffers otherwise migrate over the same few cores (e2e at N = 8)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per] or cores)
+        except (AttributeError, OSError):
+            pass
         torch.cuda.set_device(local_rank)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
