@@ -520,6 +520,11 @@ class GraphRunner:
 
     def timed(self, steps, warmup, world, dev):
         self.run(warmup)
+        if self.graphs is not None and steps >= self.n:
+            # the timed region replays the whole-round graph; its FIRST launch uploads it to the device (hundreds of
+            # microseconds, and at N > 1 every rank waits for the slowest inside the kernels' rendezvous): launch it
+            # once more, untimed, whatever W was (these n extra steps are reported as "warmup_graph_steps")
+            self.round.replay()
         aligned_start(world, dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -774,6 +779,7 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": config_dict(cfg, batch, world),
+        "warmup_graph_steps": n_sets if (use_graph and steps >= n_sets) else 0,
         "run": {"buffer_sets": f"rotating {n_sets} buffer sets of {set_bytes / 2**20:.1f} MiB "
                                f"({n_sets * set_bytes / 2**20:.0f} MiB > 126 MiB L2): HBM-cold every step",
                 "launch": launch_mode, "schedule": schedule},
