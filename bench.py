@@ -461,17 +461,11 @@ def barrier(world):
 
 
 def aligned_start(world, dev):
-    """barrier + synchronize, then (N > 1) every rank leaves at the same wall-clock instant: with 20-step timed
-    regions (0.6 ms) the tens of microseconds by which ranks leave an NCCL barrier apart would otherwise be
-    charged to the first step's in-kernel rendezvous.  One node: the ranks share the system clock."""
+    """barrier + synchronize.  (Tried: letting every rank leave at one agreed wall-clock instant 3 ms later -- the GPUs
+    idle meanwhile and the first timed steps then run 3x slower: 103 instead of 28 us/step over a 20-step region at
+    N = 8.  What aligns the ranks instead is an untimed pre-roll of the step graph right in front of the timed region,
+    see GraphRunner.timed.)"""
     barrier(world)
-    if world == 1:
-        return
-    t = torch.tensor([time.time() + 0.003], dtype=torch.float64, device=dev)
-    torch.distributed.broadcast(t, 0)
-    t0 = float(t.item())
-    while time.time() < t0:
-        pass
 
 
 def max_over_ranks(ms, world, dev):
@@ -520,12 +514,14 @@ class GraphRunner:
 
     def timed(self, steps, warmup, world, dev):
         self.run(warmup)
-        if self.graphs is not None and steps >= self.n:
-            # the timed region replays the whole-round graph; its FIRST launch uploads it to the device (hundreds of
-            # microseconds, and at N > 1 every rank waits for the slowest inside the kernels' rendezvous): launch it
-            # once more, untimed, whatever W was (these n extra steps are reported as "warmup_graph_steps")
-            self.round.replay()
         aligned_start(world, dev)
+        if self.graphs is not None and steps >= self.n:
+            # Pre-roll, untimed and NOT followed by a host synchronisation: one whole round of the step graph right in
+            # front of the timed region (reported as "warmup_graph_steps").  The timed region replays this graph, whose
+            # first launch uploads it to the device (hundreds of microseconds); and at N > 1 the steps' own rendezvous
+            # (in-kernel mailboxes / NCCL) brings the ranks, which leave a host barrier tens of microseconds apart, into
+            # lockstep before the start event is reached in stream order.
+            self.round.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         self.run(steps)
