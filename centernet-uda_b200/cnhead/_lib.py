@@ -171,6 +171,11 @@ def require(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
         raise RuntimeError(f"cnhead: {name} is on {t.device}; this path runs on CUDA only (no CPU fallback)")
     if t.dtype != dtype:
         raise RuntimeError(f"cnhead: {name} must be {dtype}, got {t.dtype}")
+    if _cur_device is not None and t.device.index != _cur_device():
+        # the library launches on the CURRENT device's current stream: a tensor of another device would be touched
+        # through a foreign pointer (illegal address, or silent peer access)
+        raise RuntimeError(f"cnhead: {name} lives on cuda:{t.device.index} but the current device is cuda:{_cur_device()}; "
+                           f"wrap the call in torch.cuda.device({t.device.index})")
     return t if t.is_contiguous() else t.contiguous()
 
 

@@ -50,10 +50,15 @@ class DetectionsFetcher:
         self.K, self.down_ratio, self.rotated = int(max_detections), float(down_ratio), bool(rotated)
         self.score_threshold, self.apply_sigmoid = score_threshold, bool(apply_sigmoid)
         self.depth, self._slots, self._next = max(1, int(depth)), {}, 0
+        self._pending = {}                     # slot key -> event of the copy that last targeted its pinned buffers
 
     def _slot(self, B, nk):
         key = (self._next % self.depth, B, nk)
         self._next += 1
+        prev = self._pending.get(key)
+        if prev is not None:                   # a result of `depth` launches ago may still be in flight into these
+            prev.synchronize()                 # buffers (or unread): never overwrite under a pending copy
+        self._last_key = key
         if key not in self._slots:
             self._slots[key] = (torch.empty(B, self.K, 7 if self.rotated else 6).pin_memory(),
                                 torch.empty(B, self.K, nk, 2).pin_memory() if nk else None,
@@ -75,5 +80,6 @@ class DetectionsFetcher:
             h_counts.copy_(counts, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dets.device))
+        self._pending[self._last_key] = ev
         return PendingDetections(ev, h_dets, h_kps if kout is not None else None,
                                  h_counts if counts is not None else None, self.rotated)

@@ -57,6 +57,7 @@ class HostFeeder:
         self._slots: List[Tuple[Dict[str, torch.Tensor], ...]] = [None] * depth   # device tensors per slot
         self._ready = [torch.cuda.Event() for _ in range(depth)]                  # copies of the slot landed
         self._free = [None] * depth                                               # consumer finished with the slot
+        self._handed = [False] * depth                                            # get() handed it out, release() not yet called
         self._head = 0                                                            # next slot to fill
         self._tail = 0                                                            # next slot to hand out
         self.bytes_per_put = 0
@@ -96,6 +97,9 @@ class HostFeeder:
         if self._head - self._tail >= self.depth:
             raise RuntimeError("HostFeeder: all slots are staged; call get() first")
         i = self._head % self.depth
+        if self._handed[i]:
+            # overwriting a slot whose consumer never told us it was done would race the copy against its kernels
+            raise RuntimeError("HostFeeder: the slot to be refilled was handed out by get() but never release()d")
         key = tuple(id(v) for d in dicts for v in d.values())
         plan = self._plans.get((i, key))
         if plan is None:                                     # first time this host set meets this slot
@@ -144,6 +148,7 @@ class HostFeeder:
         i = self._tail % self.depth
         torch.cuda.current_stream(self.device).wait_event(self._ready[i])
         self._tail += 1
+        self._handed[i] = True
         return self._slots[i][0]
 
     def release(self) -> None:
@@ -152,3 +157,4 @@ class HostFeeder:
         ev = self._free[i] or torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self._free[i] = ev
+        self._handed[i] = False

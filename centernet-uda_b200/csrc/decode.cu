@@ -68,12 +68,24 @@ struct DecGeo {
   u64* cand;                              // [B][tiles_per_sample * slot]  dense per-sample lists
   long long* dbg;
   // candidate lists (cand.cuh): filled by decode_stream_kernel or by the detection-loss kernels, consumed by
-  // decode_finish_kernel
+  // finish_sample (inside decode_cluster_kernel, only_overflow)
   CandGeo cl;
   int only_overflow;                      // cluster kernel launched as the fallback: samples without the flag exit at once
   int verify_rows;                        // finish: candidates of the first / last row of every `verify_rows`-row tile were
                                           // tested without the row beyond the tile (0: every candidate is a verified peak)
 };
+
+// leave a sample's candidate-list state (histograms, slice sizes) zeroed for the next launch; first 256 threads
+__device__ __forceinline__ void cand_state_clear(const DecGeo& g, int b) {
+  const int tid = threadIdx.x;
+  if (tid >= 256) return;
+  unsigned* const shist = g.cl.shist + (long long)b * kSuperBins;
+  unsigned* const fhist = g.cl.fhist + (long long)b * kFineBins;
+  unsigned* const cta_cnt = g.cl.cta_cnt + (long long)b * g.cl.G;
+  for (int q = tid; q < kFineBins; q += 256) fhist[q] = 0u;
+  if (tid < kSuperBins) shist[tid] = 0u;
+  for (int q = tid; q < g.cl.G; q += 256) cta_cnt[q] = 0u;
+}
 
 constexpr int kMaxStages = 8;
 template <int KEYS>
@@ -914,6 +926,8 @@ __device__ __forceinline__ void scan_rows_group(u64* keys, unsigned* key_cnt, un
   }
 }
 
+__device__ __forceinline__ void finish_sample(const cnh_decode_args& a, const DecGeo& g, MergeSmem& s, int b);
+
 // ---- cluster path: one thread-block cluster per sample, ONE launch, no global scratch ------------------
 // The CS CTAs of a cluster split the sample's tiles (tile t -> CTA t % CS), each walking its share
 // with a TMA ring and keeping a running candidate set in shared memory: whenever the set outgrows
@@ -1017,9 +1031,18 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next PDL launch (the next step's loss) may be placed
   asm volatile("griddepcontrol.wait;" ::: "memory");        // PDL: the producer of `heat` has completed
-  // launched behind the streaming path as its fallback: only samples whose overflow flag is up are redone (every CTA
-  // of the cluster reads the same word, before anyone can have cleared it: the leader does so after the last barrier)
-  if (g.only_overflow && __ldcg(&g.cl.state[b].overflow) == 0u) return;
+  // Launched behind a kernel that left per-sample candidate lists (the streaming decode kernel, or a detection-loss
+  // launch): the usual sample is FINISHED from its lists by the first 256 threads of its cluster's leader (the other
+  // CTAs and warps exit at once); a sample whose candidate buffers ran over is redone from the heat map by the whole
+  // cluster, exactly (every CTA of the cluster reads the same word, before anyone can have cleared it: the leader does
+  // so after the last cluster barrier).
+  if (g.only_overflow) {
+    if (__ldcg(&g.cl.state[b].overflow) == 0u) {
+      if (rank != 0 || tid >= kThreads) return;
+      finish_sample(a, g, *reinterpret_cast<MergeSmem*>(smem_raw), b);
+      return;
+    }
+  }
   if (tid == 0) {
     s.cnt = 0;
     s.cnt2 = 0;
@@ -1193,9 +1216,10 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
   dbg_stamp(g.dbg, 7);
   cluster.sync();                                           // release/acquire: the inbox is complete
   if (rank != 0) return;
-  // redone here: the finish kernel, if it runs behind this launch (only_overflow == 1), must still skip the sample
-  // and clears the word itself
-  if (g.only_overflow && tid == 0) g.cl.state[b].overflow = g.only_overflow == 1 ? 2u : 0u;
+  if (g.only_overflow) {                                    // redone here: the lists are void, the flag comes down
+    if (tid == 0) g.cl.state[b].overflow = 0u;
+    cand_state_clear(g, b);
+  }
   dbg_stamp(g.dbg, 3);
 
   // ---- leader: final selection (all warps) + sort + gather (warps 0-7) -------------------------------------
@@ -1285,10 +1309,10 @@ decode_cluster_kernel(const __grid_constant__ cnh_decode_args a, const __grid_co
 //   warps 0-7 (consumers): each scans 4 rows of the staged tile (threshold-first, 3x3 test from shared memory)
 //           and appends its peaks to the stage's buffer; one mbarrier arrival per warp frees the stage.
 // The histogram counts only keys already forwarded, so every threshold derived from it is valid (at least K real
-// peaks reach it) however far the CTAs of a sample have drifted apart.  decode_finish_kernel (one CTA per sample,
-// launched with programmatic stream serialisation) selects, sorts and emits.  A stage buffer or slice that runs
-// over (plateaus of ties: thousands of equal scores) raises the sample's overflow flag; the cluster kernel,
-// launched behind as a fallback that exits at once for every other sample, then redoes that sample exactly.
+// peaks reach it) however far the CTAs of a sample have drifted apart.  ONE cluster launch follows (programmatic
+// stream serialisation): the leader CTA of each sample's cluster selects, sorts and emits from the lists
+// (finish_sample; the other CTAs exit at once).  A stage buffer or slice that runs over (plateaus of ties: thousands of
+// equal scores) raises the sample's overflow flag; that sample's whole cluster then redoes it from the heat map, exactly.
 // ================================================================================================
 constexpr int kStRows = 32;                               // tile rows
 constexpr int kStStages = 4;                              // ring depth
@@ -1449,97 +1473,118 @@ decode_stream_kernel(const __grid_constant__ cnh_decode_args a, const __grid_con
   if (tid == 0) dbg_stamp(g.dbg, 1);
 }
 
-// One CTA per sample: final threshold from the sample's two-level histogram, survivors from the G slices into
-// shared memory, selection + sort + filler + gather + boxes (select_sort_emit), and the sample's global state
-// left zeroed for the next launch.  Samples whose overflow flag is up are left to the cluster kernel.
-__global__ void __launch_bounds__(kThreads)
-decode_finish_kernel(const cnh_decode_args a, const DecGeo g) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  MergeSmem& s = *reinterpret_cast<MergeSmem*>(smem_raw);
+// Finish of one sample from its candidate lists (256 threads; barriers are the named 256-thread barrier, so this runs
+// as a kernel of its own or inside the first 256 threads of the cluster kernel's leader): threshold = lower edge of the
+// fine bin of the K-th counted key (two dependent L2 loads, issued beside the load of the slice sizes), survivors of
+// the G slices into shared memory (slices dealt to warps, 16-byte loads, four in flight per lane), selection + sort +
+// filler + gather + boxes (select_sort_emit), and the sample's global state left zeroed for the next launch.
+__device__ __forceinline__ void finish_sample(const cnh_decode_args& a, const DecGeo& g, MergeSmem& s, int b) {
   constexpr int kKeyCap = MergeSmem::kKeyCap;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int b = (int)blockIdx.x, K = a.K;
-  const int G = g.cl.G;
+  const int K = a.K, G = g.cl.G;
   unsigned* const shist = g.cl.shist + (long long)b * kSuperBins;
   unsigned* const fhist = g.cl.fhist + (long long)b * kFineBins;
   unsigned* const cta_cnt = g.cl.cta_cnt + (long long)b * G;
   const u64* const slices = g.cl.slices + (long long)b * G * kSliceCap;
   for (int q = 0; q < kFineBins / 2 / kThreads; ++q) s.hist[tid + q * kThreads] = 0u;
   if (tid == 0) { s.cnt = 0; s.cnt2 = 0; s.sh_thr = 0u; }
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");        // PDL: the stream kernel's writes are visible from here
   dbg_stamp(g.dbg, 5);
-  const unsigned ovf = __ldcg(&g.cl.state[b].overflow);  // 1: the cluster kernel will redo this sample, 2: it has
-  const bool skip = ovf != 0u;
   unsigned* const n_slice = reinterpret_cast<unsigned*>(s.stage);           // [G] keys per slice (`stage` is free until the sort)
   for (int q = tid; q < G; q += kThreads) n_slice[q] = __ldcg(cta_cnt + q);
-  __syncthreads();
-  if (!skip) {
-    // (no threshold walk here: the producers re-pruned their slices against the latest threshold on their way out;
-    // what is left -- the top K plus a few hundred keys -- is cut by select_sort_emit's local histogram)
-    const unsigned thr_final = 0u;
-    dbg_stamp(g.dbg, 6);
-    // ---- survivors of every slice -> shared memory keys + packed fine histogram ----
-    // Candidates that came out of a tile scanned WITHOUT its halo rows (the detection-loss kernels emit them from their
-    // own 32-row chunks) were tested against the neighbours inside the tile only: those of a tile's first / last row
-    // are checked here against the three pixels of the row beyond it (read from the heat map: a few dozen keys).
-    auto verified = [&](u64 key) -> bool {
-      if (g.verify_rows == 0 || key == 0ull) return true;
-      const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffu);
-      const unsigned cls = flat / (unsigned)g.HW, pix = flat - cls * (unsigned)g.HW;
-      const int y = (int)(pix / (unsigned)a.W), x = (int)(pix - (unsigned)y * (unsigned)a.W);
-      const int r = y % g.verify_rows;
-      int yy = -1;
-      if (r == 0 && y > 0) yy = y - 1;
-      else if (r == g.verify_rows - 1 && y < a.H - 1) yy = y + 1;
-      if (yy < 0) return true;
-      const float score = __uint_as_float((unsigned)(key >> 32));
-      const float* row = a.heat + ((long long)b * a.C + cls) * g.HW + (long long)yy * a.W;
-      float m = __ldcg(row + x);
-      if (x > 0) m = fmaxf(m, __ldcg(row + x - 1));
-      if (x < a.W - 1) m = fmaxf(m, __ldcg(row + x + 1));
-      return m <= score;
-    };
-    // Slices are dealt to the warps (f may vote: warp-uniform trip counts); two keys per 16-byte load, four loads in
-    // flight per lane.  The slice sizes were read in one go (n_slice, shared memory).
-    auto for_each_survivor = [&](auto f) {
-      for (int jj = tid >> 5; jj < G; jj += kWarps) {
-        const unsigned nc = n_slice[jj];
-        const ulonglong2* cand = reinterpret_cast<const ulonglong2*>(slices + (long long)jj * kSliceCap);
-        const unsigned np = (nc + 1u) >> 1;                  // pairs
-        for (unsigned e0 = 0; e0 < np; e0 += 4 * 32) {
-          ulonglong2 k[4];
+  group_sync();
+  // ---- the K-th counted key's fine bin (warp 0; the same two-level walk as the producers') ----
+  if (tid < 32) {
+    const uint2 v = __ldcg(reinterpret_cast<const uint2*>(shist) + lane);
+    unsigned mine = v.x + v.y, incl = mine;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const unsigned e = e0 + q * 32 + lane;
-            k[q] = (e < np) ? __ldcg(cand + e) : make_ulonglong2(0ull, 0ull);
-          }
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned u = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += u;
+    }
+    unsigned above = incl - mine;
+    int sel = -1;
+    unsigned ab = 0;
+    if (above < (unsigned)K && incl >= (unsigned)K) {
+      if (above + v.y >= (unsigned)K) { sel = 2 * lane + 1; ab = above; }
+      else { sel = 2 * lane; ab = above + v.y; }
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, sel >= 0);
+    if (who != 0u) {
+      const int src = __ffs(who) - 1;
+      const int sb = __shfl_sync(0xffffffffu, sel, src);
+      const unsigned above_sb = __shfl_sync(0xffffffffu, ab, src);
+      const uint2 f = __ldcg(reinterpret_cast<const uint2*>(fhist + sb * 64) + lane);
+      mine = f.x + f.y;
+      incl = mine;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (e0 + q * 32 >= np) break;                    // warp-uniform
-            const unsigned e = e0 + q * 32 + lane;
-            f(2 * e < nc && (unsigned)(k[q].x >> 32) >= thr_final && verified(k[q].x), k[q].x);
-            f(2 * e + 1 < nc && (unsigned)(k[q].y >> 32) >= thr_final && verified(k[q].y), k[q].y);
-          }
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += u;
+      }
+      above = above_sb + incl - mine;
+      if (above < (unsigned)K && above + mine >= (unsigned)K)
+        s.sh_thr = __float_as_uint((float)(sb * 64 + ((above + f.y >= (unsigned)K) ? 2 * lane + 1 : 2 * lane)) *
+                                   (1.0f / (float)kFineBins));
+    }
+  }
+  group_sync();
+  const unsigned thr_final = s.sh_thr;                       // 0: fewer than K counted peaks, keep everything
+  dbg_stamp(g.dbg, 6);
+  // Candidates that came out of a tile scanned WITHOUT its halo rows (the detection-loss kernels emit them from their
+  // own 32-row chunks) were tested against the neighbours inside the tile only: those of a tile's first / last row
+  // are checked here against the three pixels of the row beyond it (read from the heat map: a few dozen keys).
+  auto verified = [&](u64 key) -> bool {
+    if (g.verify_rows == 0 || key == 0ull) return true;
+    const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+    const unsigned cls = flat / (unsigned)g.HW, pix = flat - cls * (unsigned)g.HW;
+    const int y = (int)(pix / (unsigned)a.W), x = (int)(pix - (unsigned)y * (unsigned)a.W);
+    const int r = y % g.verify_rows;
+    int yy = -1;
+    if (r == 0 && y > 0) yy = y - 1;
+    else if (r == g.verify_rows - 1 && y < a.H - 1) yy = y + 1;
+    if (yy < 0) return true;
+    const float score = __uint_as_float((unsigned)(key >> 32));
+    const float* row = a.heat + ((long long)b * a.C + cls) * g.HW + (long long)yy * a.W;
+    float m = __ldcg(row + x);
+    if (x > 0) m = fmaxf(m, __ldcg(row + x - 1));
+    if (x < a.W - 1) m = fmaxf(m, __ldcg(row + x + 1));
+    return m <= score;
+  };
+  // Slices are dealt to the warps (f may vote: warp-uniform trip counts); two keys per 16-byte load, four loads in
+  // flight per lane.  The slice sizes were read in one go (n_slice, shared memory).
+  auto for_each_survivor = [&](auto f) {
+    for (int jj = tid >> 5; jj < G; jj += kWarps) {
+      const unsigned nc = n_slice[jj];
+      const ulonglong2* cand = reinterpret_cast<const ulonglong2*>(slices + (long long)jj * kSliceCap);
+      const unsigned np = (nc + 1u) >> 1;                  // pairs
+      for (unsigned e0 = 0; e0 < np; e0 += 4 * 32) {
+        ulonglong2 k[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const unsigned e = e0 + q * 32 + lane;
+          k[q] = (e < np) ? __ldcg(cand + e) : make_ulonglong2(0ull, 0ull);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (e0 + q * 32 >= np) break;                    // warp-uniform
+          const unsigned e = e0 + q * 32 + lane;
+          f(2 * e < nc && (unsigned)(k[q].x >> 32) >= thr_final && verified(k[q].x), k[q].x);
+          f(2 * e + 1 < nc && (unsigned)(k[q].y >> 32) >= thr_final && verified(k[q].y), k[q].y);
         }
       }
-    };
-    for_each_survivor([&](bool ok, u64 k) {
-      append_if(ok, k, s.keys, &s.cnt, (unsigned)kKeyCap);
-      if (ok) hist_add(s.hist, fine_bin((unsigned)(k >> 32)));
-    });
-    __syncthreads();
-    dbg_stamp(g.dbg, 7);
-    select_sort_emit(a, g, s, b, s.keys, (int)s.cnt, kKeyCap,
-                     [&](auto f) { for_each_survivor([&](bool ok, u64 k) { f(ok ? k : 0ull); }); });   // convergent: f may vote
-    dbg_stamp(g.dbg, 10);
-  }
-  // ---- leave the sample's global state zeroed for the next launch ----
-  __syncthreads();
-  if (tid == 0 && ovf == 2u) g.cl.state[b].overflow = 0u;
-  for (int q = tid; q < kFineBins; q += kThreads) fhist[q] = 0u;
-  if (tid < kSuperBins) shist[tid] = 0u;
-  for (int q = tid; q < G; q += kThreads) cta_cnt[q] = 0u;
+    }
+  };
+  for_each_survivor([&](bool ok, u64 k) {
+    append_if(ok, k, s.keys, &s.cnt, (unsigned)kKeyCap);
+    if (ok) hist_add(s.hist, fine_bin((unsigned)(k >> 32)));
+  });
+  group_sync();
+  dbg_stamp(g.dbg, 7);
+  select_sort_emit(a, g, s, b, s.keys, (int)s.cnt, kKeyCap,
+                   [&](auto f) { for_each_survivor([&](bool ok, u64 k) { f(ok ? k : 0ull); }); });   // convergent: f may vote
+  dbg_stamp(g.dbg, 10);
+  group_sync();
+  cand_state_clear(g, b);
 }
 
 // ---- host ---------------------------------------------------------------------------------------
@@ -1755,7 +1800,6 @@ static int launch_stream(const cnh_decode_args* a, void* workspace, int dev, cud
     int n = 0;
     if (cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_stream_kernel, kStThreads, kStSmemBytes) != cudaSuccess || n < 1) {
       cudaGetLastError();
       return kClusterUnavailable;
@@ -1778,53 +1822,20 @@ static int launch_stream(const cnh_decode_args* a, void* workspace, int dev, cud
   lc.blockDim = dim3(kStThreads);
   lc.dynamicSmemBytes = kStSmemBytes;
   CNH_CUDA(cudaLaunchKernelEx(&lc, decode_stream_kernel, *a, g));
-  // the fallback sits BETWEEN the stream and the finish kernel (it exits at once unless a flag is up, its launch hides
-  // under the stream kernel's tail): behind the finish kernel its launch and drain end the step 4 us later (measured)
+  // (a separate finish kernel with the cluster kernel as a pure fallback BEHIND it ended the step 4 us later, between the
+  // two 2-3 us later than this single launch: measured)
   return launch_finish(a, g, cs, st);
 }
 
-// fallback cluster launch (exits at once unless a sample's overflow flag is up) + finish kernel over the candidate
-// lists in g.cl; CNH_DECODE_FALLBACK_LAST: the fallback behind the finish kernel (experiments)
+// ONE cluster launch behind whatever left the candidate lists in g.cl: finishes the usual samples from their lists,
+// redoes the overflowed ones from the heat map (decode_cluster_kernel, only_overflow)
 static int launch_finish(const cnh_decode_args* a, const DecGeo& g, int cs, cudaStream_t st) {
-  static const bool use_pdl = (getenv("CNH_NO_PDL") == nullptr);
-  static const bool fallback_last = getenv("CNH_DECODE_FALLBACK_LAST") != nullptr;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cudaLaunchConfig_t lc;
-  memset(&lc, 0, sizeof(lc));
-  lc.stream = st;
-  lc.attrs = attr;
-  lc.numAttrs = use_pdl ? 1 : 0;
-  lc.gridDim = dim3((unsigned)a->B);
-  lc.blockDim = dim3(kThreads);
-  lc.dynamicSmemBytes = sizeof(MergeSmem);
-  if (!fallback_last) {
-    const int rc = launch_cluster_rows<32>(a, g, cs, st, 1);
-    CNH_REQUIRE(rc != kClusterUnavailable, CNH_E_UNSUPPORTED, "decode: the cluster launch of the candidate path's fallback was refused");
-    if (rc != CNH_OK) return rc;
-  }
-  CNH_CUDA(cudaLaunchKernelEx(&lc, decode_finish_kernel, *a, g));
-  if (fallback_last) {
-    const int rc = launch_cluster_rows<32>(a, g, cs, st, 2);
-    CNH_REQUIRE(rc != kClusterUnavailable, CNH_E_UNSUPPORTED, "decode: the cluster launch of the candidate path's fallback was refused");
-    return rc;
-  }
-  return CNH_OK;
+  const int rc = launch_cluster_rows<32>(a, g, cs, st, 1);
+  CNH_REQUIRE(rc != kClusterUnavailable, CNH_E_UNSUPPORTED, "decode: the cluster launch that finishes the candidate lists was refused");
+  return rc;
 }
 
-static bool finish_attr(int dev) {
-  static bool set[64] = {false};
-  if (dev < 0 || dev >= 64) return false;
-  if (!set[dev]) {
-    if (cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)) != cudaSuccess) {
-      cudaGetLastError();
-      return false;
-    }
-    set[dev] = true;
-  }
-  return true;
-}
+static bool finish_attr(int) { return true; }
 
 static bool want_stream(const cnh_decode_args* a) {
   const int force = decode_env().stream;

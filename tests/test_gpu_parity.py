@@ -526,6 +526,19 @@ def test_host_feeder_round_trip_from_a_pinned_arena():
         f.get()
 
 
+def test_host_feeder_refuses_to_overwrite_an_unreleased_slot():
+    from cnhead.feeder import HostFeeder
+    host = HostFeeder.pinned_sets([({"x": torch.randn(4, 8)},), ({"x": torch.randn(4, 8)},)])
+    f = HostFeeder("cuda", depth=1)
+    f.put(*host[0])
+    f.get()                                         # handed out, never released
+    with pytest.raises(RuntimeError, match="never release"):
+        f.put(*host[1])
+    f.release()
+    f.put(*host[1])
+    assert torch.equal(f.get()[0]["x"].cpu(), host[1][0]["x"])
+
+
 def test_decode_K_larger_than_plane_raises():
     from backends.decode import decode_detection
     with pytest.raises(RuntimeError):
