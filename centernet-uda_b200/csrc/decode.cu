@@ -417,30 +417,43 @@ __device__ __forceinline__ void select_sort_emit(const cnh_decode_args& a, const
   }
   group_sync();
   dbg_stamp(g.dbg, 8);
+  const float* payload = nullptr;
+  int n_payload = 0;
   if (got <= kThreads) {
-    // <= 256 keys: one key per thread, bitonic sort (descending; padding 0 sorts last).  Exchange
-    // distances below 32 are warp shuffles, the rest go through shared memory.
-    u64 k = (tid < got) ? sort_src[tid] : 0ull;
-    group_sync();                                       // sort_src may alias `sorted`'s neighbours: settle reads
-    for (int size = 2; size <= kThreads; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        u64 other;
-        if (stride >= 32) {
-          sorted[tid] = k;
-          group_sync();
-          other = sorted[tid ^ stride];
-          group_sync();
-        } else {
-          other = __shfl_xor_sync(0xffffffffu, k, stride);
-        }
-        const bool up = ((tid & size) == 0);               // this block sorts descending
-        const bool lower = ((tid & stride) == 0);
-        const bool take_max = (up == lower);
-        const u64 mx = k > other ? k : other, mn = k > other ? other : k;
-        k = take_max ? mx : mn;
+    // <= 256 keys: one key per thread, rank sort (keys are unique: position = number of larger keys; ~got broadcast
+    // LDS.64 per thread, no barrier inside).  The key's reg / wh values are loaded BEFORE the scan (their round trip
+    // hides under it) and land at the key's rank in `payload` -- the upper half of the key buffer, free by now.
+    float* const pay = reinterpret_cast<float*>(const_cast<u64*>(keys) + key_cap / 2);
+    const bool act = tid < got;
+    const u64 k = act ? sort_src[tid] : 0ull;
+    float pv[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (act) {
+      const unsigned pix = (0xffffffffu - (unsigned)(k & 0xffffffffu)) % (unsigned)g.HW;
+      if (a.reg) {
+        pv[0] = __ldg(a.reg + ((long long)b * 2 + 0) * g.HW + pix);
+        pv[1] = __ldg(a.reg + ((long long)b * 2 + 1) * g.HW + pix);
       }
+      pv[2] = __ldg(a.wh + ((long long)b * a.D + 0) * g.HW + pix);
+      pv[3] = __ldg(a.wh + ((long long)b * a.D + 1) * g.HW + pix);
+      if (a.rotated) pv[4] = __ldg(a.wh + ((long long)b * a.D + 2) * g.HW + pix);
     }
-    sorted[tid] = k;
+    int rank = 0;
+    if (act) {
+      int j = 0;
+      for (; j + 3 < got; j += 4) {                         // four independent loads in flight
+        const u64 k0 = sort_src[j], k1 = sort_src[j + 1], k2 = sort_src[j + 2], k3 = sort_src[j + 3];
+        rank += (k0 > k) + (k1 > k) + (k2 > k) + (k3 > k);
+      }
+      for (; j < got; ++j) rank += (sort_src[j] > k);
+    }
+    group_sync();                                           // sort_src may be `sorted`'s neighbour: settle the reads
+    if (act) {
+      sorted[rank] = k;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) pay[5 * rank + c] = pv[c];
+    }
+    payload = pay;
+    n_payload = got;
   } else {
   // rank sort (keys are unique): position = number of larger keys.  T lanes share a key when there
   // are fewer keys than threads (T = 8, 4, 2 or 1), each scanning every T-th key.
@@ -469,7 +482,7 @@ __device__ __forceinline__ void select_sort_emit(const cnh_decode_args& a, const
   dbg_stamp(g.dbg, 11);
   if (g.dbg && tid == 0) { g.dbg[(long long)blockIdx.x * 16 + 12] = m; g.dbg[(long long)blockIdx.x * 16 + 13] = got; }
   group_sync();
-  emit_sorted(a, g, s, b, got, nullptr, 0);
+  emit_sorted(a, g, s, b, got, payload, n_payload);
 }
 
 // ---- the tail of select_sort_emit: s.stage[0..got) sorted descending -> filler, counts, gather, boxes -------------
