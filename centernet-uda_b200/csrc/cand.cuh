@@ -57,185 +57,6 @@ __device__ __forceinline__ void red_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Scan of a HALO-LESS candidate tile: 32 rows x 128 columns of clamped probabilities in shared memory (what a
-// detection-loss chunk leaves of one class plane), four rows per warp (warp w of 8: rows 4w..4w+3), lane owns
-// columns [4*lane, 4*lane+4).  The rows above row 0 and below row 31 belong to other chunks and are taken as 0: a
-// pixel of those two rows is tested against its five neighbours inside the tile only (the finish kernel checks the
-// other three, see `verify_rows`).  Peaks >= thr are appended to keys[*key_cnt ...] (bounded by cap; the counter may
-// run past it).  Key = (score bits << 32) | ~(flat index): descending key order = score descending, ties to the lower
-// index.
-__device__ __forceinline__ void scan_chunk_rows(u64* keys, unsigned* key_cnt, unsigned cap, const float* tile, unsigned thr,
-                                                unsigned flat_tile0, int warp) {
-  constexpr int W = 128, RW = 4;
-  const int lane = threadIdx.x & 31;
-  const int r0 = RW * warp;
-  const float* base_row = tile + r0 * W + 4 * lane;                               // the warp's first row
-  const float thr_eff = fmaxf(__uint_as_float(thr), __uint_as_float(1u));      // >= thr and > 0
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 up = r0 > 0 ? *reinterpret_cast<const float4*>(base_row - W) : zero;
-  float4 mid = *reinterpret_cast<const float4*>(base_row);
-  unsigned flags = 0;                                                             // bit 4*rr + e
-#pragma unroll
-  for (int rr = 0; rr < RW; ++rr) {
-    const float4 dn = (r0 + rr + 1 < kCandRows) ? *reinterpret_cast<const float4*>(base_row + (rr + 1) * W) : zero;
-    const bool any = fmaxf(fmaxf(mid.x, mid.y), fmaxf(mid.z, mid.w)) >= thr_eff;
-    if (__ballot_sync(0xffffffffu, any) != 0u) {
-      const unsigned pass = (mid.x >= thr_eff ? 1u : 0u) | (mid.y >= thr_eff ? 2u : 0u) | (mid.z >= thr_eff ? 4u : 0u) |
-                            (mid.w >= thr_eff ? 8u : 0u);
-      const float v0 = fmaxf(fmaxf(up.x, mid.x), dn.x), v1 = fmaxf(fmaxf(up.y, mid.y), dn.y);
-      const float v2 = fmaxf(fmaxf(up.z, mid.z), dn.z), v3 = fmaxf(fmaxf(up.w, mid.w), dn.w);
-      float left = __shfl_up_sync(0xffffffffu, v3, 1), right = __shfl_down_sync(0xffffffffu, v0, 1);
-      if (lane == 0) left = 0.f;
-      if (lane == 31) right = 0.f;
-      const float h0 = fmaxf(fmaxf(left, v0), v1), h1 = fmaxf(fmaxf(v0, v1), v2);
-      const float h2 = fmaxf(fmaxf(v1, v2), v3), h3 = fmaxf(fmaxf(v2, v3), right);
-      const unsigned f = pass & ((mid.x == h0 ? 1u : 0u) | (mid.y == h1 ? 2u : 0u) | (mid.z == h2 ? 4u : 0u) |
-                                 (mid.w == h3 ? 8u : 0u));
-      flags |= f << (4 * rr);
-    }
-    up = mid;
-    mid = dn;
-  }
-  if (__ballot_sync(0xffffffffu, flags != 0u) == 0u) return;
-  const int mine = __popc(flags);
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    incl += (lane >= o) ? v : 0;
-  }
-  unsigned base = 0;
-  if (lane == 31) base = atomicAdd(key_cnt, (unsigned)incl);
-  base = __shfl_sync(0xffffffffu, base, 31);
-  unsigned pos = base + (unsigned)(incl - mine);
-  const unsigned flat_lane0 = flat_tile0 + (unsigned)r0 * (unsigned)W + 4u * (unsigned)lane;
-  while (flags) {
-    const int bit = __ffs(flags) - 1;
-    flags &= flags - 1u;
-    const int rr = bit >> 2, e = bit & 3;
-    const float v = base_row[rr * W + e];
-    if (pos < cap) keys[pos] = ((u64)__float_as_uint(v) << 32) | (u64)(0xffffffffu - (flat_lane0 + (unsigned)(rr * W + e)));
-    ++pos;
-  }
-}
-// The same scan by ONE warp over rows [r_begin, r_end) of the tile, built for a warp that has nobody to hide its
-// latencies behind.  Pass 1: every lane marks, in four 32-bit row masks (one per column it owns), its pixels >= thr --
-// 32 independent LDS.128, no votes.  Pass 2: as long as any lane has a marked pixel, every such lane takes one and
-// tests it against its eight neighbours with scalar loads (0 beyond the tile: see scan_chunk_rows), all lanes at once:
-// the trip count is the largest number of marked pixels of any lane (one or two once the threshold has tightened),
-// not the number of rows that hold one.  Keys are appended to keys[n ...]; the new count is returned (it may run
-// past cap, the excess is not stored).
-__device__ __forceinline__ unsigned scan_chunk_warp(u64* keys, unsigned n, unsigned cap, const float* tile, unsigned thr,
-                                                    unsigned flat_tile0, int r_begin, int r_end) {
-  constexpr int W = 128;
-  const int lane = threadIdx.x & 31;
-  const float* col = tile + 4 * lane;
-  const float thr_eff = fmaxf(__uint_as_float(thr), __uint_as_float(1u));      // >= thr and > 0
-  unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-#pragma unroll
-  for (int r = 0; r < kCandRows; ++r) {
-    if (r >= r_begin && r < r_end) {
-      const float4 v = *reinterpret_cast<const float4*>(col + r * W);
-      m0 |= (v.x >= thr_eff ? 1u : 0u) << r;
-      m1 |= (v.y >= thr_eff ? 1u : 0u) << r;
-      m2 |= (v.z >= thr_eff ? 1u : 0u) << r;
-      m3 |= (v.w >= thr_eff ? 1u : 0u) << r;
-    }
-  }
-  while (__any_sync(0xffffffffu, (m0 | m1 | m2 | m3) != 0u)) {
-    int e = -1, r = 0;
-    if (m0) { e = 0; r = __ffs(m0) - 1; m0 &= m0 - 1u; }
-    else if (m1) { e = 1; r = __ffs(m1) - 1; m1 &= m1 - 1u; }
-    else if (m2) { e = 2; r = __ffs(m2) - 1; m2 &= m2 - 1u; }
-    else if (m3) { e = 3; r = __ffs(m3) - 1; m3 &= m3 - 1u; }
-    bool peak = false;
-    float v = 0.f;
-    int x = 0;
-    if (e >= 0) {
-      x = 4 * lane + e;
-      const float* p = tile + r * W + x;
-      v = p[0];
-      const bool l = x > 0, rt = x < W - 1, u = r > 0, d = r < kCandRows - 1;
-      float mx = v;
-      if (l) mx = fmaxf(mx, p[-1]);
-      if (rt) mx = fmaxf(mx, p[1]);
-      if (u) {
-        mx = fmaxf(mx, p[-W]);
-        if (l) mx = fmaxf(mx, p[-W - 1]);
-        if (rt) mx = fmaxf(mx, p[-W + 1]);
-      }
-      if (d) {
-        mx = fmaxf(mx, p[W]);
-        if (l) mx = fmaxf(mx, p[W - 1]);
-        if (rt) mx = fmaxf(mx, p[W + 1]);
-      }
-      peak = (v == mx);
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, peak);
-    if (peak) {
-      const unsigned pos = n + (unsigned)__popc(bal & ((1u << lane) - 1u));
-      if (pos < cap) keys[pos] = ((u64)__float_as_uint(v) << 32) | (u64)(0xffffffffu - (flat_tile0 + (unsigned)(r * W + x)));
-    }
-    n += (unsigned)__popc(bal);
-  }
-  return n;
-}
-
-// The 3x3 test of a LIST of pixels of the tile (offsets inside the 32 x 128 tile, noted by the loss warps as they
-// produced the probabilities): lane k takes entry k, k + 32, ...  Pixels below thr (the threshold may have risen
-// since they were noted) are dropped.  Same key / append conventions as scan_chunk_warp.
-__device__ __forceinline__ unsigned test_pending_warp(u64* keys, unsigned n, unsigned cap, const float* tile,
-                                                      const unsigned short* pend, unsigned n_pend, unsigned thr,
-                                                      unsigned flat_tile0) {
-  constexpr int W = 128;
-  const int lane = threadIdx.x & 31;
-  const float thr_eff = fmaxf(__uint_as_float(thr), __uint_as_float(1u));
-  for (unsigned k0 = 0; k0 < n_pend; k0 += 32) {
-    const unsigned k = k0 + (unsigned)lane;
-    bool peak = false;
-    float v = 0.f;
-    int off = 0;
-    if (k < n_pend) {
-      off = (int)pend[k];
-      const int r = off >> 7, x = off & (W - 1);
-      const float* p = tile + off;
-      v = p[0];
-      if (v >= thr_eff) {
-        const bool l = x > 0, rt = x < W - 1, u = r > 0, d = r < kCandRows - 1;
-        float mx = v;
-        if (l) mx = fmaxf(mx, p[-1]);
-        if (rt) mx = fmaxf(mx, p[1]);
-        if (u) {
-          mx = fmaxf(mx, p[-W]);
-          if (l) mx = fmaxf(mx, p[-W - 1]);
-          if (rt) mx = fmaxf(mx, p[-W + 1]);
-        }
-        if (d) {
-          mx = fmaxf(mx, p[W]);
-          if (l) mx = fmaxf(mx, p[W - 1]);
-          if (rt) mx = fmaxf(mx, p[W + 1]);
-        }
-        peak = (v == mx);
-      }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, peak);
-    if (peak) {
-      const unsigned pos = n + (unsigned)__popc(bal & ((1u << lane) - 1u));
-      if (pos < cap) keys[pos] = ((u64)__float_as_uint(v) << 32) | (u64)(0xffffffffu - (flat_tile0 + (unsigned)off));
-    }
-    n += (unsigned)__popc(bal);
-  }
-  return n;
-}
-
-// may a key of such a tile enter the threshold histogram?  Only if its 3x3 test was complete.
-__device__ __forceinline__ bool chunk_key_verified(u64 key, int HW, int H) {
-  const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffu);
-  const int y = (int)((flat % (unsigned)HW) >> 7);           // W == 128
-  const int r = y & (kCandRows - 1);
-  return !((r == 0 && y > 0) || (r == kCandRows - 1 && y < H - 1));
-}
-
 // One warp forwards candidate keys to its CTA's slice of a sample's list, counts them into the sample's two-level
 // histogram (fire-and-forget REDs) and derives the pruning threshold from that histogram: the lower edge of the fine
 // bin of the K-th counted key.  Only keys already forwarded are counted, so every threshold is valid (at least K real
@@ -244,7 +65,8 @@ struct CandEmitter {
   unsigned* shist;
   unsigned* fhist;
   u64* slice;
-  unsigned local_cnt, thr;
+  unsigned local_cnt, thr, cap;            // keys in the slice, threshold (score bits), keys the slice may hold
+  unsigned* shared_cnt;                    // not null: several warps share the slice, push4 draws its positions here
   bool overflow;
   int K, lane;
   int pending, sb_sel, issued_at;          // refresh pipeline: 0 idle, 1 super bins in flight, 2 fine bins in flight
@@ -256,6 +78,8 @@ struct CandEmitter {
     slice = c.slices + ((long long)b * c.G + j) * kSliceCap;
     local_cnt = 0;
     thr = 0;
+    cap = (unsigned)kSliceCap;
+    shared_cnt = nullptr;
     overflow = false;
     K = K_;
     lane = threadIdx.x & 31;
@@ -269,7 +93,7 @@ struct CandEmitter {
   template <class Counted>
   __device__ __forceinline__ void forward(const u64* keys, unsigned n, unsigned cap, Counted counted) {
     if (n > cap) { overflow = true; n = cap; }
-    if (local_cnt + n > (unsigned)kSliceCap) { overflow = true; n = (unsigned)kSliceCap - local_cnt; }
+    if (local_cnt + n > cap) { overflow = true; n = cap - local_cnt; }
     // Keys of one 32-lane step that fall into the same bin are counted with ONE RED (match.any): the top bins of a
     // sample are hit by every CTA that serves it, and same-address atomics serialise in the L2 slice.
     for (unsigned k0 = 0; k0 < n; k0 += 32) {
@@ -295,7 +119,7 @@ struct CandEmitter {
     const unsigned bal = __ballot_sync(0xffffffffu, has);
     if (bal == 0u) return;
     const unsigned n = (unsigned)__popc(bal);
-    if (local_cnt + n > (unsigned)kSliceCap) {
+    if (local_cnt + n > cap) {
       overflow = true;
       return;
     }
@@ -323,11 +147,16 @@ struct CandEmitter {
       incl += (lane >= o) ? v : 0;
     }
     const unsigned n = (unsigned)__shfl_sync(0xffffffffu, incl, 31);
-    if (local_cnt + n > (unsigned)kSliceCap) {
+    unsigned first = local_cnt;
+    if (shared_cnt != nullptr) {                             // (shared-memory counter: one atomic per warp and call)
+      if (lane == 31) first = atomicAdd(shared_cnt, n);
+      first = __shfl_sync(0xffffffffu, first, 31);
+    }
+    if (first + n > cap) {
       overflow = true;
       return;
     }
-    unsigned pos = local_cnt + (unsigned)(incl - mine);
+    unsigned pos = first + (unsigned)(incl - mine);
 #pragma unroll
     for (int e = 0; e < 4; ++e)
       if (flags & (1u << e)) {
@@ -446,7 +275,10 @@ struct CandEmitter {
 
 // ---- the emitter warp of the detection-loss kernels: peak tests on a 32 x 128 probability tile that lies in GLOBAL
 // memory (the chunk the CTA's other warps have just written; read through L2, so no shared-memory stage is held).
-// Rows beyond the tile are taken as 0 (see scan_chunk_rows / `verify_rows`).
+// A tile is HALO-LESS: the rows above row 0 and below row 31 belong to other chunks and are taken as 0, so a pixel of
+// those two rows is tested against its five neighbours inside the tile only; such keys are forwarded but not counted
+// into the threshold histogram, and the finish kernel checks the other three neighbours (`verify_rows`).
+// Key = (score bits << 32) | ~(flat index): descending key order = score descending, ties to the lower index.
 struct GTile {
   const float* p;                          // tile origin (row 0, column 0), 128 floats per row
   unsigned flat0;                          // flat index (inside the sample) of its first pixel

@@ -171,6 +171,17 @@ __device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// one non-blocking test of the phase with `parity` (true: completed)
+__device__ __forceinline__ bool mbar_test(u64* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0u;
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u64* bar, int x, int y, int z) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"

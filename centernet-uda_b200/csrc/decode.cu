@@ -1848,8 +1848,6 @@ static int launch_finish(const cnh_decode_args* a, const DecGeo& g, int cs, cuda
   return rc;
 }
 
-static bool finish_attr(int) { return true; }
-
 static bool want_stream(const cnh_decode_args* a) {
   const int force = decode_env().stream;
   if (a->apply_sigmoid || force == 0) return false;
@@ -1893,7 +1891,7 @@ extern "C" int cnh_decode_candidates(const cnh_decode_args* a, const cnh_cand* c
   CNH_REQUIRE(cand_ws_bytes(cand->B, cand->G) <= cand->workspace_bytes, CNH_E_WORKSPACE, "decode_candidates: candidate workspace too small");
   int dev = 0;
   CNH_CUDA(cudaGetDevice(&dev));
-  CNH_REQUIRE(cluster_attrs(dev) && finish_attr(dev), CNH_E_UNSUPPORTED, "decode_candidates: kernel attributes refused");
+  CNH_REQUIRE(cluster_attrs(dev), CNH_E_UNSUPPORTED, "decode_candidates: kernel attributes refused");
   DecGeo g = make_geo(a, nullptr, kStRows);
   const int cs = pick_cluster_size(a->B, g.tiles_per_sample, dev);
   CNH_REQUIRE(cs >= 1, CNH_E_UNSUPPORTED, "decode_candidates: no cluster launch possible on this device");

@@ -169,8 +169,8 @@ struct Geo {
   unsigned* next_b;        // [B] candidate emission: per-sample chunk tickets (zero between launches)
   CandGeo cand;            // candidate emission (cand.cuh): where the peaks of the probability tiles go
   int cand_K;              // top-K the candidates are pruned for (0: no emission)
-  int cand_dbg;            // tools/: 1 = the emitter relays the stage without scanning (cost of the schedule alone)
   long long* dbg;
+  int xdbg;                // TEMP experiment switches
 };
 
 // ---- exact accumulation ---------------------------------------------------------------------
@@ -439,18 +439,19 @@ __device__ __forceinline__ void loss_acc_add(LossAcc& la, float v) {
 // known (NEED_GRAD && !KEEP), or (KEEP, single wave) it replaces the logits in the stage, unscaled.
 // Loss terms and num_pos go to the thread-local accumulators.  No barrier inside: a thread only
 // touches its own slots of the stage (WAIT: the stage is filled by bulk copies, wait for each sub-block).
-// PTILE (candidate emission): every pixel whose probability reaches the pruning threshold `pend.thr` is noted in the
+// NOTE (candidate emission): every pixel whose probability reaches the pruning threshold `pend.thr` is noted in the
 // stage's pending list (its offset in the chunk, 16 bits; one warp-aggregated shared-memory atomic per warp and
 // sub-block THAT HAS ONE -- rare once the threshold has tightened; six instructions otherwise).  thr == 0: nothing is
 // noted (the emitter scans the whole tile).
 constexpr int kPendCap = 256;                 // pending pixels per list; more: the emitter scans the whole tile
 constexpr int kPendSlots = 8;                 // lists in flight between the consumers and the emitter (a ring of its own)
+constexpr int kEmitSliceKeys = kSliceCap - kPendSlots * kPendCap * 2 / 8;   // keys of a slice; the lists take its tail
 struct Pending {
   unsigned short* list;                       // [kPendCap]
   unsigned* count;
   float thr;                                  // 0: do not note
 };
-template <bool NEED_GRAD, bool FAST, bool WAIT, bool KEEP, bool PTILE = false>
+template <bool NEED_GRAD, bool FAST, bool WAIT, bool KEEP, bool NOTE = false>
 __device__ __forceinline__ void process_chunk(const cnh_detloss_args& a, const ChunkRef& r, Stage& st, u64* bar,
                                               unsigned parity, unsigned gmask, float scale, LossAcc& la,
                                               const Pending pend = Pending{nullptr, nullptr, 0.f}) {
@@ -515,7 +516,7 @@ __device__ __forceinline__ void process_chunk(const cnh_detloss_args& a, const C
         }
     }
     if (NEED_GRAD && KEEP) *reinterpret_cast<float4*>(st.x + off) = make_float4(gr[0], gr[1], gr[2], gr[3]);
-    if (PTILE) {
+    if (NOTE) {
       if (pend.thr > 0.f) {
         const bool any = fmaxf(fmaxf(ps[0], ps[1]), fmaxf(ps[2], ps[3])) >= pend.thr;
         const unsigned who = __ballot_sync(0xffffffffu, any);
@@ -1417,35 +1418,35 @@ detloss_stash_kernel(const cnh_detloss_args a, const Geo g) {
 //   Every CTA serves ONE sample (CTA i: sample i % B, chunk tickets per sample), so a slice holds one sample's keys.
 // The decode (cnh_decode_candidates) then never reads the heat map: 4*C*H*W bytes per sample and a launch less.
 constexpr int kEmitThreads = kStashThreads + 32;
-constexpr int kEmitCap = kChunk * 4 / 8;                    // keys the target half of a stage holds
 template <int MODE, bool FAST, bool VEC, bool EMIT = false>
 __global__ void __launch_bounds__(EMIT ? kEmitThreads : kStashThreads, 2)
 detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Stage* const stages = reinterpret_cast<Stage*>(smem_raw);
-  __shared__ u64 full[kMaxStages * kSubs];
-  __shared__ u64 empty[kMaxStages];
+  __shared__ u64 full[kStreamStages * kSubs];   // (static shared memory is kept under 1 KB: two CTAs of three stages
+                                               // then fit the 196 KB carve-out, and the L1 keeps 60 KB for the spills)
+  __shared__ u64 empty[kStreamStages];
   __shared__ long long red_l[2 * kWarps];
   __shared__ int red_i[kWarps];
   __shared__ long long sh_tot[CNH_TOTALS];
   __shared__ unsigned sh_ticket, sh_parity;
   __shared__ long long sh_gnorm[4];           // peers: batch-wide mask counts of head 0..2, num_pos (-1: a peer timed out)
   __shared__ unsigned long long sh_tag;
-  __shared__ unsigned sh_mask[kMaxStages];
-  __shared__ int sh_chunk[kMaxStages];
+  __shared__ unsigned sh_mask[kStreamStages];
+  __shared__ int sh_chunk[kStreamStages];
   // EMIT: a ring of kPendSlots pending lists between the consumers and the emitter (slot = chunk count % kPendSlots)
   __shared__ u64 scanned[kPendSlots];          // the eight consumer warps are done with the slot's chunk
   __shared__ u64 pend_free[kPendSlots];        // the emitter has taken the slot's list
   __shared__ int sh_pchunk[kPendSlots];        // the chunk the list belongs to (-1: no more)
   __shared__ unsigned sh_npend[kPendSlots];    // pending pixels of the chunk (may run past kPendCap)
   __shared__ unsigned sh_fullscan[kPendSlots]; // some warp had no threshold yet: the emitter scans the whole tile
-  __shared__ unsigned short sh_pend[EMIT ? kPendSlots : 1][EMIT ? kPendCap : 1];
   __shared__ float sh_thr;                     // EMIT: the emitter's current threshold, read by the consumers per chunk
+  __shared__ unsigned sh_boot_cnt, sh_boot;    // EMIT: keys of the CTA's first chunk (tested by the consumers); first threshold is out
   const int bid = blockIdx.x, grid = gridDim.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool consumer = warp < kWarps;
   constexpr bool kGrad = (MODE == M_PRECOUNT || MODE == M_MAIN);
-  const int S = g.n_stages;
+  constexpr int S = kStreamStages;
   // EMIT: this CTA's sample and slice (CTAs beyond B * G draw no chunks)
   const int my_b = EMIT ? bid % a.B : 0, my_j = EMIT ? bid / a.B : 0;
   const bool has_sample = !EMIT || my_j < g.cand.G;
@@ -1465,6 +1466,8 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
           sh_fullscan[i] = 0u;
         }
         sh_thr = 0.f;
+        sh_boot_cnt = 0u;
+        sh_boot = 0u;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -1556,12 +1559,30 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
     // ---- the streaming pass -----------------------------------------------------------------------
     // ticket t -> chunk: reverse order after a pre-count (the tail of the target is still in L2)
     // (EMIT: tickets are per sample, t counts this sample's chunks)
-    const int n_tickets = EMIT ? (has_sample ? g.cps : 0) : g.n_chunks;
-    unsigned* const ticket_ctr = EMIT ? g.next_b + my_b : &g.hdr->next;
+    const bool xglobal = EMIT && (g.xdbg & 8);
+    const int n_tickets = (EMIT && !xglobal) ? (has_sample ? g.cps : 0) : g.n_chunks;
+    unsigned* const ticket_ctr = (EMIT && !xglobal) ? g.next_b + my_b : &g.hdr->next;
     auto chunk_of = [&](int t) {
-      if (EMIT) return my_b * g.cps + ((MODE == M_PRECOUNT) ? g.cps - 1 - t : t);
+      if (EMIT && !xglobal) return my_b * g.cps + ((MODE == M_PRECOUNT) ? g.cps - 1 - t : t);
       return (MODE == M_PRECOUNT) ? g.n_chunks - 1 - t : t;
     };
+    // EMIT: chunk -> its 32 x 128 tile of probabilities: rows [32*ty, 32*ty+32) of class plane c of sample my_b
+    const int tiles_per_plane = a.H / kCandRows;
+    auto tile_of = [&](int chunk) {
+      const int jc = chunk - my_b * g.cps;                   // = c * tiles_per_plane + ty
+      GTile t;
+      t.p = a.prob + (long long)chunk * kChunk;
+      t.flat0 = (unsigned)jc * (unsigned)kChunk;
+      t.y0 = (jc % tiles_per_plane) * kCandRows;
+      t.H = a.H;
+      t.HW = g.HW;
+      return t;
+    };
+    // EMIT: the pending lists live in the last 4 KB of the CTA's slice of the candidate workspace (global memory, read
+    // back through L2 like the tile: a handful of 16-bit entries per chunk)
+    unsigned short* const pend_lists =
+        EMIT ? reinterpret_cast<unsigned short*>(g.cand.slices + ((long long)my_b * g.cand.G + (has_sample ? my_j : 0)) * kSliceCap + kEmitSliceKeys)
+             : nullptr;
     LossAcc la = {0ll, 0ll, 0};
     // regression units first (the last CTAs get them): the chunk tickets are dynamic, a CTA that is busy
     // here simply draws fewer chunks -- nothing is left to do after the streaming loop
@@ -1640,64 +1661,104 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
       }
     } else if (EMIT && warp == kWarps + 1) {
       // ---- emitter ----
+      // The CTA's FIRST chunk is tested whole, unpruned, by the consumer warps (below: eight warps in parallel; this warp
+      // runs at ~10 cycles per dependent instruction, see the kernel's header, and would need 10 us for it): by then the
+      // histogram holds one chunk of every CTA of the sample, ~5 % of it, and the first threshold already leaves a few
+      // dozen pixels per chunk.  From there on this warp works a ring of kPendSlots pending lists behind the consumers,
+      // up to kBatch chunks per pass: the lists of a batch are flattened over the lanes (one noted pixel per lane and
+      // trip), so the instructions of a pass are shared by several chunks.
       CandEmitter em;
       em.init(g.cand, my_b, has_sample ? my_j : 0, g.cand_K);
+      em.cap = (unsigned)kEmitSliceKeys;
+      constexpr int kBatch = 4;
+      auto release = [&](int s) {                            // the slot's list is taken: the consumers may reuse it
+        if (lane == 0) { sh_npend[s] = 0u; sh_fullscan[s] = 0u; mbar_arrive(&pend_free[s]); }
+      };
+      bool done = false;
 #pragma unroll 1
-      for (int i = 0;; ++i) {
-        const int s = i % kPendSlots;
-        const unsigned ph = (unsigned)((i / kPendSlots) & 1);
-        // (only `scanned` is waited on: the producer may refill the stage -- and complete its `full` barrier a second time
-        // -- before this warp gets here; the consumers cannot run more than S chunks ahead, see pend_free)
-        long long te0 = 0;
-        if (g.dbg != nullptr && lane == 0) te0 = clock64();
-        mbar_wait(&scanned[s], ph);                          // the chunk's probabilities are in global memory, its list complete
-        const int chunk = sh_pchunk[s];
-        if (chunk < 0) break;
-        if (g.dbg != nullptr && lane == 0) { const long long t = clock64(); g.dbg[(long long)bid * 16 + 12] += t - te0; te0 = t; }
-        // chunk -> rows [32*ty, 32*ty+32) of class plane c of sample my_b; jc = c * (H/32) + ty
-        const int jc = chunk - my_b * g.cps;
-        GTile t;
-        t.p = a.prob + (long long)chunk * kChunk;
-        t.flat0 = (unsigned)jc * (unsigned)kChunk;
-        t.y0 = (jc % (a.H / kCandRows)) * kCandRows;
-        t.H = a.H;
-        t.HW = g.HW;
-        const unsigned n_pend = *reinterpret_cast<volatile unsigned*>(&sh_npend[s]);
-        const bool fullscan = i == 0 || *reinterpret_cast<volatile unsigned*>(&sh_fullscan[s]) != 0u || n_pend > (unsigned)kPendCap;
-        // the list is taken (into a register when it has at most one entry per lane), the stage's list is free again
-        int my_off = -1;
-        const bool small = !fullscan && n_pend <= 32u;
-        if (small && (unsigned)lane < n_pend) my_off = (int)sh_pend[s][lane];
-        __syncwarp();
-        if (small || fullscan) {
-          if (lane == 0) { sh_npend[s] = 0u; sh_fullscan[s] = 0u; mbar_arrive(&pend_free[s]); }
+      for (int i = 0; !done;) {
+        // ---- gather a batch: chunks i .. i + nb - 1 whose lists are short; a chunk that needs a full scan goes alone ----
+        int nb = 0, slot_q[kBatch];
+        GTile tile_q[kBatch];
+        unsigned cnt_q[kBatch], total = 0;
+        bool alone = false;
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+          if (nb != q) break;                                // (the batch ended before q)
+          const int s = (i + q) % kPendSlots;
+          const unsigned ph = (unsigned)(((i + q) / kPendSlots) & 1);
+          // (only `scanned` is waited on: the producer may refill a stage -- and complete its `full` barrier a second
+          // time -- before this warp gets here; the consumers cannot run more than kPendSlots chunks ahead: pend_free)
+          if (q == 0) {
+            const long long tw = (g.dbg != nullptr) ? clock64() : 0;
+            mbar_wait(&scanned[s], ph);
+            if (g.dbg != nullptr && lane == 0) g.dbg[(long long)bid * 16 + 12] += clock64() - tw;
+          } else if (!mbar_test(&scanned[s], ph)) {
+            break;                                           // later chunks join the batch only if they are ready
+          }
+          const int chunk = sh_pchunk[s];
+          if (chunk < 0) { done = true; break; }
+          const unsigned n_pend = *reinterpret_cast<volatile unsigned*>(&sh_npend[s]);
+          const bool whole = (i + q) == 0 || *reinterpret_cast<volatile unsigned*>(&sh_fullscan[s]) != 0u ||
+                             n_pend > (unsigned)kPendCap;
+          if (whole && q > 0) break;                         // (waits for the next pass)
+          tile_q[q] = tile_of(chunk);
+          slot_q[q] = s;
+          cnt_q[q] = whole ? 0u : n_pend;
+          total += cnt_q[q];
+          nb = q + 1;
+          if (whole) { alone = true; break; }
         }
-        if (g.cand_dbg & 1) {
-        } else if (i == 0) {
-          // The first chunk, with no threshold yet: its first eight rows are tested unpruned; their peaks are forwarded
-          // and the first threshold is waited for (two L2 round trips, once -- by then the histogram holds the first
-          // rows of most CTAs of the sample); the other 24 rows follow with it.
-          gtile_rows_unpruned(em, t, 0);
-          gtile_rows_unpruned(em, t, 4);
-          __threadfence();
-          __nanosleep(600);                                  // the sample's other CTAs are at the same point: let their REDs land
+        if (nb == 0) break;                                  // (the sentinel came first)
+        const long long tw1 = (g.dbg != nullptr) ? clock64() : 0;
+        if (alone && i == 0) {
+          // the consumers have tested and forwarded the first chunk: take over the slice, wait for the first threshold
+          // (two L2 round trips, once -- the sample's other CTAs are at the same point: let their REDs land first)
+          em.local_cnt = min(*reinterpret_cast<volatile unsigned*>(&sh_boot_cnt), (unsigned)kEmitSliceKeys);
+          __nanosleep(600);
           em.refresh_blocking();
-          gtile_scan(em, t, 8);
-        } else if (fullscan) {
-          gtile_scan(em, t, 0);
-        } else if (small) {
-          const float thr_eff = fmaxf(__uint_as_float(em.thr), __uint_as_float(1u));
-          gtile_test_push(em, t, my_off >= 0, my_off >= 0 ? my_off : 0, thr_eff);
+          if (lane == 0) {
+            *reinterpret_cast<volatile float*>(&sh_thr) = __uint_as_float(em.thr);
+            __threadfence_block();
+            *reinterpret_cast<volatile unsigned*>(&sh_boot) = 1u;
+          }
+          release(slot_q[0]);
+        } else if (alone) {
+          release(slot_q[0]);
+          gtile_scan(em, tile_q[0], 0);
+        } else if (g.xdbg & 2) {
+          for (int q = 0; q < kBatch; ++q)
+            if (q < nb) release(slot_q[q]);
         } else {
-          gtile_pending(em, t, sh_pend[s], n_pend);
-          if (lane == 0) { sh_npend[s] = 0u; sh_fullscan[s] = 0u; mbar_arrive(&pend_free[s]); }
+          // ---- the batch's noted pixels, flattened: entry e of the batch = entry (e - first) of chunk q ----
+          const float thr_eff = fmaxf(__uint_as_float(em.thr), __uint_as_float(1u));
+          for (unsigned e0 = 0; e0 < total; e0 += 32) {
+            const unsigned e = e0 + (unsigned)lane;
+            GTile t = tile_q[0];
+            int slot = slot_q[0];
+            unsigned first = 0, end = cnt_q[0];
+#pragma unroll
+            for (int q = 1; q < kBatch; ++q)
+              if (q < nb && e >= end) { first = end; end += cnt_q[q]; t = tile_q[q]; slot = slot_q[q]; }
+            const bool has = e < total;
+            const int off = has ? (int)__ldcg(pend_lists + slot * kPendCap + (int)(e - first)) : 0;
+            gtile_test_push(em, t, has, off, thr_eff);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < kBatch; ++q)
+            if (q < nb) release(slot_q[q]);
         }
-        if (g.dbg != nullptr && lane == 0) { const long long tt = clock64(); g.dbg[(long long)bid * 16 + 11] += tt - te0; te0 = tt; }
-        // the threshold: one step of the pipelined refresh per chunk (loads issued at the previous chunk have landed
-        // by now: nothing is waited for)
-        if (!(g.cand_dbg & 4)) em.refresh_step<1>(i, true);
+        if (g.dbg != nullptr && lane == 0) {
+          g.dbg[(long long)bid * 16 + (alone ? 13 : 11)] += clock64() - tw1;
+          g.dbg[(long long)bid * 16 + 15] += alone ? (1ll << 32) : 1ll;
+          g.dbg[(long long)bid * 16 + 14] = (long long)em.local_cnt | ((long long)total << 32);
+        }
+        i += nb;
+        // the threshold: one step of the pipelined refresh per pass (loads issued at the previous pass have landed by
+        // now: nothing is waited for)
+        em.refresh_step<1>(i, true);
         if (lane == 0) *reinterpret_cast<volatile float*>(&sh_thr) = __uint_as_float(em.thr);
-        if (g.dbg != nullptr && lane == 0) { g.dbg[(long long)bid * 16 + 13] += clock64() - te0; g.dbg[(long long)bid * 16 + 14] = (long long)em.local_cnt; }
         __syncwarp();
       }
       if (has_sample) {
@@ -1722,7 +1783,11 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
         if (EMIT) {
           // the emitter has taken the list this slot held kPendSlots chunks ago (it lags that far only rarely); then the
           // chunk is handed to it by name -- sh_chunk[s] may be overwritten by the next refill before it looks
-          if (i >= kPendSlots) mbar_wait(&pend_free[ps], (unsigned)(((i / kPendSlots) - 1) & 1));
+          if (i >= kPendSlots) {
+            const long long tw = (g.dbg != nullptr && tid == 0) ? clock64() : 0;
+            mbar_wait(&pend_free[ps], (unsigned)(((i / kPendSlots) - 1) & 1));
+            if (g.dbg != nullptr && tid == 0) g.dbg[(long long)bid * 16 + 6] += clock64() - tw;
+          }
           if (tid == 0) sh_pchunk[ps] = chunk;
           if (chunk < 0) {
             __syncwarp();
@@ -1732,20 +1797,39 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
         if (chunk < 0) break;
         const unsigned m = sh_mask[s];
         Pending pend = {nullptr, nullptr, 0.f};
-        if (EMIT) {
+        if (EMIT && i > 0) {
           // Every warp takes the emitter's threshold as it stands (no agreement needed: it only rises, so whatever the
-          // emitter still wants when it gets to this tile has been noted by every warp).  A warp that finds none yet
-          // notes nothing and tells the emitter to scan the whole tile.
-          pend.list = sh_pend[ps];
+          // emitter still wants when it gets to this tile has been noted by every warp).  A warp that finds none
+          // (fewer than K peaks counted so far) notes nothing and tells the emitter to scan the whole tile.
+          if (i == 1) {                                      // the first threshold is on its way: ~3 us, once
+            if (lane == 0)
+              while (*reinterpret_cast<volatile unsigned*>(&sh_boot) == 0u) __nanosleep(100);
+            __syncwarp();
+          }
+          pend.list = pend_lists + ps * kPendCap;
           pend.count = &sh_npend[ps];
           pend.thr = *reinterpret_cast<volatile float*>(&sh_thr);
+          if (g.xdbg & 1) pend.thr = 0.f;
+          else
           if (pend.thr == 0.f && lane == 0) sh_fullscan[ps] = 1u;
         }
         process_chunk<kGrad, FAST, true, false, EMIT>(a, chunk_ref(g, chunk), stages[s], &full[s * kSubs], ph, m, scale, la, pend);
         __syncwarp();
-        if (lane == 0) {
-          if (EMIT) mbar_arrive(&scanned[ps]);               // this warp's probabilities and pending pixels of the chunk are out
-          mbar_arrive(&empty[s]);
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (EMIT) {
+          if (i == 0 && !(g.xdbg & 4)) {
+            // the CTA's first chunk: once all of it is out, every warp tests four of its rows against no threshold at
+            // all and forwards the peaks (read back through L2; positions in the slice from a shared-memory counter)
+            sync_compute();
+            CandEmitter boot;
+            boot.init(g.cand, my_b, my_j, g.cand_K);
+            boot.shared_cnt = &sh_boot_cnt;
+            boot.cap = (unsigned)kEmitSliceKeys;
+            gtile_rows_unpruned(boot, tile_of(chunk), 4 * warp);
+            if (boot.overflow && lane == 0) g.cand.state[my_b].overflow = 1u;
+            __syncwarp();
+          }
+          if (lane == 0) mbar_arrive(&scanned[ps]);          // this warp's probabilities, pending pixels (and keys) of the chunk are out
         }
       }
     }
@@ -1957,10 +2041,9 @@ static Geo make_geo(const cnh_detloss_args* a, void* ws) {
   g.sparse = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + kHeaderBytes);
   g.next_b = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + kHeaderBytes + sparse_bytes(a));
   g.cand_K = 0;
-  static const int cand_dbg = getenv("CNH_EMIT_DEBUG") ? atoi(getenv("CNH_EMIT_DEBUG")) : 0;
-  g.cand_dbg = cand_dbg;
   g.cand = cand_geo(nullptr, a->B, 0);
   g.dbg = debug_buffer();
+  { const char* e = getenv("CNH_EMIT_X"); g.xdbg = e ? atoi(e) : 0; }
   return g;
 }
 

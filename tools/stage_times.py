@@ -44,12 +44,15 @@ for rep in range(2):
         dbg.zero_(); torch.cuda.synchronize()
         L.check(lib.cnh_detloss_fused(C.byref(d.loss_args[rep]), d.ws_loss.data_ptr(), d.ws_loss.numel(), L.stream_ptr()), "f")
         show(f"detloss+emit {name} rep{rep}", 5)
-        d.decode_step(rep); torch.cuda.synchronize()
+        torch.cuda.synchronize()
         t = dbg.cpu(); u2 = t[:, 9] > 0
         f = lambda c: (t[u2, c].float() / 1965.0)        # SM cycles -> us at 1965 MHz
-        print("  EMIT (clock64, us at 1965 MHz): consumer blocked on full median/max:", round(f(8).median().item(), 2), round(f(8).max().item(), 2),
-              "| emitter: wait scanned", round(f(12).median().item(), 2), "scan+forward", round(f(11).median().item(), 2), "refresh", round(f(13).median().item(), 2),
-              "| keys forwarded per CTA median/max", t[u2, 14].median().item(), t[u2, 14].max().item())
+        med = lambda x: round(x.float().median().item(), 2)
+        print("  EMIT (clock64, us at 1965 MHz) medians/max: consumers blocked on full", med(f(8)), "on pend_free", med(f(6)), round(f(6).max().item(), 2),
+              "| emitter: wait scanned", med(f(12)), "pending passes", med(f(11)), round(f(11).max().item(), 2), "full scans", med(f(13)), round(f(13).max().item(), 2),
+              "| passes", med(t[u2, 15] & 0xffffffff), "full scans", med(t[u2, 15] >> 32), (t[u2, 15] >> 32).max().item(),
+              "| keys kept per CTA median/max", med(t[u2, 14] & 0xffffffff), (t[u2, 14] & 0xffffffff).max().item())
+        d.decode_step(rep); torch.cuda.synchronize()
         t = dbg.cpu()
     if name == "cfg5":
         u2 = t[:, 9] > 0
