@@ -247,7 +247,7 @@ struct CandEmitter {
   template <class Touch>
   __device__ __forceinline__ void reprune(Touch touch) {
     if (overflow || local_cnt == 0u) return;
-    if (pending == 2) fine_step();
+    if (pending == 2) { fine_step(); pending = 0; }
     unsigned kept = 0;
     constexpr int kBatch = 8;
     for (unsigned k0 = 0; k0 < local_cnt; k0 += 32 * kBatch) {

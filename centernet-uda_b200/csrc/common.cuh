@@ -194,6 +194,7 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigne
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 // start `bytes` (multiple of 16) at a 16-byte aligned global address on their way into L2
+__device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void l2_prefetch_bulk(const void* src, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }

@@ -1502,13 +1502,91 @@ __device__ __forceinline__ void finish_sample(const cnh_decode_args& a, const De
   for (int q = 0; q < kFineBins / 2 / kThreads; ++q) s.hist[tid + q * kThreads] = 0u;
   if (tid == 0) { s.cnt = 0; s.cnt2 = 0; s.sh_thr = 0u; }
   dbg_stamp(g.dbg, 5);
+  // ---- round trip 1: the slice sizes and (warp 0) the super bins, side by side ----
   unsigned* const n_slice = reinterpret_cast<unsigned*>(s.stage);           // [G] keys per slice (`stage` is free until the sort)
   for (int q = tid; q < G; q += kThreads) n_slice[q] = __ldcg(cta_cnt + q);
+  uint2 sv = make_uint2(0u, 0u);
+  if (tid < 32) sv = __ldcg(reinterpret_cast<const uint2*>(shist) + lane);
   group_sync();
-  // ---- the K-th counted key's fine bin (warp 0; the same two-level walk as the producers') ----
+  unsigned thr_final = 0u;                                   // 0: fewer than K counted peaks, keep everything
+  // Candidates that came out of a tile scanned WITHOUT its halo rows (the detection-loss kernels emit them from their
+  // own 32-row chunks) were tested against the neighbours inside the tile only: those of a tile's first / last row
+  // are checked here against the three pixels of the row beyond it (read from the heat map: a few dozen keys).
+  auto verified = [&](u64 key) -> bool {
+    if (g.verify_rows == 0 || key == 0ull) return true;
+    const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+    const unsigned cls = flat / (unsigned)g.HW, pix = flat - cls * (unsigned)g.HW;
+    const int y = (int)(pix / (unsigned)a.W), x = (int)(pix - (unsigned)y * (unsigned)a.W);
+    const int r = y % g.verify_rows;
+    int yy = -1;
+    if (r == 0 && y > 0) yy = y - 1;
+    else if (r == g.verify_rows - 1 && y < a.H - 1) yy = y + 1;
+    if (yy < 0) return true;
+    const float* row = a.heat + ((long long)b * a.C + cls) * g.HW + (long long)yy * a.W + x;
+    // (clamped at the borders: a pixel read twice does not change the maximum; three independent loads)
+    const float m = fmaxf(fmaxf(__ldcg(row - (x > 0 ? 1 : 0)), __ldcg(row)), __ldcg(row + (x < a.W - 1 ? 1 : 0)));
+    return m <= __uint_as_float((unsigned)(key >> 32));
+  };
+  // Slices are dealt to the warps, kSl of them per warp and round: 16-byte loads (two keys each) of all of them are in
+  // flight together -- one L2 round trip for G <= 24 slices of <= 128 keys, the usual case.  f(in_range_and_above_thr,
+  // key) may vote: trip counts are warp-uniform.
+  constexpr int kSl = 3, kLd = 2;
+  struct Round { ulonglong2 k[kSl][kLd]; };
+  auto load_round = [&](int j0, unsigned p0, Round& r) {     // pairs [p0, p0 + kLd * 32) of slices j0, j0 + kWarps, ...
+#pragma unroll
+    for (int sl = 0; sl < kSl; ++sl) {
+      const int jj = j0 + sl * kWarps;
+      const unsigned np = jj < G ? (n_slice[jj] + 1u) >> 1 : 0u;
+      const ulonglong2* cand = reinterpret_cast<const ulonglong2*>(slices + (long long)jj * kSliceCap);
+#pragma unroll
+      for (int q = 0; q < kLd; ++q) {
+        const unsigned e = p0 + (unsigned)(q * 32 + lane);
+        r.k[sl][q] = (e < np) ? __ldcg(cand + e) : make_ulonglong2(0ull, 0ull);
+      }
+    }
+  };
+  auto pairs_of_round = [&](int j0) {                        // the longest of the round's slices, in pairs (warp-uniform)
+    unsigned np = 0;
+#pragma unroll
+    for (int sl = 0; sl < kSl; ++sl) {
+      const int jj = j0 + sl * kWarps;
+      if (jj < G) np = max(np, (n_slice[jj] + 1u) >> 1);
+    }
+    return np;
+  };
+  auto consume_round = [&](int j0, unsigned p0, const Round& r, auto f) {
+#pragma unroll
+    for (int sl = 0; sl < kSl; ++sl) {
+      const int jj = j0 + sl * kWarps;
+      if (jj >= G) break;                                    // warp-uniform
+      const unsigned nc = n_slice[jj], np = (nc + 1u) >> 1;
+#pragma unroll
+      for (int q = 0; q < kLd; ++q) {
+        if (p0 + (unsigned)(q * 32) >= np) break;            // warp-uniform
+        const unsigned e = p0 + (unsigned)(q * 32 + lane);
+        f(2 * e < nc && (unsigned)(r.k[sl][q].x >> 32) >= thr_final, r.k[sl][q].x);
+        f(2 * e + 1 < nc && (unsigned)(r.k[sl][q].y >> 32) >= thr_final, r.k[sl][q].y);
+      }
+    }
+  };
+  // skip_first: the round (j0 = warp, p0 = 0) has been taken care of by the caller
+  auto for_each_round = [&](bool skip_first, auto f) {
+    for (int j0 = tid >> 5; j0 < G; j0 += kWarps * kSl) {
+      const unsigned np = pairs_of_round(j0);
+      for (unsigned p0 = 0; p0 < np; p0 += (unsigned)(kLd * 32)) {
+        if (skip_first && j0 == (tid >> 5) && p0 == 0u) continue;
+        Round r;
+        load_round(j0, p0, r);
+        consume_round(j0, p0, r, f);
+      }
+    }
+  };
+  // ---- round trip 2: every warp's first round of keys, and (warp 0) the fine bins of the K-th counted key's super bin
+  // -- the same two-level walk as the producers' ----
+  Round first;
+  load_round(tid >> 5, 0u, first);
   if (tid < 32) {
-    const uint2 v = __ldcg(reinterpret_cast<const uint2*>(shist) + lane);
-    unsigned mine = v.x + v.y, incl = mine;
+    unsigned mine = sv.x + sv.y, incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned u = __shfl_down_sync(0xffffffffu, incl, o);
@@ -1518,8 +1596,8 @@ __device__ __forceinline__ void finish_sample(const cnh_decode_args& a, const De
     int sel = -1;
     unsigned ab = 0;
     if (above < (unsigned)K && incl >= (unsigned)K) {
-      if (above + v.y >= (unsigned)K) { sel = 2 * lane + 1; ab = above; }
-      else { sel = 2 * lane; ab = above + v.y; }
+      if (above + sv.y >= (unsigned)K) { sel = 2 * lane + 1; ab = above; }
+      else { sel = 2 * lane; ab = above + sv.y; }
     }
     const unsigned who = __ballot_sync(0xffffffffu, sel >= 0);
     if (who != 0u) {
@@ -1541,56 +1619,41 @@ __device__ __forceinline__ void finish_sample(const cnh_decode_args& a, const De
     }
   }
   group_sync();
-  const unsigned thr_final = s.sh_thr;                       // 0: fewer than K counted peaks, keep everything
+  thr_final = s.sh_thr;
   dbg_stamp(g.dbg, 6);
-  // Candidates that came out of a tile scanned WITHOUT its halo rows (the detection-loss kernels emit them from their
-  // own 32-row chunks) were tested against the neighbours inside the tile only: those of a tile's first / last row
-  // are checked here against the three pixels of the row beyond it (read from the heat map: a few dozen keys).
-  auto verified = [&](u64 key) -> bool {
-    if (g.verify_rows == 0 || key == 0ull) return true;
-    const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffu);
-    const unsigned cls = flat / (unsigned)g.HW, pix = flat - cls * (unsigned)g.HW;
-    const int y = (int)(pix / (unsigned)a.W), x = (int)(pix - (unsigned)y * (unsigned)a.W);
-    const int r = y % g.verify_rows;
-    int yy = -1;
-    if (r == 0 && y > 0) yy = y - 1;
-    else if (r == g.verify_rows - 1 && y < a.H - 1) yy = y + 1;
-    if (yy < 0) return true;
-    const float score = __uint_as_float((unsigned)(key >> 32));
-    const float* row = a.heat + ((long long)b * a.C + cls) * g.HW + (long long)yy * a.W;
-    float m = __ldcg(row + x);
-    if (x > 0) m = fmaxf(m, __ldcg(row + x - 1));
-    if (x < a.W - 1) m = fmaxf(m, __ldcg(row + x + 1));
-    return m <= score;
-  };
-  // Slices are dealt to the warps (f may vote: warp-uniform trip counts); two keys per 16-byte load, four loads in
-  // flight per lane.  The slice sizes were read in one go (n_slice, shared memory).
-  auto for_each_survivor = [&](auto f) {
-    for (int jj = tid >> 5; jj < G; jj += kWarps) {
-      const unsigned nc = n_slice[jj];
-      const ulonglong2* cand = reinterpret_cast<const ulonglong2*>(slices + (long long)jj * kSliceCap);
-      const unsigned np = (nc + 1u) >> 1;                  // pairs
-      for (unsigned e0 = 0; e0 < np; e0 += 4 * 32) {
-        ulonglong2 k[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const unsigned e = e0 + q * 32 + lane;
-          k[q] = (e < np) ? __ldcg(cand + e) : make_ulonglong2(0ull, 0ull);
+  // ---- the keys at or above the threshold -> shared memory ----
+  auto take = [&](bool ok, u64 k) { append_if(ok, k, s.keys, &s.cnt, (unsigned)kKeyCap); };
+  consume_round(tid >> 5, 0u, first, take);
+  for_each_round(true, take);
+  group_sync();
+  // ---- the rows beyond a tile for those that need them (all in flight together: one more round trip), the fine
+  // histogram of what stays, and the lines the boxes will be gathered from started towards L2.  The list is compacted
+  // in place, 256 keys per wave (a wave is read before anything at or below it is written).  A list that ran over
+  // shared memory (plateaus of ties) is left alone: select_sort_emit then goes through the slices again, slowly. ----
+  const unsigned n_taken = s.cnt;
+  if (n_taken <= (unsigned)kKeyCap) {
+    group_sync();                                            // (everyone has read s.cnt)
+    if (tid == 0) s.cnt = 0u;
+    for (unsigned i0 = 0; i0 < n_taken; i0 += kThreads) {
+      const unsigned i = i0 + (unsigned)tid;
+      const u64 k = i < n_taken ? s.keys[i] : 0ull;
+      const bool good = i < n_taken && verified(k);
+      group_sync();
+      append_if(good, k, s.keys, &s.cnt, (unsigned)kKeyCap);
+      if (good) {
+        hist_add(s.hist, fine_bin((unsigned)(k >> 32)));
+        const unsigned pix = (0xffffffffu - (unsigned)(k & 0xffffffffu)) % (unsigned)g.HW;
+        if (a.reg) {
+          l2_prefetch(a.reg + ((long long)b * 2 + 0) * g.HW + pix);
+          l2_prefetch(a.reg + ((long long)b * 2 + 1) * g.HW + pix);
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (e0 + q * 32 >= np) break;                    // warp-uniform
-          const unsigned e = e0 + q * 32 + lane;
-          f(2 * e < nc && (unsigned)(k[q].x >> 32) >= thr_final && verified(k[q].x), k[q].x);
-          f(2 * e + 1 < nc && (unsigned)(k[q].y >> 32) >= thr_final && verified(k[q].y), k[q].y);
-        }
+        l2_prefetch(a.wh + ((long long)b * a.D + 0) * g.HW + pix);
+        l2_prefetch(a.wh + ((long long)b * a.D + 1) * g.HW + pix);
+        if (a.rotated) l2_prefetch(a.wh + ((long long)b * a.D + 2) * g.HW + pix);
       }
     }
-  };
-  for_each_survivor([&](bool ok, u64 k) {
-    append_if(ok, k, s.keys, &s.cnt, (unsigned)kKeyCap);
-    if (ok) hist_add(s.hist, fine_bin((unsigned)(k >> 32)));
-  });
+  }
+  auto for_each_survivor = [&](auto f) { for_each_round(false, [&](bool ok, u64 k) { f(ok && verified(k), k); }); };
   group_sync();
   dbg_stamp(g.dbg, 7);
   select_sort_emit(a, g, s, b, s.keys, (int)s.cnt, kKeyCap,

@@ -440,9 +440,8 @@ __device__ __forceinline__ void loss_acc_add(LossAcc& la, float v) {
 // Loss terms and num_pos go to the thread-local accumulators.  No barrier inside: a thread only
 // touches its own slots of the stage (WAIT: the stage is filled by bulk copies, wait for each sub-block).
 // NOTE (candidate emission): every pixel whose probability reaches the pruning threshold `pend.thr` is noted in the
-// stage's pending list (its offset in the chunk, 16 bits; one warp-aggregated shared-memory atomic per warp and
-// sub-block THAT HAS ONE -- rare once the threshold has tightened; six instructions otherwise).  thr == 0: nothing is
-// noted (the emitter scans the whole tile).
+// chunk's pending list (its offset in the chunk, 16 bits; one shared-memory atomic per noted pixel -- rare once the
+// threshold has tightened; four instructions otherwise).  thr == 0: nothing is noted (the emitter scans the whole tile).
 constexpr int kPendCap = 256;                 // pending pixels per list; more: the emitter scans the whole tile
 constexpr int kPendSlots = 8;                 // lists in flight between the consumers and the emitter (a ring of its own)
 constexpr int kEmitSliceKeys = kSliceCap - kPendSlots * kPendCap * 2 / 8;   // keys of a slice; the lists take its tail
@@ -517,30 +516,15 @@ __device__ __forceinline__ void process_chunk(const cnh_detloss_args& a, const C
     }
     if (NEED_GRAD && KEEP) *reinterpret_cast<float4*>(st.x + off) = make_float4(gr[0], gr[1], gr[2], gr[3]);
     if (NOTE) {
-      if (pend.thr > 0.f) {
-        const bool any = fmaxf(fmaxf(ps[0], ps[1]), fmaxf(ps[2], ps[3])) >= pend.thr;
-        const unsigned who = __ballot_sync(0xffffffffu, any);
-        if (who != 0u) {                                       // (warp-uniform)
-          const unsigned bits = (ps[0] >= pend.thr ? 1u : 0u) | (ps[1] >= pend.thr ? 2u : 0u) | (ps[2] >= pend.thr ? 4u : 0u) |
-                                (ps[3] >= pend.thr ? 8u : 0u);
-          const int mine = __popc(bits), lane = threadIdx.x & 31;
-          int incl = mine;
+      // (no vote, no prefix sum: a lane that holds such a pixel draws its own position -- rare once the threshold has
+      // tightened, and the lanes that hold none skip the branch in four instructions)
+      if (pend.thr > 0.f && fmaxf(fmaxf(ps[0], ps[1]), fmaxf(ps[2], ps[3])) >= pend.thr) {
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            incl += (lane >= o) ? t : 0;
+        for (int e = 0; e < 4; ++e)
+          if (ps[e] >= pend.thr) {
+            const unsigned pos = atomicAdd(pend.count, 1u);
+            if (pos < (unsigned)kPendCap) pend.list[pos] = (unsigned short)(off + e);
           }
-          unsigned base = 0;
-          if (lane == 31) base = atomicAdd(pend.count, (unsigned)incl);
-          base = __shfl_sync(0xffffffffu, base, 31);
-          unsigned pos = base + (unsigned)(incl - mine);
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (bits & (1u << e)) {
-              if (pos < (unsigned)kPendCap) pend.list[pos] = (unsigned short)(off + e);
-              ++pos;
-            }
-        }
       }
     }
   }
@@ -1441,7 +1425,7 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
   __shared__ unsigned sh_npend[kPendSlots];    // pending pixels of the chunk (may run past kPendCap)
   __shared__ unsigned sh_fullscan[kPendSlots]; // some warp had no threshold yet: the emitter scans the whole tile
   __shared__ float sh_thr;                     // EMIT: the emitter's current threshold, read by the consumers per chunk
-  __shared__ unsigned sh_boot_cnt, sh_boot;    // EMIT: keys of the CTA's first chunk (tested by the consumers); first threshold is out
+  __shared__ unsigned sh_boot_cnt;             // EMIT: keys of the CTA's first chunk (tested and forwarded by the consumers)
   const int bid = blockIdx.x, grid = gridDim.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool consumer = warp < kWarps;
@@ -1467,7 +1451,6 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
         }
         sh_thr = 0.f;
         sh_boot_cnt = 0u;
-        sh_boot = 0u;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -1674,7 +1657,8 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
       auto release = [&](int s) {                            // the slot's list is taken: the consumers may reuse it
         if (lane == 0) { sh_npend[s] = 0u; sh_fullscan[s] = 0u; mbar_arrive(&pend_free[s]); }
       };
-      bool done = false;
+      bool done = false, repruned = false;
+      constexpr int kRepruneAt = 6;
 #pragma unroll 1
       for (int i = 0; !done;) {
         // ---- gather a batch: chunks i .. i + nb - 1 whose lists are short; a chunk that needs a full scan goes alone ----
@@ -1717,11 +1701,7 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
           em.local_cnt = min(*reinterpret_cast<volatile unsigned*>(&sh_boot_cnt), (unsigned)kEmitSliceKeys);
           __nanosleep(600);
           em.refresh_blocking();
-          if (lane == 0) {
-            *reinterpret_cast<volatile float*>(&sh_thr) = __uint_as_float(em.thr);
-            __threadfence_block();
-            *reinterpret_cast<volatile unsigned*>(&sh_boot) = 1u;
-          }
+          if (lane == 0) *reinterpret_cast<volatile float*>(&sh_thr) = __uint_as_float(em.thr);
           release(slot_q[0]);
         } else if (alone) {
           release(slot_q[0]);
@@ -1755,6 +1735,13 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
           g.dbg[(long long)bid * 16 + 14] = (long long)em.local_cnt | ((long long)total << 32);
         }
         i += nb;
+        // The slice once against the threshold as soon as that has settled somewhat: nearly all of what the slice holds
+        // then are the unpruned keys of the first chunk (the keys added later passed a threshold close to the final one:
+        // no second pass on the way out, where the whole CTA would wait for it).
+        if (!repruned && i >= kRepruneAt && em.thr != 0u) {
+          em.reprune([](u64) {});
+          repruned = true;
+        }
         // the threshold: one step of the pipelined refresh per pass (loads issued at the previous pass have landed by
         // now: nothing is waited for)
         em.refresh_step<1>(i, true);
@@ -1762,7 +1749,7 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
         __syncwarp();
       }
       if (has_sample) {
-        em.reprune([](u64) {});
+        if (!repruned) em.reprune([](u64) {});
         if (lane == 0) {
           g.cand.cta_cnt[(long long)my_b * g.cand.G + my_j] = em.local_cnt;
           if (em.overflow) g.cand.state[my_b].overflow = 1u;
@@ -1770,6 +1757,7 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
       }
     } else if (consumer) {
       // ---- consumers ----
+      dbg_stamp(g.dbg, 7);
 #pragma unroll 1
       for (int i = 0;; ++i) {
         const int s = i % S;
@@ -1799,13 +1787,9 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
         Pending pend = {nullptr, nullptr, 0.f};
         if (EMIT && i > 0) {
           // Every warp takes the emitter's threshold as it stands (no agreement needed: it only rises, so whatever the
-          // emitter still wants when it gets to this tile has been noted by every warp).  A warp that finds none
-          // (fewer than K peaks counted so far) notes nothing and tells the emitter to scan the whole tile.
-          if (i == 1) {                                      // the first threshold is on its way: ~3 us, once
-            if (lane == 0)
-              while (*reinterpret_cast<volatile unsigned*>(&sh_boot) == 0u) __nanosleep(100);
-            __syncwarp();
-          }
+          // emitter still wants when it gets to this tile has been noted by every warp).  A warp that finds none (the
+          // first threshold is still on its way, or fewer than K peaks have been counted so far) notes nothing and tells
+          // the emitter to scan the whole tile.
           pend.list = pend_lists + ps * kPendCap;
           pend.count = &sh_npend[ps];
           pend.thr = *reinterpret_cast<volatile float*>(&sh_thr);
@@ -1813,13 +1797,16 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
           else
           if (pend.thr == 0.f && lane == 0) sh_fullscan[ps] = 1u;
         }
+        const long long tp0 = (g.dbg != nullptr && tid == 0) ? clock64() : 0;
         process_chunk<kGrad, FAST, true, false, EMIT>(a, chunk_ref(g, chunk), stages[s], &full[s * kSubs], ph, m, scale, la, pend);
+        if (g.dbg != nullptr && tid == 0) g.dbg[(long long)bid * 16 + 5] += clock64() - tp0;
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
         if (EMIT) {
           if (i == 0 && !(g.xdbg & 4)) {
             // the CTA's first chunk: once all of it is out, every warp tests four of its rows against no threshold at
             // all and forwards the peaks (read back through L2; positions in the slice from a shared-memory counter)
+            const long long tb0 = (g.dbg != nullptr && tid == 0) ? clock64() : 0;
             sync_compute();
             CandEmitter boot;
             boot.init(g.cand, my_b, my_j, g.cand_K);
@@ -1828,6 +1815,7 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
             gtile_rows_unpruned(boot, tile_of(chunk), 4 * warp);
             if (boot.overflow && lane == 0) g.cand.state[my_b].overflow = 1u;
             __syncwarp();
+            if (g.dbg != nullptr && tid == 0) g.dbg[(long long)bid * 16 + 6] += clock64() - tb0;
           }
           if (lane == 0) mbar_arrive(&scanned[ps]);          // this warp's probabilities, pending pixels (and keys) of the chunk are out
         }

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-for k in 1 2 3; do
-timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "candidates" --timeout=60 2>&1 | grep -v "^$" | tail -25 | cut -c1-220
-done
+timeout 100 python tools/step_events.py cfg5 --fuse 2>&1 | tail -1
+timeout 100 python tools/step_events.py cfg5 --fuse 2>&1 | tail -1
+timeout 100 python tools/stage_times.py cfg5 --emit 2>&1 | grep -A11 "detloss+emit cfg5 rep1" | cut -c1-600

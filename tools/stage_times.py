@@ -40,19 +40,25 @@ for rep in range(2):
     d.loss_only(rep)
     show(f"detloss {name} rep{rep}", 8)
     t = dbg.cpu(); used = (t[:, 0] != 0) & (t[:, 1] != 0)
+    if name == "cfg5":
+        print("  plain consumers (tid 0): process_chunk us", round((t[t[:, 9] > 0, 5].float() / 1965.0).median().item(), 2))
     if name == "cfg5" and "--emit" in sys.argv:
         dbg.zero_(); torch.cuda.synchronize()
         L.check(lib.cnh_detloss_fused(C.byref(d.loss_args[rep]), d.ws_loss.data_ptr(), d.ws_loss.numel(), L.stream_ptr()), "f")
-        show(f"detloss+emit {name} rep{rep}", 5)
+        show(f"detloss+emit {name} rep{rep}", 8)
         torch.cuda.synchronize()
         t = dbg.cpu(); u2 = t[:, 9] > 0
         f = lambda c: (t[u2, c].float() / 1965.0)        # SM cycles -> us at 1965 MHz
         med = lambda x: round(x.float().median().item(), 2)
+        print("  EMIT consumers (tid 0): process_chunk", med(f(5)), "boot + pend_free", med(f(6)))
         print("  EMIT (clock64, us at 1965 MHz) medians/max: consumers blocked on full", med(f(8)), "on pend_free", med(f(6)), round(f(6).max().item(), 2),
               "| emitter: wait scanned", med(f(12)), "pending passes", med(f(11)), round(f(11).max().item(), 2), "full scans", med(f(13)), round(f(13).max().item(), 2),
               "| passes", med(t[u2, 15] & 0xffffffff), "full scans", med(t[u2, 15] >> 32), (t[u2, 15] >> 32).max().item(),
               "| keys kept per CTA median/max", med(t[u2, 14] & 0xffffffff), (t[u2, 14] & 0xffffffff).max().item())
+        dbg.zero_(); torch.cuda.synchronize()
         d.decode_step(rep); torch.cuda.synchronize()
+        show(f"finish-from-candidates {name} rep{rep}", 12)
+        tt = dbg.cpu(); uu = tt[:, 13] > 0; print("  survivors m / selected:", tt[uu, 12].tolist(), tt[uu, 13].tolist())
         t = dbg.cpu()
     if name == "cfg5":
         u2 = t[:, 9] > 0
