@@ -170,7 +170,6 @@ struct Geo {
   CandGeo cand;            // candidate emission (cand.cuh): where the peaks of the probability tiles go
   int cand_K;              // top-K the candidates are pruned for (0: no emission)
   long long* dbg;
-  int xdbg;                // TEMP experiment switches
 };
 
 // ---- exact accumulation ---------------------------------------------------------------------
@@ -1542,11 +1541,10 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
     // ---- the streaming pass -----------------------------------------------------------------------
     // ticket t -> chunk: reverse order after a pre-count (the tail of the target is still in L2)
     // (EMIT: tickets are per sample, t counts this sample's chunks)
-    const bool xglobal = EMIT && (g.xdbg & 8);
-    const int n_tickets = (EMIT && !xglobal) ? (has_sample ? g.cps : 0) : g.n_chunks;
-    unsigned* const ticket_ctr = (EMIT && !xglobal) ? g.next_b + my_b : &g.hdr->next;
+    const int n_tickets = EMIT ? (has_sample ? g.cps : 0) : g.n_chunks;
+    unsigned* const ticket_ctr = EMIT ? g.next_b + my_b : &g.hdr->next;
     auto chunk_of = [&](int t) {
-      if (EMIT && !xglobal) return my_b * g.cps + ((MODE == M_PRECOUNT) ? g.cps - 1 - t : t);
+      if (EMIT) return my_b * g.cps + ((MODE == M_PRECOUNT) ? g.cps - 1 - t : t);
       return (MODE == M_PRECOUNT) ? g.n_chunks - 1 - t : t;
     };
     // EMIT: chunk -> its 32 x 128 tile of probabilities: rows [32*ty, 32*ty+32) of class plane c of sample my_b
@@ -1706,9 +1704,6 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
         } else if (alone) {
           release(slot_q[0]);
           gtile_scan(em, tile_q[0], 0);
-        } else if (g.xdbg & 2) {
-          for (int q = 0; q < kBatch; ++q)
-            if (q < nb) release(slot_q[q]);
         } else {
           // ---- the batch's noted pixels, flattened: entry e of the batch = entry (e - first) of chunk q ----
           const float thr_eff = fmaxf(__uint_as_float(em.thr), __uint_as_float(1u));
@@ -1793,8 +1788,6 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
           pend.list = pend_lists + ps * kPendCap;
           pend.count = &sh_npend[ps];
           pend.thr = *reinterpret_cast<volatile float*>(&sh_thr);
-          if (g.xdbg & 1) pend.thr = 0.f;
-          else
           if (pend.thr == 0.f && lane == 0) sh_fullscan[ps] = 1u;
         }
         const long long tp0 = (g.dbg != nullptr && tid == 0) ? clock64() : 0;
@@ -1803,7 +1796,7 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
         if (EMIT) {
-          if (i == 0 && !(g.xdbg & 4)) {
+          if (i == 0) {
             // the CTA's first chunk: once all of it is out, every warp tests four of its rows against no threshold at
             // all and forwards the peaks (read back through L2; positions in the slice from a shared-memory counter)
             const long long tb0 = (g.dbg != nullptr && tid == 0) ? clock64() : 0;
@@ -2031,7 +2024,6 @@ static Geo make_geo(const cnh_detloss_args* a, void* ws) {
   g.cand_K = 0;
   g.cand = cand_geo(nullptr, a->B, 0);
   g.dbg = debug_buffer();
-  { const char* e = getenv("CNH_EMIT_X"); g.xdbg = e ? atoi(e) : 0; }
   return g;
 }
 

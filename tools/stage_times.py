@@ -58,7 +58,7 @@ for rep in range(2):
         dbg.zero_(); torch.cuda.synchronize()
         d.decode_step(rep); torch.cuda.synchronize()
         show(f"finish-from-candidates {name} rep{rep}", 12)
-        tt = dbg.cpu(); uu = tt[:, 13] > 0; print("  survivors m / selected:", tt[uu, 12].tolist(), tt[uu, 13].tolist())
+        tt = dbg.cpu(); uu = tt[:, 13] > 0; print("  survivors m / selected:", tt[uu, 12].tolist()[:4], tt[uu, 13].tolist()[:4], "rank loop cycles", tt[uu, 14].tolist()[:6], "sync", (tt[uu, 15] >> 32).tolist()[:6], "pv wait + store", (tt[uu, 15] & 0xffffffff).tolist()[:6])
         t = dbg.cpu()
     if name == "cfg5":
         u2 = t[:, 9] > 0
