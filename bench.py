@@ -61,9 +61,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg5 / shapes blocks and the sharded parity check")
-    ap.add_argument("--fuse", action="store_true",
-                    help="let the loss launch emit the decode's peak candidates (cnh_cand; large shapes only). Built and "
-                         "bit-exact, but measured slower than loss + streaming decode so far (DESIGN 4.4): off by default")
+    ap.add_argument("--fuse", default="auto", choices=["auto", "off"],
+                    help="auto: the loss launch emits the decode's peak candidates (cnh_cand) where the library supports "
+                         "it -- streaming launches of 128-wide maps, i.e. the cfg5 shard; the single-wave launch of cfg2 "
+                         "never does -- and the decode then runs from them (DESIGN 4.4); off: loss + streaming decode")
     return ap.parse_args()
 
 
@@ -243,7 +244,7 @@ class DeviceStep:
     NVLink-mapped mailboxes; the totals by a one-warp launch forked next to decode) or 'nccl' (sharded:
     count -> all-reduce -> main -> all-reduce (forked next to decode) -> finalize)."""
 
-    FUSE = False         # --fuse: the loss launch emits the decode's peak candidates when the shape allows it
+    FUSE = True          # --fuse auto: the loss launch emits the decode's peak candidates when the shape allows it
 
     def __init__(self, sets, cfg, world, group, schedule="auto"):
         import ctypes as C
@@ -264,7 +265,7 @@ class DeviceStep:
                                     norm=s.norm, norm_out=s.norm, b_global=s.hm.shape[0] * world)
             self.plain_args.append(F.fill_detloss_args(s.hm, s.gt, s.ind, s.heads, 1.0, s.prob, s.grads, s.scalars, s.totals,
                                                        norm=s.norm, norm_out=s.norm, b_global=s.hm.shape[0] * world))
-            if DeviceStep.FUSE:
+            if DeviceStep.FUSE and not getattr(cfg, "advent", False):   # (the ADVENT step has no decode to consume them)
                 a.cand = C.pointer(self.cand)
             sc = L.ScaleArgs()
             sc.n_tensors = 3
@@ -635,6 +636,24 @@ def workload_block(cfg, batch, rank, world, dev, steps, warmup, use_graph, peak,
     return blk, w
 
 
+def emission_parity(w):
+    """Outside any timed region: the detections a step decodes from the loss launch's candidates against the regular
+    decode of the same probability map (set 0).  Must be bit-identical; raises on mismatch."""
+    d, s = w.dstep, w.sets[0]
+    with torch.cuda.stream(w.stream):
+        d.step(0)
+        w.stream.synchronize()
+        if not d.fused_decode():
+            return None
+        from_cand = s.dets.clone()
+        s.dets.zero_()
+        d.decode_only(0)
+        w.stream.synchronize()
+    if not torch.equal(from_cand, s.dets):
+        raise RuntimeError("emission parity: detections decoded from the loss launch's candidates differ from the regular decode")
+    return "detections from the loss launch's candidates bit-identical to the regular decode of the same map"
+
+
 def sharded_parity(w, rank, world, dev):
     """N > 1, outside any timed region: this rank's sharded step (set 0) against ONE single-device launch over the
     all-gathered batch.  Scalars, probabilities, heat-map gradients and detections must be bit-identical; the
@@ -693,7 +712,7 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device for --impl ours"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    DeviceStep.FUSE = bool(args.fuse)
+    DeviceStep.FUSE = args.fuse != "off"
     steps, warmup = args.steps, max(3, args.warmup)
     use_graph = not args.no_graph
     peak, peak_src = hbm_peak()
@@ -734,6 +753,9 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
         if cfg.name != "cfg5":
             c5 = synthetic.CONFIGS["cfg5"]
             blk, w5 = workload_block(c5, 16, rank, world, dev, x_steps, x_warm, use_graph, peak)
+            ep = emission_parity(w5)
+            if ep:
+                blk["candidate_emission"] = ep
             if world > 1:
                 parity["cfg5"] = sharded_parity(w5, rank, world, dev)
             sched5 = w5.dstep.schedule

@@ -295,18 +295,19 @@ struct GTile {
   }
 };
 
-// (A) rows [r0, r0 + 4) with NO threshold, row-wise in registers (six 16-byte loads per lane, one round trip)
+// (A) rows [r0, r0 + kR) with NO threshold, row-wise in registers (kR + 2 16-byte loads per lane, one round trip)
+template <int kR = 4>
 __device__ __forceinline__ void gtile_rows_unpruned(CandEmitter& em, const GTile& t, int r0) {
   const int lane = threadIdx.x & 31;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 row[6];
+  float4 row[kR + 2];
 #pragma unroll
-  for (int q = 0; q < 6; ++q) {
+  for (int q = 0; q < kR + 2; ++q) {
     const int r = r0 - 1 + q;
     row[q] = (r >= 0 && r < kCandRows) ? __ldcg(reinterpret_cast<const float4*>(t.p + r * 128) + lane) : zero;
   }
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
+  for (int rr = 0; rr < kR; ++rr) {
     const float4 up = row[rr], mid = row[rr + 1], dn = row[rr + 2];
     const float v0 = fmaxf(fmaxf(up.x, mid.x), dn.x), v1 = fmaxf(fmaxf(up.y, mid.y), dn.y);
     const float v2 = fmaxf(fmaxf(up.z, mid.z), dn.z), v3 = fmaxf(fmaxf(up.w, mid.w), dn.w);

@@ -443,6 +443,7 @@ __device__ __forceinline__ void loss_acc_add(LossAcc& la, float v) {
 // threshold has tightened; four instructions otherwise).  thr == 0: nothing is noted (the emitter scans the whole tile).
 constexpr int kPendCap = 256;                 // pending pixels per list; more: the emitter scans the whole tile
 constexpr int kPendSlots = 8;                 // lists in flight between the consumers and the emitter (a ring of its own)
+constexpr int kBootRows = 4;                  // rows of the CTA's first chunk each consumer warp tests unpruned (8 warps)
 constexpr int kEmitSliceKeys = kSliceCap - kPendSlots * kPendCap * 2 / 8;   // keys of a slice; the lists take its tail
 struct Pending {
   unsigned short* list;                       // [kPendCap]
@@ -1608,12 +1609,14 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
             asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(m) : "l"(g.sparse + chunk_of((int)t)));
           return m;
         };
-        unsigned t_a = atomicAdd(ticket_ctr, 1u);
-        unsigned t_b = atomicAdd(ticket_ctr, 1u);
+        // (a CTA that serves no sample must not draw: a ticket drawn is a chunk nobody else will take)
+        auto draw = [&]() -> unsigned { return has_sample ? atomicAdd(ticket_ctr, 1u) : 0xffffffffu; };
+        unsigned t_a = draw();
+        unsigned t_b = draw();
         unsigned m_a = load_mask(t_a);
         for (int j = 0;; ++j) {
           const int s = j % S;
-          const unsigned t_c = atomicAdd(ticket_ctr, 1u);
+          const unsigned t_c = draw();
           const unsigned m_b = load_mask(t_b);
           if (t_b < (unsigned)n_tickets) {                                   // next issue's chunk: start it towards L2 now
             const ChunkRef nr = chunk_ref(g, chunk_of((int)t_b));
@@ -1701,6 +1704,7 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
           em.refresh_blocking();
           if (lane == 0) *reinterpret_cast<volatile float*>(&sh_thr) = __uint_as_float(em.thr);
           release(slot_q[0]);
+          if (kBootRows * kWarps < kCandRows) gtile_scan(em, tile_q[0], kBootRows * kWarps);   // the rest of the chunk, pruned
         } else if (alone) {
           release(slot_q[0]);
           gtile_scan(em, tile_q[0], 0);
@@ -1805,7 +1809,7 @@ detloss_stream_kernel(const cnh_detloss_args a, const Geo g) {
             boot.init(g.cand, my_b, my_j, g.cand_K);
             boot.shared_cnt = &sh_boot_cnt;
             boot.cap = (unsigned)kEmitSliceKeys;
-            gtile_rows_unpruned(boot, tile_of(chunk), 4 * warp);
+            gtile_rows_unpruned<kBootRows>(boot, tile_of(chunk), kBootRows * warp);
             if (boot.overflow && lane == 0) g.cand.state[my_b].overflow = 1u;
             __syncwarp();
             if (g.dbg != nullptr && tid == 0) g.dbg[(long long)bid * 16 + 6] += clock64() - tb0;
@@ -2163,7 +2167,10 @@ static int launch_stream(const cnh_detloss_args* a, Geo& g, bool fast, bool vec,
   if (a->cand != nullptr) {
     const void* ke = pick_stream_emit<MODE>(fast);
     const int grid = stream_grid(ke, g, units, kStreamStages, kEmitThreads);
-    if (setup_emission(a, g, vec, grid)) return launch(ke, cooperative, grid, kStreamStages, a, g, st, kEmitThreads);
+    // (exactly G CTAs per sample: a CTA beyond B * G would serve no sample, and the tickets its producer draws ahead
+    // would be lost to the sample it is numbered into)
+    if (setup_emission(a, g, vec, grid))
+      return launch(ke, cooperative, a->cand->G * a->B, kStreamStages, a, g, st, kEmitThreads);
   }
   const void* k = pick_stream<MODE>(fast, vec);
   return launch(k, cooperative, stream_grid(k, g, units), kStreamStages, a, g, st, kStashThreads);

@@ -708,6 +708,28 @@ def test_decode_from_loss_candidates(need_grad, sigma, shift):
     assert torch.equal(again, ref)
 
 
+@pytest.mark.parametrize("batch", [6, 16])
+def test_decode_from_loss_candidates_uneven_grid(batch):
+    """batches that do not divide the launch's resident CTAs (296 = 16 * 18 + 8 = 6 * 49 + 2 on a B200): every sample
+    gets the same number of CTAs and none is left over -- a CTA numbered into a sample it does not serve used to draw
+    (and lose) three of that sample's chunk tickets.  Loss, probabilities, gradients and detections must equal the
+    launch without emission bit for bit; batch 16 is the BASELINE config-5 shard the bench runs."""
+    from cnhead import synthetic
+    cfg = synthetic.CONFIGS["cfg5"]
+    data = synthetic.make_inputs(cfg, batch=batch, hm_sigma=2.0, seed_offset=3)
+    kw = synthetic.loss_kwargs(cfg)
+    loss_c, prob, dets_c, used, out_c = _loss_then_decode(data, kw, cfg.K, True, cfg.K)
+    assert used, "the streaming loss launch should have emitted candidates for this shape"
+    loss_r, prob_r, dets_r, used_r, out_r = _loss_then_decode(data, kw, cfg.K, True, None)
+    assert not used_r
+    assert torch.equal(loss_c, loss_r) and torch.equal(prob, prob_r)
+    for k in out_c:
+        assert torch.equal(out_c[k].grad, out_r[k].grad), k
+    assert torch.equal(dets_c, dets_r), "decode from candidates must equal the regular decode bit for bit"
+    ref = oracle.decode_stable(prob.cpu(), data["output"]["wh"], data["output"]["reg"], K=cfg.K)[0]
+    assert torch.equal(dets_c, ref)
+
+
 def test_undecoded_candidates_do_not_leak_into_the_next_step():
     """training steps that never decode leave candidate lists behind: the next emitting launch starts clean"""
     from cnhead import synthetic
