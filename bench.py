@@ -740,11 +740,17 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     # `e2e` (the headline leg): every input of the step from pinned host memory -- the head maps and, when the
     # targets are rasterisable on the device (no angle channel), the object lists they are made from; else the
     # dataset's dense targets.  e2e_dense_targets / e2e_targets_only: see run_e2e.
-    e2e = e2e_dense = e2e_tonly = None
+    # Every leg runs the step as ONE CUDA graph per feeder slot (cnhead.graphed.HostStep: the same plugin calls,
+    # captured once); e2e_eager is the headline leg again with the plugin calls made one by one from Python.
+    e2e = e2e_dense = e2e_tonly = e2e_eager = None
     if not args.no_e2e:
-        e2e_dense = run_e2e(cfg, batch, rank, world, dev, steps, warmup, "dense")
-        e2e = run_e2e(cfg, batch, rank, world, dev, steps, warmup, "boxes") if not cfg.angle else e2e_dense
-        e2e_tonly = run_e2e(cfg, batch, rank, world, dev, steps, warmup, "targets_only")
+        graphed = not args.no_graph
+        main_mode = "boxes" if not cfg.angle else "dense"
+        e2e_dense = run_e2e(cfg, batch, rank, world, dev, steps, warmup, "dense", graphed)
+        e2e = run_e2e(cfg, batch, rank, world, dev, steps, warmup, "boxes", graphed) if not cfg.angle else e2e_dense
+        e2e_tonly = run_e2e(cfg, batch, rank, world, dev, steps, warmup, "targets_only", graphed)
+        if graphed:
+            e2e_eager = run_e2e(cfg, batch, rank, world, dev, steps, warmup, main_mode, False)
 
     # ---- the other named shapes: BASELINE config 5's per-GPU shard at every N; cfg1 / cfg3 / cfg4 ------
     extra = {}
@@ -807,6 +813,7 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
         "e2e": e2e,
         "e2e_dense_targets": e2e_dense,
         "e2e_targets_only": e2e_tonly,
+        "e2e_eager": e2e_eager,
         "gpu_launches": launches_per_step * steps,
         "clocks": clk,
     }
@@ -821,7 +828,7 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_e2e(cfg, batch, rank, world, dev, steps, warmup, mode="dense"):
+def run_e2e(cfg, batch, rank, world, dev, steps, warmup, mode="dense", graphed=True):
     """the step through the plugin API with HOST inputs.  mode: 'dense' -- head maps and the dataset's dense targets
     from pinned host memory; 'boxes' -- head maps and object lists (the targets are rasterised on the device,
     SURVEY 8f N2); 'targets_only' -- the head maps stay on the device, as they do behind the reference's backbone
@@ -859,22 +866,8 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup, mode="dense"):
     # pin_memory() allocations copy at 20-40 GB/s depending on the box: tools/h2d_probe.py)
     host = HostFeeder.pinned_sets(host)
     h2d = sum(v.numel() * v.element_size() for grp in host[0] for v in grp.values())
-    dets_host = torch.empty(batch, cfg.K, 7 if cfg.rotated else 6).pin_memory()
-    loss_host = torch.empty(1).pin_memory()
-    d2h = dets_host.numel() * 4 + 4
-
-    feeder = HostFeeder(dev, depth=2)
-
-    def stage(i):
-        feeder.put(*host[i % n_host])
-
-    def step(i):
-        stage(i + 1)                                        # H2D of the NEXT step rides the copy engine under this one
-        got = feeder.get()
-        if heads_on_device:
-            o, b = dev_heads[i % n_host], got[0]
-        else:
-            o, b = got
+    def head_step(o, b):
+        """the calls a user of the plugin modules makes for one step (uda/base.py:31-82 around the head path)"""
         out = {k: v.detach().requires_grad_(True) for k, v in o.items()}
         work = dict(out)
         if from_boxes:
@@ -882,22 +875,55 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup, mode="dense"):
         loss, stats = crit(work, b)
         loss.backward()
         dets = decode_detection(work["hm"], work["wh"].detach(), work["reg"].detach(), K=cfg.K, rotated=cfg.rotated)
-        dets_host.copy_(dets, non_blocking=True)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        feeder.release()
-        torch.cuda.current_stream().synchronize()          # the caller reads the results every step
+        return {"loss": loss.detach().reshape(1), "dets": dets, "grad_hm": out["hm"].grad}
+
+    d2h = batch * cfg.K * (7 if cfg.rotated else 6) * 4 + 4
+    if graphed:
+        from cnhead.graphed import HostStep
+        hstep = HostStep(head_step, dev, fetch=("loss", "dets"), depth=2)
+        feeder = hstep.feeder
+
+        def stage(i):
+            hstep.stage(*host[i % n_host])
+
+        def step(i):
+            stage(i + 1)                                    # H2D of the NEXT step rides the copy engine under this one
+            res = hstep.run(resident=(dev_heads[i % n_host],) if heads_on_device else None)
+            res.wait()                                      # the caller reads loss and detections every step
+            return res
+    else:
+        feeder = HostFeeder(dev, depth=2)
+        dets_host = torch.empty(batch, cfg.K, 7 if cfg.rotated else 6).pin_memory()
+        loss_host = torch.empty(1).pin_memory()
+
+        def stage(i):
+            feeder.put(*host[i % n_host])
+
+        def step(i):
+            stage(i + 1)                                    # H2D of the NEXT step rides the copy engine under this one
+            got = feeder.get()
+            if heads_on_device:
+                o, b = dev_heads[i % n_host], got[0]
+            else:
+                o, b = got
+            res = head_step(o, b)
+            dets_host.copy_(res["dets"], non_blocking=True)
+            loss_host.copy_(res["loss"], non_blocking=True)
+            feeder.release()
+            torch.cuda.current_stream().synchronize()      # the caller reads the results every step
 
     e2e_steps = min(steps, 1000)
     w = min(warmup, 10)
     stage(0)
-    for i in range(w):
+    prime = 2 * n_host if graphed else 0                    # every (slot, resident set) pair meets once: graphs captured
+    for i in range(prime + w):
         step(i)
-    torch.cuda.current_stream().wait_stream(feeder.copy_stream)   # the primed copy of step w is outside the region
+    torch.cuda.current_stream().wait_stream(feeder.copy_stream)   # the primed copy of the next step is outside the region
     aligned_start(world, dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(e2e_steps):                              # exactly K puts (H2D) and K gets/compute/D2H inside
-        step(w + i)
+        step(prime + w + i)
     torch.cuda.current_stream().wait_stream(feeder.copy_stream)
     e1.record()
     barrier(world)
@@ -907,11 +933,14 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup, mode="dense"):
     return {"value": batch * world * e2e_steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "ms_per_step": ms / e2e_steps, "steps": e2e_steps,
             "h2d_GBps": h2d / (ms / e2e_steps * 1e-3) / 1e9, "host_inputs": what,
-            "api": "cnhead.feeder.HostFeeder (double-buffered H2D from pinned memory on a copy stream) + "
+            "launch": "one CUDA graph per feeder slot (cnhead.graphed.HostStep: the plugin calls captured once, replayed)"
+                      if graphed else "eager plugin calls",
+            "api": ("cnhead.graphed.HostStep = " if graphed else "") +
+                   "cnhead.feeder.HostFeeder (double-buffered H2D from pinned memory on a copy stream) + "
                    + ("cnhead.functional.raster_targets (targets rasterised on the device from object lists) + "
                       if from_boxes else "") +
                    "losses.centernet.DetectionLoss + loss.backward() + backends.decode.decode_detection + D2H of "
-                   "loss and detections, stream-synchronised every step"}
+                   "loss and detections, host-synchronised every step"}
 
 
 def main():

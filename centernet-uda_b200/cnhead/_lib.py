@@ -133,6 +133,8 @@ def lib() -> C.CDLL:
         L.cnh_cand_state_bytes.argtypes = [C.POINTER(Cand)]
         L.cnh_decode_candidates.restype = C.c_int
         L.cnh_decode_candidates.argtypes = [C.POINTER(DecodeArgs), C.POINTER(Cand), st]
+        L.cnh_copy_async.restype = C.c_int
+        L.cnh_copy_async.argtypes = [vp, vp, sz, st]
         L.cnh_raster_targets.restype = C.c_int
         L.cnh_raster_targets.argtypes = [C.POINTER(RasterArgs), st]
         _lib = L

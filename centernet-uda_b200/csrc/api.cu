@@ -43,3 +43,13 @@ extern "C" void cnh_debug_set_buffer(void* p) { cnh::g_debug = static_cast<long 
 
 extern "C" int cnh_version(void) { return CNH_VERSION; }
 extern "C" const char* cnh_last_error(void) { return cnh::g_err; }
+
+extern "C" int cnh_copy_async(void* dst, const void* src, size_t bytes, cnh_stream_t stream) {
+  if (bytes == 0) return CNH_OK;
+  if (dst == nullptr || src == nullptr) {
+    cnh::set_error("copy_async: NULL pointer");
+    return CNH_E_NULL;
+  }
+  const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? CNH_OK : cnh::cuda_fail(e, "copy_async");
+}

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CNH_VERSION 102 /* major*100 + minor */
+#define CNH_VERSION 103 /* major*100 + minor */
 
 typedef void* cnh_stream_t; /* cudaStream_t */
 
@@ -203,6 +203,11 @@ typedef struct cnh_scale_args {
   const float* fb[4];
 } cnh_scale_args;
 int cnh_scale_inplace(const cnh_scale_args* a, cnh_stream_t stream);
+
+/* Plumbing for steps captured into CUDA graphs (cnhead/graphed.py): one cudaMemcpyAsync(cudaMemcpyDefault) on
+ * `stream` -- the `.cpu()` of uda/base.py:84-88 into PINNED host memory as a copy node of the captured step.  No data
+ * is touched; dst/src may be device or page-locked host pointers. */
+int cnh_copy_async(void* dst, const void* src, size_t bytes, cnh_stream_t stream);
 
 /* ---- UDA target-domain losses over a channel softmax ---------------------------------
  * mode: 0 entropy (losses/entropy.py:24-25), 1 entropy with eta (losses/entropy.py:18-22),

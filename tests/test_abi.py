@@ -38,7 +38,7 @@ def test_header_declares_the_expected_entry_points():
 def test_library_exports_every_declared_symbol(library):
     for name in declared_symbols():
         assert hasattr(library, name), name
-    assert library.cnh_version() == 102
+    assert library.cnh_version() == 103
 
 
 def test_struct_layouts_match_header():

@@ -526,6 +526,59 @@ def test_host_feeder_round_trip_from_a_pinned_arena():
         f.get()
 
 
+@pytest.mark.parametrize("resident", [False, True])
+def test_graphed_host_step_equals_eager_calls(resident):
+    """cnhead.graphed.HostStep: the plugin calls of one step (rasterise targets, DetectionLoss, backward, decode) captured
+    once per feeder slot and replayed give, step after step, exactly what the same calls give eagerly -- loss, detections
+    (through the graph's own D2H copy into pinned memory) and the heat-map gradient, bit for bit.  resident: the head
+    maps stay on the device and only the object lists are staged (train.py:148-150 moves only the batch)."""
+    from cnhead import synthetic, functional as F
+    from cnhead.feeder import HostFeeder
+    from cnhead.graphed import HostStep
+    from losses.centernet import DetectionLoss
+    from backends.decode import decode_detection
+    cfg = synthetic.CONFIGS["cfg2"]
+    crit = DetectionLoss(**synthetic.loss_kwargs(cfg))
+    sets, heads = [], []
+    for i in range(3):
+        d = synthetic.make_inputs(cfg, batch=4, hm_sigma=2.0, seed_offset=40 + i)
+        bt = d["batch"]
+        cx = (bt["ind"] % cfg.width).float() + bt["reg"][..., 0]
+        cy = (bt["ind"] // cfg.width).float() + bt["reg"][..., 1]
+        w, h = bt["wh"][..., 0], bt["wh"][..., 1]
+        g = torch.Generator().manual_seed(7 + i)
+        lists = {"boxes": torch.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], dim=-1).contiguous(),
+                 "classes": torch.randint(0, cfg.classes, bt["ind"].shape, generator=g, dtype=torch.int32),
+                 "n_obj": bt["reg_mask"].sum(1).to(torch.int32)}
+        heads.append(d["output"])
+        sets.append((lists,) if resident else (d["output"], lists))
+    host = HostFeeder.pinned_sets(sets)
+    dev_heads = [dev(o) for o in heads]
+
+    def fn(o, b):
+        out = {k: v.detach().requires_grad_(True) for k, v in o.items()}
+        work = dict(out)
+        t = F.raster_targets(b["boxes"], b["classes"], b["n_obj"], cfg.classes, cfg.height, cfg.width)
+        loss, _ = crit(work, t)
+        loss.backward()
+        dets = decode_detection(work["hm"], work["wh"].detach(), work["reg"].detach(), K=cfg.K)
+        return {"loss": loss.detach().reshape(1), "dets": dets, "grad_hm": out["hm"].grad, "grad_wh": out["wh"].grad}
+
+    step = HostStep(fn, "cuda", fetch=("loss", "dets"), depth=2)
+    step.stage(*host[0])
+    for i in range(7):
+        j = i % 3
+        step.stage(*host[(i + 1) % 3])
+        res = step.run(resident=(dev_heads[j],) if resident else None).wait()
+        got = {"loss": res.host["loss"].clone(), "dets": res.host["dets"].clone(),
+               "grad_hm": res.device["grad_hm"].clone(), "grad_wh": res.device["grad_wh"].clone()}
+        want = fn(dev_heads[j], dev(sets[j][-1]))
+        assert torch.equal(got["loss"], want["loss"].cpu()), i
+        assert torch.equal(got["dets"], want["dets"].cpu()), i
+        assert torch.equal(got["grad_hm"], want["grad_hm"]) and torch.equal(got["grad_wh"], want["grad_wh"]), i
+    assert step.graphed.n_graphs <= (6 if resident else 2)        # captured per (slot, resident set), then replayed
+
+
 def test_host_feeder_refuses_to_overwrite_an_unreleased_slot():
     from cnhead.feeder import HostFeeder
     host = HostFeeder.pinned_sets([({"x": torch.randn(4, 8)},), ({"x": torch.randn(4, 8)},)])

@@ -107,6 +107,14 @@ def test_host_feeder_and_fetcher_refuse_to_run_without_cuda():
         HostFeeder("cuda", depth=0)
 
 
+def test_graphed_step_refuses_to_run_without_cuda():
+    from cnhead.graphed import GraphedFn, HostStep
+    with pytest.raises(RuntimeError):
+        GraphedFn(lambda: {}, "cpu")
+    with pytest.raises(RuntimeError):
+        HostStep(lambda: {}, "cpu")
+
+
 def test_host_feeder_span_detection():
     """HostFeeder ships a set as one copy only when it is a dense, aligned run of slices of ONE storage."""
     from cnhead.feeder import HostFeeder
