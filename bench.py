@@ -887,10 +887,10 @@ def run_e2e(cfg, batch, rank, world, dev, steps, warmup, mode="dense", graphed=T
             hstep.stage(*host[i % n_host])
 
         def step(i):
-            stage(i + 1)                                    # H2D of the NEXT step rides the copy engine under this one
             res = hstep.run(resident=(dev_heads[i % n_host],) if heads_on_device else None)
-            res.wait()                                      # the caller reads loss and detections every step
-            return res
+            stage(i + 1)                                    # H2D of the NEXT step rides the copy engine under this one
+            res.wait()                                      # (queued while the graph runs) the caller reads loss and
+            return res                                      # detections every step
     else:
         feeder = HostFeeder(dev, depth=2)
         dets_host = torch.empty(batch, cfg.K, 7 if cfg.rotated else 6).pin_memory()

@@ -18,8 +18,8 @@ and replays the captured launches afterwards:
     step = HostStep(fn, device, fetch=('loss', 'dets'))   # results copied to pinned host memory inside the graph
     step.stage(host_out, host_batch)                      # pinned host tensors -> slot, asynchronous (copy stream)
     for ...:
-        step.stage(next_out, next_batch)                  # H2D of step i+1 rides the copy engine under step i
         res = step.run()                                  # ONE graph launch: kernels + D2H of the fetched results
+        step.stage(next_out, next_batch)                  # H2D of step i+1 rides the copy engine under step i
         res.wait(); res.host['loss'], res.host['dets']    # pinned host tensors;  res.device[...]: everything fn returned
 
 Nothing numerical changes: the graph holds exactly the launches the eager calls make (tests/test_gpu_parity.py::
