@@ -60,7 +60,8 @@ def to_bytes(unit, v):
 launches()
 traffic = {}
 for rep, name, cfg in (("prof_detloss.ncu-rep", "detloss_cfg2", "cfg2"), ("prof_decode.ncu-rep", "decode_cfg2", None),
-                       ("prof_detloss_cfg5.ncu-rep", "detloss_cfg5", "cfg5"), ("prof_decode_cfg5.ncu-rep", "decode_cfg5", None)):
+                       ("prof_detloss_cfg5.ncu-rep", "detloss_cfg5_emit", "cfg5_emit"), ("prof_decode_cfg5.ncu-rep", "decode_cfg5", None),
+                       ("prof_finish_cfg5.ncu-rep", "finish_cfg5", None), ("prof_detloss_cfg5_plain.ncu-rep", "detloss_cfg5", "cfg5")):
     r = full(rep, name)
     if r and cfg and "dram__bytes_read.sum" in r:
         ur, vr = r["dram__bytes_read.sum"]; uw, vw = r["dram__bytes_write.sum"]

@@ -46,25 +46,25 @@ def main():
 
         def fused(flags):
             def f(i):
-                a = d.loss_args[i]
+                a = d.plain_args[i]
                 a.flags = flags
                 a.scalars = sets[i].scalars.data_ptr()
                 L.check(lib.cnh_detloss_fused(C.byref(a), d.ws_loss.data_ptr(), d.ws_loss.numel(), L.stream_ptr()), "f")
             return f
 
         def fwd_only(i):
-            a = d.loss_args[i]
+            a = d.plain_args[i]
             keep = (a.grad_hm, a.heads[0].grad, a.heads[1].grad)
             a.grad_hm, a.heads[0].grad, a.heads[1].grad = None, None, None
             L.check(lib.cnh_detloss_fused(C.byref(a), d.ws_loss.data_ptr(), d.ws_loss.numel(), L.stream_ptr()), "f")
             a.grad_hm, a.heads[0].grad, a.heads[1].grad = keep
 
         def count(i):
-            a = d.loss_args[i]
+            a = d.plain_args[i]
             L.check(lib.cnh_detloss_count(C.byref(a), d.ws_loss.data_ptr(), d.ws_loss.numel(), L.stream_ptr()), "c")
 
         def main_(i):
-            a = d.loss_args[i]
+            a = d.plain_args[i]
             a.scalars = None
             L.check(lib.cnh_detloss_main(C.byref(a), d.ws_loss.data_ptr(), d.ws_loss.numel(), L.stream_ptr()), "m")
             a.scalars = sets[i].scalars.data_ptr()
@@ -97,6 +97,7 @@ def main():
                                 ("count", count, batch * 4 * cfg.classes * hw), ("main", main_, loss_bytes),
                                 ("scale_noop", scale, 0), ("decode", decode, dec_bytes),
                                 ("torch_copy_hm", copy, batch * 8 * cfg.classes * hw), *uda,
+                                ("loss_emitting_plus_decode_from_candidates", d.loss_decode_pair, loss_bytes + dec_bytes),
                                 ("full_step", d.step, batch * cfg.bytes_per_sample())):
             us = timed(fn, n_sets)
             us_eager = timed(fn, n_sets, graph=False) if tag in ("fused_stash", "decode", "full_step") else None
