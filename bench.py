@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg5 / shapes blocks and the sharded parity check")
-    ap.add_argument("--fuse", default="auto", choices=["auto", "off"],
+    ap.add_argument("--fuse", default="auto", choices=["auto", "on", "off"],
                     help="auto: the loss launch emits the decode's peak candidates (cnh_cand) where the library supports "
                          "it -- streaming launches of 128-wide maps, i.e. the cfg5 shard; the single-wave launch of cfg2 "
                          "never does -- and the decode then runs from them (DESIGN 4.4); off: loss + streaming decode")
@@ -713,7 +713,9 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device for --impl ours"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    DeviceStep.FUSE = args.fuse != "off"
+    # auto: emission on one GPU only -- measured (profiles/r02_bench_n8.json, `other_emission_setting`): with the ranks'
+    # skew in front of the in-kernel exchange the longer emitting launch loses what the shorter decode wins
+    DeviceStep.FUSE = args.fuse == "on" or (args.fuse == "auto" and world == 1)
     steps, warmup = args.steps, max(3, args.warmup)
     use_graph = not args.no_graph
     peak, peak_src = hbm_peak()
@@ -778,7 +780,19 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
             if world > 1:
                 parity["cfg5"] = sharded_parity(w5, rank, world, dev)
             sched5 = w5.dstep.schedule
+            fuse_now = DeviceStep.FUSE and w5.dstep.fused_decode()
             w5.close()
+            if args.fuse != "off" and not int(bad.item()):
+                # the same step under the OTHER emission setting, timed on the same box: an A/B in every record
+                DeviceStep.FUSE = not fuse_now
+                alt, wa = workload_block(c5, 16, rank, world, dev, x_steps, x_warm, use_graph, peak, kernels=False)
+                other = {"candidate_emission": "on" if wa.dstep.fused_decode() else "off",
+                         "ms_per_step": alt["ms_per_step"], "step_hbm_frac": alt["step_hbm_frac"]}
+                if wa.dstep.fused_decode():
+                    other["parity"] = emission_parity(wa) or "MISMATCH against the regular decode"
+                wa.close()
+                blk["other_emission_setting"] = other
+                DeviceStep.FUSE = fuse_now
             if world > 1 and sched5 != "nccl":
                 # the schedule north_star names, measured beside the in-kernel exchange: one NCCL all-reduce of
                 # the normalisers between the count and the main launch, one of the exact totals next to decode
