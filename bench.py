@@ -62,9 +62,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg5 / shapes blocks and the sharded parity check")
     ap.add_argument("--fuse", default="auto", choices=["auto", "on", "off"],
-                    help="auto: the loss launch emits the decode's peak candidates (cnh_cand) where the library supports "
+                    help="on: the loss launch emits the decode's peak candidates (cnh_cand) where the library supports "
                          "it -- streaming launches of 128-wide maps, i.e. the cfg5 shard; the single-wave launch of cfg2 "
-                         "never does -- and the decode then runs from them (DESIGN 4.4); off: loss + streaming decode")
+                         "never does -- and the decode then runs from them (DESIGN 4.4); off: loss + streaming decode; "
+                         "auto: on, and the cfg5 block times both settings and reports the faster (and the other)")
     return ap.parse_args()
 
 
@@ -713,9 +714,8 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device for --impl ours"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    # auto: emission on one GPU only -- measured (profiles/r02_bench_n8.json, `other_emission_setting`): with the ranks'
-    # skew in front of the in-kernel exchange the longer emitting launch loses what the shorter decode wins
-    DeviceStep.FUSE = args.fuse == "on" or (args.fuse == "auto" and world == 1)
+    # auto: the cfg5 block times its step under both settings and keeps the faster (reporting both); on / off: fixed
+    DeviceStep.FUSE = args.fuse != "off"
     steps, warmup = args.steps, max(3, args.warmup)
     use_graph = not args.no_graph
     peak, peak_src = hbm_peak()
@@ -791,6 +791,18 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
                 if wa.dstep.fused_decode():
                     other["parity"] = emission_parity(wa) or "MISMATCH against the regular decode"
                 wa.close()
+                mism = isinstance(other.get("parity"), str) and other["parity"].startswith("MISMATCH")
+                if args.fuse == "auto" and other["ms_per_step"] < blk["ms_per_step"] and not mism:
+                    # start-up calibration, as a deployment would do it: the faster setting is the block's number
+                    mine = {"candidate_emission": "on" if fuse_now else "off", "ms_per_step": blk["ms_per_step"],
+                            "step_hbm_frac": blk["step_hbm_frac"]}
+                    blk["ms_per_step"], blk["step_hbm_frac"] = other["ms_per_step"], other["step_hbm_frac"]
+                    blk["value"] = 16 * world / (blk["ms_per_step"] * 1e-3)
+                    blk["schedule"], blk["gpu_launches_per_step"] = alt["schedule"], alt["gpu_launches_per_step"]
+                    blk["candidate_emission"] = other.get("parity", "off")
+                    other = mine
+                blk["emission_setting"] = ("on" if (blk.get("candidate_emission") or "off") != "off" else "off") + \
+                                          (" (the faster of the two on this box)" if args.fuse == "auto" else " (--fuse)")
                 blk["other_emission_setting"] = other
                 DeviceStep.FUSE = fuse_now
             if world > 1 and sched5 != "nccl":
