@@ -304,10 +304,12 @@ class DeviceStep:
                 self.uda_scale.append(sc)
         self.box = None
         self.schedule = "single"
+        # the backward scale (and, sharded, what only the loss VALUE needs) runs on a side stream NEXT TO the decode:
+        # neither reads what the other writes; joined before the step ends
+        self.side = torch.cuda.Stream(device=dev)
+        self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         if world > 1:
             self.schedule = "nccl"
-            self.side = torch.cuda.Stream(device=dev)
-            self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
             self.single_wave = bool(self.lib.cnh_detloss_single_wave(C.byref(self.loss_args[0])))
             if schedule in ("auto", "peers"):
                 try:
@@ -334,7 +336,7 @@ class DeviceStep:
 
     def _describe(self):
         if self.schedule == "single":
-            return "single GPU: fused loss launch + backward scale + decode"
+            return "single GPU: fused loss launch, then the backward scale (side stream) next to the decode"
         if self.schedule == "peers":
             where = ("single wave: the finaliser CTA posts, the chunk CTAs poll" if self.single_wave else
                      "pre-count schedule: CTA 0 posts after the count phase's grid barrier, every CTA polls")
@@ -426,27 +428,25 @@ class DeviceStep:
             self.sharded.exchange_normalisers(s.norm, self.group)
             L.check(self.lib.cnh_detloss_main(C.byref(a), self.ws_loss.data_ptr(), self.ws_loss.numel(), st), "main")
             a.scalars = s.scalars.data_ptr()
-        if self.schedule != "single":
-            # fork: what only the loss VALUE needs (the totals' exchange and the scalars) runs on a side stream
-            # next to the backward scale and the decode; joined before the step ends
-            main = torch.cuda.current_stream()
-            self.ev_fork.record(main)
-            self.side.wait_event(self.ev_fork)
-            with torch.cuda.stream(self.side):
-                if self.schedule == "peers":
-                    L.check(self.lib.cnh_detloss_peers_finalize(C.byref(a), C.byref(self.box.c), self.ws_loss.data_ptr(),
-                                                                self.ws_loss.numel(), L.stream_ptr()), "peers_finalize")
-                else:
-                    self.sharded.reduce_totals(s.totals, self.group)
-                    L.check(self.lib.cnh_detloss_finalize(C.byref(a), s.totals.data_ptr(), L.stream_ptr()), "finalize")
-                self.ev_join.record(self.side)
-        L.check(self.lib.cnh_scale_inplace(C.byref(self.scale_args[i]), st), "scale")            # backward
+        # fork: the backward scale and what only the loss VALUE needs (the totals' exchange and the scalars) run on a
+        # side stream next to the decode; joined before the step ends
+        main = torch.cuda.current_stream()
+        self.ev_fork.record(main)
+        self.side.wait_event(self.ev_fork)
+        with torch.cuda.stream(self.side):
+            L.check(self.lib.cnh_scale_inplace(C.byref(self.scale_args[i]), L.stream_ptr()), "scale")    # backward
+            if self.schedule == "peers":
+                L.check(self.lib.cnh_detloss_peers_finalize(C.byref(a), C.byref(self.box.c), self.ws_loss.data_ptr(),
+                                                            self.ws_loss.numel(), L.stream_ptr()), "peers_finalize")
+            elif self.schedule == "nccl":
+                self.sharded.reduce_totals(s.totals, self.group)
+                L.check(self.lib.cnh_detloss_finalize(C.byref(a), s.totals.data_ptr(), L.stream_ptr()), "finalize")
+            self.ev_join.record(self.side)
         if self.advent:
             self.advent_tail(i, st)
         else:
             self.decode_step(i)
-        if self.schedule != "single":
-            torch.cuda.current_stream().wait_event(self.ev_join)
+        main.wait_event(self.ev_join)
         if self.ws_soft is not None:               # cfg4: EntropyLoss and MaxSquareLoss fwd+bwd on the target batch
             N, Cc, H, W, n_total = self.uda_dims
             for j, mode in enumerate((L.SOFTMAX_ENTROPY, L.SOFTMAX_MAX_SQUARE)):
