@@ -749,6 +749,20 @@ def run_ours(args, cfg, batch, rank, local_rank, world):
     e2e = e2e_dense = e2e_tonly = e2e_eager = None
     if not args.no_e2e:
         graphed = not args.no_graph
+        if graphed and world > 1:
+            # HostStep captures the sharded step only with the in-kernel peer exchange (cnhead/graphed.py: the NCCL
+            # schedule's all-reduces do not replay through it); every rank must take the same branch
+            from cnhead import sharded
+            ok = 1
+            try:
+                sharded.PeerMailbox.get(None)
+            except Exception:                               # noqa: BLE001
+                ok = 0
+            flag = torch.tensor([ok], device=dev)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            graphed = bool(int(flag.item()))
+            if not graphed and rank == 0:
+                print("[bench] peer mailboxes unavailable: e2e legs run the plugin calls eagerly", file=sys.stderr)
         main_mode = "boxes" if not cfg.angle else "dense"
         e2e_dense = run_e2e(cfg, batch, rank, world, dev, steps, warmup, "dense", graphed)
         e2e = run_e2e(cfg, batch, rank, world, dev, steps, warmup, "boxes", graphed) if not cfg.angle else e2e_dense

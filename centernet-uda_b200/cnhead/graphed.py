@@ -28,6 +28,12 @@ addresses (HostFeeder hands out ``depth`` slots, so ``depth`` graphs), after ``w
 workspaces.  What ``fn`` may not do under capture is what CUDA forbids there: synchronise, or read device results on the
 host (``.item()``, ``float(t)``); ``fn`` must be a pure function of the tensors it is given (anything else it reads is
 frozen at capture time).
+
+Sharded runs: the in-kernel peer exchange (``make_sharded_loss(exchange='peers')``, what ``'auto'`` picks when the
+peers' memory can be mapped) captures and replays like the single-GPU loss (tests/test_gpu_multi.py::
+test_graphed_host_step_with_sharded_loss_two_gpus: bit-identical to the single-device eager calls).  The NCCL schedule
+(``exchange='nccl'``: two ``all_reduce`` calls inside the step) is NOT supported here -- captured through this class it
+hung both ranks of that test; run such a step eagerly.
 """
 from __future__ import annotations
 

@@ -89,3 +89,72 @@ def test_sharded_loss_two_gpus(cfg_name, exchange):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), cfg_name, exchange, out), nprocs=world, join=True)
     assert len(out) == world and out[0] == out[1]
+
+
+def _worker_graphed(rank, world, port, exchange, out):
+    """cnhead.graphed.HostStep around the SHARDED loss: each rank stages its slice from pinned host memory and replays
+    its captured step; loss, probabilities, heat-map gradient and detections equal the single-device eager calls."""
+    for p in (PKG, ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from cnhead import sharded, synthetic
+    from cnhead.feeder import HostFeeder
+    from cnhead.graphed import HostStep
+    from losses.centernet import DetectionLoss
+    from backends.decode import decode_detection
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        cfg = synthetic.CONFIGS["cfg2"]
+        B = 8
+        kw = synthetic.loss_kwargs(cfg)
+        wholes = [synthetic.make_inputs(cfg, batch=B, hm_sigma=2.0, seed_offset=60 + i) for i in range(3)]
+        sl = sharded.shard_slice(B, rank, world)
+        host = HostFeeder.pinned_sets([({k: v[sl].contiguous() for k, v in w["output"].items()},
+                                        {k: v[sl].contiguous() for k, v in w["batch"].items()}) for w in wholes])
+        crit = sharded.make_sharded_loss(DetectionLoss)(exchange=exchange, **kw)
+
+        def fn(o, b):
+            o = {k: v.detach().requires_grad_(True) for k, v in o.items()}
+            work = dict(o)
+            loss, _ = crit(work, b)
+            loss.backward()
+            dets = decode_detection(work["hm"], work["wh"].detach(), work["reg"].detach(), K=cfg.K)
+            return {"loss": loss.detach().reshape(1), "dets": dets, "grad_hm": o["hm"].grad, "prob": work["hm"]}
+
+        step = HostStep(fn, torch.device("cuda", rank), fetch=("loss", "dets"), depth=2)
+        step.stage(*host[0])
+        for i in range(6):
+            j = i % 3
+            res = step.run()
+            step.stage(*host[(i + 1) % 3])
+            res.wait()
+            o1 = {k: v.cuda().requires_grad_(True) for k, v in wholes[j]["output"].items()}
+            b1 = {k: v.cuda() for k, v in wholes[j]["batch"].items()}
+            work1 = dict(o1)
+            loss1, _ = DetectionLoss(**kw)(work1, b1)
+            loss1.backward()
+            dets1 = decode_detection(work1["hm"], work1["wh"].detach(), work1["reg"].detach(), K=cfg.K)
+            torch.cuda.synchronize()
+            assert torch.equal(res.host["loss"], loss1.detach().reshape(1).cpu()), (i, float(res.host["loss"]), float(loss1))
+            assert torch.equal(res.device["prob"], work1["hm"][sl]), i
+            assert torch.equal(res.device["grad_hm"], o1["hm"].grad[sl]), i
+            assert torch.equal(res.host["dets"], dets1[sl].cpu()), i
+        assert step.graphed.n_graphs == 2
+        out[rank] = float(res.host["loss"])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("exchange", ["peers"])
+def test_graphed_host_step_with_sharded_loss_two_gpus(exchange):
+    """(exchange='nccl' is NOT supported under HostStep: with the two all-reduces of the NCCL schedule inside the
+    captured step both ranks hung in this test -- cnhead/graphed.py says so, bench.py captures the e2e step only when
+    the in-kernel exchange is available)"""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_graphed, args=(world, _free_port(), exchange, out), nprocs=world, join=True)
+    assert len(out) == world and out[0] == out[1]
