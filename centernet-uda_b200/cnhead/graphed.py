@@ -116,8 +116,8 @@ class GraphedFn:
                     t = t.contiguous()
                 if t.shape != c.host[k].shape:
                     raise RuntimeError(f"cnhead.graphed: result '{k}' changed shape between runs")
-                # a copy node of the graph (the library's cudaMemcpyAsync: torch's pinned-memory bookkeeping of
-                # non_blocking copies records events, which a capture does not take)
+                # a copy node of the graph (the library's plain cudaMemcpyAsync; torch's non_blocking copy into pinned
+                # memory also records host-allocator events on the copying stream: not something to rely on under capture)
                 L.check(L.lib().cnh_copy_async(c.host[k].data_ptr(), t.data_ptr(), t.numel() * t.element_size(),
                                                L.stream_ptr()), "copy_async")
                 temps.append(t)
