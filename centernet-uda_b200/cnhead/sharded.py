@@ -187,6 +187,12 @@ class _ShardedDetectionLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, hm, *maps):
         gt, ind, specs, hm_weight, group = meta
+        if torch.cuda.is_current_stream_capturing():
+            # cnhead.graphed.HostStep around this schedule hung both ranks of the 2-GPU test (suspected: the process
+            # group's watchdog polling the warm-up collectives' events while another thread captures in global mode);
+            # the in-kernel exchange captures fine.  Fail loudly instead of hanging.
+            raise RuntimeError("cnhead: the NCCL schedule of the sharded DetectionLoss (exchange='nccl') cannot be "
+                               "captured into a CUDA graph through the plugin wrapper; use exchange='peers' or run it eagerly")
         heads = [F.HeadSpec(m, s.target, s.mask, s.weight, s.angle_weight, s.angle_mode, s.elementwise_mask, s.pairs)
                  for m, s in zip(maps, specs)]
         world = dist.get_world_size(group) if dist.is_initialized() else 1
