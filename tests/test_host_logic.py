@@ -143,3 +143,35 @@ def test_pinned_arena_layout_arithmetic():
     from cnhead.feeder import PinnedArena
     ts = [torch.empty(3, 5), torch.empty(7, dtype=torch.int64), torch.empty(1, dtype=torch.uint8)]
     assert PinnedArena.bytes_for(ts) == 3 * 4096 and PinnedArena.MIN_BYTES >= 256 << 20
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys,
+    the same `config` dict the GPU arm prints, `--warmup` honoured, and no CUDA needed."""
+    import json
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "heatmaps/s" and line["higher_is_better"] is True
+    assert line["steps"] == 2 and line["warmup"] == 3 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    _sys.path.insert(0, root)
+    import bench
+    from cnhead import synthetic
+    assert line["config"] == bench.config_dict(synthetic.CONFIGS["cfg2"], 16, 1)
+
+
+def test_bench_gpu_arm_fails_loudly_without_cuda():
+    import subprocess
+    import sys as _sys
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "CUDA" in r.stderr
