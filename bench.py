@@ -8,20 +8,25 @@
 One step = one pass of the hot path over one synthetic batch of the workload (default cfg2: batch 16,
 6 classes, 128x128 heat maps, max_detections 150, per GPU -- weak scaling): DetectionLoss forward,
 its backward, and decode_detection of the same head tensors.
-  value  : device-resident inputs, the three launches of a step replayed from CUDA graphs over
-           rotating buffer sets that together exceed the L2 (HBM-cold), timed with CUDA events.
-  e2e    : the same step through the reference-facing plugin API (losses.centernet.DetectionLoss,
-           loss.backward(), backends.decode.decode_detection) with PINNED HOST inputs: H2D copy of the
-           head maps and targets (cnhead.feeder.HostFeeder: step i+1's copy rides a copy stream under
-           step i), D2H read of the loss and the detections inside the timed region, stream-synchronised
-           every step.  e2e_boxes: same, with the targets rasterised on the device from object lists
-           (cnhead.functional.raster_targets) -- the host ships boxes instead of the dense heat-map target.
+  value  : device-resident inputs, the three launches of a step (loss, then the backward scale on a side stream
+           next to the decode) replayed from CUDA graphs over rotating buffer sets that together exceed the L2
+           (HBM-cold), timed with CUDA events.
+  e2e    : the same step through the reference-facing plugin API (cnhead.functional.raster_targets,
+           losses.centernet.DetectionLoss, loss.backward(), backends.decode.decode_detection) with PINNED HOST inputs:
+           H2D copy of the head maps and of the object lists the targets are rasterised from (cnhead.feeder.HostFeeder:
+           step i+1's copy rides a copy stream under step i), D2H read of the loss and the detections inside the timed
+           region, the host waiting for them every step.  The plugin calls run as ONE CUDA graph per feeder slot
+           (cnhead.graphed.HostStep: captured from those very calls the first time a slot is used).
+           e2e_eager: the same leg with the plugin calls made one by one from Python; e2e_dense_targets: the
+           dataset's dense targets shipped instead of object lists; e2e_targets_only: head maps device-resident
+           (as behind the reference's backbone), only the object lists shipped.
   roofline: the dominant kernel (fused detection-loss launch) timed alone with CUDA events.
   cpu_baseline / --impl reference: the oracle port of the reference's PyTorch path on the host cores.
   cfg5   : (every N) the same step on BASELINE config 5's per-GPU shard (16 x 80 x 128^2 of the 128-sample
            COCO-scale batch): ms_per_step, step_hbm_frac, per-kernel {us, frac}; at N > 1 the schedule
            north_star names (count -> all-reduce -> main -> all-reduce -> finalize over NCCL) with the
-           all-reduce time.
+           all-reduce time.  --fuse auto: the step is timed with and without the loss launch emitting the decode's
+           peak candidates; the faster is the block's number, the other is reported beside it.
   shapes : step_hbm_frac of the other named shapes (cfg1, cfg3, cfg4), short runs.
   sharded_parity (N > 1, outside the timed region): one sharded step per schedule is compared with a
            single-device launch over the all-gathered batch -- scalars, probabilities, heat-map gradients and
